@@ -1,0 +1,190 @@
+/*
+ * xeq_b200.h -- C ABI of libxeq_b200.so (sm_100a only).
+ *
+ * Drop-in boundary for the XPaiNN message-passing hot path of X1X1010/XequiNet.  The
+ * reference has no FFI layer; its boundary is a set of Python calls into third-party
+ * packages.  Each entry point below names the reference call site
+ * (paths relative to /root/reference/xequinet/) whose device work it replaces.
+ *
+ * Conventions
+ *   - plain pointers and sizes only; every pointer is a DEVICE pointer unless the
+ *     parameter name ends in _host;  all feature tensors are row-major fp32;
+ *   - the caller owns every buffer (outputs and workspace); a *_workspace_bytes()
+ *     query precedes each call that needs scratch;
+ *   - every call is asynchronous on `stream` (a cudaStream_t), performs no allocation
+ *     and no host synchronisation, and keeps no global mutable state;
+ *   - return value 0 = success, negative = error (xeq_last_error() gives a thread-local
+ *     message).  No C++ exceptions cross the ABI.  There is no CPU fallback.
+ *
+ * Internal feature layout ("cm", component-major) of equivariant tensors [N, D]:
+ *     [ mul0 scalars | l=1: 3 blocks (m=-1,0,1) of mul1 | l=2: 5 blocks (m=-2..2) of mul2 ]
+ * i.e. within each l the multiplicity index is fastest, so a warp that owns 32
+ * consecutive channels reads 128 contiguous bytes per component.  The reference (e3nn)
+ * layout is mul-major / m-fastest; xeq_layout_convert() maps between the two.
+ */
+#ifndef XEQ_B200_H
+#define XEQ_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define XEQ_OK 0
+#define XEQ_ERR_INVALID -1     /* bad argument / unsupported shape */
+#define XEQ_ERR_CUDA -2        /* a CUDA runtime call failed */
+#define XEQ_ERR_WORKSPACE -3   /* workspace too small */
+
+typedef void* xeq_stream_t; /* cudaStream_t */
+
+/* Model widths: nn/model.py:57-67.  mul0 must equal node_dim (true for every documented
+ * config, docs/config.md:64-65); mul* must be multiples of 32; num_basis <= 23. */
+typedef struct {
+  int32_t node_dim; /* C   */
+  int32_t mul0;     /* number of 0e irreps */
+  int32_t mul1;     /* number of 1o irreps */
+  int32_t mul2;     /* number of 2e irreps */
+  int32_t num_basis;/* B   */
+  float cutoff;     /* r_c */
+} xeq_dims_t;
+
+/* Neighbour structure produced by xeq_radius_graph_* / xeq_csr_from_coo + xeq_csr_transpose.
+ * Edge e = (center <- neighbor) (keys.py:16-17); canonical order = CSR by center. */
+typedef struct {
+  int32_t n_nodes;
+  int32_t n_edges;
+  int32_t n_graphs;
+  int32_t _pad;
+  const int32_t* rowptr;    /* [N+1]  CSR by center                                   */
+  const int32_t* col;       /* [E]    neighbor of edge e                              */
+  const int32_t* t_rowptr;  /* [N+1]  CSR by neighbor (transposed)                    */
+  const int32_t* t_row;     /* [E]    center of transposed slot                       */
+  const int32_t* t_eid;     /* [E]    canonical edge id of transposed slot            */
+  const int8_t* offsets;    /* [E,4]  integer cell offsets (x,y,z,0) or NULL (no PBC) */
+  const float* cell;        /* [G,3,3] lattice rows or NULL                           */
+  const int32_t* node_graph;/* [N]    graph id per node (needed when cell && G > 1)   */
+} xeq_graph_t;
+
+int xeq_version(void);
+const char* xeq_last_error(void);
+/* Number of SMs of the current device (grid sizing is done inside the library). */
+int xeq_num_sms(void);
+
+/* ------------------------------------------------------------------------------------
+ * K1  radius graph.  Replaces torch_cluster.radius_graph (data/transform.py:58-64) and
+ * radius_graph_pbc (data/radius_graph.py:35-192, called at data/transform.py:43-49).
+ *
+ * Non-periodic (cell == NULL): all ordered pairs a != b of the same graph with
+ *   (xa-xb)^2 + (ya-yb)^2 + (za-zb)^2 < r^2   (fp32, no FMA contraction, strict).
+ * Periodic: positions are wrapped into the cell (data/radius_graph.py:6-32), images
+ *   -rep..rep per periodic axis (rep_host, data/radius_graph.py:61-89) are enumerated and
+ *   pairs with 0.01 < sqrt(sum (a - (b + o@cell))^2) < r kept (:125); offsets are referred
+ *   back to the unwrapped positions (:186-190).  Self-image pairs (a == b, o != 0) are kept.
+ * Large single graphs use a cell list (bins >= r_c); small/batched graphs a per-graph scan.
+ *
+ * Two phases (the host reads rowptr[N] in between to size the outputs):
+ *   count: degree -> exclusive scan -> rowptr[N+1]
+ *   fill : col[E], offsets[E,4] (periodic), optional COO edge_index[2,E] (int64) and
+ *          cell_offsets[E,3] (float) for API compatibility with the reference.
+ * Rows come out sorted by (neighbor, ox, oy, oz) => the COO output is canonically sorted.
+ * ---------------------------------------------------------------------------------- */
+size_t xeq_radius_graph_workspace_bytes(int32_t n_nodes, int32_t n_graphs, int periodic);
+
+int xeq_radius_graph_count(const float* pos, int32_t n_nodes,
+                           const int32_t* graph_ptr /* [G+1] */, const int32_t* node_graph /* [N] */,
+                           int32_t n_graphs, const float* cell /* [G,3,3] or NULL */,
+                           const int32_t* pbc_host /* [3] */, const int32_t* rep_host /* [3] */,
+                           float cutoff, int32_t* rowptr /* [N+1] out */,
+                           void* workspace, size_t workspace_bytes, xeq_stream_t stream);
+
+int xeq_radius_graph_fill(const float* pos, int32_t n_nodes,
+                          const int32_t* graph_ptr, const int32_t* node_graph, int32_t n_graphs,
+                          const float* cell, const int32_t* pbc_host, const int32_t* rep_host,
+                          float cutoff, const int32_t* rowptr, int32_t* col /* [E] out */,
+                          int8_t* offsets /* [E,4] out or NULL */,
+                          int64_t* edge_index /* [2,E] out or NULL */,
+                          float* cell_offsets /* [E,3] out or NULL */,
+                          void* workspace, size_t workspace_bytes, xeq_stream_t stream);
+
+/* CSR from a caller-supplied COO edge list that is already sorted by center
+ * (edge_index[0] non-decreasing): rowptr from segment boundaries, col = int32(edge_index[1]),
+ * offsets = int8(cell_offsets).  Entry for graphs that did not come from K1
+ * (the reference model takes `edge_index` from the data dict, nn/basic.py:67). */
+int xeq_csr_from_sorted_coo(const int64_t* edge_index /* [2,E] */, const float* cell_offsets /* [E,3] or NULL */,
+                            int32_t n_nodes, int32_t n_edges, int32_t* rowptr, int32_t* col,
+                            int8_t* offsets /* [E,4] or NULL */, xeq_stream_t stream);
+
+/* Transposed structure (edges grouped by neighbor), deterministic slot order (by edge id). */
+size_t xeq_csr_transpose_workspace_bytes(int32_t n_nodes, int32_t n_edges);
+int xeq_csr_transpose(const int32_t* rowptr, const int32_t* col, int32_t n_nodes, int32_t n_edges,
+                      int32_t* t_rowptr, int32_t* t_row, int32_t* t_eid,
+                      void* workspace, size_t workspace_bytes, xeq_stream_t stream);
+
+/* ------------------------------------------------------------------------------------
+ * K2  fused edge message.  Replaces, per XPainnMessage.forward (nn/xpainn.py:140-159):
+ * rbf/cutoff/SphericalHarmonics (nn/xpainn.py:66-74, nn/rbf.py:43-57,143-150), rbf_lin addmm,
+ * index_select x2, 2x ElementwiseTensorProduct, index_add x2 -- and the edge-vector
+ * preparation of compute_edge_data (nn/basic.py:114-131).  Nothing E-sized is materialised.
+ *
+ *   r_e = pos[i] - pos[j] - o_e @ cell,  d = |r_e|,  psi_0 = chi(d), psi_k = chi(d) phi_k(d)
+ *   w_e[h] = b[h] psi_0 + sum_k W[h,k] psi_k            (h < H = C + 2M)
+ *   x_out[i]        = x_in[i]        + sum_e s[j, 2M+c] w_e[2M+c]
+ *   V_out[i,(q,m)]  = V_in[i,(q,m)]  + sum_e s[j,q] w_e[q] v[j,(q,m)] + s[j,M+q] w_e[M+q] Y_lm(r_e)
+ * x_in / V_in may be NULL (treated as zero).  One CTA walks whole CSR rows with one thread
+ * per irrep channel; the segment sum lives in registers (no atomics, deterministic).
+ * ---------------------------------------------------------------------------------- */
+int xeq_edge_message_fwd(const xeq_graph_t* g, const xeq_dims_t* dims, const float* pos,
+                         const float* s /* [N,H] */, const float* v /* [N,D] cm */,
+                         const float* x_in /* [N,C] */, const float* V_in /* [N,D] cm */,
+                         const float* W_rbf /* [H,B] */, const float* b_rbf /* [H] */, const float* freq /* [B] */,
+                         float* x_out, float* V_out, xeq_stream_t stream);
+
+/* K2b  first derivatives (forces; nn/basic.py:143-159 replays the ops above in reverse).
+ * Given gx = dL/dx_out [N,C], gV = dL/dV_out [N,D]:  gs [N,H], gv [N,D], gpos [N,3] and, when
+ * gW != NULL, gW [H,B], gb [H], gfreq [B] (gfreq is *written*, the caller sums over layers;
+ * nn/rbf.py:143-144 shares freq).  dL/dx_in = gx and dL/dV_in = gV are the identity.
+ * Any of gs/gv/gpos may be NULL (skipped). */
+size_t xeq_edge_message_bwd_workspace_bytes(const xeq_graph_t* g, const xeq_dims_t* dims, int want_wgrad);
+int xeq_edge_message_bwd(const xeq_graph_t* g, const xeq_dims_t* dims, const float* pos,
+                         const float* s, const float* v,
+                         const float* W_rbf, const float* b_rbf, const float* freq,
+                         const float* gx, const float* gV,
+                         float* gs, float* gv, float* gpos,
+                         float* gW, float* gb, float* gfreq,
+                         void* workspace, size_t workspace_bytes, xeq_stream_t stream);
+
+/* K2bb  double backward (force training: utils/trainer.py:295-302 calls loss.backward()
+ * through forces obtained with create_graph=True, nn/basic.py:150-156).
+ * With Phi = <gx, dx> + <gV, dV> the outputs of K2b are dPhi/d(s, v, pos).  Given cotangents
+ * (a_s, a_v, a_pos) of (gs, gv, gpos) (any may be NULL = zero) this returns the gradient of
+ *   Psi = <a_s, dPhi/ds> + <a_v, dPhi/dv> + <a_pos, dPhi/dpos>
+ * with respect to gx, gV, s, v, pos, W_rbf, b_rbf, freq.  Output pointers may be NULL. */
+size_t xeq_edge_message_bwdbwd_workspace_bytes(const xeq_graph_t* g, const xeq_dims_t* dims, int want_wgrad);
+int xeq_edge_message_bwdbwd(const xeq_graph_t* g, const xeq_dims_t* dims, const float* pos,
+                            const float* s, const float* v,
+                            const float* W_rbf, const float* b_rbf, const float* freq,
+                            const float* gx, const float* gV,
+                            const float* a_s, const float* a_v, const float* a_pos,
+                            float* o_gx, float* o_gV, float* o_s, float* o_v, float* o_pos,
+                            float* o_W, float* o_b, float* o_freq,
+                            void* workspace, size_t workspace_bytes, xeq_stream_t stream);
+
+/* ------------------------------------------------------------------------------------
+ * Segment sum over contiguous segments: out[g] = sum_{ptr[g] <= n < ptr[g+1]} src[n].
+ * Replaces torch_scatter.scatter_sum(atomic_energies, batch) (nn/output.py:124) for the
+ * sorted `batch` every collated batch has (keys.py:9-10).
+ * ---------------------------------------------------------------------------------- */
+int xeq_segment_sum(const float* src, const int32_t* seg_ptr /* [G+1] */, int32_t n_segments,
+                    float* out, xeq_stream_t stream);
+
+/* e3nn (mul-major, m-fastest) <-> cm (component-major) layout of [N, D] tensors.
+ * direction 0: e3nn -> cm, 1: cm -> e3nn. */
+int xeq_layout_convert(const float* src, float* dst, int32_t n_nodes, const xeq_dims_t* dims,
+                       int direction, xeq_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* XEQ_B200_H */

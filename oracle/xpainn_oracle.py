@@ -614,3 +614,41 @@ def make_small_pbc(n_atoms: int = 12, box: float = 6.0, seed: int = 0, dtype=tor
         "cell": cell.unsqueeze(0).to(dtype),
         "pbc": torch.tensor([list(pbc)]),
     }
+
+
+# ----------------------------------------------------------------------------
+# stand-alone edge message (one XPainnMessage aggregation), used to check K2/K2b/K2bb
+# ----------------------------------------------------------------------------
+def edge_message(x, V, s, vn, pos, W_rbf, b_rbf, freq, edge_index, cfg: XPaiNNConfig,
+                 cell=None, cell_offsets=None, batch=None):
+    """nn/xpainn.py:140-159 restated as a function of (x, V, s, vn, pos, weights), e3nn layout.
+    Returns (x_out, V_out)."""
+    M = cfg.M
+    m0, m1, m2 = cfg.muls
+    center, neighbor = edge_index[0], edge_index[1]
+    vec, dist = edge_vectors(pos, edge_index, cell, cell_offsets, batch)
+    d1 = dist.unsqueeze(-1)
+    rbf = bessel_rbf(d1, freq.view(1, -1), cfg.cutoff)
+    fcut = cosine_cutoff(d1, cfg.cutoff)
+    Y = spherical_harmonics_l2(vec)
+    rsh = torch.cat([Y[:, 0:1].repeat(1, m0), Y[:, 1:4].repeat(1, m1), Y[:, 4:9].repeat(1, m2)], dim=1)
+    w = F.linear(rbf, W_rbf, b_rbf) * fcut
+    h = s.index_select(0, neighbor) * w
+    g_state, g_edge, m_s = h[:, :M], h[:, M : 2 * M], h[:, 2 * M :]
+    m_e = vn.index_select(0, neighbor) * expand_gate(g_state, cfg) + rsh * expand_gate(g_edge, cfg)
+    return x.index_add(0, center, m_s), V.index_add(0, center, m_e)
+
+
+def to_cm(V: torch.Tensor, cfg: XPaiNNConfig) -> torch.Tensor:
+    """e3nn layout [mul][m] -> component-major [m][mul] per l (include/xeq_b200.h)."""
+    outs = []
+    for off, mul, d in _blocks(cfg):
+        outs.append(V[:, off : off + mul * d].reshape(-1, mul, d).transpose(1, 2).reshape(-1, mul * d))
+    return torch.cat(outs, dim=1)
+
+
+def from_cm(V: torch.Tensor, cfg: XPaiNNConfig) -> torch.Tensor:
+    outs = []
+    for off, mul, d in _blocks(cfg):
+        outs.append(V[:, off : off + mul * d].reshape(-1, d, mul).transpose(1, 2).reshape(-1, mul * d))
+    return torch.cat(outs, dim=1)

@@ -1,0 +1,241 @@
+// Per-thread channel arithmetic of the fused edge kernels (K2 / K2b / K2bb).
+//
+// "Center" threads own one irrep channel q (all of its 2l+1 components, its state gate,
+// its edge gate and -- for l = 0 -- the scalar-message channel) and walk a CSR row of the
+// *receiving* node: forward message and the forward-mode tangent used by the double backward.
+// "Neighbor" threads own one filter channel h < H and walk a transposed-CSR row of the
+// *sending* node: first and second derivatives.
+//
+// Templated on the scalar type so tests/host_emul can run the same code in float64.
+// Notation follows SURVEY.md Appendix A; see DESIGN.md for the second-order derivation.
+#pragma once
+#include "edge_math.cuh"
+
+namespace xeq {
+
+template <int L> struct YOff { static constexpr int value = (L == 1) ? 0 : 3; };  // offset into Y[8]
+
+template <typename T>
+XEQ_HD T dot_nbp(const T* __restrict__ w, const T* __restrict__ p, int nk) {
+  T acc = T(0);
+#pragma unroll
+  for (int k = 0; k < NBP; ++k)
+    if (k < nk) acc += w[k] * p[k];
+  return acc;
+}
+
+// ------------------------------------------------------------------------------------------
+// Center threads (K2 forward, and the JVP half of K2bb)
+// ------------------------------------------------------------------------------------------
+template <typename T, int L>
+struct CenterThread {
+  static constexpr int NC = 2 * L + 1;
+  T Ws[NBP], We[NBP], Wx[NBP];  // rows of [b | W_rbf] for the state gate, edge gate, scalar channel
+  T accV[NC];
+  T accx;
+
+  XEQ_HD void reset() {
+#pragma unroll
+    for (int m = 0; m < NC; ++m) accV[m] = T(0);
+    accx = T(0);
+  }
+
+  // forward message of one edge: psi[NBP], Y[8]; s_* are s[j, .] of the neighbor, v its v[j, (q, m)]
+  XEQ_HD void fwd(const T* psi, const T* Y, int nk, T s_state, T s_edge, T s_x, const T* v) {
+    const T gs = s_state * dot_nbp(Ws, psi, nk);
+    const T ge = s_edge * dot_nbp(We, psi, nk);
+    if (L == 0) {
+      accV[0] += gs * v[0] + ge;
+      accx += s_x * dot_nbp(Wx, psi, nk);
+    } else {
+#pragma unroll
+      for (int m = 0; m < NC; ++m) accV[m] += gs * v[m] + ge * Y[YOff<L>::value + m];
+    }
+  }
+
+  // tangent of the forward message along (sdot, vdot, rdot): d/deps of fwd()
+  XEQ_HD void jvp(const T* psi, const T* dpsi, const T* Y, const T* Ydot, T ddot, int nk, T s_state, T s_edge,
+                  T s_x, const T* v, T sd_state, T sd_edge, T sd_x, const T* vd) {
+    const T ws = dot_nbp(Ws, psi, nk), we = dot_nbp(We, psi, nk);
+    const T dws = dot_nbp(Ws, dpsi, nk) * ddot, dwe = dot_nbp(We, dpsi, nk) * ddot;
+    const T gs = s_state * ws, ge = s_edge * we;
+    const T gsd = sd_state * ws + s_state * dws;
+    const T ged = sd_edge * we + s_edge * dwe;
+    if (L == 0) {
+      accV[0] += gsd * v[0] + gs * vd[0] + ged;
+      accx += sd_x * dot_nbp(Wx, psi, nk) + s_x * dot_nbp(Wx, dpsi, nk) * ddot;
+    } else {
+#pragma unroll
+      for (int m = 0; m < NC; ++m)
+        accV[m] += gsd * v[m] + gs * vd[m] + ged * Y[YOff<L>::value + m] + ge * Ydot[YOff<L>::value + m];
+    }
+  }
+};
+
+// ------------------------------------------------------------------------------------------
+// Neighbor threads (K2b, and the reverse half of K2bb)
+// ------------------------------------------------------------------------------------------
+enum Role : int { ROLE_STATE = 0, ROLE_EDGE = 1, ROLE_SCALAR = 2 };
+
+// geometry of one edge as the neighbor threads see it (kernels keep this in shared memory)
+template <typename T>
+struct NbrEdge {
+  const T* psi;    // [NBP]
+  const T* dpsi;   // [NBP]
+  const T* ddpsi;  // [NBP]  second order only
+  const T* xi;     // [NBP]  wgrad only
+  const T* dxi;    // [NBP]  second order + wgrad only
+  const T* Y;      // [8]
+  const T* G;      // [3*8]  G[x*8+m]
+  const T* Hm;     // [3*8]  second order only
+  const T* Ydot;   // [8]    second order only
+  const T* u;      // [3]
+  const T* rp;     // [3]    second order only
+  T ddot;          //        second order only
+};
+
+template <typename T, int L, int ROLE, bool WGRAD>
+struct NeighborThread {
+  static constexpr int NC = (ROLE == ROLE_SCALAR) ? 1 : 2 * L + 1;
+  static constexpr int YO = YOff<L>::value;
+  T Wt[NBP];          // row h of [b | W_rbf]
+  T s, sd;            // s[j,h] and its cotangent a_s[j,h] (second order)
+  T v[NC], vd[NC];    // ROLE_STATE: v[j,(q,:)] and a_v[j,(q,:)]
+  T acc_s;            // -> gs[j,h]        (first order) / o_s[j,h] (second order)
+  T acc_v[NC];        // -> gv[j,(q,:)]    (ROLE_STATE)
+  T GW[NBP], GF[NBP]; // wgrad accumulators (GW[0] is the bias gradient)
+
+  XEQ_HD void reset_node() {
+    acc_s = T(0);
+#pragma unroll
+    for (int m = 0; m < NC; ++m) acc_v[m] = T(0);
+  }
+  XEQ_HD void reset_wgrad() {
+#pragma unroll
+    for (int k = 0; k < NBP; ++k) GW[k] = GF[k] = T(0);
+  }
+
+  // First derivatives.  g = gV[i,(q,:)] (state/edge roles) or gx[i,c] (scalar role).
+  // pr[3] receives this thread's share of dPhi/dr_e.
+  XEQ_HD void first(const NbrEdge<T>& e, int nk, const T* g, T pr[3]) {
+    const T w = dot_nbp(Wt, e.psi, nk);
+    const T dw = dot_nbp(Wt, e.dpsi, nk);
+    T pw;  // dPhi/dw_e[h]
+    T cy[NC];
+    if (ROLE == ROLE_STATE) {
+      T A = T(0);
+#pragma unroll
+      for (int m = 0; m < NC; ++m) A += g[m] * v[m];
+      acc_s += A * w;
+      const T sw = s * w;
+#pragma unroll
+      for (int m = 0; m < NC; ++m) acc_v[m] += sw * g[m];
+      pw = A * s;
+    } else if (ROLE == ROLE_EDGE) {
+      T B = T(0);
+      if (L == 0) {
+        B = g[0];
+      } else {
+#pragma unroll
+        for (int m = 0; m < NC; ++m) B += g[m] * e.Y[YO + m];
+      }
+      acc_s += B * w;
+      pw = B * s;
+      const T sw = s * w;
+#pragma unroll
+      for (int m = 0; m < NC; ++m) cy[m] = sw * g[m];
+    } else {
+      acc_s += g[0] * w;
+      pw = g[0] * s;
+    }
+    const T dpart = pw * dw;
+#pragma unroll
+    for (int x = 0; x < 3; ++x) {
+      T p = e.u[x] * dpart;
+      if (ROLE == ROLE_EDGE && L > 0) {
+#pragma unroll
+        for (int m = 0; m < NC; ++m) p += e.G[x * 8 + YO + m] * cy[m];
+      }
+      pr[x] = p;
+    }
+    if (WGRAD) {
+#pragma unroll
+      for (int k = 0; k < NBP; ++k)
+        if (k < nk) {
+          GW[k] += pw * e.psi[k];
+          GF[k] += pw * e.xi[k];
+        }
+    }
+  }
+
+  // Second derivatives: gradient of Psi_e (the tangent of Phi_e along (sd, vd, rdot)).
+  XEQ_HD void second(const NbrEdge<T>& e, int nk, const T* g, T pr[3]) {
+    const T w = dot_nbp(Wt, e.psi, nk);
+    const T dw = dot_nbp(Wt, e.dpsi, nk);
+    const T ddw = dot_nbp(Wt, e.ddpsi, nk);
+    const T dwd = dw * e.ddot;  // tangent of w
+    T alpha, beta;
+    T cy[NC], cz[NC];
+    if (ROLE == ROLE_STATE) {
+      T A = T(0), Ad = T(0);
+#pragma unroll
+      for (int m = 0; m < NC; ++m) {
+        A += g[m] * v[m];
+        Ad += g[m] * vd[m];
+      }
+      alpha = sd * A + s * Ad;
+      beta = s * A;
+      acc_s += dwd * A + w * Ad;
+      const T c = sd * w + s * dwd;
+#pragma unroll
+      for (int m = 0; m < NC; ++m) acc_v[m] += c * g[m];
+    } else if (ROLE == ROLE_EDGE) {
+      T B = T(0), Bd = T(0);
+      if (L == 0) {
+        B = g[0];
+      } else {
+#pragma unroll
+        for (int m = 0; m < NC; ++m) {
+          B += g[m] * e.Y[YO + m];
+          Bd += g[m] * e.Ydot[YO + m];
+        }
+      }
+      alpha = sd * B + s * Bd;
+      beta = s * B;
+      acc_s += dwd * B + w * Bd;
+      const T c = sd * w + s * dwd;
+      const T sw = s * w;
+#pragma unroll
+      for (int m = 0; m < NC; ++m) {
+        cy[m] = c * g[m];
+        cz[m] = sw * g[m];
+      }
+    } else {
+      alpha = g[0] * sd;
+      beta = g[0] * s;
+      acc_s += g[0] * dwd;
+    }
+    const T P = alpha * dw + e.ddot * beta * ddw;
+    const T R1 = beta * dw;
+#pragma unroll
+    for (int x = 0; x < 3; ++x) {
+      T p = e.u[x] * P + R1 * e.rp[x];
+      if (ROLE == ROLE_EDGE && L > 0) {
+#pragma unroll
+        for (int m = 0; m < NC; ++m) p += e.G[x * 8 + YO + m] * cy[m] + e.Hm[x * 8 + YO + m] * cz[m];
+      }
+      pr[x] = p;
+    }
+    if (WGRAD) {
+      const T bd = beta * e.ddot;
+#pragma unroll
+      for (int k = 0; k < NBP; ++k)
+        if (k < nk) {
+          GW[k] += alpha * e.psi[k] + bd * e.dpsi[k];
+          GF[k] += alpha * e.xi[k] + bd * e.dxi[k];
+        }
+    }
+  }
+};
+
+}  // namespace xeq
