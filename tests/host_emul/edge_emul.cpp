@@ -70,7 +70,7 @@ static void center_node(const Dims& D, int i, int q, const int* rowptr, const in
                         const T* a_s, const T* a_v, const T* a_pos, T* outx, T* outV) {
   const int M = D.m0 + D.m1 + D.m2, Dd = D.m0 + 3 * D.m1 + 5 * D.m2, H = D.C + 2 * M, nk = D.B + 1;
   Chan c = chan_of_q(D, q);
-  CenterThread<T, L> th;
+  CenterThread<T, L, 21> th;
   load_wrow(W, b, q, D.B, th.Ws);
   load_wrow(W, b, M + q, D.B, th.We);
   if (L == 0) load_wrow(W, b, 2 * M + q, D.B, th.Wx);
@@ -85,8 +85,8 @@ static void center_node(const Dims& D, int i, int q, const int* rowptr, const in
     T vv[5], vd[5];
     for (int m = 0; m < 2 * L + 1; ++m) { vv[m] = v[(size_t)j * Dd + c.vbase + m * c.vstride]; vd[m] = jv ? a_v[(size_t)j * Dd + c.vbase + m * c.vstride] : 0; }
     T ss = s[(size_t)j * H + q], se = s[(size_t)j * H + M + q], sx = L == 0 ? s[(size_t)j * H + 2 * M + q] : 0;
-    if (!jv) th.fwd(g.psi, g.Y, nk, ss, se, sx, vv);
-    else th.jvp(g.psi, g.dpsi, g.Y, g.Ydot, g.ddot, nk, ss, se, sx, vv, a_s[(size_t)j * H + q], a_s[(size_t)j * H + M + q],
+    if (!jv) th.fwd(g.psi, g.Y, ss, se, sx, vv);
+    else th.jvp(g.psi, g.dpsi, g.Y, g.Ydot, g.ddot, ss, se, sx, vv, a_s[(size_t)j * H + q], a_s[(size_t)j * H + M + q],
                 L == 0 ? a_s[(size_t)j * H + 2 * M + q] : 0, vd);
   }
   for (int m = 0; m < 2 * L + 1; ++m) outV[(size_t)i * Dd + c.vbase + m * c.vstride] += th.accV[m];
@@ -119,13 +119,13 @@ static void nbr_node(const Dims& D, int second, int j, int h, int q, const int* 
                      const T* freq, const T* gx, const T* gV, const T* a_s, const T* a_v, const T* a_pos, T* o_s, T* o_v,
                      T* gr /*[E,3] accumulated*/, T* GW /*[H,NBP]*/, T* GF) {
   const int M = D.m0 + D.m1 + D.m2, Dd = D.m0 + 3 * D.m1 + 5 * D.m2, H = D.C + 2 * M, nk = D.B + 1;
-  NeighborThread<T, L, ROLE, true> th;
+  NeighborThread<T, L, ROLE, true, 21> th;
   load_wrow(W, b, h, D.B, th.Wt);
   th.reset_node(); th.reset_wgrad();
   Chan c = chan_of_q(D, ROLE == ROLE_SCALAR ? 0 : q);
   th.s = s[(size_t)j * H + h];
   th.sd = second && a_s ? a_s[(size_t)j * H + h] : 0;
-  constexpr int NC = NeighborThread<T, L, ROLE, true>::NC;
+  constexpr int NC = NeighborThread<T, L, ROLE, true, 21>::NC;
   if (ROLE == ROLE_STATE)
     for (int m = 0; m < NC; ++m) { th.v[m] = v[(size_t)j * Dd + c.vbase + m * c.vstride]; th.vd[m] = second && a_v ? a_v[(size_t)j * Dd + c.vbase + m * c.vstride] : 0; }
   for (int sl = t_rowptr[j]; sl < t_rowptr[j + 1]; ++sl) {
@@ -139,7 +139,7 @@ static void nbr_node(const Dims& D, int second, int j, int h, int q, const int* 
     if (ROLE == ROLE_SCALAR) gg[0] = gx[(size_t)i * D.C + (h - 2 * M)];
     else for (int m = 0; m < NC; ++m) gg[m] = gV[(size_t)i * Dd + c.vbase + m * c.vstride];
     T pr[3];
-    if (second) th.second(ne, nk, gg, pr); else th.first(ne, nk, gg, pr);
+    if (second) th.second(ne, gg, pr); else th.first(ne, gg, pr);
     for (int x = 0; x < 3; ++x) gr[3 * (size_t)e + x] += pr[x];
   }
   o_s[(size_t)j * H + h] = th.acc_s;

@@ -1,0 +1,248 @@
+"""GPU parity tests (run on the B200 box): every CUDA entry point, called through the C ABI,
+against the oracle on seeded inputs and against the golden vectors produced by the reference.
+
+Tolerances: edge lists bit-exact after canonical sort; energies 1e-5 relative and forces
+1e-4 eV/A absolute in fp32 (north_star), judged against the fp64 oracle with the fp32
+noise-floor rule of SURVEY.md section 7 where the reference's own fp32 run exceeds 1e-4."""
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+from helpers import cast_data, embed_table, grad_digest, load_golden
+from oracle import xpainn_oracle as orc
+
+pytestmark = pytest.mark.gpu
+
+import xequinet_b200 as xb  # noqa: E402
+from xequinet_b200 import keys, ops  # noqa: E402
+from xequinet_b200.graph import build_graph, graph_from_edge_index  # noqa: E402
+
+DEV = "cuda"
+
+
+def _dev(data):
+    return {k: (v.to(DEV) if torch.is_tensor(v) else v) for k, v in data.items()}
+
+
+# ---------------------------------------------------------------------------------------
+# K1 radius graph
+# ---------------------------------------------------------------------------------------
+@pytest.mark.parametrize("n_mol,atoms,seed", [(64, 18, 0), (7, (1, 40), 3), (1, 200, 5), (3, 1, 1)])
+def test_radius_graph_matches_oracle(n_mol, atoms, seed):
+    d = orc.make_molecule_batch(n_mol, atoms, seed=seed)
+    ei_ref, _ = orc.canonical_sort(d["edge_index"])
+    ei = xb.radius_graph(d["pos"].to(DEV), 5.0, batch=d["batch"].to(DEV))
+    assert ei.dtype == torch.int64
+    assert torch.equal(ei.cpu(), ei_ref)  # K1 emits canonical order directly
+    g, _, _ = build_graph(d["pos"].to(DEV), 5.0, batch=d["batch"].to(DEV))
+    assert torch.equal(g.edge_index().cpu(), ei_ref)
+    # transposed structure: slots grouped by neighbor, ordered by edge id
+    order = torch.sort(ei_ref[1], stable=True)[1]
+    assert torch.equal(g.t_eid[: g.n_edges].cpu().long(), order)
+    assert torch.equal(g.t_row[: g.n_edges].cpu().long(), ei_ref[0][order])
+
+
+def test_radius_graph_empty_and_isolated():
+    pos = torch.tensor([[0.0, 0, 0], [100.0, 0, 0], [200.0, 0, 0]], device=DEV)
+    ei = xb.radius_graph(pos, 5.0)
+    assert ei.shape == (2, 0)
+    ei = xb.radius_graph(torch.tensor([[0.0, 0, 0], [1.0, 0, 0], [50.0, 0, 0]], device=DEV), 5.0)
+    assert ei.cpu().tolist() == [[0, 1], [1, 0]]
+
+
+@pytest.mark.parametrize("name", ["pbc_small", "pbc_tiny", "pbc_slab", "pbc_two_graphs"])
+def test_radius_graph_pbc_matches_reference_golden(name):
+    z, cfg, data = load_golden(name)
+    n = (data["ptr"][1:] - data["ptr"][:-1])
+    ei, co = xb.radius_graph_pbc(data["pos"].to(DEV), n.to(DEV), data["pbc"].to(DEV), data["cell"].to(DEV), 5.0)
+    assert torch.equal(ei.cpu(), data["edge_index"])
+    assert torch.equal(co.cpu(), data["cell_offsets"])
+
+
+def test_radius_graph_pbc_water_golden():
+    z = np.load(__import__("helpers").GOLDEN / "water_edges.npz")
+    pos, cell, pbc = (torch.from_numpy(z[k]).to(DEV) for k in ("pos", "cell", "pbc"))
+    ei, co = xb.radius_graph_pbc(pos, torch.tensor([pos.shape[0]], device=DEV), pbc, cell, 5.0)
+    assert np.array_equal(ei.cpu().numpy(), z["edge_index"].astype(np.int64))
+    assert np.array_equal(co.cpu().numpy().astype(np.int8), z["cell_offsets"])
+
+
+def test_graph_from_unsorted_edge_index():
+    d = orc.make_molecule_batch(5, (4, 12), seed=9)
+    ei = d["edge_index"]
+    perm = torch.randperm(ei.shape[1], generator=torch.Generator().manual_seed(0))
+    g = graph_from_edge_index(ei[:, perm].to(DEV), d["pos"].shape[0])
+    got = g.edge_index().cpu()
+    ref, _ = orc.canonical_sort(ei)
+    # rows are grouped by center; within a row the caller's order is kept
+    assert torch.equal(torch.sort(got[0] * 10_000 + got[1])[0], ref[0] * 10_000 + ref[1])
+
+
+# ---------------------------------------------------------------------------------------
+# K2 / K2b / K2bb against fp64 autograd of the oracle's edge message
+# ---------------------------------------------------------------------------------------
+def _edge_case(kind, cfg):
+    if kind == "mol":
+        d = orc.make_molecule_batch(24, (6, 22), seed=2)
+        ei, co, cell = d["edge_index"], None, None
+    elif kind == "pbc":
+        d = orc.make_small_pbc(14, 6.5, seed=3, triclinic=True)
+        ei, co = orc.radius_graph_pbc(d["pos"], torch.tensor([14]), d["pbc"], d["cell"], 5.0)
+        cell = d["cell"]
+    else:  # two periodic graphs
+        z, _, d = load_golden("pbc_two_graphs")
+        ei, co, cell = d["edge_index"], d["cell_offsets"], d["cell"]
+    N = d["pos"].shape[0]
+    g = torch.Generator().manual_seed(4)
+    rnd = lambda *s: torch.randn(*s, generator=g, dtype=torch.float64)
+    t = dict(pos=d["pos"].double(), s=rnd(N, cfg.H_msg), v=rnd(N, cfg.D), x=rnd(N, cfg.node_dim), V=rnd(N, cfg.D),
+             W=0.3 * rnd(cfg.H_msg, cfg.num_basis), b=0.3 * rnd(cfg.H_msg),
+             freq=torch.pi * torch.arange(1, cfg.num_basis + 1, dtype=torch.float64) / cfg.cutoff + 0.1 * rnd(cfg.num_basis),
+             gx=rnd(N, cfg.node_dim), gV=rnd(N, cfg.D), a_s=rnd(N, cfg.H_msg), a_v=rnd(N, cfg.D), a_pos=rnd(N, 3))
+    return d, ei, co, cell, t
+
+
+def _rel(got, ref):
+    ref = ref.double()
+    return float((got.double().cpu() - ref).abs().max() / (ref.abs().max() + 1e-30))
+
+
+@pytest.mark.parametrize("kind", ["mol", "pbc", "pbc2"])
+@pytest.mark.parametrize("cfg", [orc.CONFIG_DEFAULT, orc.CONFIG_C4], ids=["c128", "c256"])
+def test_edge_kernels_match_oracle_autograd(kind, cfg):
+    d, ei, co, cell, t = _edge_case(kind, cfg)
+    N = d["pos"].shape[0]
+    G = d["ptr"].numel() - 1
+    # fp64 oracle: value, first derivatives, second derivatives
+    req = {k: t[k].clone().requires_grad_(True) for k in ("pos", "s", "v", "W", "b", "freq", "gx", "gV")}
+    xo, Vo = orc.edge_message(t["x"], t["V"], req["s"], req["v"], req["pos"], req["W"], req["b"], req["freq"], ei, cfg,
+                              cell.double() if cell is not None else None, co, d["batch"])
+    Phi = (req["gx"] * xo).sum() + (req["gV"] * Vo).sum()
+    first = torch.autograd.grad(Phi, [req[k] for k in ("s", "v", "pos", "W", "b", "freq")], create_graph=True)
+    Psi = (t["a_s"] * first[0]).sum() + (t["a_v"] * first[1]).sum() + (t["a_pos"] * first[2]).sum()
+    second = torch.autograd.grad(Psi, [req[k] for k in ("gx", "gV", "s", "v", "pos", "W", "b", "freq")])
+
+    dims = ops.Dims(cfg.node_dim, *cfg.muls, cfg.num_basis, cfg.cutoff)
+    graph = graph_from_edge_index(ei.to(DEV), N, G, cell_offsets=co.to(DEV) if co is not None else None,
+                                  cell=cell.to(DEV) if cell is not None else None, batch=d["batch"].to(DEV))
+    f32 = lambda a: a.float().to(DEV).contiguous()
+    cmf = lambda a: orc.to_cm(a, cfg).float().to(DEV).contiguous()
+    pos, s, W, b, freq, gx = (f32(t[k]) for k in ("pos", "s", "W", "b", "freq", "gx"))
+    v, V, gV, a_v = (cmf(t[k]) for k in ("v", "V", "gV", "a_v"))
+    x, a_s, a_pos = f32(t["x"]), f32(t["a_s"]), f32(t["a_pos"])
+    tol = 2e-5  # fp32 kernels vs fp64 oracle, relative to the largest entry
+
+    x_out, V_out = ops.edge_message_fwd_raw(graph, dims, pos, s, v, x, V, W, b, freq)
+    assert _rel(x_out, xo.detach()) < tol
+    assert _rel(orc.from_cm(V_out.cpu(), cfg), Vo.detach()) < tol
+
+    gs, gv, gpos, gW, gb, gf = ops.edge_message_bwd_raw(graph, dims, pos, s, v, W, b, freq, gx, gV, need_w=True)
+    for got, ref, name in zip((gs, orc.from_cm(gv.cpu(), cfg), gpos, gW, gb, gf), first, "s v pos W b f".split()):
+        assert _rel(got, ref.detach()) < tol, f"first/{name}"
+    # force-only variant (no weight gradients) takes a different kernel instantiation
+    gs2, gv2, gpos2, *_ = ops.edge_message_bwd_raw(graph, dims, pos, s, v, W, b, freq, gx, gV, need_w=False)
+    assert torch.equal(gs2, gs) and torch.equal(gv2, gv) and torch.equal(gpos2, gpos)
+
+    o = ops.edge_message_bwdbwd_raw(graph, dims, pos, s, v, W, b, freq, gx, gV, a_s, a_v, a_pos)
+    got = (o[0], orc.from_cm(o[1].cpu(), cfg), o[2], orc.from_cm(o[3].cpu(), cfg), o[4], o[5], o[6], o[7])
+    for gt, ref, name in zip(got, second, "gx gV s v pos W b f".split()):
+        assert _rel(gt, ref) < 5e-5, f"second/{name}"
+
+    # deterministic: bitwise identical on a second run
+    x_out2, V_out2 = ops.edge_message_fwd_raw(graph, dims, pos, s, v, x, V, W, b, freq)
+    assert torch.equal(x_out, x_out2) and torch.equal(V_out, V_out2)
+
+
+def test_layout_convert_roundtrip():
+    cfg = orc.CONFIG_DEFAULT
+    dims = ops.Dims(cfg.node_dim, *cfg.muls, cfg.num_basis, cfg.cutoff)
+    V = torch.randn(33, cfg.D, device=DEV)
+    Vc = ops.layout_convert(V, dims, to_cm=True)
+    assert torch.equal(Vc.cpu(), orc.to_cm(V.cpu(), cfg))
+    assert torch.equal(ops.layout_convert(Vc, dims, to_cm=False), V)
+
+
+# ---------------------------------------------------------------------------------------
+# whole model: energy / forces / parameter gradients
+# ---------------------------------------------------------------------------------------
+def _model(cfg, seed, train=False):
+    model = xb.resolve_model("xpainn", **cfg.model_kwargs())
+    model.load_state_dict(orc.synthetic_state_dict(cfg, seed), strict=False)
+    model = model.to(DEV)
+    return model.train() if train else model.eval()
+
+
+def _force_gate(F_new, F_ref64, F_ref32):
+    """err_new <= max(1e-4, 1.5 * err_ref32) against the fp64 reference."""
+    err_new = np.abs(F_new - F_ref64).max()
+    err_ref = np.abs(F_ref32 - F_ref64).max()
+    assert err_new <= max(1e-4, 1.5 * err_ref), (err_new, err_ref)
+
+
+@pytest.mark.parametrize("name", ["mol_small", "mol_c4_small", "pbc_small", "pbc_tiny", "pbc_slab", "pbc_two_graphs"])
+def test_model_matches_reference_golden(name):
+    z, cfg, data = load_golden(name)
+    model = _model(cfg, int(z["sd_seed"]))
+    d = _dev(cast_data(data, torch.float32))
+    d.pop("pbc", None)
+    out = model(d, compute_forces=True)
+    assert set(out) == {"energy", "atomic_energies", "forces"}
+    E, Ea, Fo = (out[k].detach().cpu().numpy() for k in ("energy", "atomic_energies", "forces"))
+    np.testing.assert_allclose(E, z["f64:energy"], rtol=1e-5, atol=1e-6)
+    np.testing.assert_allclose(Ea, z["f64:atomic_energies"], rtol=1e-4, atol=2e-6)
+    _force_gate(Fo, z["f64:forces"], z["f32:forces"])
+    # direct fp32-vs-fp32 numbers as well (same tolerance as the reference's own noise allows)
+    np.testing.assert_allclose(Fo, z["f32:forces"], rtol=0, atol=3e-4)
+
+
+def test_model_matches_oracle_c1_shape():
+    """config c1: 64 molecules x 18 atoms, E+F inference, with K1 building the graph."""
+    cfg = orc.CONFIG_DEFAULT
+    data = orc.make_molecule_batch(64, 18, seed=0, with_edges=False)
+    sd = orc.synthetic_state_dict(cfg, 1234, torch.float64)
+    d64 = cast_data(data, torch.float64)
+    d64["edge_index"] = orc.radius_graph(data["pos"], 5.0, data["batch"])
+    ref = orc.xpainn_energy_forces(sd, embed_table(), d64, cfg)
+    sd32 = {k: v.float() for k, v in sd.items()}
+    ref32 = orc.xpainn_energy_forces(sd32, embed_table().float(), cast_data(d64, torch.float32), cfg)
+    model = _model(cfg, 1234)
+    d = xb.NeighborTransform(5.0)(_dev(data))
+    assert torch.equal(d["edge_index"].cpu(), orc.canonical_sort(d64["edge_index"])[0])
+    out = model(d, compute_forces=True)
+    np.testing.assert_allclose(out["energy"].detach().cpu().numpy(), ref["energy"].detach().numpy(), rtol=1e-5, atol=1e-6)
+    _force_gate(out["forces"].cpu().numpy(), ref["forces"].numpy(), ref32["forces"].numpy())
+    # physics: net force per molecule vanishes
+    net = torch.zeros(64, 3, device=DEV).index_add(0, d["batch"], out["forces"])
+    assert float(net.abs().max()) < 5e-5
+
+
+@pytest.mark.parametrize("name", ["mol_small", "pbc_small"])
+@pytest.mark.parametrize("use_forces", [False, True], ids=["E-loss", "EF-loss"])
+def test_param_grads_match_reference_golden(name, use_forces):
+    """Training semantics (utils/trainer.py:295-302): loss.backward() through forces -> K2bb."""
+    z, cfg, data = load_golden(name)
+    model = _model(cfg, int(z["sd_seed"]), train=True)
+    d = _dev(cast_data(data, torch.float32))
+    d.pop("pbc", None)
+    out = model(d, compute_forces=use_forces)
+    tE = torch.from_numpy(z["f64:target_energy"]).float().to(DEV)
+    tF = torch.from_numpy(z["f64:target_forces"]).float().to(DEV)
+    loss = F.smooth_l1_loss(out["energy"], tE)
+    if use_forces:
+        loss = loss + 100.0 * F.smooth_l1_loss(out["forces"], tF)
+    tag = "gEF" if use_forces else "gE"
+    np.testing.assert_allclose(loss.item(), float(z[f"f64:loss_{tag}"]), rtol=2e-5)
+    loss.backward()
+    checked = 0
+    for k, p in model.named_parameters():
+        key = f"f64:{tag}:sum:{k}"
+        if key not in z.files:
+            continue
+        s, smp = grad_digest(p.grad)
+        ref_s, ref_smp = z[key], z[f"f64:{tag}:smp:{k}"]
+        scale = max(np.abs(ref_smp).max(), ref_s[1] / np.sqrt(p.numel()), 1e-12)
+        assert np.abs(smp - ref_smp).max() <= 2e-3 * scale + 1e-7, (k, np.abs(smp - ref_smp).max(), scale)
+        assert abs(s[1] - ref_s[1]) <= 1e-3 * ref_s[1] + 1e-7, (k, s, ref_s)
+        checked += 1
+    assert checked > 50

@@ -1,0 +1,94 @@
+"""CPU tests of the host-side mirror of the reference's module API: state_dict layout,
+hyper-parameter handling and the node-level (cm-layout) blocks against the oracle."""
+import pytest
+import torch
+
+import xequinet_b200 as xb
+from oracle import xpainn_oracle as orc
+from xequinet_b200.nn import cm
+from xequinet_b200.nn.irreps import parse_irreps
+from xequinet_b200.nn.layers import EquivariantLayerNorm, Invariant, O3Linear
+from xequinet_b200.nn.xpainn import XPainnUpdate
+from xequinet_b200 import keys
+
+
+def test_parse_irreps():
+    assert parse_irreps("128x0e + 64x1o + 32x2e") == (128, 64, 32)
+    assert parse_irreps("256x0e+128x1o+64x2e") == (256, 128, 64)
+    assert parse_irreps([(8, "0e"), (4, "1o")]) == (8, 4, 0)
+    with pytest.raises(NotImplementedError):
+        parse_irreps("8x0e + 4x3o")
+
+
+@pytest.mark.parametrize("cfg", [orc.CONFIG_DEFAULT, orc.CONFIG_C4])
+def test_state_dict_layout_matches_reference(cfg):
+    """Parameter names/shapes of SURVEY.md 8a (S0), as observed on the reference model."""
+    model = xb.resolve_model("xpainn", **cfg.model_kwargs())
+    sd = model.state_dict()
+    spec = orc.state_dict_spec(cfg)
+    for name, shape, _ in spec:
+        assert name in sd, name
+        assert tuple(sd[name].shape) == shape, name
+    learnable = {n for n, _ in model.named_parameters()}
+    assert learnable == {n for n, _, _ in spec}
+    assert sum(p.numel() for p in model.parameters()) == (865141 if cfg is orc.CONFIG_DEFAULT else sum(p.numel() for p in model.parameters()))
+    # e3nn-internal buffers keep their reference names
+    for k in ("mods.message_0.o3norm.scalar_index", "mods.update_0.update_U.output_mask",
+              "mods.update_0.invariant.tp.weight", "mods.message_0.rsh_conv.output_mask",
+              "mods.embedding.embedding.0.embed_ten"):
+        assert k in sd
+    res = model.load_state_dict(orc.synthetic_state_dict(cfg), strict=False)
+    assert not res.unexpected_keys
+
+
+def test_defaults_and_unsupported_options():
+    m = xb.resolve_model("xpainn")
+    assert m.cutoff_radius == 5.0 and list(m.mods)[:3] == ["embedding", "message_0", "update_0"]
+    assert list(m.mods)[-1] == "output_energy" and m.extra_properties == ["energy", "atomic_energies"]
+    with pytest.raises(NotImplementedError):
+        xb.resolve_model("painn")
+    with pytest.raises(NotImplementedError):
+        xb.resolve_model("xpainn", rbf_kernel="gaussian")
+
+
+def test_cm_blocks_match_oracle():
+    cfg = orc.XPaiNNConfig(node_dim=16, muls=(16, 8, 4))
+    g = torch.Generator().manual_seed(0)
+    N = 7
+    V = torch.randn(N, cfg.D, generator=g, dtype=torch.float64)  # e3nn layout
+    Vc = orc.to_cm(V, cfg)
+    gam, bet = torch.randn(cfg.M, generator=g, dtype=torch.float64), torch.randn(16, generator=g, dtype=torch.float64)
+    ln = EquivariantLayerNorm(cfg.muls).double()
+    ln.affine_weight.data, ln.affine_bias.data = gam, bet
+    torch.testing.assert_close(orc.from_cm(ln(Vc), cfg), orc.equivariant_layer_norm(V, gam, bet, cfg))
+    torch.testing.assert_close(Invariant(cfg.muls)(Vc), orc.invariant(V, cfg))
+    lin = O3Linear(cfg.muls).double()
+    lin.bias.data = torch.randn(16, generator=g, dtype=torch.float64)
+    torch.testing.assert_close(orc.from_cm(lin(Vc), cfg), orc.o3_linear(V, lin.weight, lin.bias, cfg))
+    gate = torch.randn(N, cfg.M, generator=g, dtype=torch.float64)
+    torch.testing.assert_close(orc.from_cm(cm.expand_gate(gate, cfg.muls) * Vc, cfg), orc.expand_gate(gate, cfg) * V)
+
+
+def test_update_block_matches_oracle_layer():
+    """XPainnUpdate (cm layout, CPU-runnable: no E-sized work) against the oracle's update math."""
+    cfg = orc.XPaiNNConfig(node_dim=32, muls=(32, 32, 32), action_blocks=1)
+    sd = orc.synthetic_state_dict(cfg, 7, torch.float64)
+    upd = XPainnUpdate(node_dim=32, node_irreps=cfg.irreps_str).double()
+    upd.load_state_dict({k[len("mods.update_0."):]: v for k, v in sd.items() if k.startswith("mods.update_0.")}, strict=False)
+    g = torch.Generator().manual_seed(1)
+    x = torch.randn(5, 32, generator=g, dtype=torch.float64)
+    V = torch.randn(5, cfg.D, generator=g, dtype=torch.float64)
+    out = upd({keys.NODE_INVARIANT: x, keys.NODE_EQUIVARIANT: orc.to_cm(V, cfg)})
+    import torch.nn.functional as F
+    p = "mods.update_0."
+    xn = F.layer_norm(x, (32,), sd[p + "norm.weight"], sd[p + "norm.bias"], 1e-5)
+    vn = orc.equivariant_layer_norm(V, sd[p + "o3norm.affine_weight"], sd[p + "o3norm.affine_bias"], cfg)
+    U = orc.o3_linear(vn, sd[p + "update_U.weight"], sd[p + "update_U.bias"], cfg)
+    W = orc.o3_linear(vn, sd[p + "update_V.weight"], sd[p + "update_V.bias"], cfg)
+    a = F.linear(F.silu(F.linear(torch.cat([xn, orc.invariant(W, cfg)], 1), sd[p + "update_mlp.0.weight"], sd[p + "update_mlp.0.bias"])),
+                 sd[p + "update_mlp.2.weight"], sd[p + "update_mlp.2.bias"])
+    M, C = cfg.M, 32
+    x_ref = x + a[:, M:M + C] * F.linear(orc.irrep_dot(U, W, cfg), sd[p + "dot_lin.weight"]) + a[:, M + C:]
+    V_ref = V + U * orc.expand_gate(a[:, :M], cfg)
+    torch.testing.assert_close(out[keys.NODE_INVARIANT], x_ref)
+    torch.testing.assert_close(orc.from_cm(out[keys.NODE_EQUIVARIANT], cfg), V_ref)

@@ -1,0 +1,91 @@
+"""ctypes binding of libxeq_b200.so (C ABI: include/xeq_b200.h).
+
+There is deliberately no CPU / eager fallback: if the library is missing, or a call is
+made with host tensors, the caller gets a loud error."""
+from __future__ import annotations
+
+import ctypes
+from ctypes import POINTER, c_char_p, c_float, c_int, c_int32, c_size_t, c_void_p
+from pathlib import Path
+
+import torch
+
+LIB_PATH = Path(__file__).resolve().parent / "libxeq_b200.so"
+
+
+class XeqDims(ctypes.Structure):
+    _fields_ = [("node_dim", c_int32), ("mul0", c_int32), ("mul1", c_int32), ("mul2", c_int32),
+                ("num_basis", c_int32), ("cutoff", c_float)]
+
+
+class XeqGraph(ctypes.Structure):
+    _fields_ = [("n_nodes", c_int32), ("n_edges", c_int32), ("n_graphs", c_int32), ("_pad", c_int32),
+                ("rowptr", c_void_p), ("col", c_void_p), ("t_rowptr", c_void_p), ("t_row", c_void_p),
+                ("t_eid", c_void_p), ("offsets", c_void_p), ("cell", c_void_p), ("node_graph", c_void_p)]
+
+
+_SIGNATURES = {
+    "xeq_version": (c_int, []),
+    "xeq_last_error": (c_char_p, []),
+    "xeq_num_sms": (c_int, []),
+    "xeq_radius_graph_workspace_bytes": (c_size_t, [c_int32, c_int32, c_int]),
+    "xeq_radius_graph_count": (c_int, [c_void_p, c_int32, c_void_p, c_void_p, c_int32, c_void_p, POINTER(c_int32),
+                                       POINTER(c_int32), c_float, c_void_p, c_void_p, c_size_t, c_void_p]),
+    "xeq_radius_graph_fill": (c_int, [c_void_p, c_int32, c_void_p, c_void_p, c_int32, c_void_p, POINTER(c_int32),
+                                      POINTER(c_int32), c_float, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
+                                      c_void_p, c_size_t, c_void_p]),
+    "xeq_csr_from_sorted_coo": (c_int, [c_void_p, c_void_p, c_int32, c_int32, c_void_p, c_void_p, c_void_p, c_void_p]),
+    "xeq_csr_transpose_workspace_bytes": (c_size_t, [c_int32, c_int32]),
+    "xeq_csr_transpose": (c_int, [c_void_p, c_void_p, c_int32, c_int32, c_void_p, c_void_p, c_void_p, c_void_p,
+                                  c_size_t, c_void_p]),
+    "xeq_edge_message_fwd": (c_int, [POINTER(XeqGraph), POINTER(XeqDims)] + [c_void_p] * 11),
+    "xeq_edge_message_bwd_workspace_bytes": (c_size_t, [POINTER(XeqGraph), POINTER(XeqDims), c_int]),
+    "xeq_edge_message_bwd": (c_int, [POINTER(XeqGraph), POINTER(XeqDims)] + [c_void_p] * 14 + [c_void_p, c_size_t, c_void_p]),
+    "xeq_edge_message_bwdbwd_workspace_bytes": (c_size_t, [POINTER(XeqGraph), POINTER(XeqDims), c_int]),
+    "xeq_edge_message_bwdbwd": (c_int, [POINTER(XeqGraph), POINTER(XeqDims)] + [c_void_p] * 19 + [c_void_p, c_size_t, c_void_p]),
+    "xeq_segment_sum": (c_int, [c_void_p, c_void_p, c_int32, c_void_p, c_void_p]),
+    "xeq_layout_convert": (c_int, [c_void_p, c_void_p, c_int32, POINTER(XeqDims), c_int, c_void_p]),
+}
+
+_lib = None
+
+
+def exported_symbols():
+    return sorted(_SIGNATURES)
+
+
+def get():
+    """The loaded library.  Raises if it has not been built (python -m xequinet_b200.build)."""
+    global _lib
+    if _lib is None:
+        if not LIB_PATH.exists():
+            raise RuntimeError(
+                f"{LIB_PATH} is missing: build it with `python xequinet_b200/build.py` "
+                "(xequinet_b200 has no CPU or eager fallback)")
+        lib = ctypes.CDLL(str(LIB_PATH))
+        for name, (res, args) in _SIGNATURES.items():
+            fn = getattr(lib, name)
+            fn.restype, fn.argtypes = res, args
+        _lib = lib
+    return _lib
+
+
+def check(rc: int, what: str):
+    if rc != 0:
+        msg = get().xeq_last_error().decode()
+        raise RuntimeError(f"{what} failed (code {rc}): {msg}")
+
+
+def ptr(t):
+    """Device pointer of a contiguous CUDA tensor (None -> NULL)."""
+    if t is None:
+        return None
+    if not t.is_cuda:
+        raise RuntimeError("xequinet_b200 ops need CUDA tensors: there is no CPU fallback")
+    if not t.is_contiguous():
+        raise RuntimeError("xequinet_b200 ops need contiguous tensors")
+    return t.data_ptr()
+
+
+def stream():
+    return torch.cuda.current_stream().cuda_stream

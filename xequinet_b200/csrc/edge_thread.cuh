@@ -15,19 +15,18 @@ namespace xeq {
 
 template <int L> struct YOff { static constexpr int value = (L == 1) ? 0 : 3; };  // offset into Y[8]
 
-template <typename T>
-XEQ_HD T dot_nbp(const T* __restrict__ w, const T* __restrict__ p, int nk) {
+template <int NK, typename T>
+XEQ_HD T dot_nk(const T* __restrict__ w, const T* __restrict__ p) {
   T acc = T(0);
 #pragma unroll
-  for (int k = 0; k < NBP; ++k)
-    if (k < nk) acc += w[k] * p[k];
+  for (int k = 0; k < NK; ++k) acc += w[k] * p[k];
   return acc;
 }
 
 // ------------------------------------------------------------------------------------------
 // Center threads (K2 forward, and the JVP half of K2bb)
 // ------------------------------------------------------------------------------------------
-template <typename T, int L>
+template <typename T, int L, int NK>
 struct CenterThread {
   static constexpr int NC = 2 * L + 1;
   T Ws[NBP], We[NBP], Wx[NBP];  // rows of [b | W_rbf] for the state gate, edge gate, scalar channel
@@ -41,12 +40,12 @@ struct CenterThread {
   }
 
   // forward message of one edge: psi[NBP], Y[8]; s_* are s[j, .] of the neighbor, v its v[j, (q, m)]
-  XEQ_HD void fwd(const T* psi, const T* Y, int nk, T s_state, T s_edge, T s_x, const T* v) {
-    const T gs = s_state * dot_nbp(Ws, psi, nk);
-    const T ge = s_edge * dot_nbp(We, psi, nk);
+  XEQ_HD void fwd(const T* psi, const T* Y, T s_state, T s_edge, T s_x, const T* v) {
+    const T gs = s_state * dot_nk<NK>(Ws, psi);
+    const T ge = s_edge * dot_nk<NK>(We, psi);
     if (L == 0) {
       accV[0] += gs * v[0] + ge;
-      accx += s_x * dot_nbp(Wx, psi, nk);
+      accx += s_x * dot_nk<NK>(Wx, psi);
     } else {
 #pragma unroll
       for (int m = 0; m < NC; ++m) accV[m] += gs * v[m] + ge * Y[YOff<L>::value + m];
@@ -54,16 +53,16 @@ struct CenterThread {
   }
 
   // tangent of the forward message along (sdot, vdot, rdot): d/deps of fwd()
-  XEQ_HD void jvp(const T* psi, const T* dpsi, const T* Y, const T* Ydot, T ddot, int nk, T s_state, T s_edge,
+  XEQ_HD void jvp(const T* psi, const T* dpsi, const T* Y, const T* Ydot, T ddot, T s_state, T s_edge,
                   T s_x, const T* v, T sd_state, T sd_edge, T sd_x, const T* vd) {
-    const T ws = dot_nbp(Ws, psi, nk), we = dot_nbp(We, psi, nk);
-    const T dws = dot_nbp(Ws, dpsi, nk) * ddot, dwe = dot_nbp(We, dpsi, nk) * ddot;
+    const T ws = dot_nk<NK>(Ws, psi), we = dot_nk<NK>(We, psi);
+    const T dws = dot_nk<NK>(Ws, dpsi) * ddot, dwe = dot_nk<NK>(We, dpsi) * ddot;
     const T gs = s_state * ws, ge = s_edge * we;
     const T gsd = sd_state * ws + s_state * dws;
     const T ged = sd_edge * we + s_edge * dwe;
     if (L == 0) {
       accV[0] += gsd * v[0] + gs * vd[0] + ged;
-      accx += sd_x * dot_nbp(Wx, psi, nk) + s_x * dot_nbp(Wx, dpsi, nk) * ddot;
+      accx += sd_x * dot_nk<NK>(Wx, psi) + s_x * dot_nk<NK>(Wx, dpsi) * ddot;
     } else {
 #pragma unroll
       for (int m = 0; m < NC; ++m)
@@ -94,7 +93,7 @@ struct NbrEdge {
   T ddot;          //        second order only
 };
 
-template <typename T, int L, int ROLE, bool WGRAD>
+template <typename T, int L, int ROLE, bool WGRAD, int NK>
 struct NeighborThread {
   static constexpr int NC = (ROLE == ROLE_SCALAR) ? 1 : 2 * L + 1;
   static constexpr int YO = YOff<L>::value;
@@ -117,9 +116,9 @@ struct NeighborThread {
 
   // First derivatives.  g = gV[i,(q,:)] (state/edge roles) or gx[i,c] (scalar role).
   // pr[3] receives this thread's share of dPhi/dr_e.
-  XEQ_HD void first(const NbrEdge<T>& e, int nk, const T* g, T pr[3]) {
-    const T w = dot_nbp(Wt, e.psi, nk);
-    const T dw = dot_nbp(Wt, e.dpsi, nk);
+  XEQ_HD void first(const NbrEdge<T>& e, const T* g, T pr[3]) {
+    const T w = dot_nk<NK>(Wt, e.psi);
+    const T dw = dot_nk<NK>(Wt, e.dpsi);
     T pw;  // dPhi/dw_e[h]
     T cy[NC];
     if (ROLE == ROLE_STATE) {
@@ -160,19 +159,18 @@ struct NeighborThread {
     }
     if (WGRAD) {
 #pragma unroll
-      for (int k = 0; k < NBP; ++k)
-        if (k < nk) {
-          GW[k] += pw * e.psi[k];
-          GF[k] += pw * e.xi[k];
-        }
+      for (int k = 0; k < NK; ++k) {
+        GW[k] += pw * e.psi[k];
+        GF[k] += pw * e.xi[k];
+      }
     }
   }
 
   // Second derivatives: gradient of Psi_e (the tangent of Phi_e along (sd, vd, rdot)).
-  XEQ_HD void second(const NbrEdge<T>& e, int nk, const T* g, T pr[3]) {
-    const T w = dot_nbp(Wt, e.psi, nk);
-    const T dw = dot_nbp(Wt, e.dpsi, nk);
-    const T ddw = dot_nbp(Wt, e.ddpsi, nk);
+  XEQ_HD void second(const NbrEdge<T>& e, const T* g, T pr[3]) {
+    const T w = dot_nk<NK>(Wt, e.psi);
+    const T dw = dot_nk<NK>(Wt, e.dpsi);
+    const T ddw = dot_nk<NK>(Wt, e.ddpsi);
     const T dwd = dw * e.ddot;  // tangent of w
     T alpha, beta;
     T cy[NC], cz[NC];
@@ -229,11 +227,10 @@ struct NeighborThread {
     if (WGRAD) {
       const T bd = beta * e.ddot;
 #pragma unroll
-      for (int k = 0; k < NBP; ++k)
-        if (k < nk) {
-          GW[k] += alpha * e.psi[k] + bd * e.dpsi[k];
-          GF[k] += alpha * e.xi[k] + bd * e.dxi[k];
-        }
+      for (int k = 0; k < NK; ++k) {
+        GW[k] += alpha * e.psi[k] + bd * e.dpsi[k];
+        GF[k] += alpha * e.xi[k] + bd * e.dxi[k];
+      }
     }
   }
 };

@@ -1,0 +1,90 @@
+// Library plumbing (version, thread-local error string, device info) and the small node-level
+// helpers of the C ABI: contiguous segment sum (nn/output.py:124) and e3nn <-> cm layout maps.
+#include <stdarg.h>
+
+#include "common.cuh"
+
+namespace xeq {
+
+static thread_local char g_err[512] = "";
+
+void set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+}
+
+int num_sms() {
+  static thread_local int cached_dev = -1, cached = 0;
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) return 148;
+  if (dev != cached_dev) {
+    int n = 0;
+    if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) n = 148;
+    cached = n;
+    cached_dev = dev;
+  }
+  return cached;
+}
+
+// one warp per segment, lanes stride over the segment, fixed-order butterfly => deterministic
+__global__ void segment_sum_kernel(const float* __restrict__ src, const int* __restrict__ ptr, int n_seg,
+                                   float* __restrict__ out) {
+  const int seg = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (seg >= n_seg) return;
+  float acc = 0.f;
+  for (int i = ptr[seg] + lane; i < ptr[seg + 1]; i += 32) acc += src[i];
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+  if (lane == 0) out[seg] = acc;
+}
+
+__global__ void layout_convert_kernel(const float* __restrict__ src, float* __restrict__ dst, int n, int m0, int m1,
+                                      int m2, int direction) {
+  const int D = m0 + 3 * m1 + 5 * m2;
+  const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= (size_t)n * D) return;
+  const int node = (int)(idx / D), p = (int)(idx % D);  // p indexes the cm layout
+  int e3;                                               // matching index in the e3nn layout
+  if (p < m0) e3 = p;
+  else if (p < m0 + 3 * m1) { const int r = p - m0, m = r / m1, u = r % m1; e3 = m0 + u * 3 + m; }
+  else { const int r = p - m0 - 3 * m1, m = r / m2, u = r % m2; e3 = m0 + 3 * m1 + u * 5 + m; }
+  if (direction == 0) dst[(size_t)node * D + p] = src[(size_t)node * D + e3];
+  else dst[(size_t)node * D + e3] = src[(size_t)node * D + p];
+}
+
+}  // namespace xeq
+
+using namespace xeq;
+
+extern "C" {
+
+int xeq_version(void) { return 100; }
+const char* xeq_last_error(void) { return g_err; }
+int xeq_num_sms(void) { return num_sms(); }
+
+int xeq_segment_sum(const float* src, const int32_t* seg_ptr, int32_t n_segments, float* out, xeq_stream_t stream) {
+  XEQ_CHECK_ARG(seg_ptr && out && n_segments >= 0, "segment_sum: bad arguments");
+  if (n_segments == 0) return XEQ_OK;
+  XEQ_CHECK_ARG(src, "segment_sum: src is NULL");
+  const int blocks = (int)(((size_t)n_segments * 32 + 255) / 256);
+  segment_sum_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(src, seg_ptr, n_segments, out);
+  XEQ_LAUNCH_CHECK();
+  return XEQ_OK;
+}
+
+int xeq_layout_convert(const float* src, float* dst, int32_t n_nodes, const xeq_dims_t* dims, int direction,
+                       xeq_stream_t stream) {
+  XEQ_CHECK_ARG(src && dst && dims && n_nodes >= 0 && src != dst, "layout_convert: bad arguments");
+  XEQ_CHECK_ARG(direction == 0 || direction == 1, "layout_convert: direction must be 0 or 1");
+  const size_t total = (size_t)n_nodes * (dims->mul0 + 3 * dims->mul1 + 5 * dims->mul2);
+  if (total == 0) return XEQ_OK;
+  layout_convert_kernel<<<(unsigned)((total + 255) / 256), 256, 0, (cudaStream_t)stream>>>(src, dst, n_nodes, dims->mul0,
+                                                                                         dims->mul1, dims->mul2, direction);
+  XEQ_LAUNCH_CHECK();
+  return XEQ_OK;
+}
+
+}  // extern "C"

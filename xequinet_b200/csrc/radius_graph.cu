@@ -1,0 +1,465 @@
+// K1: radius graph (non-periodic batched / periodic with image enumeration), CSR utilities.
+// Replaces torch_cluster.radius_graph (data/transform.py:58-64) and radius_graph_pbc
+// (data/radius_graph.py:35-192).  See include/xeq_b200.h for the contract.
+//
+// Edge test arithmetic mirrors the reference so that the edge SET is bit-identical away
+// from 1-ulp ties at the cutoff:
+//   non-periodic: (dx*dx + dy*dy) + dz*dz < r*r        fp32, no FMA contraction, strict
+//   periodic    : 0.01 < sqrt((dx*dx + dy*dy) + dz*dz) < r  on wrapped + image coordinates
+#include "common.cuh"
+
+namespace xeq {
+
+// ------------------------------------------------------------------------------------------
+// exclusive scan of int32 (two-level, deterministic)
+// ------------------------------------------------------------------------------------------
+constexpr int SCAN_THREADS = 1024;
+constexpr int SCAN_ITEMS = 4;
+constexpr int SCAN_BLOCK = SCAN_THREADS * SCAN_ITEMS;
+
+__device__ __forceinline__ int warp_incl_scan(int v) {
+  const int lane = threadIdx.x & 31;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    int t = __shfl_up_sync(0xffffffffu, v, o);
+    if (lane >= o) v += t;
+  }
+  return v;
+}
+
+// block-wide exclusive scan of one value per thread; returns the exclusive prefix, total in *total
+__device__ __forceinline__ int block_excl_scan(int v, int* total) {
+  __shared__ int warp_sums[32];
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  int incl = warp_incl_scan(v);
+  if (lane == 31) warp_sums[wid] = incl;
+  __syncthreads();
+  if (wid == 0) {
+    int ws = (lane < (blockDim.x >> 5)) ? warp_sums[lane] : 0;
+    ws = warp_incl_scan(ws);
+    warp_sums[lane] = ws;
+  }
+  __syncthreads();
+  const int warp_off = wid ? warp_sums[wid - 1] : 0;
+  *total = warp_sums[(blockDim.x >> 5) - 1];
+  __syncthreads();
+  return warp_off + incl - v;
+}
+
+// out[i] = exclusive prefix within the block; block_tot[b] = block sum
+__global__ void __launch_bounds__(SCAN_THREADS) scan_blocks_kernel(const int* __restrict__ in, int* __restrict__ out,
+                                                                   int* __restrict__ block_tot, int n) {
+  const int base = blockIdx.x * SCAN_BLOCK + threadIdx.x * SCAN_ITEMS;
+  int v[SCAN_ITEMS], sum = 0;
+#pragma unroll
+  for (int k = 0; k < SCAN_ITEMS; ++k) {
+    v[k] = (base + k < n) ? in[base + k] : 0;
+    sum += v[k];
+  }
+  int total;
+  int pre = block_excl_scan(sum, &total);
+#pragma unroll
+  for (int k = 0; k < SCAN_ITEMS; ++k) {
+    if (base + k < n) out[base + k] = pre;
+    pre += v[k];
+  }
+  if (threadIdx.x == 0) block_tot[blockIdx.x] = total;
+}
+
+// single block: exclusive scan of up to SCAN_BLOCK block totals, in place; grand total -> *grand
+__global__ void __launch_bounds__(SCAN_THREADS) scan_totals_kernel(int* __restrict__ block_tot, int nblocks,
+                                                                   int* __restrict__ grand) {
+  const int base = threadIdx.x * SCAN_ITEMS;
+  int v[SCAN_ITEMS], sum = 0;
+#pragma unroll
+  for (int k = 0; k < SCAN_ITEMS; ++k) {
+    v[k] = (base + k < nblocks) ? block_tot[base + k] : 0;
+    sum += v[k];
+  }
+  int total;
+  int pre = block_excl_scan(sum, &total);
+#pragma unroll
+  for (int k = 0; k < SCAN_ITEMS; ++k) {
+    if (base + k < nblocks) block_tot[base + k] = pre;
+    pre += v[k];
+  }
+  if (threadIdx.x == 0) *grand = total;
+}
+
+__global__ void add_offsets_kernel(int* __restrict__ out, const int* __restrict__ block_off, int n) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) out[i] += block_off[i / SCAN_BLOCK];
+}
+
+// in[n] -> out[n+1] (out[n] = total).  scratch: ceil(n/SCAN_BLOCK) ints.  n <= SCAN_BLOCK^2.
+static int exclusive_scan(const int* in, int* out, int n, int* scratch, cudaStream_t st) {
+  if (n == 0) {
+    XEQ_CUDA(cudaMemsetAsync(out, 0, sizeof(int), st));
+    return XEQ_OK;
+  }
+  const int nblocks = (n + SCAN_BLOCK - 1) / SCAN_BLOCK;
+  XEQ_CHECK_ARG(nblocks <= SCAN_BLOCK, "exclusive_scan: n=%d too large", n);
+  scan_blocks_kernel<<<nblocks, SCAN_THREADS, 0, st>>>(in, out, scratch, n);
+  scan_totals_kernel<<<1, SCAN_THREADS, 0, st>>>(scratch, nblocks, out + n);
+  if (nblocks > 1) add_offsets_kernel<<<(n + 255) / 256, 256, 0, st>>>(out, scratch, n);
+  XEQ_LAUNCH_CHECK();
+  return XEQ_OK;
+}
+
+static inline size_t scan_scratch_ints(int n) { return (size_t)(n + SCAN_BLOCK - 1) / SCAN_BLOCK + 1; }
+
+// ------------------------------------------------------------------------------------------
+// periodic wrapping (data/radius_graph.py:6-32)
+// ------------------------------------------------------------------------------------------
+struct PbcParams {
+  int pbc[3];
+  int rep[3];
+};
+
+__device__ __forceinline__ void inv3x3(const float* c, float* inv) {
+  const float a = c[0], b = c[1], cc = c[2], d = c[3], e = c[4], f = c[5], g = c[6], h = c[7], i = c[8];
+  const float A = e * i - f * h, B = -(d * i - f * g), C = d * h - e * g;
+  const float det = a * A + b * B + cc * C;
+  const float id = 1.0f / det;
+  inv[0] = A * id;  inv[1] = -(b * i - cc * h) * id; inv[2] = (b * f - cc * e) * id;
+  inv[3] = B * id;  inv[4] = (a * i - cc * g) * id;  inv[5] = -(a * f - cc * d) * id;
+  inv[6] = C * id;  inv[7] = -(a * h - b * g) * id;  inv[8] = (a * e - b * d) * id;
+}
+
+// pw = (frac - floor(frac)) @ cell on periodic axes; shift = floor(frac) (0 on open axes)
+__global__ void wrap_positions_kernel(const float* __restrict__ pos, const int* __restrict__ node_graph,
+                                      const float* __restrict__ cell, PbcParams pp, int n, float* __restrict__ pw,
+                                      int* __restrict__ shift) {
+  const int a = blockIdx.x * blockDim.x + threadIdx.x;
+  if (a >= n) return;
+  const float* c = cell + 9 * (node_graph ? node_graph[a] : 0);
+  float inv[9];
+  inv3x3(c, inv);
+  const float p[3] = {pos[3 * a], pos[3 * a + 1], pos[3 * a + 2]};
+  float fr[3];
+  int sh[3];
+#pragma unroll
+  for (int x = 0; x < 3; ++x) {
+    float f = __fadd_rn(__fadd_rn(__fmul_rn(p[0], inv[x]), __fmul_rn(p[1], inv[3 + x])), __fmul_rn(p[2], inv[6 + x]));
+    float fl = pp.pbc[x] ? floorf(f) : 0.0f;
+    sh[x] = (int)fl;
+    fr[x] = f - fl;
+  }
+#pragma unroll
+  for (int x = 0; x < 3; ++x) {
+    pw[3 * a + x] =
+        __fadd_rn(__fadd_rn(__fmul_rn(fr[0], c[x]), __fmul_rn(fr[1], c[3 + x])), __fmul_rn(fr[2], c[6 + x]));
+    shift[3 * a + x] = sh[x];
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// per-graph scan: one warp per center atom, lanes stride over (neighbor, image) candidates in
+// canonical order, so rows come out sorted by (neighbor, ox, oy, oz).
+// ------------------------------------------------------------------------------------------
+template <bool PERIODIC>
+__device__ __forceinline__ bool edge_test(const float* pa, const float* pb, const float* c, int ox, int oy, int oz,
+                                          float r, float r2, bool same_atom) {
+  if (!PERIODIC) {
+    if (same_atom) return false;
+    const float dx = pa[0] - pb[0], dy = pa[1] - pb[1], dz = pa[2] - pb[2];
+    const float d2 = __fadd_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)), __fmul_rn(dz, dz));
+    return d2 < r2;
+  } else {
+    float b[3];
+#pragma unroll
+    for (int x = 0; x < 3; ++x) {
+      const float img = __fadd_rn(__fadd_rn(__fmul_rn((float)ox, c[x]), __fmul_rn((float)oy, c[3 + x])),
+                                  __fmul_rn((float)oz, c[6 + x]));
+      b[x] = __fadd_rn(pb[x], img);
+    }
+    const float dx = pa[0] - b[0], dy = pa[1] - b[1], dz = pa[2] - b[2];
+    const float D = __fsqrt_rn(__fadd_rn(__fadd_rn(__fmul_rn(dx, dx), __fmul_rn(dy, dy)), __fmul_rn(dz, dz)));
+    return D < r && D > 0.01f;
+  }
+}
+
+template <bool PERIODIC, bool FILL>
+__global__ void __launch_bounds__(256) graph_scan_kernel(const float* __restrict__ p /* pos or wrapped pos */,
+                                                          const int* __restrict__ shift, const int* __restrict__ graph_ptr,
+                                                          const int* __restrict__ node_graph, const float* __restrict__ cell,
+                                                          PbcParams pp, float r, int n, int* __restrict__ deg,
+                                                          const int* __restrict__ rowptr, int* __restrict__ col,
+                                                          int8_t* __restrict__ offsets, long long* __restrict__ edge_index,
+                                                          float* __restrict__ cell_offsets, long long n_edges) {
+  const int a = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (a >= n) return;
+  const int g = node_graph ? node_graph[a] : 0;
+  const int g0 = graph_ptr[g], g1 = graph_ptr[g + 1];
+  const float r2 = __fmul_rn(r, r);
+  const float pa[3] = {p[3 * a], p[3 * a + 1], p[3 * a + 2]};
+  float c[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
+  int n1 = 1, n2 = 1, nimg = 1;
+  if (PERIODIC) {
+#pragma unroll
+    for (int k = 0; k < 9; ++k) c[k] = cell[9 * g + k];
+    n1 = 2 * pp.rep[1] + 1;
+    n2 = 2 * pp.rep[2] + 1;
+    nimg = (2 * pp.rep[0] + 1) * n1 * n2;
+  }
+  const long long total = (long long)(g1 - g0) * nimg;
+  int running = 0;
+  const int base = FILL ? rowptr[a] : 0;
+  for (long long it = 0; it < total; it += 32) {
+    const long long idx = it + lane;
+    bool pass = false;
+    int b = 0, ox = 0, oy = 0, oz = 0;
+    if (idx < total) {
+      int img = 0;
+      if (PERIODIC) {
+        b = g0 + (int)(idx / nimg);
+        img = (int)(idx % nimg);
+        oz = img % n2 - pp.rep[2];
+        oy = (img / n2) % n1 - pp.rep[1];
+        ox = img / (n2 * n1) - pp.rep[0];
+      } else {
+        b = g0 + (int)idx;
+      }
+      const float pb[3] = {p[3 * b], p[3 * b + 1], p[3 * b + 2]};
+      pass = edge_test<PERIODIC>(pa, pb, c, ox, oy, oz, r, r2, a == b);
+    }
+    const unsigned m = __ballot_sync(0xffffffffu, pass);
+    if (FILL && pass) {
+      const int e = base + running + __popc(m & ((1u << lane) - 1u));
+      col[e] = b;
+      int fx = ox, fy = oy, fz = oz;
+      if (PERIODIC) {  // refer offsets to the unwrapped positions (data/radius_graph.py:186-190)
+        fx += shift[3 * a] - shift[3 * b];
+        fy += shift[3 * a + 1] - shift[3 * b + 1];
+        fz += shift[3 * a + 2] - shift[3 * b + 2];
+        if (offsets) {
+          offsets[4 * (size_t)e] = (int8_t)fx;
+          offsets[4 * (size_t)e + 1] = (int8_t)fy;
+          offsets[4 * (size_t)e + 2] = (int8_t)fz;
+          offsets[4 * (size_t)e + 3] = 0;
+        }
+        if (cell_offsets) {
+          cell_offsets[3 * (size_t)e] = (float)fx;
+          cell_offsets[3 * (size_t)e + 1] = (float)fy;
+          cell_offsets[3 * (size_t)e + 2] = (float)fz;
+        }
+      }
+      if (edge_index) {
+        edge_index[e] = a;
+        edge_index[n_edges + e] = b;
+      }
+    }
+    running += __popc(m);
+  }
+  if (!FILL && lane == 0) deg[a] = running;
+}
+
+// ------------------------------------------------------------------------------------------
+// COO -> CSR for center-sorted edge lists, and the transposed structure
+// ------------------------------------------------------------------------------------------
+__global__ void coo_to_csr_kernel(const long long* __restrict__ ei, const float* __restrict__ co, int n_nodes, int n_edges,
+                                  int* __restrict__ rowptr, int* __restrict__ col, int8_t* __restrict__ offsets) {
+  const int e = blockIdx.x * blockDim.x + threadIdx.x;
+  if (e >= n_edges) return;
+  const int c = (int)ei[e];
+  const int prev = e > 0 ? (int)ei[e - 1] : -1;
+  for (int nn = prev + 1; nn <= c; ++nn) rowptr[nn] = e;
+  if (e == n_edges - 1)
+    for (int nn = c + 1; nn <= n_nodes; ++nn) rowptr[nn] = n_edges;
+  col[e] = (int)ei[(size_t)n_edges + e];
+  if (offsets) {
+    offsets[4 * (size_t)e + 0] = co ? (int8_t)rintf(co[3 * (size_t)e + 0]) : 0;
+    offsets[4 * (size_t)e + 1] = co ? (int8_t)rintf(co[3 * (size_t)e + 1]) : 0;
+    offsets[4 * (size_t)e + 2] = co ? (int8_t)rintf(co[3 * (size_t)e + 2]) : 0;
+    offsets[4 * (size_t)e + 3] = 0;
+  }
+}
+
+__global__ void count_cols_kernel(const int* __restrict__ col, int n_edges, int* __restrict__ cnt) {
+  const int e = blockIdx.x * blockDim.x + threadIdx.x;
+  if (e < n_edges) atomicAdd(&cnt[col[e]], 1);
+}
+
+__global__ void fill_transposed_kernel(const int* __restrict__ rowptr, const int* __restrict__ col, int n_nodes,
+                                       const int* __restrict__ t_rowptr, int* __restrict__ cursor, int* __restrict__ t_row,
+                                       int* __restrict__ t_eid) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n_nodes) return;
+  for (int e = rowptr[i]; e < rowptr[i + 1]; ++e) {
+    const int j = col[e];
+    const int slot = t_rowptr[j] + atomicAdd(&cursor[j], 1);
+    t_row[slot] = i;
+    t_eid[slot] = e;
+  }
+}
+
+// slots of one transposed row sorted by edge id (== by center): deterministic order
+__global__ void sort_transposed_rows_kernel(const int* __restrict__ t_rowptr, int n_nodes, int* __restrict__ t_row,
+                                            int* __restrict__ t_eid) {
+  const int j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= n_nodes) return;
+  const int b = t_rowptr[j], e = t_rowptr[j + 1];
+  for (int a = b + 1; a < e; ++a) {
+    const int ke = t_eid[a], kr = t_row[a];
+    int k = a - 1;
+    while (k >= b && t_eid[k] > ke) {
+      t_eid[k + 1] = t_eid[k];
+      t_row[k + 1] = t_row[k];
+      --k;
+    }
+    t_eid[k + 1] = ke;
+    t_row[k + 1] = kr;
+  }
+}
+
+}  // namespace xeq
+
+using namespace xeq;
+
+extern "C" {
+
+size_t xeq_radius_graph_workspace_bytes(int32_t n_nodes, int32_t n_graphs, int periodic) {
+  (void)n_graphs;
+  size_t b = 256;
+  b += align_up(sizeof(int) * (size_t)(n_nodes + 1), 256);                 // degrees
+  b += align_up(sizeof(int) * scan_scratch_ints(n_nodes + 1), 256);        // scan scratch
+  if (periodic) {
+    b += align_up(sizeof(float) * 3 * (size_t)n_nodes, 256);               // wrapped positions
+    b += align_up(sizeof(int) * 3 * (size_t)n_nodes, 256);                 // integer shifts
+  }
+  return b;
+}
+
+static int rg_common(const float* pos, int32_t n, const int32_t* graph_ptr, const int32_t* node_graph, int32_t G,
+                     const float* cell, const int32_t* pbc_host, const int32_t* rep_host, float cutoff, void* ws,
+                     size_t ws_bytes, bool* periodic, PbcParams* pp) {
+  XEQ_CHECK_ARG(pos && graph_ptr && n >= 0 && G >= 1, "radius_graph: bad arguments");
+  XEQ_CHECK_ARG(cutoff > 0.f, "radius_graph: cutoff must be positive");
+  XEQ_CHECK_ARG(G == 1 || node_graph, "radius_graph: node_graph required for batched graphs");
+  *periodic = cell != nullptr;
+  for (int x = 0; x < 3; ++x) {
+    pp->pbc[x] = (*periodic && pbc_host) ? (pbc_host[x] != 0) : 0;
+    pp->rep[x] = (*periodic && rep_host && pp->pbc[x]) ? rep_host[x] : 0;
+    XEQ_CHECK_ARG(pp->rep[x] >= 0 && pp->rep[x] <= 60, "radius_graph: image repeat %d out of range", pp->rep[x]);
+  }
+  XEQ_CHECK_ARG(ws && ws_bytes >= xeq_radius_graph_workspace_bytes(n, G, *periodic), "radius_graph: workspace too small");
+  return XEQ_OK;
+}
+
+int xeq_radius_graph_count(const float* pos, int32_t n, const int32_t* graph_ptr, const int32_t* node_graph, int32_t G,
+                           const float* cell, const int32_t* pbc_host, const int32_t* rep_host, float cutoff,
+                           int32_t* rowptr, void* ws, size_t ws_bytes, xeq_stream_t stream) {
+  cudaStream_t st = (cudaStream_t)stream;
+  bool periodic;
+  PbcParams pp;
+  int rc = rg_common(pos, n, graph_ptr, node_graph, G, cell, pbc_host, rep_host, cutoff, ws, ws_bytes, &periodic, &pp);
+  if (rc) return rc;
+  XEQ_CHECK_ARG(rowptr, "radius_graph_count: rowptr is NULL");
+  Carver cv(ws);
+  int* deg = cv.take<int>(n + 1);
+  int* scratch = cv.take<int>(scan_scratch_ints(n + 1));
+  if (n == 0) {
+    XEQ_CUDA(cudaMemsetAsync(rowptr, 0, sizeof(int), st));
+    return XEQ_OK;
+  }
+  const int blocks = (int)(((size_t)n * 32 + 255) / 256);
+  if (periodic) {
+    float* pw = cv.take<float>(3 * (size_t)n);
+    int* shift = cv.take<int>(3 * (size_t)n);
+    wrap_positions_kernel<<<(n + 255) / 256, 256, 0, st>>>(pos, node_graph, cell, pp, n, pw, shift);
+    graph_scan_kernel<true, false><<<blocks, 256, 0, st>>>(pw, shift, graph_ptr, node_graph, cell, pp, cutoff, n, deg,
+                                                           nullptr, nullptr, nullptr, nullptr, nullptr, 0);
+  } else {
+    graph_scan_kernel<false, false><<<blocks, 256, 0, st>>>(pos, nullptr, graph_ptr, node_graph, nullptr, pp, cutoff, n,
+                                                            deg, nullptr, nullptr, nullptr, nullptr, nullptr, 0);
+  }
+  XEQ_LAUNCH_CHECK();
+  return exclusive_scan(deg, rowptr, n, scratch, st);
+}
+
+int xeq_radius_graph_fill(const float* pos, int32_t n, const int32_t* graph_ptr, const int32_t* node_graph, int32_t G,
+                          const float* cell, const int32_t* pbc_host, const int32_t* rep_host, float cutoff,
+                          const int32_t* rowptr, int32_t* col, int8_t* offsets, int64_t* edge_index, float* cell_offsets,
+                          void* ws, size_t ws_bytes, xeq_stream_t stream) {
+  cudaStream_t st = (cudaStream_t)stream;
+  bool periodic;
+  PbcParams pp;
+  int rc = rg_common(pos, n, graph_ptr, node_graph, G, cell, pbc_host, rep_host, cutoff, ws, ws_bytes, &periodic, &pp);
+  if (rc) return rc;
+  XEQ_CHECK_ARG(rowptr && col, "radius_graph_fill: rowptr/col is NULL");
+  if (n == 0) return XEQ_OK;
+  // n_edges is needed for the COO layout; the caller sized the outputs from rowptr[n], re-read it here
+  // only when the COO output is requested (tiny D2H; the Python layer already synchronised on it).
+  long long n_edges = 0;
+  if (edge_index) {
+    int e32 = 0;
+    XEQ_CUDA(cudaMemcpyAsync(&e32, rowptr + n, sizeof(int), cudaMemcpyDeviceToHost, st));
+    XEQ_CUDA(cudaStreamSynchronize(st));
+    n_edges = e32;
+  }
+  Carver cv(ws);
+  (void)cv.take<int>(n + 1);
+  (void)cv.take<int>(scan_scratch_ints(n + 1));
+  const int blocks = (int)(((size_t)n * 32 + 255) / 256);
+  if (periodic) {
+    float* pw = cv.take<float>(3 * (size_t)n);
+    int* shift = cv.take<int>(3 * (size_t)n);
+    wrap_positions_kernel<<<(n + 255) / 256, 256, 0, st>>>(pos, node_graph, cell, pp, n, pw, shift);
+    graph_scan_kernel<true, true><<<blocks, 256, 0, st>>>(pw, shift, graph_ptr, node_graph, cell, pp, cutoff, n, nullptr,
+                                                          rowptr, col, offsets, (long long*)edge_index, cell_offsets,
+                                                          n_edges);
+  } else {
+    graph_scan_kernel<false, true><<<blocks, 256, 0, st>>>(pos, nullptr, graph_ptr, node_graph, nullptr, pp, cutoff, n,
+                                                           nullptr, rowptr, col, nullptr, (long long*)edge_index, nullptr,
+                                                           n_edges);
+  }
+  XEQ_LAUNCH_CHECK();
+  return XEQ_OK;
+}
+
+int xeq_csr_from_sorted_coo(const int64_t* edge_index, const float* cell_offsets, int32_t n_nodes, int32_t n_edges,
+                            int32_t* rowptr, int32_t* col, int8_t* offsets, xeq_stream_t stream) {
+  cudaStream_t st = (cudaStream_t)stream;
+  XEQ_CHECK_ARG(rowptr && n_nodes >= 0 && n_edges >= 0, "csr_from_sorted_coo: bad arguments");
+  if (n_edges == 0) {
+    XEQ_CUDA(cudaMemsetAsync(rowptr, 0, sizeof(int) * (size_t)(n_nodes + 1), st));
+    return XEQ_OK;
+  }
+  XEQ_CHECK_ARG(edge_index && col, "csr_from_sorted_coo: NULL edge_index/col");
+  coo_to_csr_kernel<<<(n_edges + 255) / 256, 256, 0, st>>>((const long long*)edge_index, cell_offsets, n_nodes, n_edges,
+                                                           rowptr, col, offsets);
+  XEQ_LAUNCH_CHECK();
+  return XEQ_OK;
+}
+
+size_t xeq_csr_transpose_workspace_bytes(int32_t n_nodes, int32_t n_edges) {
+  (void)n_edges;
+  return 256 + align_up(sizeof(int) * (size_t)(n_nodes + 1), 256) + align_up(sizeof(int) * scan_scratch_ints(n_nodes + 1), 256);
+}
+
+int xeq_csr_transpose(const int32_t* rowptr, const int32_t* col, int32_t n_nodes, int32_t n_edges, int32_t* t_rowptr,
+                      int32_t* t_row, int32_t* t_eid, void* ws, size_t ws_bytes, xeq_stream_t stream) {
+  cudaStream_t st = (cudaStream_t)stream;
+  XEQ_CHECK_ARG(rowptr && t_rowptr && n_nodes >= 0 && n_edges >= 0, "csr_transpose: bad arguments");
+  XEQ_CHECK_ARG(ws && ws_bytes >= xeq_csr_transpose_workspace_bytes(n_nodes, n_edges), "csr_transpose: workspace too small");
+  Carver cv(ws);
+  int* cnt = cv.take<int>(n_nodes + 1);
+  int* scratch = cv.take<int>(scan_scratch_ints(n_nodes + 1));
+  XEQ_CUDA(cudaMemsetAsync(cnt, 0, sizeof(int) * (size_t)(n_nodes + 1), st));
+  if (n_edges > 0) {
+    XEQ_CHECK_ARG(col && t_row && t_eid, "csr_transpose: NULL col/t_row/t_eid");
+    count_cols_kernel<<<(n_edges + 255) / 256, 256, 0, st>>>(col, n_edges, cnt);
+  }
+  int rc = exclusive_scan(cnt, t_rowptr, n_nodes, scratch, st);
+  if (rc) return rc;
+  if (n_edges > 0 && n_nodes > 0) {
+    XEQ_CUDA(cudaMemsetAsync(cnt, 0, sizeof(int) * (size_t)(n_nodes + 1), st));
+    fill_transposed_kernel<<<(n_nodes + 127) / 128, 128, 0, st>>>(rowptr, col, n_nodes, t_rowptr, cnt, t_row, t_eid);
+    sort_transposed_rows_kernel<<<(n_nodes + 127) / 128, 128, 0, st>>>(t_rowptr, n_nodes, t_row, t_eid);
+  }
+  XEQ_LAUNCH_CHECK();
+  return XEQ_OK;
+}
+
+}  // extern "C"

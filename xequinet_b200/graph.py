@@ -1,0 +1,239 @@
+"""Neighbour lists on the GPU (K1) and the CSR structure the edge kernels consume.
+
+Drop-in counterparts of the reference's neighbour-list entry points:
+  radius_graph(...)       <- torch_cluster.radius_graph as called at data/transform.py:58-64
+  radius_graph_pbc(...)   <- xequinet/data/radius_graph.py:35-192
+  NeighborTransform       <- xequinet/data/transform.py:21-69
+"""
+from __future__ import annotations
+
+import ctypes
+import math
+from typing import Dict, Optional, Tuple
+
+import torch
+
+from . import _lib, keys
+
+
+class NeighborGraph:
+    """Device-resident CSR (by center) + transposed CSR (by neighbor) of one batch."""
+
+    def __init__(self, n_nodes: int, n_graphs: int, rowptr, col, offsets=None, cell=None, node_graph=None):
+        self.n_nodes = int(n_nodes)
+        self.n_graphs = int(n_graphs)
+        self.rowptr = rowptr
+        self.col = col
+        self.n_edges = int(col.numel())
+        self.offsets = offsets  # int8 [E,4] or None
+        self.cell = cell  # float32 [G,3,3] or None
+        self.node_graph = node_graph  # int32 [N] or None
+        self.t_rowptr = self.t_row = self.t_eid = None
+        self._struct = None
+        self._transpose()
+
+    def _transpose(self):
+        lib = _lib.get()
+        dev = self.rowptr.device
+        N, E = self.n_nodes, self.n_edges
+        self.t_rowptr = torch.empty(N + 1, dtype=torch.int32, device=dev)
+        self.t_row = torch.empty(max(E, 1), dtype=torch.int32, device=dev)
+        self.t_eid = torch.empty(max(E, 1), dtype=torch.int32, device=dev)
+        nbytes = lib.xeq_csr_transpose_workspace_bytes(N, E)
+        ws = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+        _lib.check(lib.xeq_csr_transpose(_lib.ptr(self.rowptr), _lib.ptr(self.col), N, E, _lib.ptr(self.t_rowptr),
+                                         _lib.ptr(self.t_row), _lib.ptr(self.t_eid), _lib.ptr(ws), nbytes,
+                                         _lib.stream()), "xeq_csr_transpose")
+
+    @property
+    def struct(self) -> _lib.XeqGraph:
+        if self._struct is None:
+            g = _lib.XeqGraph()
+            g.n_nodes, g.n_edges, g.n_graphs = self.n_nodes, self.n_edges, self.n_graphs
+            g.rowptr, g.col = self.rowptr.data_ptr(), self.col.data_ptr()
+            g.t_rowptr, g.t_row, g.t_eid = self.t_rowptr.data_ptr(), self.t_row.data_ptr(), self.t_eid.data_ptr()
+            g.offsets = self.offsets.data_ptr() if self.offsets is not None else None
+            g.cell = self.cell.data_ptr() if self.cell is not None else None
+            g.node_graph = self.node_graph.data_ptr() if self.node_graph is not None else None
+            self._struct = g
+        return self._struct
+
+    def edge_index(self) -> torch.Tensor:
+        """COO [2,E] int64 in canonical order (row 0 = center, row 1 = neighbor; keys.py:16-17)."""
+        counts = (self.rowptr[1:] - self.rowptr[:-1]).long()
+        center = torch.repeat_interleave(torch.arange(self.n_nodes, device=self.rowptr.device), counts)
+        return torch.stack([center, self.col[: self.n_edges].long()])
+
+
+def _image_repeats(cell: torch.Tensor, pbc, cutoff: float):
+    """Images per axis = ceil(rc * |a_j x a_k| / V), max over graphs (data/radius_graph.py:61-89).
+    Tiny host-side computation on the [G,3,3] lattice (the reference also syncs here, :89)."""
+    c = cell.detach().to("cpu", torch.float32)
+    cross = [torch.cross(c[:, 1], c[:, 2], dim=-1), torch.cross(c[:, 2], c[:, 0], dim=-1),
+             torch.cross(c[:, 0], c[:, 1], dim=-1)]
+    vol = torch.sum(c[:, 0] * cross[0], dim=-1, keepdim=True)
+    reps = []
+    for ax in range(3):
+        if pbc[ax]:
+            inv_min = torch.norm(cross[ax] / vol, p=2, dim=-1)
+            reps.append(int(torch.ceil(cutoff * inv_min).max().item()))
+        else:
+            reps.append(0)
+    return reps
+
+
+def build_graph(pos: torch.Tensor, cutoff: float, ptr: Optional[torch.Tensor] = None,
+                batch: Optional[torch.Tensor] = None, cell: Optional[torch.Tensor] = None, pbc=None,
+                want_coo: bool = False):
+    """K1: radius graph of a (batched, optionally periodic) structure.  Returns
+    (NeighborGraph, edge_index or None, cell_offsets or None)."""
+    lib = _lib.get()
+    if not pos.is_cuda:
+        raise RuntimeError("build_graph needs CUDA tensors: xequinet_b200 has no CPU fallback")
+    dev = pos.device
+    pos32 = pos.detach().to(torch.float32).contiguous()
+    N = pos32.shape[0]
+    if ptr is None:
+        if batch is None:
+            ptr = torch.tensor([0, N], dtype=torch.int32, device=dev)
+        else:
+            G = int(batch.max().item()) + 1 if N else 1
+            counts = torch.bincount(batch, minlength=G)
+            ptr = torch.zeros(G + 1, dtype=torch.int32, device=dev)
+            ptr[1:] = torch.cumsum(counts, 0)
+    ptr32 = ptr.to(device=dev, dtype=torch.int32).contiguous()
+    G = ptr32.numel() - 1
+    if batch is not None:
+        node_graph = batch.to(device=dev, dtype=torch.int32).contiguous()
+    elif G > 1:
+        node_graph = torch.repeat_interleave(torch.arange(G, device=dev, dtype=torch.int32),
+                                             (ptr32[1:] - ptr32[:-1]).long())
+    else:
+        node_graph = None
+    periodic = cell is not None
+    pbc_arr = (ctypes.c_int32 * 3)(0, 0, 0)
+    rep_arr = (ctypes.c_int32 * 3)(0, 0, 0)
+    cell32 = None
+    if periodic:
+        cell32 = cell.detach().to(device=dev, dtype=torch.float32).reshape(-1, 3, 3).contiguous()
+        if cell32.shape[0] != G:
+            raise ValueError("cell must be [n_graphs, 3, 3]")
+        if pbc is None:
+            pbc_l = [True, True, True]
+        else:
+            p = torch.as_tensor(pbc).reshape(-1, 3).cpu()
+            # PBC must be the same for all graphs (data/radius_graph.py:50-51)
+            assert bool(torch.all(p[0] == p)), "PBC must be the same for all graphs"
+            pbc_l = [bool(v) for v in p[0].tolist()]
+        reps = _image_repeats(cell32, pbc_l, cutoff)
+        for k in range(3):
+            pbc_arr[k], rep_arr[k] = int(pbc_l[k]), reps[k]
+    nbytes = lib.xeq_radius_graph_workspace_bytes(N, G, int(periodic))
+    ws = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+    rowptr = torch.empty(N + 1, dtype=torch.int32, device=dev)
+    st = _lib.stream()
+    _lib.check(lib.xeq_radius_graph_count(_lib.ptr(pos32), N, _lib.ptr(ptr32), _lib.ptr(node_graph), G,
+                                          _lib.ptr(cell32), pbc_arr, rep_arr, float(cutoff), _lib.ptr(rowptr),
+                                          _lib.ptr(ws), nbytes, st), "xeq_radius_graph_count")
+    E = int(rowptr[-1].item())  # the one host sync of the neighbour search: sizes the edge arrays
+    col = torch.empty(max(E, 1), dtype=torch.int32, device=dev)
+    offsets = torch.empty((max(E, 1), 4), dtype=torch.int8, device=dev) if periodic else None
+    ei = torch.empty((2, E), dtype=torch.int64, device=dev) if want_coo else None
+    co = torch.empty((E, 3), dtype=torch.float32, device=dev) if (want_coo and periodic) else None
+    _lib.check(lib.xeq_radius_graph_fill(_lib.ptr(pos32), N, _lib.ptr(ptr32), _lib.ptr(node_graph), G,
+                                         _lib.ptr(cell32), pbc_arr, rep_arr, float(cutoff), _lib.ptr(rowptr),
+                                         _lib.ptr(col), _lib.ptr(offsets), _lib.ptr(ei) if E else None,
+                                         _lib.ptr(co) if (co is not None and E) else None, _lib.ptr(ws), nbytes, st),
+               "xeq_radius_graph_fill")
+    g = NeighborGraph(N, G, rowptr, col[:E] if E else col[:0], offsets[:E] if (periodic and E) else (offsets[:0] if periodic else None),
+                      cell32, node_graph if (periodic and G > 1) else None)
+    return g, ei, co
+
+
+def graph_from_edge_index(edge_index: torch.Tensor, n_nodes: int, n_graphs: int = 1,
+                          cell_offsets: Optional[torch.Tensor] = None, cell: Optional[torch.Tensor] = None,
+                          batch: Optional[torch.Tensor] = None) -> NeighborGraph:
+    """CSR structure for a caller-supplied COO edge list (any order; nn/basic.py:67 takes
+    `edge_index` from the data dict).  Unsorted lists are first put in canonical order."""
+    lib = _lib.get()
+    if not edge_index.is_cuda:
+        raise RuntimeError("graph_from_edge_index needs CUDA tensors: xequinet_b200 has no CPU fallback")
+    dev = edge_index.device
+    ei = edge_index.to(torch.int64)
+    E = ei.shape[1]
+    co = cell_offsets
+    if E > 1 and bool((ei[0, 1:] < ei[0, :-1]).any()):
+        order = torch.sort(ei[0], stable=True)[1]
+        ei = ei[:, order]
+        co = co[order] if co is not None else None
+    ei = ei.contiguous()
+    periodic = cell is not None
+    if periodic and co is None:
+        raise ValueError("PBC and cell must be both defined or both undefined.")
+    co32 = co.to(torch.float32).contiguous() if co is not None else None
+    rowptr = torch.empty(n_nodes + 1, dtype=torch.int32, device=dev)
+    col = torch.empty(max(E, 1), dtype=torch.int32, device=dev)
+    offsets = torch.empty((max(E, 1), 4), dtype=torch.int8, device=dev) if periodic else None
+    _lib.check(lib.xeq_csr_from_sorted_coo(_lib.ptr(ei) if E else None, _lib.ptr(co32) if (periodic and E) else None,
+                                           n_nodes, E, _lib.ptr(rowptr), _lib.ptr(col), _lib.ptr(offsets),
+                                           _lib.stream()), "xeq_csr_from_sorted_coo")
+    cell32 = cell.detach().to(device=dev, dtype=torch.float32).reshape(-1, 3, 3).contiguous() if periodic else None
+    node_graph = None
+    if periodic and n_graphs > 1:
+        if batch is None:
+            raise ValueError("batch is required for multi-graph periodic input")
+        node_graph = batch.to(device=dev, dtype=torch.int32).contiguous()
+    g = NeighborGraph(n_nodes, n_graphs, rowptr, col[:E], offsets[:E] if periodic else None, cell32, node_graph)
+    g.sorted_edge_index = ei
+    return g
+
+
+# ------------------------------------------------------------------------------------------
+# reference-compatible entry points
+# ------------------------------------------------------------------------------------------
+def radius_graph(x: torch.Tensor, r: float, batch: Optional[torch.Tensor] = None, loop: bool = False,
+                 max_num_neighbors: int = 32, flow: str = "source_to_target", num_workers: int = 1,
+                 batch_size: Optional[int] = None) -> torch.Tensor:
+    """Signature of torch_cluster.radius_graph.  As at the reference's call site
+    (data/transform.py:57-64) the neighbour cap is never binding, so it is not applied here;
+    row 0 = center, row 1 = neighbor, canonically sorted."""
+    if loop:
+        raise NotImplementedError("loop=True is not used by XequiNet (data/transform.py:58-64)")
+    _, ei, _ = build_graph(x, r, batch=batch, want_coo=True)
+    return ei
+
+
+def radius_graph_pbc(pos: torch.Tensor, n_nodes_per_graph: torch.Tensor, pbc: torch.Tensor, cell: torch.Tensor,
+                     cutoff: float) -> Tuple[torch.Tensor, torch.Tensor]:
+    """Signature of xequinet.data.radius_graph.radius_graph_pbc (data/radius_graph.py:36-42).
+    Returns (edge_index [2,E] int64, cell_offsets [E,3] float), canonically sorted."""
+    n = n_nodes_per_graph.to(pos.device)
+    ptr = torch.zeros(n.numel() + 1, dtype=torch.int32, device=pos.device)
+    ptr[1:] = torch.cumsum(n, 0)
+    _, ei, co = build_graph(pos, cutoff, ptr=ptr, cell=cell, pbc=pbc, want_coo=True)
+    return ei, co.to(pos.dtype)
+
+
+class NeighborTransform:
+    """xequinet/data/transform.py:21-69 for dict-shaped data: adds `edge_index` (and
+    `cell_offsets` under PBC) plus the prebuilt CSR structure the model reuses."""
+
+    def __init__(self, cutoff: float) -> None:
+        self.cutoff = cutoff
+
+    def __call__(self, data: Dict[str, torch.Tensor]) -> Dict[str, torch.Tensor]:
+        pos = data[keys.POSITIONS]
+        has_pbc = keys.PBC in data and bool(torch.as_tensor(data[keys.PBC]).any())
+        has_cell = keys.CELL in data
+        if has_pbc != has_cell:
+            raise ValueError("PBC and cell must be both defined or both undefined.")
+        ptr, batch = data.get(keys.BATCH_PTR), data.get(keys.BATCH)
+        if has_pbc:
+            g, ei, co = build_graph(pos, self.cutoff, ptr=ptr, batch=batch, cell=data[keys.CELL], pbc=data[keys.PBC],
+                                    want_coo=True)
+            data[keys.CELL_OFFSETS] = co.to(pos.dtype)
+        else:
+            g, ei, _ = build_graph(pos, self.cutoff, ptr=ptr, batch=batch, want_coo=True)
+        data[keys.EDGE_INDEX] = ei
+        data[keys.GRAPH] = g
+        return data

@@ -1,0 +1,27 @@
+"""String contract of the data / result dictionaries (same values as the reference's
+xequinet/keys.py:4-40, so dictionaries are interchangeable)."""
+POSITIONS = "pos"
+ATOMIC_NUMBERS = "atomic_numbers"
+EDGE_INDEX = "edge_index"
+CELL_OFFSETS = "cell_offsets"
+CELL = "cell"
+PBC = "pbc"
+BATCH = "batch"
+BATCH_PTR = "ptr"
+NUM_GRAPHS = "num_graphs"
+
+CENTER_IDX = 0
+NEIGHBOR_IDX = 1
+
+NODE_INVARIANT = "node_invariant"
+NODE_EQUIVARIANT = "node_equivariant"  # held in the component-major layout (include/xeq_b200.h)
+
+ATOMIC_ENERGIES = "atomic_energies"
+TOTAL_ENERGY = "energy"
+FORCES = "forces"
+VIRIAL = "virial"
+
+# private entries this package adds to the data dict
+GRAPH = "_xeq_graph"
+RBF_FREQ = "_xeq_rbf_freq"
+RBF_CUTOFF = "_xeq_rbf_cutoff"

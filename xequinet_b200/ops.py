@@ -1,0 +1,212 @@
+"""torch.autograd glue over the C ABI (include/xeq_b200.h).
+
+Each op is a `torch.autograd.Function` whose backward is itself an autograd Function backed
+by a hand-written kernel, so that `torch.autograd.grad(E, pos, create_graph=True)` followed by
+`loss.backward()` (nn/basic.py:150-156, utils/trainer.py:302) runs K2 -> K2b -> K2bb without
+any eager fallback."""
+from __future__ import annotations
+
+from dataclasses import dataclass
+from typing import Optional
+
+import torch
+
+from . import _lib
+from .graph import NeighborGraph
+
+
+@dataclass(frozen=True)
+class Dims:
+    node_dim: int
+    mul0: int
+    mul1: int
+    mul2: int
+    num_basis: int
+    cutoff: float
+
+    @property
+    def M(self):
+        return self.mul0 + self.mul1 + self.mul2
+
+    @property
+    def D(self):
+        return self.mul0 + 3 * self.mul1 + 5 * self.mul2
+
+    @property
+    def H(self):
+        return self.node_dim + 2 * self.M
+
+    def struct(self) -> _lib.XeqDims:
+        return _lib.XeqDims(self.node_dim, self.mul0, self.mul1, self.mul2, self.num_basis, self.cutoff)
+
+
+def _c(t: Optional[torch.Tensor]) -> Optional[torch.Tensor]:
+    if t is None:
+        return None
+    if t.dtype != torch.float32:
+        raise RuntimeError(f"xequinet_b200 kernels compute in fp32, got {t.dtype}")
+    return t.contiguous()
+
+
+def _workspace(nbytes: int, device) -> torch.Tensor:
+    return torch.empty(max(int(nbytes), 256), dtype=torch.uint8, device=device)
+
+
+# ------------------------------------------------------------------------------------------
+# raw kernel calls (no autograd)
+# ------------------------------------------------------------------------------------------
+def edge_message_fwd_raw(graph: NeighborGraph, dims: Dims, pos, s, v, x_in, V_in, W, b, freq):
+    lib = _lib.get()
+    N = graph.n_nodes
+    x_out = torch.empty((N, dims.node_dim), dtype=torch.float32, device=s.device)
+    V_out = torch.empty((N, dims.D), dtype=torch.float32, device=s.device)
+    d = dims.struct()
+    _lib.check(lib.xeq_edge_message_fwd(graph.struct, d, _lib.ptr(pos), _lib.ptr(s), _lib.ptr(v), _lib.ptr(x_in),
+                                        _lib.ptr(V_in), _lib.ptr(W), _lib.ptr(b), _lib.ptr(freq), _lib.ptr(x_out),
+                                        _lib.ptr(V_out), _lib.stream()), "xeq_edge_message_fwd")
+    return x_out, V_out
+
+
+def edge_message_bwd_raw(graph: NeighborGraph, dims: Dims, pos, s, v, W, b, freq, gx, gV, need_s=True, need_v=True,
+                         need_pos=True, need_w=False):
+    lib = _lib.get()
+    N, dev = graph.n_nodes, s.device
+    new = lambda *shape: torch.empty(shape, dtype=torch.float32, device=dev)
+    gs = new(N, dims.H) if need_s else None
+    gv = new(N, dims.D) if need_v else None
+    gpos = new(N, 3) if need_pos else None
+    gW = new(dims.H, dims.num_basis) if need_w else None
+    gb = new(dims.H) if need_w else None
+    gf = new(dims.num_basis) if need_w else None
+    d = dims.struct()
+    nbytes = lib.xeq_edge_message_bwd_workspace_bytes(graph.struct, d, int(need_w))
+    ws = _workspace(nbytes, dev)
+    _lib.check(lib.xeq_edge_message_bwd(graph.struct, d, _lib.ptr(pos), _lib.ptr(s), _lib.ptr(v), _lib.ptr(W),
+                                        _lib.ptr(b), _lib.ptr(freq), _lib.ptr(gx), _lib.ptr(gV), _lib.ptr(gs),
+                                        _lib.ptr(gv), _lib.ptr(gpos), _lib.ptr(gW), _lib.ptr(gb), _lib.ptr(gf),
+                                        _lib.ptr(ws), nbytes, _lib.stream()), "xeq_edge_message_bwd")
+    return gs, gv, gpos, gW, gb, gf
+
+
+def edge_message_bwdbwd_raw(graph: NeighborGraph, dims: Dims, pos, s, v, W, b, freq, gx, gV, a_s, a_v, a_pos,
+                            need_g=True, need_s=True, need_v=True, need_pos=True, need_w=True):
+    lib = _lib.get()
+    N, dev = graph.n_nodes, s.device
+    new = lambda *shape: torch.empty(shape, dtype=torch.float32, device=dev)
+    o_gx = new(N, dims.node_dim) if need_g else None
+    o_gV = new(N, dims.D) if need_g else None
+    o_s = new(N, dims.H) if need_s else None
+    o_v = new(N, dims.D) if need_v else None
+    o_pos = new(N, 3) if need_pos else None
+    o_W = new(dims.H, dims.num_basis) if need_w else None
+    o_b = new(dims.H) if need_w else None
+    o_f = new(dims.num_basis) if need_w else None
+    d = dims.struct()
+    nbytes = lib.xeq_edge_message_bwdbwd_workspace_bytes(graph.struct, d, int(need_w))
+    ws = _workspace(nbytes, dev)
+    _lib.check(lib.xeq_edge_message_bwdbwd(graph.struct, d, _lib.ptr(pos), _lib.ptr(s), _lib.ptr(v), _lib.ptr(W),
+                                           _lib.ptr(b), _lib.ptr(freq), _lib.ptr(gx), _lib.ptr(gV), _lib.ptr(a_s),
+                                           _lib.ptr(a_v), _lib.ptr(a_pos), _lib.ptr(o_gx), _lib.ptr(o_gV), _lib.ptr(o_s),
+                                           _lib.ptr(o_v), _lib.ptr(o_pos), _lib.ptr(o_W), _lib.ptr(o_b), _lib.ptr(o_f),
+                                           _lib.ptr(ws), nbytes, _lib.stream()), "xeq_edge_message_bwdbwd")
+    return o_gx, o_gV, o_s, o_v, o_pos, o_W, o_b, o_f
+
+
+# ------------------------------------------------------------------------------------------
+# autograd
+# ------------------------------------------------------------------------------------------
+class _EdgeMessageBwd(torch.autograd.Function):
+    """K2b as a differentiable function of (gx, gV, s, v, pos, W, b, freq); its backward is K2bb."""
+
+    @staticmethod
+    def forward(ctx, gx, gV, s, v, pos, W, b, freq, graph, dims, needs):
+        need_s, need_v, need_pos, need_w = needs
+        gx, gV = _c(gx), _c(gV)
+        gs, gv, gpos, gW, gb, gf = edge_message_bwd_raw(graph, dims, pos, s, v, W, b, freq, gx, gV, need_s, need_v,
+                                                         need_pos, need_w)
+        ctx.save_for_backward(gx, gV, s, v, pos, W, b, freq)
+        ctx.graph, ctx.dims, ctx.needs = graph, dims, needs
+        outs = (gs, gv, gpos, gW, gb, gf)
+        ctx.mark_non_differentiable(*[o for o in outs[3:] if o is not None])
+        return outs
+
+    @staticmethod
+    @torch.autograd.function.once_differentiable
+    def backward(ctx, a_s, a_v, a_pos, a_W, a_b, a_f):
+        gx, gV, s, v, pos, W, b, freq = ctx.saved_tensors
+        ni = ctx.needs_input_grad
+        if a_s is None and a_v is None and a_pos is None:
+            return (None,) * 11
+        need_g = ni[0] or ni[1]
+        need_w = ni[5] or ni[6] or ni[7]
+        o = edge_message_bwdbwd_raw(ctx.graph, ctx.dims, pos, s, v, W, b, freq, gx, gV, _c(a_s), _c(a_v), _c(a_pos),
+                                    need_g=need_g, need_s=ni[2], need_v=ni[3], need_pos=ni[4], need_w=need_w)
+        o_gx, o_gV, o_s, o_v, o_pos, o_W, o_b, o_f = o
+        return o_gx, o_gV, o_s, o_v, o_pos, o_W, o_b, (o_f.view_as(freq) if o_f is not None else None), None, None, None
+
+
+class _EdgeMessage(torch.autograd.Function):
+    """K2: (x, V, s, v, pos, W_rbf, b_rbf, freq) -> (x + sum m_s, V + sum m_e)."""
+
+    @staticmethod
+    def forward(ctx, x, V, s, v, pos, W, b, freq, graph, dims):
+        x, V, s, v, pos, W, b = (_c(t) for t in (x, V, s, v, pos, W, b))
+        freq = _c(freq)
+        x_out, V_out = edge_message_fwd_raw(graph, dims, pos, s, v, x, V, W, b, freq)
+        ctx.save_for_backward(s, v, pos, W, b, freq)
+        ctx.graph, ctx.dims = graph, dims
+        return x_out, V_out
+
+    @staticmethod
+    def backward(ctx, gx, gV):
+        s, v, pos, W, b, freq = ctx.saved_tensors
+        ni = ctx.needs_input_grad
+        if gx is None:
+            gx = torch.zeros((s.shape[0], ctx.dims.node_dim), dtype=s.dtype, device=s.device)
+        if gV is None:
+            gV = torch.zeros((s.shape[0], ctx.dims.D), dtype=s.dtype, device=s.device)
+        need_w = ni[5] or ni[6] or ni[7]
+        needs = (ni[2], ni[3], ni[4], need_w)
+        gs = gv = gpos = gW = gb = gf = None
+        if any(needs):
+            gs, gv, gpos, gW, gb, gf = _EdgeMessageBwd.apply(gx, gV, s, v, pos, W, b, freq, ctx.graph, ctx.dims, needs)
+            if gf is not None:
+                gf = gf.view_as(freq)
+        return (gx if ni[0] else None, gV if ni[1] else None, gs, gv, gpos, gW, gb, gf, None, None)
+
+
+def edge_message(x, V, s, v, pos, W_rbf, b_rbf, freq, graph: NeighborGraph, dims: Dims):
+    """Fused XPainnMessage aggregation (nn/xpainn.py:140-159); V and v in the cm layout."""
+    return _EdgeMessage.apply(x, V, s, v, pos, W_rbf, b_rbf, freq, graph, dims)
+
+
+class _SegmentSum(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, src, seg_ptr, node_graph):
+        lib = _lib.get()
+        src = _c(src)
+        G = seg_ptr.numel() - 1
+        out = torch.empty(G, dtype=torch.float32, device=src.device)
+        _lib.check(lib.xeq_segment_sum(_lib.ptr(src), _lib.ptr(seg_ptr), G, _lib.ptr(out), _lib.stream()),
+                   "xeq_segment_sum")
+        ctx.save_for_backward(node_graph)
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        (node_graph,) = ctx.saved_tensors
+        return g.index_select(0, node_graph), None, None
+
+
+def segment_sum(src: torch.Tensor, seg_ptr: torch.Tensor, node_graph: torch.Tensor) -> torch.Tensor:
+    """scatter_sum(src, batch) for the sorted `batch` of a collated batch (nn/output.py:124)."""
+    return _SegmentSum.apply(src, seg_ptr, node_graph)
+
+
+def layout_convert(V: torch.Tensor, dims: Dims, to_cm: bool) -> torch.Tensor:
+    lib = _lib.get()
+    V = _c(V)
+    out = torch.empty_like(V)
+    _lib.check(lib.xeq_layout_convert(_lib.ptr(V), _lib.ptr(out), V.shape[0], dims.struct(), 0 if to_cm else 1,
+                                      _lib.stream()), "xeq_layout_convert")
+    return out
