@@ -26,5 +26,5 @@ def cast_data(data, dtype):
 
 
 def grad_digest(g):
-    g = g.detach().double().reshape(-1)
+    g = g.detach().double().reshape(-1).cpu()
     return np.array([g.sum().item(), g.norm().item()]), g[:: max(1, g.numel() // 64)][:64].numpy()
