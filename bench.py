@@ -1,0 +1,404 @@
+#!/usr/bin/env python
+"""bench.py -- molecules/s for XPaiNN energy+forces on B200 (BASELINE.json metric).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload c1|c2|c3|c4|c5] [--impl reference]
+
+One "step" is one pass of the hot path over one batch of synthetic molecules:
+  c3 (default; the configuration the metric is quoted on at 1/2/4/8 GPUs): aspirin-shaped
+     (21 atoms) energy+force TRAINING step -- neighbour list (K1), forward, forces with
+     create_graph (K2/K2b), smooth-L1 E+F loss, backward through the forces (K2bb), gradient
+     all-reduce (N > 1), AdamW -- on 256 molecules per GPU (weak scaling).
+  c1: E+F inference, 64 x 18 atoms.   c2: energy-only training, 256 x 18 atoms.
+  c4: E+F inference, 256 channels, 128 drug-like molecules (30..70 atoms) per GPU.
+  c5: periodic water box (~10k atoms), E+F inference incl. neighbour rebuild (replicas for N > 1).
+
+Output: ONE JSON line (rank 0).  `value` = whole-job molecules/s with the inputs resident in
+HBM; `e2e` = the same through the public API with pinned-host inputs copied in and the loss /
+energies read back every step; `roofline` = the dominant hand-written kernel of the step
+(CUDA events on the launching stream, algorithmic bytes per DESIGN.md) against the measured
+HBM peak; `cpu_baseline` = the CPU oracle (port of the reference path) on the host cores.
+`--impl reference` times that CPU path alone.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+from pathlib import Path
+
+import numpy as np
+import torch
+import torch.nn.functional as F
+
+ROOT = Path(__file__).resolve().parent
+sys.path.insert(0, str(ROOT))
+
+from oracle import xpainn_oracle as orc  # noqa: E402  (cpu_baseline / reference arm only)
+
+METRIC = "molecules/sec energy+forces"
+UNIT = "molecules/s"
+
+WORKLOADS = {
+    "c1": dict(desc="XPaiNN E+F inference, QM9-shaped 64 x 18 atoms", cfg=orc.CONFIG_DEFAULT, n_mol=64, train=False, forces=True),
+    "c2": dict(desc="XPaiNN energy-only training, QM9-shaped 256 x 18 atoms, fp32", cfg=orc.CONFIG_DEFAULT, n_mol=256, train=True, forces=False),
+    "c3": dict(desc="XPaiNN E+F training (double-backward force loss), MD17/aspirin-shaped 256 x 21 atoms per GPU", cfg=orc.CONFIG_DEFAULT, n_mol=256, train=True, forces=True),
+    "c4": dict(desc="XPaiNN-256ch E+F inference, SPICE-shaped 128 x (30..70) atoms per GPU", cfg=orc.CONFIG_C4, n_mol=128, train=False, forces=True),
+    "c5": dict(desc="periodic water box 10125 atoms, PBC radius graph + E+F inference", cfg=orc.CONFIG_DEFAULT, n_mol=1, train=False, forces=True),
+}
+
+
+def make_batch(workload: str, n_mol: int, seed: int):
+    if workload in ("c1", "c2"):
+        d = orc.make_molecule_batch(n_mol, 18, seed=seed, with_edges=False)
+    elif workload == "c3":
+        d = orc.make_aspirin_batch(n_mol, seed=seed, with_edges=False)
+    elif workload == "c4":
+        d = orc.make_molecule_batch(n_mol, (30, 70), seed=seed, z_table=orc._Z_SPICE, with_edges=False)
+    else:
+        d = orc.make_water_box(15, seed=seed)
+    g = torch.Generator().manual_seed(1000 + seed)
+    G = d["ptr"].numel() - 1
+    d["target_energy"] = torch.randn(G, generator=g)
+    d["target_forces"] = torch.randn(d["pos"].shape[0], 3, generator=g)
+    return d
+
+
+def loss_fn(out, batch, forces: bool):
+    loss = F.smooth_l1_loss(out["energy"], batch["target_energy"])
+    if forces:
+        loss = loss + 100.0 * F.smooth_l1_loss(out["forces"], batch["target_forces"])
+    return loss
+
+
+# ----------------------------------------------------------------------------------------------
+# CPU oracle arm (cpu_baseline and --impl reference)
+# ----------------------------------------------------------------------------------------------
+def cpu_step_fn(workload: str, n_mol: int):
+    """Returns (step callable, molecules per step, description) for the CPU oracle."""
+    w = WORKLOADS[workload]
+    cfg = w["cfg"]
+    torch.set_num_threads(os.cpu_count() or 1)
+    table = torch.from_numpy(np.load(ROOT / "xequinet_b200" / "data" / "gfn2-xtb_aux56.npy")).float()
+    sd = {k: v.requires_grad_(w["train"]) for k, v in orc.synthetic_state_dict(cfg, 1234).items()}
+    if workload == "c5":
+        batch = orc.make_water_box(6, seed=0)  # 648 atoms: bounded sample of the box
+        n = torch.tensor([batch["pos"].shape[0]])
+    else:
+        batch = make_batch(workload, n_mol, 0)
+    opt = torch.optim.AdamW(list(sd.values()), lr=5e-4) if w["train"] else None
+
+    def step():
+        d = dict(batch)
+        if workload == "c5":
+            d["edge_index"], d["cell_offsets"] = orc.radius_graph_pbc(d["pos"], n, d["pbc"], d["cell"], cfg.cutoff)
+        else:
+            d["edge_index"] = orc.radius_graph(d["pos"], cfg.cutoff, d["batch"])
+        if w["forces"]:
+            out = orc.xpainn_energy_forces(sd, table, d, cfg, create_graph=w["train"])
+        else:
+            e, ea = orc.xpainn_energy(sd, table, d, cfg)
+            out = {"energy": e}
+        if w["train"]:
+            opt.zero_grad(set_to_none=True)
+            loss_fn(out, d, w["forces"]).backward()
+            opt.step()
+        return out
+
+    mols = batch["ptr"].numel() - 1
+    frac = 1.0 if workload != "c5" else batch["pos"].shape[0] / 10125.0
+    return step, mols * frac, f"{mols} molecule(s), {batch['pos'].shape[0]} atoms per step"
+
+
+def time_cpu(workload: str, n_mol: int, steps: int, warmup: int):
+    step, mols, sample = cpu_step_fn(workload, n_mol)
+    for _ in range(warmup):
+        step()
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        step()
+    dt = (time.perf_counter() - t0) / steps
+    return mols / dt, dt * 1e3, sample
+
+
+# ----------------------------------------------------------------------------------------------
+# clocks
+# ----------------------------------------------------------------------------------------------
+class ClockSampler(threading.Thread):
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index: int):
+        super().__init__(daemon=True)
+        self.gpu = gpu_index
+        self.stop_flag = threading.Event()
+        self.samples = []
+
+    def run(self):
+        while not self.stop_flag.is_set():
+            try:
+                out = subprocess.run(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-i", str(self.gpu)],
+                                     capture_output=True, text=True, timeout=5).stdout.strip()
+                if out:
+                    self.samples.append([c.strip() for c in out.split(",")])
+            except Exception:
+                pass
+            self.stop_flag.wait(0.2)
+
+    def summary(self):
+        sm, mx, reasons = [], 0.0, set()
+        for s in self.samples:
+            try:
+                sm.append(float(s[1]))
+                mx = max(mx, float(s[2]))
+                for name, col in (("hw_slowdown", 5), ("hw_thermal_slowdown", 6), ("sw_thermal_slowdown", 7), ("sw_power_cap", 8)):
+                    if s[col].lower().startswith("active"):
+                        reasons.add(name)
+            except Exception:
+                continue
+        # the GPU idles between the first samples; "under load" = upper half of the samples
+        sm.sort()
+        load = sm[len(sm) // 2:] if sm else []
+        return {"sm_mhz": float(np.median(load)) if load else None, "sm_max_mhz": mx or None, "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+# ----------------------------------------------------------------------------------------------
+# roofline bookkeeping (DESIGN.md "algorithmic bytes")
+# ----------------------------------------------------------------------------------------------
+def algorithmic_bytes(kind: str, cfg: orc.XPaiNNConfig, N: int, E: int, periodic: bool) -> float:
+    C, D, H = cfg.node_dim, cfg.D, cfg.H_msg
+    csr = 4 * (N + 1) + 4 * E + (4 * E if periodic else 0)
+    if kind == "edge_fwd":  # read s, v once; read+write residual x, V; pos; CSR  
+        return 4 * N * (H + D) + 8 * N * (C + D) + 12 * N + csr
+    if kind in ("edge_bwd", "edge_bwd_wgrad"):  # read s, v, gx, gV; write gs, gv, gpos; pos; transposed CSR (+ eid)
+        return 4 * N * (2 * (H + D) + (C + D) + 3) + 12 * N + csr + 8 * E
+    if kind == "edge_bwdbwd":  # JVP pass + reverse pass: read s, v, a_s, a_v (twice), gx, gV; write o_gx, o_gV, o_s, o_v, o_pos
+        return 4 * N * (4 * (H + D) + 2 * (C + D) + (H + D) + 3) + 36 * N + 2 * csr + 8 * E
+    raise KeyError(kind)
+
+
+def measured_hbm_peak():
+    p = ROOT / "MEASURED_PEAKS.json"
+    if p.exists():
+        try:
+            return float(json.loads(p.read_text())["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+# ----------------------------------------------------------------------------------------------
+# GPU arm
+# ----------------------------------------------------------------------------------------------
+def run_gpu(args):
+    import torch.distributed as dist
+
+    import xequinet_b200 as xb
+    from xequinet_b200 import _lib, ops
+
+    rank = int(os.environ.get("RANK", 0))
+    world = int(os.environ.get("WORLD_SIZE", 1))
+    local_rank = int(os.environ.get("LOCAL_RANK", 0))
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    w = WORKLOADS[args.workload]
+    cfg, train, forces = w["cfg"], w["train"], w["forces"]
+    n_mol = args.molecules or w["n_mol"]
+
+    model = xb.resolve_model("xpainn", **cfg.model_kwargs())
+    model.load_state_dict(orc.synthetic_state_dict(cfg, 1234), strict=False)  # random-init weights
+    model = model.to(dev)
+    model.train(train)
+    params = [p for p in model.parameters()]
+    if not train:
+        for p in params:
+            p.requires_grad_(False)
+    opt = torch.optim.AdamW(params, lr=5e-4, fused=True) if train else None
+    transform = xb.NeighborTransform(cfg.cutoff)
+
+    # distinct synthetic batches per rank, pinned on the host
+    n_batches = 4 if args.workload != "c5" else 1
+    host = []
+    for b in range(n_batches):
+        d = make_batch(args.workload, n_mol, seed=100 * rank + b)
+        host.append({k: (v.pin_memory() if torch.is_tensor(v) else v) for k, v in d.items()})
+    resident = [{k: v.to(dev) for k, v in d.items()} for d in host]
+    h2d_keys = ["pos", "atomic_numbers", "batch", "ptr"] + (["target_energy", "target_forces"] if train else []) + \
+               (["cell", "pbc"] if args.workload == "c5" else [])
+    loss_host = torch.zeros(1).pin_memory()
+    energy_host = torch.zeros(host[0]["ptr"].numel() - 1).pin_memory()
+
+    def step(batch, e2e: bool):
+        if e2e:
+            d = {k: batch[k].to(dev, non_blocking=True) for k in h2d_keys}
+        else:
+            d = {k: batch[k] for k in h2d_keys}
+        d = transform(d)  # K1 (+ transposed CSR)
+        out = model(d, compute_forces=forces)
+        if train:
+            loss = loss_fn(out, d, forces)
+            opt.zero_grad(set_to_none=True)
+            loss.backward()
+            if world > 1:
+                flat = torch.cat([p.grad.reshape(-1) for p in params])
+                dist.all_reduce(flat)  # NCCL over NVLink; 3.5 MB -> latency bound, one flat bucket
+                flat /= world
+                off = 0
+                for p in params:
+                    p.grad.copy_(flat[off:off + p.numel()].view_as(p.grad))
+                    off += p.numel()
+            opt.step()
+            result = loss.detach()
+            if e2e:
+                loss_host.copy_(result.reshape(1), non_blocking=True)
+        else:
+            result = out["energy"]
+            if e2e:
+                energy_host.copy_(result.detach(), non_blocking=True)
+        return result
+
+    flush_buf = torch.empty(256 * 1024 * 1024 // 4, dtype=torch.float32, device=dev)  # > 126 MB L2
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(e2e: bool, steps: int, warmup: int, record_kernels: bool):
+        src = host if e2e else resident
+        for i in range(warmup):
+            step(src[i % n_batches], e2e)
+        barrier()
+        ops.KernelTimer.records = []
+        ops.KernelTimer.enabled = record_kernels
+        launches0 = _lib.get().xeq_launch_count()
+        total_ms = 0.0
+        for i in range(steps):
+            flush_buf.zero_()  # L2 flush between timed iterations (not timed)
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            torch.cuda.synchronize()
+            a.record()
+            step(src[i % n_batches], e2e)
+            b.record()
+            torch.cuda.synchronize()
+            total_ms += a.elapsed_time(b)
+        barrier()
+        ops.KernelTimer.enabled = False
+        launches = _lib.get().xeq_launch_count() - launches0
+        t = torch.tensor([total_ms], device=dev, dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)  # max over ranks
+        return float(t.item()), launches
+
+    sampler = ClockSampler(local_rank) if rank == 0 else None
+    if sampler:
+        sampler.start()
+    total_ms, launches = timed(False, args.steps, args.warmup, True)
+    kern = ops.KernelTimer.summary()
+    e2e_ms, _ = timed(True, args.steps, max(3, args.warmup // 2), False)
+    if sampler:
+        sampler.stop_flag.set()
+        sampler.join(timeout=2)
+
+    mols_per_step = n_mol * world
+    ms_per_step = total_ms / args.steps
+    value = mols_per_step / (ms_per_step * 1e-3)
+    e2e_value = mols_per_step / (e2e_ms / args.steps * 1e-3)
+    h2d = sum(host[0][k].numel() * host[0][k].element_size() for k in h2d_keys)
+    d2h = 4 if train else energy_host.numel() * 4
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    # roofline of the dominant hand-written kernel (by share of the step)
+    peak, peak_src = measured_hbm_peak()
+    periodic = args.workload == "c5"
+    kernels = {}
+    dom, dom_share = None, -1.0
+    for kind, (cnt, mean_ms, N, E) in kern.items():
+        by = algorithmic_bytes(kind, cfg, N, E, periodic)
+        share = cnt * mean_ms / total_ms
+        kernels[kind] = {"launches_per_step": cnt / args.steps, "mean_ms": round(mean_ms, 5), "share_of_step": round(share, 4),
+                         "algorithmic_GB_s": round(by / (mean_ms * 1e-3) / 1e9, 2)}
+        if share > dom_share:
+            dom, dom_share = kind, share
+    roofline = None
+    if dom is not None:
+        cnt, mean_ms, N, E = kern[dom]
+        achieved = algorithmic_bytes(dom, cfg, N, E, periodic) / (mean_ms * 1e-3) / 1e9
+        roofline = {"kernel": dom, "bound": "hbm", "achieved": round(achieved, 2), "peak": peak, "unit": "GB/s",
+                    "frac": round(achieved / peak, 5), "traffic": None, "peak_source": peak_src,
+                    "n_nodes": N, "n_edges": E, "mean_launch_ms": round(mean_ms, 5)}
+
+    # CPU oracle on the host cores, bounded sample
+    cpu_mols = {"c1": 64, "c2": 64, "c3": 32, "c4": 8, "c5": 1}[args.workload]
+    cpu_val, cpu_ms, cpu_sample = time_cpu(args.workload, cpu_mols, steps=2, warmup=1)
+
+    line = {
+        "metric": METRIC, "value": round(value, 2), "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": round(ms_per_step, 4), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f32", "data": "synthetic (seeded generators of SURVEY.md 8d), random-init weights",
+        "config": {"workload": f"{args.workload}: {w['desc']}", "molecules_per_gpu": n_mol,
+                   "atoms_per_gpu": int(host[0]["pos"].shape[0]), "l2": "flushed between timed steps (256 MB write, untimed)",
+                   "parallelism": f"dp{world}" if args.workload != "c5" else f"replicas{world}"},
+        "e2e": {"value": round(e2e_value, 2), "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h)},
+        "gpu_launches": int(launches),
+        "roofline": roofline,
+        "kernels": kernels,
+        "cpu_baseline": {"value": round(cpu_val, 3), "unit": UNIT, "cores": os.cpu_count(), "kind": "port",
+                         "sample": f"CPU oracle (oracle/xpainn_oracle.py), {cpu_sample}, {round(cpu_ms, 1)} ms/step, 2 timed steps"},
+        "clocks": sampler.summary() if sampler else None,
+    }
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def run_reference(args):
+    """The reference's CPU path (oracle port: the reference itself is Python + uninstallable
+    third-party wheels, it cannot travel to the GPU box) on all host cores, bounded sample."""
+    rank = int(os.environ.get("RANK", 0))
+    if rank != 0:
+        return
+    cpu_mols = {"c1": 64, "c2": 64, "c3": 32, "c4": 8, "c5": 1}[args.workload]
+    steps, warmup = min(args.steps, 3), min(args.warmup, 1)
+    val, ms, sample = time_cpu(args.workload, cpu_mols, steps=steps, warmup=warmup)
+    w = WORKLOADS[args.workload]
+    line = {
+        "impl": "reference", "metric": METRIC, "value": round(val, 3), "unit": UNIT, "n_gpus": int(os.environ.get("WORLD_SIZE", 1)),
+        "steps": steps, "warmup": warmup, "ms_per_step": round(ms, 2), "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": f"{args.workload}: {w['desc']}", "sample": sample},
+        "cpu_baseline": {"value": round(val, 3), "unit": UNIT, "cores": os.cpu_count(), "kind": "port", "sample": sample},
+        "e2e": {"value": round(val, 3), "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--workload", default="c3", choices=sorted(WORKLOADS))
+    ap.add_argument("--molecules", type=int, default=0, help="molecules per GPU (default: the workload's)")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3)
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_gpu(args)
+
+
+if __name__ == "__main__":
+    main()

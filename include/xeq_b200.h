@@ -65,12 +65,16 @@ typedef struct {
   const int8_t* offsets;    /* [E,4]  integer cell offsets (x,y,z,0) or NULL (no PBC) */
   const float* cell;        /* [G,3,3] lattice rows or NULL                           */
   const int32_t* node_graph;/* [N]    graph id per node (needed when cell && G > 1)   */
+  const int32_t* tile_ptr;  /* [E/Tc+2] node bounds of Tc-edge tiles of the CSR (xeq_csr_tile_bounds, Tc = xeq_center_tile_edges())   */
+  const int32_t* t_tile_ptr;/* [E/Tn+2] same for the transposed CSR, Tn = xeq_neighbor_tile_edges()                                */
 } xeq_graph_t;
 
 int xeq_version(void);
 const char* xeq_last_error(void);
 /* Number of SMs of the current device (grid sizing is done inside the library). */
 int xeq_num_sms(void);
+/* Number of kernels this library has launched in this process (bench.py's gpu_launches). */
+long long xeq_launch_count(void);
 
 /* ------------------------------------------------------------------------------------
  * K1  radius graph.  Replaces torch_cluster.radius_graph (data/transform.py:58-64) and
@@ -121,6 +125,14 @@ size_t xeq_csr_transpose_workspace_bytes(int32_t n_nodes, int32_t n_edges);
 int xeq_csr_transpose(const int32_t* rowptr, const int32_t* col, int32_t n_nodes, int32_t n_edges,
                       int32_t* t_rowptr, int32_t* t_row, int32_t* t_eid,
                       void* workspace, size_t workspace_bytes, xeq_stream_t stream);
+
+/* Work partition of the edge kernels: tile k = the nodes whose CSR row starts inside edges
+ * [k*T, (k+1)*T); tile_ptr[k] = first such node, k = 0 .. n_edges/T + 1 (last entry = n_nodes).
+ * Node-aligned tiles let one CTA own whole rows, so segment sums need no atomics. */
+int xeq_center_tile_edges(void);
+int xeq_neighbor_tile_edges(void);
+int xeq_csr_tile_bounds(const int32_t* rowptr, int32_t n_nodes, int32_t n_edges, int32_t tile_edges,
+                        int32_t* tile_ptr /* [n_edges/tile_edges + 2] out */, xeq_stream_t stream);
 
 /* ------------------------------------------------------------------------------------
  * K2  fused edge message.  Replaces, per XPainnMessage.forward (nn/xpainn.py:140-159):

@@ -21,13 +21,15 @@ class XeqDims(ctypes.Structure):
 class XeqGraph(ctypes.Structure):
     _fields_ = [("n_nodes", c_int32), ("n_edges", c_int32), ("n_graphs", c_int32), ("_pad", c_int32),
                 ("rowptr", c_void_p), ("col", c_void_p), ("t_rowptr", c_void_p), ("t_row", c_void_p),
-                ("t_eid", c_void_p), ("offsets", c_void_p), ("cell", c_void_p), ("node_graph", c_void_p)]
+                ("t_eid", c_void_p), ("offsets", c_void_p), ("cell", c_void_p), ("node_graph", c_void_p),
+                ("tile_ptr", c_void_p), ("t_tile_ptr", c_void_p)]
 
 
 _SIGNATURES = {
     "xeq_version": (c_int, []),
     "xeq_last_error": (c_char_p, []),
     "xeq_num_sms": (c_int, []),
+    "xeq_launch_count": (ctypes.c_longlong, []),
     "xeq_radius_graph_workspace_bytes": (c_size_t, [c_int32, c_int32, c_int]),
     "xeq_radius_graph_count": (c_int, [c_void_p, c_int32, c_void_p, c_void_p, c_int32, c_void_p, POINTER(c_int32),
                                        POINTER(c_int32), c_float, c_void_p, c_void_p, c_size_t, c_void_p]),
@@ -38,6 +40,9 @@ _SIGNATURES = {
     "xeq_csr_transpose_workspace_bytes": (c_size_t, [c_int32, c_int32]),
     "xeq_csr_transpose": (c_int, [c_void_p, c_void_p, c_int32, c_int32, c_void_p, c_void_p, c_void_p, c_void_p,
                                   c_size_t, c_void_p]),
+    "xeq_center_tile_edges": (c_int, []),
+    "xeq_neighbor_tile_edges": (c_int, []),
+    "xeq_csr_tile_bounds": (c_int, [c_void_p, c_int32, c_int32, c_int32, c_void_p, c_void_p]),
     "xeq_edge_message_fwd": (c_int, [POINTER(XeqGraph), POINTER(XeqDims)] + [c_void_p] * 11),
     "xeq_edge_message_bwd_workspace_bytes": (c_size_t, [POINTER(XeqGraph), POINTER(XeqDims), c_int]),
     "xeq_edge_message_bwd": (c_int, [POINTER(XeqGraph), POINTER(XeqDims)] + [c_void_p] * 14 + [c_void_p, c_size_t, c_void_p]),

@@ -18,7 +18,7 @@ NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
     "-lineinfo", "-O3", "-std=c++17",
     "-Xcompiler", "-fPIC",
-    "--expt-relaxed-constexpr",
+    "--expt-relaxed-constexpr", "-diag-suppress", "170",
 ]
 
 

@@ -10,6 +10,7 @@ namespace xeq {
 
 void set_error(const char* fmt, ...);
 int num_sms();
+void count_launches(int n);  // feeds xeq_launch_count()
 
 #define XEQ_CHECK_ARG(cond, ...)          \
   do {                                    \
@@ -29,6 +30,12 @@ int num_sms();
   } while (0)
 
 #define XEQ_LAUNCH_CHECK() XEQ_CUDA(cudaGetLastError())
+// after a batch of n kernel launches: check and count
+#define XEQ_LAUNCHED(n)   \
+  do {                    \
+    XEQ_LAUNCH_CHECK();   \
+    xeq::count_launches(n); \
+  } while (0)
 
 static inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
 

@@ -2,17 +2,20 @@
 // Replaces nn/xpainn.py:66-74,140-159 + nn/basic.py:114-131 and their autograd replays
 // (nn/basic.py:143-159, utils/trainer.py:302).  Contract: include/xeq_b200.h.
 //
-// Two kernel families, both persistent over node-aligned edge tiles, no global atomics:
-//   center_kernel   : CTA walks CSR rows of receiving nodes, one thread per irrep channel q
-//                     (state gate, edge gate, 2l+1 components, + scalar channel for l = 0);
-//                     the segment sum lives in registers.  Forward message, or (JVP) its
-//                     tangent along (a_s, a_v, a_pos) = d/d(gx, gV) half of the double backward.
-//   neighbor_kernel : CTA walks transposed-CSR rows of sending nodes, one thread per filter
-//                     channel h; produces d/ds, d/dv (registers), per-edge d/dr (warp shuffle
-//                     + shared memory) and weight-gradient partials (registers).  ORDER 1 = K2b,
-//                     ORDER 2 = reverse half of K2bb.
+// Three kernel families, all persistent over node-aligned edge tiles, no global atomics:
+//   center_kernel  : walks CSR rows of the RECEIVING node, one thread per irrep channel q (its
+//                    state gate, edge gate, 2l+1 components, + the scalar channel for l = 0);
+//                    the segment sum lives in registers.  Forward message, or (JVP) its tangent
+//                    along (a_s, a_v, a_pos) = the d/d(gx, gV) half of the double backward.
+//   nbr_main_kernel: walks transposed-CSR rows of the SENDING node with the same thread <-> q
+//                    mapping; d/ds, d/dv in registers, per-edge d/dr by warp shuffle + shared
+//                    memory.  ORDER 1 = K2b (forces), ORDER 2 = reverse half of K2bb.
+//   nbr_wgrad_kernel: one thread per filter channel h, weight-gradient partials in registers
+//                    (needs no W rows at all), reduced in fixed order by wgrad_reduce_kernel.
 // Per-edge geometry (r, d, Y, chi * phi_k and derivatives) is recomputed per chunk into shared
-// memory; nothing E-sized except the 12-byte d/dr record ever touches HBM.
+// memory by a 3-stage software pipeline (geometry of chunk c+2 / radial terms of chunk c+1 /
+// message of chunk c) with ONE __syncthreads per chunk; nothing E-sized except the 12-byte
+// d/dr record ever touches HBM.
 #include "common.cuh"
 #include "edge_thread.cuh"
 
@@ -20,19 +23,69 @@ namespace xeq {
 
 constexpr int NB_ = 20;       // num_basis instantiated
 constexpr int NK_ = NB_ + 1;  // + bias/cutoff term
+constexpr int CT = 64;        // edges per chunk, center kernels
+constexpr int NT = 32;        // slots per chunk, neighbor kernels
+constexpr int WTHREADS = 288; // nbr_wgrad: filter channels per CTA; grid.y = H / 288 slices
 
-__device__ __forceinline__ int lower_bound_nodes(const int* __restrict__ rowptr, int n_nodes, int x) {
-  int lo = 0, hi = n_nodes;  // first node with rowptr[node] >= x, n_nodes if none
-  while (lo < hi) {
-    const int mid = (lo + hi) >> 1;
-    if (rowptr[mid] < x) lo = mid + 1; else hi = mid;
+// ------------------------------------------------------------------------------------------
+// chunk stream: the (tile, chunk) work items of one CTA, in order
+// ------------------------------------------------------------------------------------------
+struct ChunkDesc {
+  int n0, n1;  // node range of the tile this chunk belongs to
+  int eb;      // first edge/slot of the chunk
+  int cnt;     // edges in the chunk (0 for an edge-less tile), -1 = end of stream
+  int first;   // first chunk of its tile
+  int last;    // last chunk of its tile
+};
+
+template <int T>
+struct ChunkCursor {
+  const int* __restrict__ rowptr;
+  const int* __restrict__ tile_ptr;
+  int n_tiles, tile, n0, n1, e0, e1, eb;
+  bool valid;
+
+  __device__ __forceinline__ void load_tile() {
+    valid = false;
+    while (tile < n_tiles) {
+      n0 = tile_ptr[tile];
+      n1 = tile_ptr[tile + 1];
+      if (n0 < n1) {
+        e0 = rowptr[n0];
+        e1 = rowptr[n1];
+        eb = e0;
+        valid = true;
+        return;
+      }
+      tile += gridDim.x;
+    }
   }
-  return lo;
-}
+  __device__ __forceinline__ void init(const int* rp, const int* tp, int nt) {
+    rowptr = rp; tile_ptr = tp; n_tiles = nt; tile = blockIdx.x;
+    load_tile();
+  }
+  __device__ __forceinline__ ChunkDesc next() {
+    ChunkDesc d;
+    if (!valid) {
+      d.n0 = d.n1 = d.eb = 0; d.cnt = -1; d.first = d.last = 0;
+      return d;
+    }
+    d.n0 = n0; d.n1 = n1; d.eb = eb;
+    d.cnt = min(T, e1 - eb);
+    d.first = (eb == e0);
+    d.last = (eb + T >= e1);
+    eb += T;
+    if (eb >= e1) {
+      tile += gridDim.x;
+      load_tile();
+    }
+    return d;
+  }
+};
 
 // node that owns edge/slot e inside [n0, n1): rowptr[i] <= e < rowptr[i+1]
 __device__ __forceinline__ int owner_of(const int* __restrict__ rowptr, int n0, int n1, int e) {
-  int lo = n0, hi = n1;  // first node with rowptr[node] > e, minus one
+  int lo = n0, hi = n1;
   while (lo < hi) {
     const int mid = (lo + hi) >> 1;
     if (rowptr[mid] <= e) lo = mid + 1; else hi = mid;
@@ -54,13 +107,12 @@ __device__ __forceinline__ void edge_vector(const xeq_graph_t& g, const float* _
   }
 }
 
-template <int NKK>
 __device__ __forceinline__ void load_wrow(const float* __restrict__ W, const float* __restrict__ b, int h, float* row) {
   row[0] = b[h];
 #pragma unroll
   for (int k = 0; k < NB_; ++k) row[k + 1] = W[(size_t)h * NB_ + k];
 #pragma unroll
-  for (int k = NKK; k < NBP; ++k) row[k] = 0.f;
+  for (int k = NK_; k < NBP; ++k) row[k] = 0.f;
 }
 
 __device__ __forceinline__ void lds_row(const float* __restrict__ src, float* dst) {
@@ -71,177 +123,296 @@ __device__ __forceinline__ void lds_row(const float* __restrict__ src, float* ds
   }
 }
 
+// ------------------------------------------------------------------------------------------
+// shared-memory geometry records and the two geometry stages
+// ------------------------------------------------------------------------------------------
+template <int T, bool NEED_G, bool SECOND>
+struct alignas(16) GeoA {  // stage A1: one thread per edge
+  float Y[T][8];
+  float u[T][4];
+  float d[T];
+  float chi[T][3];
+  int gat[T];  // node whose rows are gathered (neighbor j for center kernels, center i for neighbor kernels)
+  int own[T];  // node that owns the row being walked
+  int eid[T];  // canonical edge id
+  float G[NEED_G ? T : 1][24];
+  float Hm[(NEED_G && SECOND) ? T : 1][24];
+  float Ydot[SECOND ? T : 1][8];
+  float rp[SECOND ? T : 1][4];
+  float ddot[SECOND ? T : 1];
+};
+
+template <int T, bool D1, bool D2, bool XI, bool DXI>
+struct alignas(16) GeoB {  // stage A2: one thread per (edge, k)
+  float psi[T][NBP];
+  float dpsi[D1 ? T : 1][NBP];
+  float ddpsi[D2 ? T : 1][NBP];
+  float xi[XI ? T : 1][NBP];
+  float dxi[DXI ? T : 1][NBP];
+};
+
+struct GeoArgs {
+  xeq_graph_t g;
+  const float* pos;
+  const float* a_pos;  // tangent of pos (second order) or NULL
+  const float* freq;
+  float rc;
+};
+
+// TRANSPOSED = false: walk CSR rows (owner = center i, gathered = neighbor j = col[e], eid = e)
+// TRANSPOSED = true : walk transposed rows (owner = neighbor j, gathered = center i = t_row[sl], eid = t_eid[sl])
+template <int T, bool TRANSPOSED, bool NEED_G, bool SECOND>
+__device__ __noinline__ void geo_stage_a1(const GeoArgs& A, const ChunkDesc d, GeoA<T, NEED_G, SECOND>& sa) {
+  const int t = threadIdx.x;
+  if (t >= d.cnt) return;
+  const xeq_graph_t& g = A.g;
+  const int sl = d.eb + t;
+  int i, j, e, owner;
+  if (!TRANSPOSED) {
+    owner = owner_of(g.rowptr, d.n0, d.n1, sl);
+    i = owner; j = g.col[sl]; e = sl;
+    sa.gat[t] = j;
+  } else {
+    owner = owner_of(g.t_rowptr, d.n0, d.n1, sl);
+    j = owner; i = g.t_row[sl]; e = g.t_eid[sl];
+    sa.gat[t] = i;
+  }
+  sa.own[t] = owner;
+  sa.eid[t] = e;
+  float r[3], dist, u[3];
+  edge_vector(g, A.pos, i, j, e, r);
+  unit_vector(r, dist, u);
+  if (!NEED_G && !SECOND) {
+    sph_harm(u, sa.Y[t]);
+  } else {
+    float G[3][8];
+    angular_first(u, dist, sa.Y[t], G);
+    if (NEED_G) {
+#pragma unroll
+      for (int x = 0; x < 3; ++x)
+#pragma unroll
+        for (int m = 0; m < 8; ++m) sa.G[t][x * 8 + m] = G[x][m];
+    }
+    if (SECOND) {
+      float Hm[3][8], rp[3], rdot[3] = {0.f, 0.f, 0.f}, dd;
+      if (A.a_pos) {
+#pragma unroll
+        for (int x = 0; x < 3; ++x) rdot[x] = A.a_pos[3 * i + x] - A.a_pos[3 * j + x];
+      }
+      angular_second(u, dist, rdot, G, dd, rp, sa.Ydot[t], Hm);
+      sa.ddot[t] = dd;
+#pragma unroll
+      for (int x = 0; x < 3; ++x) {
+        sa.rp[t][x] = rp[x];
+        if (NEED_G) {
+#pragma unroll
+          for (int m = 0; m < 8; ++m) sa.Hm[t][x * 8 + m] = Hm[x][m];
+        }
+      }
+    }
+  }
+#pragma unroll
+  for (int x = 0; x < 3; ++x) sa.u[t][x] = u[x];
+  const Cutoff<float> c = cutoff_terms(dist, A.rc);
+  sa.d[t] = dist;
+  sa.chi[t][0] = c.chi; sa.chi[t][1] = c.dchi; sa.chi[t][2] = c.ddchi;
+}
+
+template <int T, int THREADS, bool NEED_G, bool SECOND, bool D1, bool D2, bool XI, bool DXI>
+__device__ __noinline__ void geo_stage_a2(const GeoArgs& A, int cnt, const GeoA<T, NEED_G, SECOND>& sa,
+                                          GeoB<T, D1, D2, XI, DXI>& sb) {
+  const int t = threadIdx.x;
+  for (int idx = t; idx < cnt * NK_; idx += THREADS) {
+    const int ee = idx / NK_, k = idx - ee * NK_;
+    Cutoff<float> c;
+    c.chi = sa.chi[ee][0]; c.dchi = sa.chi[ee][1]; c.ddchi = sa.chi[ee][2];
+    if (k == 0) {  // bias / cutoff term, plus the zero padding of the row
+      sb.psi[ee][0] = c.chi;
+      if (D1) sb.dpsi[ee][0] = c.dchi;
+      if (D2) sb.ddpsi[ee][0] = c.ddchi;
+      if (XI) sb.xi[ee][0] = 0.f;
+      if (DXI) sb.dxi[ee][0] = 0.f;
+#pragma unroll
+      for (int kk = NK_; kk < NBP; ++kk) {
+        sb.psi[ee][kk] = 0.f;
+        if (D1) sb.dpsi[ee][kk] = 0.f;
+        if (D2) sb.ddpsi[ee][kk] = 0.f;
+        if (XI) sb.xi[ee][kk] = 0.f;
+        if (DXI) sb.dxi[ee][kk] = 0.f;
+      }
+    } else {
+      const Radial<float> rr = radial_term(sa.d[ee], A.freq[k - 1], A.rc, c);
+      sb.psi[ee][k] = rr.psi;
+      if (D1) sb.dpsi[ee][k] = rr.dpsi;
+      if (D2) sb.ddpsi[ee][k] = rr.ddpsi;
+      if (XI) sb.xi[ee][k] = rr.xi;
+      if (DXI) sb.dxi[ee][k] = rr.dxi;
+    }
+  }
+}
+
 // ==========================================================================================
 // center kernel
 // ==========================================================================================
-constexpr int CT = 64;  // edges per chunk
+template <bool JVP> struct CenterChunk { static constexpr int value = JVP ? 48 : CT; };  // 48 KB static smem
 
 template <bool JVP>
 struct CenterSmem {
-  float psi[CT][NBP];
-  float dpsi[JVP ? CT : 1][NBP];
-  float Y[CT][8];
-  float Ydot[JVP ? CT : 1][8];
-  float ddot[CT];
-  float d[CT];
-  float chi[CT][2];
-  int nbr[CT];
-  int ctr[CT];
+  static constexpr int TC = CenterChunk<JVP>::value;
+  GeoA<TC, false, JVP> a[3];
+  GeoB<TC, JVP, false, false, false> b[2];
 };
 
 struct CenterArgs {
-  xeq_graph_t g;
-  float rc;
-  const float *pos, *s, *v, *x_in, *V_in, *W, *b, *freq;
-  const float *a_s, *a_v, *a_pos;  // JVP only
+  GeoArgs geo;
+  const float *s, *v, *x_in, *V_in, *W, *b;
+  const float *a_s, *a_v;  // JVP only
   float *x_out, *V_out;
-  int n_tiles;
 };
 
 template <int L, int C, int M1, int M2, bool JVP>
 __device__ __forceinline__ void center_role(const CenterArgs& A, CenterSmem<JVP>& sm) {
   constexpr int M = C + M1 + M2, D = C + 3 * M1 + 5 * M2, H = C + 2 * M, NC = 2 * L + 1;
   constexpr int THREADS = M;
+  constexpr int TC = CenterChunk<JVP>::value;
   const int t = threadIdx.x;
-  const int q = t;  // thread index == irrep channel (types are contiguous ranges)
+  const int q = t;  // thread index == irrep channel (the l-types are contiguous ranges)
   const int vbase = (L == 0) ? t : (L == 1 ? C + (t - C) : C + 3 * M1 + (t - C - M1));
   constexpr int vstride = (L == 0) ? 0 : (L == 1 ? M1 : M2);
-  const xeq_graph_t& g = A.g;
-  const int N = g.n_nodes;
+  const xeq_graph_t& g = A.geo.g;
 
   CenterThread<float, L, NK_> th;
-  load_wrow<NK_>(A.W, A.b, q, th.Ws);
-  load_wrow<NK_>(A.W, A.b, M + q, th.We);
-  if (L == 0) load_wrow<NK_>(A.W, A.b, 2 * M + q, th.Wx);
+  load_wrow(A.W, A.b, q, th.Ws);
+  load_wrow(A.W, A.b, M + q, th.We);
+  if (L == 0) load_wrow(A.W, A.b, 2 * M + q, th.Wx);
+  th.reset();
 
-  auto emit = [&](int node, bool with_acc) {
+  // residual rows of a node are fetched when its row starts (fetch_base) and consumed when it ends
+  auto emit_copy = [&](int node) {
 #pragma unroll
     for (int m = 0; m < NC; ++m) {
       const size_t idx = (size_t)node * D + vbase + m * vstride;
-      const float base = A.V_in ? A.V_in[idx] : 0.f;
-      A.V_out[idx] = with_acc ? base + th.accV[m] : base;
+      A.V_out[idx] = A.V_in ? A.V_in[idx] : 0.f;
     }
     if (L == 0) {
       const size_t idx = (size_t)node * C + t;
-      const float base = A.x_in ? A.x_in[idx] : 0.f;
-      A.x_out[idx] = with_acc ? base + th.accx : base;
+      A.x_out[idx] = A.x_in ? A.x_in[idx] : 0.f;
     }
   };
 
-  for (int tile = blockIdx.x; tile < A.n_tiles; tile += gridDim.x) {
-    const int n0 = lower_bound_nodes(g.rowptr, N, tile * CT);
-    const int n1 = lower_bound_nodes(g.rowptr, N, (tile + 1) * CT);
-    if (n0 == n1) continue;
-    const int e0 = g.rowptr[n0], e1 = g.rowptr[n1];
-    int cur = -1;
-    for (int eb = e0; eb < e1; eb += CT) {
-      const int cnt = min(CT, e1 - eb);
-      __syncthreads();
-      if (t < cnt) {  // ---- geometry, one thread per edge
-        const int e = eb + t;
-        const int i = owner_of(g.rowptr, n0, n1, e);
-        const int j = g.col[e];
-        float r[3], d, u[3];
-        edge_vector(g, A.pos, i, j, e, r);
-        unit_vector(r, d, u);
-        if (!JVP) {
-          sph_harm(u, sm.Y[t]);
-        } else {
-          float G[3][8], Hm[3][8], rp[3], rdot[3] = {0.f, 0.f, 0.f}, dd;
-          angular_first(u, d, sm.Y[t], G);
-          if (A.a_pos) {
+  struct Gathered {
+    float ss, se, sx, v[NC], sds, sde, sdx, vd[NC];
+  };
+  auto gather = [&](const GeoA<TC, false, JVP>& sa, int ee, Gathered& o) {
+    const int j = sa.gat[ee];
+    const float* sj = A.s + (size_t)j * H;
+    o.ss = sj[q];
+    o.se = sj[M + q];
+    o.sx = (L == 0) ? sj[2 * M + q] : 0.f;
+    const float* vj = A.v + (size_t)j * D + vbase;
 #pragma unroll
-            for (int x = 0; x < 3; ++x) rdot[x] = A.a_pos[3 * i + x] - A.a_pos[3 * j + x];
-          }
-          angular_second(u, d, rdot, G, dd, rp, sm.Ydot[t], Hm);
-          sm.ddot[t] = dd;
-        }
-        const Cutoff<float> c = cutoff_terms(d, A.rc);
-        sm.d[t] = d;
-        sm.chi[t][0] = c.chi;
-        sm.chi[t][1] = c.dchi;
-        sm.psi[t][0] = c.chi;
-#pragma unroll
-        for (int k = NK_; k < NBP; ++k) sm.psi[t][k] = 0.f;
-        if (JVP) {
-          sm.dpsi[t][0] = c.dchi;
-#pragma unroll
-          for (int k = NK_; k < NBP; ++k) sm.dpsi[t][k] = 0.f;
-        }
-        sm.nbr[t] = j;
-        sm.ctr[t] = i;
+    for (int m = 0; m < NC; ++m) o.v[m] = vj[m * vstride];
+    if (JVP) {
+      o.sds = o.sde = o.sdx = 0.f;
+      if (A.a_s) {
+        const float* aj = A.a_s + (size_t)j * H;
+        o.sds = aj[q];
+        o.sde = aj[M + q];
+        if (L == 0) o.sdx = aj[2 * M + q];
       }
-      __syncthreads();
-      for (int idx = t; idx < cnt * NB_; idx += THREADS) {  // ---- radial terms, one thread per (edge, k)
-        const int ee = idx / NB_, k = idx - ee * NB_;
-        Cutoff<float> c;
-        c.chi = sm.chi[ee][0];
-        c.dchi = sm.chi[ee][1];
-        c.ddchi = 0.f;
-        const Radial<float> rr = radial_term(sm.d[ee], A.freq[k], A.rc, c);
-        sm.psi[ee][k + 1] = rr.psi;
-        if (JVP) sm.dpsi[ee][k + 1] = rr.dpsi;
-      }
-      __syncthreads();
-
-      // ---- message accumulation: software-pipelined gathers of the neighbor rows
-      float ss, se, sx = 0.f, vv[NC], sds = 0.f, sde = 0.f, sdx = 0.f, vd[NC];
-      auto gather = [&](int ee, float& a_ss, float& a_se, float& a_sx, float* a_v, float& a_sds, float& a_sde,
-                        float& a_sdx, float* a_vd) {
-        const int j = sm.nbr[ee];
-        const float* sj = A.s + (size_t)j * H;
-        a_ss = sj[q];
-        a_se = sj[M + q];
-        if (L == 0) a_sx = sj[2 * M + q];
-        const float* vj = A.v + (size_t)j * D + vbase;
 #pragma unroll
-        for (int m = 0; m < NC; ++m) a_v[m] = vj[m * vstride];
-        if (JVP) {
-          if (A.a_s) {
-            const float* aj = A.a_s + (size_t)j * H;
-            a_sds = aj[q];
-            a_sde = aj[M + q];
-            if (L == 0) a_sdx = aj[2 * M + q];
-          }
-#pragma unroll
-          for (int m = 0; m < NC; ++m) a_vd[m] = A.a_v ? A.a_v[(size_t)j * D + vbase + m * vstride] : 0.f;
-        }
-      };
-      gather(0, ss, se, sx, vv, sds, sde, sdx, vd);
-      for (int ee = 0; ee < cnt; ++ee) {
-        float nss = 0.f, nse = 0.f, nsx = 0.f, nv[NC], nsds = 0.f, nsde = 0.f, nsdx = 0.f, nvd[NC];
-#pragma unroll
-        for (int m = 0; m < NC; ++m) nv[m] = nvd[m] = 0.f;
-        if (ee + 1 < cnt) gather(ee + 1, nss, nse, nsx, nv, nsds, nsde, nsdx, nvd);
-        const int i = sm.ctr[ee];
-        if (i != cur) {
-          if (cur >= 0) emit(cur, true);
-          for (int nn = (cur >= 0 ? cur + 1 : n0); nn < i; ++nn) emit(nn, false);
-          cur = i;
-          th.reset();
-        }
-        float p[NBP];
-        lds_row(sm.psi[ee], p);
-        if (!JVP) {
-          th.fwd(p, sm.Y[ee], ss, se, sx, vv);
-        } else {
-          float dp[NBP];
-          lds_row(sm.dpsi[ee], dp);
-          th.jvp(p, dp, sm.Y[ee], sm.Ydot[ee], sm.ddot[ee], ss, se, sx, vv, sds, sde, sdx, vd);
-        }
-        ss = nss; se = nse; sx = nsx; sds = nsds; sde = nsde; sdx = nsdx;
-#pragma unroll
-        for (int m = 0; m < NC; ++m) { vv[m] = nv[m]; vd[m] = nvd[m]; }
-      }
+      for (int m = 0; m < NC; ++m) o.vd[m] = A.a_v ? A.a_v[(size_t)j * D + vbase + m * vstride] : 0.f;
     }
-    if (cur >= 0) emit(cur, true);
-    for (int nn = (cur >= 0 ? cur + 1 : n0); nn < n1; ++nn) emit(nn, false);
+  };
+
+  ChunkCursor<TC> cur_it;
+  cur_it.init(g.rowptr, g.tile_ptr, g.n_edges / CT + 1);
+  float base_x = 0.f, base_V[NC];
+#pragma unroll
+  for (int m = 0; m < NC; ++m) base_V[m] = 0.f;
+  // pipeline prologue
+  ChunkDesc d0 = cur_it.next();  // chunk being processed
+  ChunkDesc d1 = cur_it.next();  // chunk whose radial terms are produced
+  ChunkDesc d2;                  // chunk whose geometry is produced
+  if (d0.cnt >= 0) geo_stage_a1<TC, false, false, JVP>(A.geo, d0, sm.a[0]);
+  __syncthreads();
+  if (d1.cnt >= 0) geo_stage_a1<TC, false, false, JVP>(A.geo, d1, sm.a[1]);
+  if (d0.cnt >= 0) geo_stage_a2<TC, THREADS>(A.geo, d0.cnt, sm.a[0], sm.b[0]);
+  __syncthreads();
+
+  int cur = -1;
+  for (int c = 0; d0.cnt >= 0; ++c) {
+    d2 = cur_it.next();
+    if (d2.cnt >= 0) geo_stage_a1<TC, false, false, JVP>(A.geo, d2, sm.a[(c + 2) % 3]);
+    if (d1.cnt >= 0) geo_stage_a2<TC, THREADS>(A.geo, d1.cnt, sm.a[(c + 1) % 3], sm.b[(c + 1) & 1]);
+
+    // ---- message accumulation over chunk c.  Gathers run two edges ahead of their use; the
+    // loop is unrolled modulo 3 so the three gather buffers are renamed statically (a register
+    // rotation by copies would wait on the in-flight loads and defeat the prefetch).
+    const GeoA<TC, false, JVP>& sa = sm.a[c % 3];
+    const GeoB<TC, JVP, false, false, false>& sb = sm.b[c & 1];
+    const int cnt = d0.cnt;
+    if (d0.first) cur = -1;
+    auto fetch_base = [&](int node) {
+#pragma unroll
+      for (int m = 0; m < NC; ++m) base_V[m] = A.V_in ? A.V_in[(size_t)node * D + vbase + m * vstride] : 0.f;
+      if (L == 0) base_x = A.x_in ? A.x_in[(size_t)node * C + t] : 0.f;
+    };
+    auto emit_acc = [&](int node) {
+#pragma unroll
+      for (int m = 0; m < NC; ++m) A.V_out[(size_t)node * D + vbase + m * vstride] = base_V[m] + th.accV[m];
+      if (L == 0) A.x_out[(size_t)node * C + t] = base_x + th.accx;
+    };
+    auto body = [&](int ee, const Gathered& gc, Gathered& gn) {
+      if (ee + 2 < cnt) gather(sa, ee + 2, gn);
+      const int i = sa.own[ee];
+      if (i != cur) {
+        if (cur >= 0) emit_acc(cur);
+        for (int nn = (cur >= 0 ? cur + 1 : d0.n0); nn < i; ++nn) emit_copy(nn);
+        cur = i;
+        fetch_base(i);
+        th.reset();
+      }
+      float p[NBP], Yl[NC], Yd[NC];
+      lds_row(sb.psi[ee], p);
+      if (L > 0) {
+#pragma unroll
+        for (int m = 0; m < NC; ++m) {
+          Yl[m] = sa.Y[ee][YOff<L>::value + m];
+          Yd[m] = JVP ? sa.Ydot[ee][YOff<L>::value + m] : 0.f;
+        }
+      }
+      if (!JVP) {
+        th.fwd(p, Yl - YOff<L>::value, gc.ss, gc.se, gc.sx, gc.v);
+      } else {
+        float dp[NBP];
+        lds_row(sb.dpsi[ee], dp);
+        th.jvp(p, dp, Yl - YOff<L>::value, Yd - YOff<L>::value, sa.ddot[ee], gc.ss, gc.se, gc.sx, gc.v, gc.sds, gc.sde,
+               gc.sdx, gc.vd);
+      }
+    };
+    Gathered g0, g1, g2;
+    if (cnt > 0) gather(sa, 0, g0);
+    if (cnt > 1) gather(sa, 1, g1);
+    for (int ee = 0; ee < cnt; ee += 3) {
+      body(ee, g0, g2);
+      if (ee + 1 < cnt) body(ee + 1, g1, g0);
+      if (ee + 2 < cnt) body(ee + 2, g2, g1);
+    }
+    if (d0.last) {
+      if (cur >= 0) emit_acc(cur);
+      for (int nn = (cur >= 0 ? cur + 1 : d0.n0); nn < d0.n1; ++nn) emit_copy(nn);
+      cur = -1;
+    }
+    __syncthreads();
+    d0 = d1;
+    d1 = d2;
   }
 }
 
 template <int C, int M1, int M2, bool JVP>
 __global__ void __launch_bounds__(C + M1 + M2) center_kernel(const CenterArgs A) {
-  __shared__ __align__(16) CenterSmem<JVP> sm;
+  __shared__ CenterSmem<JVP> sm;
   const int t = threadIdx.x;
   if (t < C) center_role<0, C, M1, M2, JVP>(A, sm);
   else if (t < C + M1) center_role<1, C, M1, M2, JVP>(A, sm);
@@ -249,257 +420,328 @@ __global__ void __launch_bounds__(C + M1 + M2) center_kernel(const CenterArgs A)
 }
 
 // ==========================================================================================
-// neighbor kernel
+// neighbor main kernel (thread per irrep channel q)
 // ==========================================================================================
-constexpr int NT = 32;        // slots per chunk
-constexpr int NTHREADS = 288; // filter channels per CTA (9 warps); grid.y = H / 288 channel slices
-constexpr int NWARPS = NTHREADS / 32;
+template <int ORDER> struct NbrChunk { static constexpr int value = (ORDER == 2) ? 24 : NT; };
 
-template <int ORDER, bool WGRAD>
-struct NeighborSmem {
-  float psi[NT][NBP];
-  float dpsi[NT][NBP];
-  float ddpsi[ORDER == 2 ? NT : 1][NBP];
-  float xi[WGRAD ? NT : 1][NBP];
-  float dxi[(WGRAD && ORDER == 2) ? NT : 1][NBP];
-  float Y[NT][8];
-  float G[NT][24];
-  float Hm[ORDER == 2 ? NT : 1][24];
-  float Ydot[ORDER == 2 ? NT : 1][8];
-  float u[NT][4];
-  float rp[ORDER == 2 ? NT : 1][4];
-  float ddot[NT];
-  float d[NT];
-  float chi[NT][3];
-  float red[NT][NWARPS][3];
-  int gat[NT];  // center i whose gx/gV row is gathered
-  int own[NT];  // sending node j (owner of the transposed row)
-  int eid[NT];  // canonical edge id
+template <int ORDER, int NW>
+struct NbrMainSmem {
+  static constexpr int TC = NbrChunk<ORDER>::value;
+  GeoA<TC, true, ORDER == 2> a[3];
+  GeoB<TC, true, ORDER == 2, false, false> b[2];
+  float red[2][TC][NW][3];
+  int red_eid[2][TC];
 };
 
 struct NeighborArgs {
-  xeq_graph_t g;
-  float rc;
-  const float *pos, *s, *v, *W, *b, *freq, *gx, *gV;
-  const float *a_s, *a_v, *a_pos;  // ORDER 2 only
-  float *o_s, *o_v;                // [N,H], [N,D]
-  float* gr;                       // [S, E, 3] per-edge d/dr partials (one slab per channel slice)
-  float* wpart;                    // [gridDim.x, H, 2*NBP] weight-gradient partials
-  int n_tiles;
+  GeoArgs geo;
+  const float *s, *v, *W, *b, *gx, *gV;
+  const float *a_s, *a_v;  // ORDER 2 only
+  float *o_s, *o_v;        // [N,H], [N,D]
+  float* gr;               // [slices, E, 3] per-edge d/dr
+  float* wpart;            // [gridDim.x, H, 2*NBP] weight-gradient partials (wgrad kernel)
 };
 
-template <int L, int ROLE, int C, int M1, int M2, int ORDER, bool WGRAD>
-__device__ __forceinline__ void neighbor_role(const NeighborArgs& A, NeighborSmem<ORDER, WGRAD>& sm) {
-  constexpr int M = C + M1 + M2, D = C + 3 * M1 + 5 * M2, H = C + 2 * M;
-  using Thread = NeighborThread<float, L, ROLE, WGRAD, NK_>;
-  constexpr int NC = Thread::NC;
+template <int L, int C, int M1, int M2, int ORDER>
+__device__ __forceinline__ void nbr_main_role(const NeighborArgs& A, NbrMainSmem<ORDER, (C + M1 + M2) / 32>& sm) {
+  constexpr int M = C + M1 + M2, D = C + 3 * M1 + 5 * M2, H = C + 2 * M, NC = 2 * L + 1;
+  constexpr int THREADS = M, NW = M / 32;
+  constexpr bool SECOND = ORDER == 2;
+  constexpr int TC = NbrChunk<ORDER>::value;
   const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
-  const int h = blockIdx.y * NTHREADS + t;
-  const int q = (ROLE == ROLE_STATE) ? h : (ROLE == ROLE_EDGE ? h - M : 0);
-  const int vbase = (ROLE == ROLE_SCALAR) ? 0 : ((L == 0) ? q : (L == 1 ? C + (q - C) : C + 3 * M1 + (q - C - M1)));
+  const int q = t;
+  const int vbase = (L == 0) ? t : (L == 1 ? C + (t - C) : C + 3 * M1 + (t - C - M1));
   constexpr int vstride = (L == 0) ? 0 : (L == 1 ? M1 : M2);
-  const xeq_graph_t& g = A.g;
-  const int N = g.n_nodes, E = g.n_edges;
-  const int* __restrict__ rp_ = g.t_rowptr;
+  const xeq_graph_t& g = A.geo.g;
+  const int E = g.n_edges;
 
-  Thread th;
-  load_wrow<NK_>(A.W, A.b, h, th.Wt);
-  if (WGRAD) th.reset_wgrad();
-  th.s = th.sd = 0.f;
+  NeighborThread<float, L, ROLE_STATE, false, NK_> st;
+  NeighborThread<float, L, ROLE_EDGE, false, NK_> ed;
+  NeighborThread<float, 0, ROLE_SCALAR, false, NK_> sc;
+  load_wrow(A.W, A.b, q, st.Wt);
+  load_wrow(A.W, A.b, M + q, ed.Wt);
+  if (L == 0) load_wrow(A.W, A.b, 2 * M + q, sc.Wt);
+  st.s = st.sd = ed.s = ed.sd = sc.s = sc.sd = 0.f;
 #pragma unroll
-  for (int m = 0; m < NC; ++m) th.v[m] = th.vd[m] = 0.f;
-  th.reset_node();
+  for (int m = 0; m < NC; ++m) st.v[m] = st.vd[m] = 0.f;
+  st.reset_node(); ed.reset_node(); sc.reset_node();
 
   auto emit = [&](int node, bool with_acc) {
-    if (A.o_s) A.o_s[(size_t)node * H + h] = with_acc ? th.acc_s : 0.f;
-    if (ROLE == ROLE_STATE && A.o_v) {
+    if (A.o_s) {
+      float* os = A.o_s + (size_t)node * H;
+      os[q] = with_acc ? st.acc_s : 0.f;
+      os[M + q] = with_acc ? ed.acc_s : 0.f;
+      if (L == 0) os[2 * M + q] = with_acc ? sc.acc_s : 0.f;
+    }
+    if (A.o_v) {
 #pragma unroll
-      for (int m = 0; m < NC; ++m) A.o_v[(size_t)node * D + vbase + m * vstride] = with_acc ? th.acc_v[m] : 0.f;
+      for (int m = 0; m < NC; ++m) A.o_v[(size_t)node * D + vbase + m * vstride] = with_acc ? st.acc_v[m] : 0.f;
     }
   };
-
-  for (int tile = blockIdx.x; tile < A.n_tiles; tile += gridDim.x) {
-    const int n0 = lower_bound_nodes(rp_, N, tile * NT);
-    const int n1 = lower_bound_nodes(rp_, N, (tile + 1) * NT);
-    if (n0 == n1) continue;
-    const int e0 = rp_[n0], e1 = rp_[n1];
-    int cur = -1;
-    for (int eb = e0; eb < e1; eb += NT) {
-      const int cnt = min(NT, e1 - eb);
-      __syncthreads();
-      if (t < cnt) {  // ---- geometry, one thread per slot
-        const int sl = eb + t;
-        const int j = owner_of(rp_, n0, n1, sl);
-        const int i = g.t_row[sl];
-        const int e = g.t_eid[sl];
-        float r[3], d, u[3];
-        edge_vector(g, A.pos, i, j, e, r);
-        unit_vector(r, d, u);
-        float G[3][8];
-        angular_first(u, d, sm.Y[t], G);
-#pragma unroll
-        for (int x = 0; x < 3; ++x) {
-#pragma unroll
-          for (int m = 0; m < 8; ++m) sm.G[t][x * 8 + m] = G[x][m];
-          sm.u[t][x] = u[x];
-        }
-        if (ORDER == 2) {
-          float Hm[3][8], rp[3], rdot[3] = {0.f, 0.f, 0.f}, dd;
-          if (A.a_pos) {
-#pragma unroll
-            for (int x = 0; x < 3; ++x) rdot[x] = A.a_pos[3 * i + x] - A.a_pos[3 * j + x];
-          }
-          angular_second(u, d, rdot, G, dd, rp, sm.Ydot[t], Hm);
-          sm.ddot[t] = dd;
-#pragma unroll
-          for (int x = 0; x < 3; ++x) {
-            sm.rp[t][x] = rp[x];
-#pragma unroll
-            for (int m = 0; m < 8; ++m) sm.Hm[t][x * 8 + m] = Hm[x][m];
-          }
-        }
-        const Cutoff<float> c = cutoff_terms(d, A.rc);
-        sm.d[t] = d;
-        sm.chi[t][0] = c.chi; sm.chi[t][1] = c.dchi; sm.chi[t][2] = c.ddchi;
-        sm.psi[t][0] = c.chi;
-        sm.dpsi[t][0] = c.dchi;
-        if (ORDER == 2) sm.ddpsi[t][0] = c.ddchi;
-        if (WGRAD) sm.xi[t][0] = 0.f;
-        if (WGRAD && ORDER == 2) sm.dxi[t][0] = 0.f;
-#pragma unroll
-        for (int k = NK_; k < NBP; ++k) {
-          sm.psi[t][k] = 0.f; sm.dpsi[t][k] = 0.f;
-          if (ORDER == 2) sm.ddpsi[t][k] = 0.f;
-          if (WGRAD) sm.xi[t][k] = 0.f;
-          if (WGRAD && ORDER == 2) sm.dxi[t][k] = 0.f;
-        }
-        sm.gat[t] = i; sm.own[t] = j; sm.eid[t] = e;
+  auto begin_node = [&](int j) {
+    st.reset_node(); ed.reset_node(); sc.reset_node();
+    const float* sj = A.s + (size_t)j * H;
+    st.s = sj[q];
+    ed.s = sj[M + q];
+    if (L == 0) sc.s = sj[2 * M + q];
+    if (SECOND) {
+      st.sd = ed.sd = sc.sd = 0.f;
+      if (A.a_s) {
+        const float* aj = A.a_s + (size_t)j * H;
+        st.sd = aj[q];
+        ed.sd = aj[M + q];
+        if (L == 0) sc.sd = aj[2 * M + q];
       }
-      __syncthreads();
-      for (int idx = t; idx < cnt * NB_; idx += NTHREADS) {  // ---- radial terms per (slot, k)
-        const int ee = idx / NB_, k = idx - ee * NB_;
-        Cutoff<float> c;
-        c.chi = sm.chi[ee][0]; c.dchi = sm.chi[ee][1]; c.ddchi = sm.chi[ee][2];
-        const Radial<float> rr = radial_term(sm.d[ee], A.freq[k], A.rc, c);
-        sm.psi[ee][k + 1] = rr.psi;
-        sm.dpsi[ee][k + 1] = rr.dpsi;
-        if (ORDER == 2) sm.ddpsi[ee][k + 1] = rr.ddpsi;
-        if (WGRAD) sm.xi[ee][k + 1] = rr.xi;
-        if (WGRAD && ORDER == 2) sm.dxi[ee][k + 1] = rr.dxi;
-      }
-      __syncthreads();
+    }
+#pragma unroll
+    for (int m = 0; m < NC; ++m) {
+      st.v[m] = A.v[(size_t)j * D + vbase + m * vstride];
+      if (SECOND) st.vd[m] = A.a_v ? A.a_v[(size_t)j * D + vbase + m * vstride] : 0.f;
+    }
+  };
+  struct Gathered {
+    float g[NC], gx;
+  };
+  auto gather = [&](const GeoA<TC, true, SECOND>& sa, int ee, Gathered& o) {
+    const int i = sa.gat[ee];
+#pragma unroll
+    for (int m = 0; m < NC; ++m) o.g[m] = A.gV[(size_t)i * D + vbase + m * vstride];
+    o.gx = (L == 0) ? A.gx[(size_t)i * C + q] : 0.f;
+  };
 
-      float gg[NC];
-      auto gather = [&](int ee, float* a) {
-        const int i = sm.gat[ee];
-        if (ROLE == ROLE_SCALAR) {
-          a[0] = A.gx[(size_t)i * C + (h - 2 * M)];
-        } else {
+  ChunkCursor<TC> cur_it;
+  cur_it.init(g.t_rowptr, g.t_tile_ptr, E / NT + 1);  // tiles are NT-edge, chunks TC-edge
+  ChunkDesc d0 = cur_it.next(), d1 = cur_it.next(), d2, dprev;
+  dprev.cnt = -1;
+  if (d0.cnt >= 0) geo_stage_a1<TC, true, true, SECOND>(A.geo, d0, sm.a[0]);
+  __syncthreads();
+  if (d1.cnt >= 0) geo_stage_a1<TC, true, true, SECOND>(A.geo, d1, sm.a[1]);
+  if (d0.cnt >= 0) geo_stage_a2<TC, THREADS>(A.geo, d0.cnt, sm.a[0], sm.b[0]);
+  __syncthreads();
+
+  int cur = -1;
+  for (int c = 0; d0.cnt >= 0 || dprev.cnt >= 0; ++c) {
+    // ---- stage D: per-edge d/dr of chunk c-1, fixed-order sum over the warps
+    if (dprev.cnt > 0 && t < dprev.cnt && A.gr) {
+      float a0 = 0.f, a1 = 0.f, a2 = 0.f;
+      const int rs = (c + 1) & 1;
 #pragma unroll
-          for (int m = 0; m < NC; ++m) a[m] = A.gV[(size_t)i * D + vbase + m * vstride];
-        }
-      };
-      gather(0, gg);
-      for (int ee = 0; ee < cnt; ++ee) {
-        float ng[NC];
-#pragma unroll
-        for (int m = 0; m < NC; ++m) ng[m] = 0.f;
-        if (ee + 1 < cnt) gather(ee + 1, ng);
-        const int j = sm.own[ee];
+      for (int w = 0; w < NW; ++w) { a0 += sm.red[rs][t][w][0]; a1 += sm.red[rs][t][w][1]; a2 += sm.red[rs][t][w][2]; }
+      float* dst = A.gr + (size_t)sm.red_eid[rs][t] * 3;
+      dst[0] = a0; dst[1] = a1; dst[2] = a2;
+    }
+    if (d0.cnt >= 0) {
+      d2 = cur_it.next();
+      if (d2.cnt >= 0) geo_stage_a1<TC, true, true, SECOND>(A.geo, d2, sm.a[(c + 2) % 3]);
+      if (d1.cnt >= 0) geo_stage_a2<TC, THREADS>(A.geo, d1.cnt, sm.a[(c + 1) % 3], sm.b[(c + 1) & 1]);
+
+      const GeoA<TC, true, SECOND>& sa = sm.a[c % 3];
+      const GeoB<TC, true, SECOND, false, false>& sb = sm.b[c & 1];
+      const int cnt = d0.cnt, rs = c & 1;
+      if (d0.first) cur = -1;
+      if (t < cnt) sm.red_eid[rs][t] = sa.eid[t];
+      auto body = [&](int ee, const Gathered& gc, Gathered& gn) {
+        if (ee + 2 < cnt) gather(sa, ee + 2, gn);
+        const int j = sa.own[ee];
         if (j != cur) {
           if (cur >= 0) emit(cur, true);
-          for (int nn = (cur >= 0 ? cur + 1 : n0); nn < j; ++nn) emit(nn, false);
+          for (int nn = (cur >= 0 ? cur + 1 : d0.n0); nn < j; ++nn) emit(nn, false);
           cur = j;
-          th.reset_node();
-          th.s = A.s[(size_t)j * H + h];
-          if (ORDER == 2) th.sd = A.a_s ? A.a_s[(size_t)j * H + h] : 0.f;
-          if (ROLE == ROLE_STATE) {
-#pragma unroll
-            for (int m = 0; m < NC; ++m) {
-              th.v[m] = A.v[(size_t)j * D + vbase + m * vstride];
-              if (ORDER == 2) th.vd[m] = A.a_v ? A.a_v[(size_t)j * D + vbase + m * vstride] : 0.f;
-            }
-          }
+          begin_node(j);
         }
-        float p[NBP], dp[NBP], ddp[NBP], xx[NBP], dxx[NBP];
-        lds_row(sm.psi[ee], p);
-        lds_row(sm.dpsi[ee], dp);
-        if (ORDER == 2) lds_row(sm.ddpsi[ee], ddp);
-        if (WGRAD) lds_row(sm.xi[ee], xx);
-        if (WGRAD && ORDER == 2) lds_row(sm.dxi[ee], dxx);
+        float p[NBP], dp[NBP], ddp[NBP];
+        lds_row(sb.psi[ee], p);
+        lds_row(sb.dpsi[ee], dp);
+        if (SECOND) lds_row(sb.ddpsi[ee], ddp);
         NbrEdge<float> ne;
-        ne.psi = p; ne.dpsi = dp; ne.ddpsi = ddp; ne.xi = xx; ne.dxi = dxx;
-        ne.Y = sm.Y[ee]; ne.G = sm.G[ee];
-        ne.Hm = (ORDER == 2) ? sm.Hm[ee] : nullptr;
-        ne.Ydot = (ORDER == 2) ? sm.Ydot[ee] : nullptr;
-        ne.u = sm.u[ee];
-        ne.rp = (ORDER == 2) ? sm.rp[ee] : nullptr;
-        ne.ddot = (ORDER == 2) ? sm.ddot[ee] : 0.f;
-        float pr[3];
-        if (ORDER == 1) th.first(ne, gg, pr); else th.second(ne, gg, pr);
+        ne.psi = p; ne.dpsi = dp; ne.ddpsi = ddp; ne.xi = nullptr; ne.dxi = nullptr;
+        ne.Y = sa.Y[ee]; ne.G = sa.G[ee];
+        ne.Hm = SECOND ? sa.Hm[ee] : nullptr;
+        ne.Ydot = SECOND ? sa.Ydot[ee] : nullptr;
+        ne.u = sa.u[ee];
+        ne.rp = SECOND ? sa.rp[ee] : nullptr;
+        ne.ddot = SECOND ? sa.ddot[ee] : 0.f;
+        float pr[3], pe[3];
+        if (!SECOND) { st.first(ne, gc.g, pr); ed.first(ne, gc.g, pe); }
+        else { st.second(ne, gc.g, pr); ed.second(ne, gc.g, pe); }
+#pragma unroll
+        for (int x = 0; x < 3; ++x) pr[x] += pe[x];
+        if (L == 0) {
+          if (!SECOND) sc.first(ne, &gc.gx, pe); else sc.second(ne, &gc.gx, pe);
+#pragma unroll
+          for (int x = 0; x < 3; ++x) pr[x] += pe[x];
+        }
 #pragma unroll
         for (int x = 0; x < 3; ++x) {
 #pragma unroll
           for (int o = 16; o > 0; o >>= 1) pr[x] += __shfl_xor_sync(0xffffffffu, pr[x], o);
         }
         if (lane == 0) {
-          sm.red[ee][warp][0] = pr[0]; sm.red[ee][warp][1] = pr[1]; sm.red[ee][warp][2] = pr[2];
+          sm.red[rs][ee][warp][0] = pr[0]; sm.red[rs][ee][warp][1] = pr[1]; sm.red[rs][ee][warp][2] = pr[2];
         }
-#pragma unroll
-        for (int m = 0; m < NC; ++m) gg[m] = ng[m];
+      };
+      Gathered g0, g1, g2;
+      if (cnt > 0) gather(sa, 0, g0);
+      if (cnt > 1) gather(sa, 1, g1);
+      for (int ee = 0; ee < cnt; ++ee) {  // (a modulo-3 unrolled variant tripled the code and ran 2x slower)
+        body(ee, g0, g2);
+        g0 = g1;
+        g1 = g2;
       }
-      __syncthreads();
-      if (t < cnt && A.gr) {  // ---- per-edge d/dr: fixed-order sum over the warps of this channel slice
-        float a0 = 0.f, a1 = 0.f, a2 = 0.f;
-#pragma unroll
-        for (int w = 0; w < NWARPS; ++w) { a0 += sm.red[t][w][0]; a1 += sm.red[t][w][1]; a2 += sm.red[t][w][2]; }
-        float* dst = A.gr + ((size_t)blockIdx.y * E + sm.eid[t]) * 3;
-        dst[0] = a0; dst[1] = a1; dst[2] = a2;
+      if (d0.last) {
+        if (cur >= 0) emit(cur, true);
+        for (int nn = (cur >= 0 ? cur + 1 : d0.n0); nn < d0.n1; ++nn) emit(nn, false);
+        cur = -1;
       }
     }
-    if (cur >= 0) emit(cur, true);
-    for (int nn = (cur >= 0 ? cur + 1 : n0); nn < n1; ++nn) emit(nn, false);
+    __syncthreads();
+    dprev = d0;
+    if (d0.cnt >= 0) { d0 = d1; d1 = d2; }
   }
-  if (WGRAD) {
-    float* dst = A.wpart + ((size_t)blockIdx.x * H + h) * (2 * NBP);
+}
+
+template <int C, int M1, int M2, int ORDER>
+__global__ void __launch_bounds__(C + M1 + M2) nbr_main_kernel(const NeighborArgs A) {
+  __shared__ NbrMainSmem<ORDER, (C + M1 + M2) / 32> sm;
+  const int t = threadIdx.x;
+  if (t < C) nbr_main_role<0, C, M1, M2, ORDER>(A, sm);
+  else if (t < C + M1) nbr_main_role<1, C, M1, M2, ORDER>(A, sm);
+  else nbr_main_role<2, C, M1, M2, ORDER>(A, sm);
+}
+
+// ==========================================================================================
+// neighbor weight-gradient kernel (thread per filter channel h; needs no W rows)
+// ==========================================================================================
+template <int ORDER>
+struct NbrWgradSmem {
+  GeoA<NT, false, ORDER == 2> a[3];
+  GeoB<NT, ORDER == 2, false, true, ORDER == 2> b[2];
+};
+
+template <int L, int ROLE, int C, int M1, int M2, int ORDER>
+__device__ __forceinline__ void nbr_wgrad_role(const NeighborArgs& A, NbrWgradSmem<ORDER>& sm) {
+  constexpr int M = C + M1 + M2, D = C + 3 * M1 + 5 * M2, H = C + 2 * M;
+  constexpr bool SECOND = ORDER == 2;
+  using Thread = NeighborThread<float, L, ROLE, true, NK_, false>;
+  constexpr int NC = Thread::NC;
+  const int t = threadIdx.x;
+  const int h = blockIdx.y * WTHREADS + t;
+  const int q = (ROLE == ROLE_STATE) ? h : (ROLE == ROLE_EDGE ? h - M : 0);
+  const int vbase = (ROLE == ROLE_SCALAR) ? 0 : ((L == 0) ? q : (L == 1 ? C + (q - C) : C + 3 * M1 + (q - C - M1)));
+  constexpr int vstride = (L == 0) ? 0 : (L == 1 ? M1 : M2);
+  const xeq_graph_t& g = A.geo.g;
+
+  Thread th;
+  th.reset_wgrad();
+  th.s = th.sd = 0.f;
 #pragma unroll
-    for (int k = 0; k < NBP; ++k) { dst[k] = th.GW[k]; dst[NBP + k] = th.GF[k]; }
+  for (int m = 0; m < NC; ++m) th.v[m] = th.vd[m] = 0.f;
+
+  auto gather = [&](const GeoA<NT, false, SECOND>& sa, int ee, float* o) {
+    const int i = sa.gat[ee];
+    if (ROLE == ROLE_SCALAR) {
+      o[0] = A.gx[(size_t)i * C + (h - 2 * M)];
+    } else {
+#pragma unroll
+      for (int m = 0; m < NC; ++m) o[m] = A.gV[(size_t)i * D + vbase + m * vstride];
+    }
+  };
+
+  ChunkCursor<NT> cur_it;
+  cur_it.init(g.t_rowptr, g.t_tile_ptr, g.n_edges / NT + 1);
+  ChunkDesc d0 = cur_it.next(), d1 = cur_it.next(), d2;
+  if (d0.cnt >= 0) geo_stage_a1<NT, true, false, SECOND>(A.geo, d0, sm.a[0]);
+  __syncthreads();
+  if (d1.cnt >= 0) geo_stage_a1<NT, true, false, SECOND>(A.geo, d1, sm.a[1]);
+  if (d0.cnt >= 0) geo_stage_a2<NT, WTHREADS>(A.geo, d0.cnt, sm.a[0], sm.b[0]);
+  __syncthreads();
+
+  int cur = -1;
+  for (int c = 0; d0.cnt >= 0; ++c) {
+    d2 = cur_it.next();
+    if (d2.cnt >= 0) geo_stage_a1<NT, true, false, SECOND>(A.geo, d2, sm.a[(c + 2) % 3]);
+    if (d1.cnt >= 0) geo_stage_a2<NT, WTHREADS>(A.geo, d1.cnt, sm.a[(c + 1) % 3], sm.b[(c + 1) & 1]);
+    const GeoA<NT, false, SECOND>& sa = sm.a[c % 3];
+    const auto& sb = sm.b[c & 1];
+    const int cnt = d0.cnt;
+    if (d0.first) cur = -1;
+    auto body = [&](int ee, const float* gc, float* gn) {
+      if (ee + 2 < cnt) gather(sa, ee + 2, gn);
+      const int j = sa.own[ee];
+      if (j != cur) {
+        cur = j;
+        th.s = A.s[(size_t)j * H + h];
+        if (SECOND) th.sd = A.a_s ? A.a_s[(size_t)j * H + h] : 0.f;
+        if (ROLE == ROLE_STATE) {
+#pragma unroll
+          for (int m = 0; m < NC; ++m) {
+            th.v[m] = A.v[(size_t)j * D + vbase + m * vstride];
+            if (SECOND) th.vd[m] = A.a_v ? A.a_v[(size_t)j * D + vbase + m * vstride] : 0.f;
+          }
+        }
+      }
+      float p[NBP], dp[NBP], xx[NBP], dxx[NBP];
+      lds_row(sb.psi[ee], p);
+      lds_row(sb.xi[ee], xx);
+      if (SECOND) { lds_row(sb.dpsi[ee], dp); lds_row(sb.dxi[ee], dxx); }
+      NbrEdge<float> ne;
+      ne.psi = p; ne.dpsi = dp; ne.ddpsi = nullptr; ne.xi = xx; ne.dxi = dxx;
+      ne.Y = sa.Y[ee]; ne.G = nullptr; ne.Hm = nullptr;
+      ne.Ydot = SECOND ? sa.Ydot[ee] : nullptr;
+      ne.u = sa.u[ee]; ne.rp = nullptr;
+      ne.ddot = SECOND ? sa.ddot[ee] : 0.f;
+      float pr[3];
+      if (!SECOND) th.first(ne, gc, pr); else th.second(ne, gc, pr);
+    };
+    float g0[NC], g1[NC], g2[NC];
+#pragma unroll
+    for (int m = 0; m < NC; ++m) g0[m] = g1[m] = g2[m] = 0.f;
+    if (cnt > 0) gather(sa, 0, g0);
+    if (cnt > 1) gather(sa, 1, g1);
+    for (int ee = 0; ee < cnt; ++ee) {
+      body(ee, g0, g2);
+#pragma unroll
+      for (int m = 0; m < NC; ++m) { g0[m] = g1[m]; g1[m] = g2[m]; }
+    }
+    __syncthreads();
+    d0 = d1;
+    d1 = d2;
   }
+  float* dst = A.wpart + ((size_t)blockIdx.x * H + h) * (2 * NBP);
+#pragma unroll
+  for (int k = 0; k < NBP; ++k) { dst[k] = th.GW[k]; dst[NBP + k] = th.GF[k]; }
 }
 
-template <int C, int M1, int M2, int ORDER, bool WGRAD>
-__global__ void __launch_bounds__(NTHREADS) neighbor_kernel(const NeighborArgs A) {
+template <int C, int M1, int M2, int ORDER>
+__global__ void __launch_bounds__(WTHREADS) nbr_wgrad_kernel(const NeighborArgs A) {
   constexpr int M = C + M1 + M2;
-  __shared__ __align__(16) NeighborSmem<ORDER, WGRAD> sm;
-  const int h = blockIdx.y * NTHREADS + threadIdx.x;
-  if (h < C) neighbor_role<0, ROLE_STATE, C, M1, M2, ORDER, WGRAD>(A, sm);
-  else if (h < C + M1) neighbor_role<1, ROLE_STATE, C, M1, M2, ORDER, WGRAD>(A, sm);
-  else if (h < M) neighbor_role<2, ROLE_STATE, C, M1, M2, ORDER, WGRAD>(A, sm);
-  else if (h < M + C) neighbor_role<0, ROLE_EDGE, C, M1, M2, ORDER, WGRAD>(A, sm);
-  else if (h < M + C + M1) neighbor_role<1, ROLE_EDGE, C, M1, M2, ORDER, WGRAD>(A, sm);
-  else if (h < 2 * M) neighbor_role<2, ROLE_EDGE, C, M1, M2, ORDER, WGRAD>(A, sm);
-  else neighbor_role<0, ROLE_SCALAR, C, M1, M2, ORDER, WGRAD>(A, sm);
+  __shared__ NbrWgradSmem<ORDER> sm;
+  const int h = blockIdx.y * WTHREADS + threadIdx.x;
+  if (h < C) nbr_wgrad_role<0, ROLE_STATE, C, M1, M2, ORDER>(A, sm);
+  else if (h < C + M1) nbr_wgrad_role<1, ROLE_STATE, C, M1, M2, ORDER>(A, sm);
+  else if (h < M) nbr_wgrad_role<2, ROLE_STATE, C, M1, M2, ORDER>(A, sm);
+  else if (h < M + C) nbr_wgrad_role<0, ROLE_EDGE, C, M1, M2, ORDER>(A, sm);
+  else if (h < M + C + M1) nbr_wgrad_role<1, ROLE_EDGE, C, M1, M2, ORDER>(A, sm);
+  else if (h < 2 * M) nbr_wgrad_role<2, ROLE_EDGE, C, M1, M2, ORDER>(A, sm);
+  else nbr_wgrad_role<0, ROLE_SCALAR, C, M1, M2, ORDER>(A, sm);
 }
 
-// gpos[n] = sum_{e in row n} gr[e] - sum_{slot in t-row n} gr[t_eid[slot]]  (summed over channel slices)
-__global__ void pos_grad_kernel(xeq_graph_t g, const float* __restrict__ gr, int n_slices, float* __restrict__ gpos) {
+// gpos[n] = sum_{e in row n} gr[e] - sum_{slot in t-row n} gr[t_eid[slot]]
+__global__ void pos_grad_kernel(xeq_graph_t g, const float* __restrict__ gr, float* __restrict__ gpos) {
   const int n = blockIdx.x * blockDim.x + threadIdx.x;
   if (n >= g.n_nodes) return;
   float a0 = 0.f, a1 = 0.f, a2 = 0.f;
-  for (int sl = 0; sl < n_slices; ++sl) {
-    const float* base = gr + (size_t)sl * g.n_edges * 3;
-    for (int e = g.rowptr[n]; e < g.rowptr[n + 1]; ++e) {
-      a0 += base[3 * (size_t)e]; a1 += base[3 * (size_t)e + 1]; a2 += base[3 * (size_t)e + 2];
-    }
-    for (int s = g.t_rowptr[n]; s < g.t_rowptr[n + 1]; ++s) {
-      const size_t e = g.t_eid[s];
-      a0 -= base[3 * e]; a1 -= base[3 * e + 1]; a2 -= base[3 * e + 2];
-    }
+  for (int e = g.rowptr[n]; e < g.rowptr[n + 1]; ++e) {
+    a0 += gr[3 * (size_t)e]; a1 += gr[3 * (size_t)e + 1]; a2 += gr[3 * (size_t)e + 2];
+  }
+  for (int s = g.t_rowptr[n]; s < g.t_rowptr[n + 1]; ++s) {
+    const size_t e = g.t_eid[s];
+    a0 -= gr[3 * e]; a1 -= gr[3 * e + 1]; a2 -= gr[3 * e + 2];
   }
   gpos[3 * n] = a0; gpos[3 * n + 1] = a1; gpos[3 * n + 2] = a2;
 }
 
-// weight-gradient partials [nblk, H, 2*NBP] -> gW [H,B], gb [H], tot_f [H, NB] (fixed order)
+// weight-gradient partials [nblk, H, 2*NBP] -> gW [H,B], gb [H], ftot [H, NB] (fixed order)
 __global__ void wgrad_reduce_kernel(const float* __restrict__ wpart, int nblk, int H, float* __restrict__ gW,
                                     float* __restrict__ gb, float* __restrict__ ftot) {
   const int h = blockIdx.x, k = threadIdx.x;  // k < 2*NBP
@@ -526,6 +768,21 @@ __global__ void freq_grad_kernel(const float* __restrict__ W, const float* __res
   if (threadIdx.x == 0) gfreq[k] = red[0];
 }
 
+// tile_ptr[k] = first node whose row starts at or after edge k * tile_edges  (k = 0 .. n_tiles)
+__global__ void tile_bounds_kernel(const int* __restrict__ rowptr, int n_nodes, int n_tiles, int tile_edges,
+                                   int* __restrict__ tile_ptr) {
+  const int k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k > n_tiles) return;
+  if (k == n_tiles) { tile_ptr[k] = n_nodes; return; }
+  const long long x = (long long)k * tile_edges;
+  int lo = 0, hi = n_nodes;
+  while (lo < hi) {
+    const int mid = (lo + hi) >> 1;
+    if (rowptr[mid] < x) lo = mid + 1; else hi = mid;
+  }
+  tile_ptr[k] = lo;
+}
+
 // ------------------------------------------------------------------------------------------
 // host side
 // ------------------------------------------------------------------------------------------
@@ -545,7 +802,9 @@ static int check_dims(const xeq_dims_t* d, int* cfg) {
 static int check_graph(const xeq_graph_t* g, bool need_t) {
   XEQ_CHECK_ARG(g && g->rowptr && g->n_nodes >= 0 && g->n_edges >= 0, "graph: bad arguments");
   XEQ_CHECK_ARG(g->n_edges == 0 || g->col, "graph: col is NULL");
-  XEQ_CHECK_ARG(!need_t || (g->t_rowptr && (g->n_edges == 0 || (g->t_row && g->t_eid))), "graph: transposed CSR missing");
+  XEQ_CHECK_ARG(g->tile_ptr, "graph: tile_ptr missing (xeq_csr_tile_bounds)");
+  XEQ_CHECK_ARG(!need_t || (g->t_rowptr && g->t_tile_ptr && (g->n_edges == 0 || (g->t_row && g->t_eid))),
+                "graph: transposed CSR missing");
   XEQ_CHECK_ARG((g->offsets == nullptr) == (g->cell == nullptr), "graph: offsets and cell must be given together");
   XEQ_CHECK_ARG(!g->cell || g->n_graphs == 1 || g->node_graph, "graph: node_graph needed for multi-graph PBC");
   return XEQ_OK;
@@ -553,11 +812,19 @@ static int check_graph(const xeq_graph_t* g, bool need_t) {
 
 static inline int dims_H(const xeq_dims_t* d) { return d->node_dim + 2 * (d->mul0 + d->mul1 + d->mul2); }
 
+template <typename Kernel>
+static int set_smem(Kernel k, size_t bytes) {
+  XEQ_CUDA(cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
+  return XEQ_OK;
+}
+
 template <int C, int M1, int M2, bool JVP>
 static int launch_center(const CenterArgs& A, cudaStream_t st) {
-  const int grid = min(A.n_tiles, num_sms() * (C == 128 ? 2 : 1));
+  const int n_tiles = A.geo.g.n_edges / CT + 1;
+  const int grid = min(n_tiles, num_sms() * (C == 128 ? 2 : 1));
+  static_assert(sizeof(CenterSmem<JVP>) <= 48 * 1024, "static shared memory limit");
   center_kernel<C, M1, M2, JVP><<<grid, C + M1 + M2, 0, st>>>(A);
-  XEQ_LAUNCH_CHECK();
+  XEQ_LAUNCHED(1);
   return XEQ_OK;
 }
 
@@ -568,36 +835,40 @@ static int run_center(const xeq_graph_t* g, const xeq_dims_t* dims, CenterArgs& 
   rc = check_graph(g, false);
   if (rc) return rc;
   if (g->n_nodes == 0) return XEQ_OK;
-  A.g = *g;
-  A.rc = dims->cutoff;
-  A.n_tiles = g->n_edges / CT + 1;
+  A.geo.g = *g;
+  A.geo.rc = dims->cutoff;
   if (cfg == 0) return jvp ? launch_center<128, 64, 32, true>(A, st) : launch_center<128, 64, 32, false>(A, st);
   return jvp ? launch_center<256, 128, 64, true>(A, st) : launch_center<256, 128, 64, false>(A, st);
 }
 
-static int neighbor_grid_x(const xeq_graph_t* g) {
-  const int n_tiles = g->n_edges / NT + 1;
-  return min(n_tiles, num_sms() * 2);
-}
+static int wgrad_grid_x(const xeq_graph_t* g) { return min(g->n_edges / NT + 1, num_sms() * 2); }
 
 static size_t neighbor_ws_bytes(const xeq_graph_t* g, const xeq_dims_t* d, int want_wgrad) {
-  const int H = dims_H(d), S = H / NTHREADS;
-  size_t b = 256 + align_up(sizeof(float) * 3 * (size_t)S * (size_t)(g->n_edges > 0 ? g->n_edges : 1), 256);
+  const int H = dims_H(d);
+  size_t b = 256 + align_up(sizeof(float) * 3 * (size_t)(g->n_edges > 0 ? g->n_edges : 1), 256);
   if (want_wgrad) {
-    b += align_up(sizeof(float) * (size_t)neighbor_grid_x(g) * H * 2 * NBP, 256);
+    b += align_up(sizeof(float) * (size_t)wgrad_grid_x(g) * H * 2 * NBP, 256);
     b += align_up(sizeof(float) * (size_t)H * NB_, 256);
   }
   return b;
 }
 
 template <int C, int M1, int M2, int ORDER>
-static int launch_neighbor(NeighborArgs& A, bool wgrad, int gx, cudaStream_t st) {
-  constexpr int H = C + 2 * (C + M1 + M2);
-  static_assert(H % NTHREADS == 0, "channel slices must tile H");
-  dim3 grid(gx, H / NTHREADS);
-  if (wgrad) neighbor_kernel<C, M1, M2, ORDER, true><<<grid, NTHREADS, 0, st>>>(A);
-  else neighbor_kernel<C, M1, M2, ORDER, false><<<grid, NTHREADS, 0, st>>>(A);
-  XEQ_LAUNCH_CHECK();
+static int launch_neighbor(NeighborArgs& A, bool main, bool wgrad, int gx, cudaStream_t st) {
+  constexpr int M = C + M1 + M2, H = C + 2 * M;
+  static_assert(H % WTHREADS == 0, "channel slices must tile H");
+  if (main) {
+    const int n_tiles = A.geo.g.n_edges / NT + 1;
+    const int grid = min(n_tiles, num_sms() * ((C == 128 && ORDER == 1) ? 2 : 1));
+    static_assert(sizeof(NbrMainSmem<ORDER, M / 32>) <= 48 * 1024, "static shared memory limit");
+    nbr_main_kernel<C, M1, M2, ORDER><<<grid, M, 0, st>>>(A);
+    XEQ_LAUNCHED(1);
+  }
+  if (wgrad) {
+    static_assert(sizeof(NbrWgradSmem<ORDER>) <= 48 * 1024, "static shared memory limit");
+    nbr_wgrad_kernel<C, M1, M2, ORDER><<<dim3(gx, H / WTHREADS), WTHREADS, 0, st>>>(A);
+    XEQ_LAUNCHED(1);
+  }
   return XEQ_OK;
 }
 
@@ -609,34 +880,34 @@ static int run_neighbor(const xeq_graph_t* g, const xeq_dims_t* dims, NeighborAr
   rc = check_graph(g, true);
   if (rc) return rc;
   const bool wgrad = o_W || o_b || o_f;
+  const bool main = A.o_s || A.o_v || o_pos;
   XEQ_CHECK_ARG(!wgrad || (o_W && o_b && o_f), "weight gradients: gW, gb and gfreq must be given together");
   XEQ_CHECK_ARG(ws && ws_bytes >= neighbor_ws_bytes(g, dims, wgrad), "edge_message backward: workspace too small");
-  const int H = dims_H(dims), S = H / NTHREADS;
+  const int H = dims_H(dims);
   if (g->n_nodes == 0) return XEQ_OK;
   Carver cv(ws);
-  float* gr = cv.take<float>(3 * (size_t)S * (size_t)(g->n_edges > 0 ? g->n_edges : 1));
-  const int gx = neighbor_grid_x(g);
+  float* gr = cv.take<float>(3 * (size_t)(g->n_edges > 0 ? g->n_edges : 1));
+  const int gx = wgrad_grid_x(g);
   float *wpart = nullptr, *ftot = nullptr;
   if (wgrad) {
     wpart = cv.take<float>((size_t)gx * H * 2 * NBP);
     ftot = cv.take<float>((size_t)H * NB_);
   }
-  A.g = *g;
-  A.rc = dims->cutoff;
-  A.n_tiles = g->n_edges / NT + 1;
+  A.geo.g = *g;
+  A.geo.rc = dims->cutoff;
   A.gr = o_pos ? gr : nullptr;
   A.wpart = wpart;
-  if (cfg == 0) rc = order == 1 ? launch_neighbor<128, 64, 32, 1>(A, wgrad, gx, st) : launch_neighbor<128, 64, 32, 2>(A, wgrad, gx, st);
-  else rc = order == 1 ? launch_neighbor<256, 128, 64, 1>(A, wgrad, gx, st) : launch_neighbor<256, 128, 64, 2>(A, wgrad, gx, st);
+  if (cfg == 0) rc = order == 1 ? launch_neighbor<128, 64, 32, 1>(A, main, wgrad, gx, st) : launch_neighbor<128, 64, 32, 2>(A, main, wgrad, gx, st);
+  else rc = order == 1 ? launch_neighbor<256, 128, 64, 1>(A, main, wgrad, gx, st) : launch_neighbor<256, 128, 64, 2>(A, main, wgrad, gx, st);
   if (rc) return rc;
   if (o_pos) {
-    pos_grad_kernel<<<(g->n_nodes + 127) / 128, 128, 0, st>>>(*g, gr, S, o_pos);
-    XEQ_LAUNCH_CHECK();
+    pos_grad_kernel<<<(g->n_nodes + 127) / 128, 128, 0, st>>>(*g, gr, o_pos);
+    XEQ_LAUNCHED(1);
   }
   if (wgrad) {
     wgrad_reduce_kernel<<<H, 2 * NBP, 0, st>>>(wpart, gx, H, o_W, o_b, ftot);
     freq_grad_kernel<<<NB_, 256, 0, st>>>(A.W, ftot, H, o_f);
-    XEQ_LAUNCH_CHECK();
+    XEQ_LAUNCHED(2);
   }
   return XEQ_OK;
 }
@@ -647,12 +918,26 @@ using namespace xeq;
 
 extern "C" {
 
+int xeq_center_tile_edges(void) { return CT; }
+int xeq_neighbor_tile_edges(void) { return NT; }
+
+int xeq_csr_tile_bounds(const int32_t* rowptr, int32_t n_nodes, int32_t n_edges, int32_t tile_edges, int32_t* tile_ptr,
+                        xeq_stream_t stream) {
+  XEQ_CHECK_ARG(rowptr && tile_ptr && n_nodes >= 0 && n_edges >= 0 && tile_edges > 0, "csr_tile_bounds: bad arguments");
+  const int n_tiles = n_edges / tile_edges + 1;
+  tile_bounds_kernel<<<(n_tiles + 1 + 255) / 256, 256, 0, (cudaStream_t)stream>>>(rowptr, n_nodes, n_tiles, tile_edges,
+                                                                                 tile_ptr);
+  XEQ_LAUNCHED(1);
+  return XEQ_OK;
+}
+
 int xeq_edge_message_fwd(const xeq_graph_t* g, const xeq_dims_t* dims, const float* pos, const float* s, const float* v,
                          const float* x_in, const float* V_in, const float* W_rbf, const float* b_rbf, const float* freq,
                          float* x_out, float* V_out, xeq_stream_t stream) {
   XEQ_CHECK_ARG(pos && s && v && W_rbf && b_rbf && freq && x_out && V_out, "edge_message_fwd: NULL argument");
   CenterArgs A{};
-  A.pos = pos; A.s = s; A.v = v; A.x_in = x_in; A.V_in = V_in; A.W = W_rbf; A.b = b_rbf; A.freq = freq;
+  A.geo.pos = pos; A.geo.freq = freq; A.geo.a_pos = nullptr;
+  A.s = s; A.v = v; A.x_in = x_in; A.V_in = V_in; A.W = W_rbf; A.b = b_rbf;
   A.x_out = x_out; A.V_out = V_out;
   return run_center(g, dims, A, false, (cudaStream_t)stream);
 }
@@ -668,7 +953,8 @@ int xeq_edge_message_bwd(const xeq_graph_t* g, const xeq_dims_t* dims, const flo
                          size_t workspace_bytes, xeq_stream_t stream) {
   XEQ_CHECK_ARG(pos && s && v && W_rbf && b_rbf && freq && gx && gV, "edge_message_bwd: NULL argument");
   NeighborArgs A{};
-  A.pos = pos; A.s = s; A.v = v; A.W = W_rbf; A.b = b_rbf; A.freq = freq; A.gx = gx; A.gV = gV;
+  A.geo.pos = pos; A.geo.freq = freq; A.geo.a_pos = nullptr;
+  A.s = s; A.v = v; A.W = W_rbf; A.b = b_rbf; A.gx = gx; A.gV = gV;
   A.o_s = gs; A.o_v = gv;
   return run_neighbor(g, dims, A, 1, gpos, gW, gb, gfreq, workspace, workspace_bytes, (cudaStream_t)stream);
 }
@@ -688,15 +974,17 @@ int xeq_edge_message_bwdbwd(const xeq_graph_t* g, const xeq_dims_t* dims, const 
   if (o_gx || o_gV) {  // d/d(gx, gV): tangent of the forward message along (a_s, a_v, a_pos)
     XEQ_CHECK_ARG(o_gx && o_gV, "edge_message_bwdbwd: o_gx and o_gV must be given together");
     CenterArgs C{};
-    C.pos = pos; C.s = s; C.v = v; C.W = W_rbf; C.b = b_rbf; C.freq = freq;
-    C.a_s = a_s; C.a_v = a_v; C.a_pos = a_pos; C.x_out = o_gx; C.V_out = o_gV;
+    C.geo.pos = pos; C.geo.freq = freq; C.geo.a_pos = a_pos;
+    C.s = s; C.v = v; C.W = W_rbf; C.b = b_rbf;
+    C.a_s = a_s; C.a_v = a_v; C.x_out = o_gx; C.V_out = o_gV;
     int rc = run_center(g, dims, C, true, st);
     if (rc) return rc;
   }
   if (o_s || o_v || o_pos || o_W) {
     NeighborArgs A{};
-    A.pos = pos; A.s = s; A.v = v; A.W = W_rbf; A.b = b_rbf; A.freq = freq; A.gx = gx; A.gV = gV;
-    A.a_s = a_s; A.a_v = a_v; A.a_pos = a_pos; A.o_s = o_s; A.o_v = o_v;
+    A.geo.pos = pos; A.geo.freq = freq; A.geo.a_pos = a_pos;
+    A.s = s; A.v = v; A.W = W_rbf; A.b = b_rbf; A.gx = gx; A.gV = gV;
+    A.a_s = a_s; A.a_v = a_v; A.o_s = o_s; A.o_v = o_v;
     return run_neighbor(g, dims, A, 2, o_pos, o_W, o_b, o_freq, workspace, workspace_bytes, st);
   }
   return XEQ_OK;

@@ -93,7 +93,10 @@ struct NbrEdge {
   T ddot;          //        second order only
 };
 
-template <typename T, int L, int ROLE, bool WGRAD, int NK>
+// MAIN : produce d/ds, d/dv (registers) and this thread's share of d/dr.
+// WGRAD: accumulate weight-gradient partials.  The kernels run MAIN and WGRAD as separate
+// passes (thread-per-irrep vs thread-per-filter-channel); the host emulation runs both at once.
+template <typename T, int L, int ROLE, bool WGRAD, int NK, bool MAIN = true>
 struct NeighborThread {
   static constexpr int NC = (ROLE == ROLE_SCALAR) ? 1 : 2 * L + 1;
   static constexpr int YO = YOff<L>::value;
@@ -117,19 +120,21 @@ struct NeighborThread {
   // First derivatives.  g = gV[i,(q,:)] (state/edge roles) or gx[i,c] (scalar role).
   // pr[3] receives this thread's share of dPhi/dr_e.
   XEQ_HD void first(const NbrEdge<T>& e, const T* g, T pr[3]) {
-    const T w = dot_nk<NK>(Wt, e.psi);
-    const T dw = dot_nk<NK>(Wt, e.dpsi);
+    const T w = MAIN ? dot_nk<NK>(Wt, e.psi) : T(0);
+    const T dw = MAIN ? dot_nk<NK>(Wt, e.dpsi) : T(0);
     T pw;  // dPhi/dw_e[h]
     T cy[NC];
     if (ROLE == ROLE_STATE) {
       T A = T(0);
 #pragma unroll
       for (int m = 0; m < NC; ++m) A += g[m] * v[m];
-      acc_s += A * w;
-      const T sw = s * w;
-#pragma unroll
-      for (int m = 0; m < NC; ++m) acc_v[m] += sw * g[m];
       pw = A * s;
+      if (MAIN) {
+        acc_s += A * w;
+        const T sw = s * w;
+#pragma unroll
+        for (int m = 0; m < NC; ++m) acc_v[m] += sw * g[m];
+      }
     } else if (ROLE == ROLE_EDGE) {
       T B = T(0);
       if (L == 0) {
@@ -138,24 +143,28 @@ struct NeighborThread {
 #pragma unroll
         for (int m = 0; m < NC; ++m) B += g[m] * e.Y[YO + m];
       }
-      acc_s += B * w;
       pw = B * s;
-      const T sw = s * w;
+      if (MAIN) {
+        acc_s += B * w;
+        const T sw = s * w;
 #pragma unroll
-      for (int m = 0; m < NC; ++m) cy[m] = sw * g[m];
-    } else {
-      acc_s += g[0] * w;
-      pw = g[0] * s;
-    }
-    const T dpart = pw * dw;
-#pragma unroll
-    for (int x = 0; x < 3; ++x) {
-      T p = e.u[x] * dpart;
-      if (ROLE == ROLE_EDGE && L > 0) {
-#pragma unroll
-        for (int m = 0; m < NC; ++m) p += e.G[x * 8 + YO + m] * cy[m];
+        for (int m = 0; m < NC; ++m) cy[m] = sw * g[m];
       }
-      pr[x] = p;
+    } else {
+      pw = g[0] * s;
+      if (MAIN) acc_s += g[0] * w;
+    }
+    if (MAIN) {
+      const T dpart = pw * dw;
+#pragma unroll
+      for (int x = 0; x < 3; ++x) {
+        T p = e.u[x] * dpart;
+        if (ROLE == ROLE_EDGE && L > 0) {
+#pragma unroll
+          for (int m = 0; m < NC; ++m) p += e.G[x * 8 + YO + m] * cy[m];
+        }
+        pr[x] = p;
+      }
     }
     if (WGRAD) {
 #pragma unroll
@@ -168,9 +177,9 @@ struct NeighborThread {
 
   // Second derivatives: gradient of Psi_e (the tangent of Phi_e along (sd, vd, rdot)).
   XEQ_HD void second(const NbrEdge<T>& e, const T* g, T pr[3]) {
-    const T w = dot_nk<NK>(Wt, e.psi);
-    const T dw = dot_nk<NK>(Wt, e.dpsi);
-    const T ddw = dot_nk<NK>(Wt, e.ddpsi);
+    const T w = MAIN ? dot_nk<NK>(Wt, e.psi) : T(0);
+    const T dw = MAIN ? dot_nk<NK>(Wt, e.dpsi) : T(0);
+    const T ddw = MAIN ? dot_nk<NK>(Wt, e.ddpsi) : T(0);
     const T dwd = dw * e.ddot;  // tangent of w
     T alpha, beta;
     T cy[NC], cz[NC];
@@ -183,10 +192,12 @@ struct NeighborThread {
       }
       alpha = sd * A + s * Ad;
       beta = s * A;
-      acc_s += dwd * A + w * Ad;
-      const T c = sd * w + s * dwd;
+      if (MAIN) {
+        acc_s += dwd * A + w * Ad;
+        const T c = sd * w + s * dwd;
 #pragma unroll
-      for (int m = 0; m < NC; ++m) acc_v[m] += c * g[m];
+        for (int m = 0; m < NC; ++m) acc_v[m] += c * g[m];
+      }
     } else if (ROLE == ROLE_EDGE) {
       T B = T(0), Bd = T(0);
       if (L == 0) {
@@ -200,29 +211,33 @@ struct NeighborThread {
       }
       alpha = sd * B + s * Bd;
       beta = s * B;
-      acc_s += dwd * B + w * Bd;
-      const T c = sd * w + s * dwd;
-      const T sw = s * w;
+      if (MAIN) {
+        acc_s += dwd * B + w * Bd;
+        const T c = sd * w + s * dwd;
+        const T sw = s * w;
 #pragma unroll
-      for (int m = 0; m < NC; ++m) {
-        cy[m] = c * g[m];
-        cz[m] = sw * g[m];
+        for (int m = 0; m < NC; ++m) {
+          cy[m] = c * g[m];
+          cz[m] = sw * g[m];
+        }
       }
     } else {
       alpha = g[0] * sd;
       beta = g[0] * s;
-      acc_s += g[0] * dwd;
+      if (MAIN) acc_s += g[0] * dwd;
     }
-    const T P = alpha * dw + e.ddot * beta * ddw;
-    const T R1 = beta * dw;
+    if (MAIN) {
+      const T P = alpha * dw + e.ddot * beta * ddw;
+      const T R1 = beta * dw;
 #pragma unroll
-    for (int x = 0; x < 3; ++x) {
-      T p = e.u[x] * P + R1 * e.rp[x];
-      if (ROLE == ROLE_EDGE && L > 0) {
+      for (int x = 0; x < 3; ++x) {
+        T p = e.u[x] * P + R1 * e.rp[x];
+        if (ROLE == ROLE_EDGE && L > 0) {
 #pragma unroll
-        for (int m = 0; m < NC; ++m) p += e.G[x * 8 + YO + m] * cy[m] + e.Hm[x * 8 + YO + m] * cz[m];
+          for (int m = 0; m < NC; ++m) p += e.G[x * 8 + YO + m] * cy[m] + e.Hm[x * 8 + YO + m] * cz[m];
+        }
+        pr[x] = p;
       }
-      pr[x] = p;
     }
     if (WGRAD) {
       const T bd = beta * e.ddot;

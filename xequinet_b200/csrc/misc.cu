@@ -2,11 +2,16 @@
 // helpers of the C ABI: contiguous segment sum (nn/output.py:124) and e3nn <-> cm layout maps.
 #include <stdarg.h>
 
+#include <atomic>
+
 #include "common.cuh"
 
 namespace xeq {
 
 static thread_local char g_err[512] = "";
+static std::atomic<long long> g_launches{0};
+
+void count_launches(int n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
 
 void set_error(const char* fmt, ...) {
   va_list ap;
@@ -64,6 +69,7 @@ extern "C" {
 int xeq_version(void) { return 100; }
 const char* xeq_last_error(void) { return g_err; }
 int xeq_num_sms(void) { return num_sms(); }
+long long xeq_launch_count(void) { return g_launches.load(std::memory_order_relaxed); }
 
 int xeq_segment_sum(const float* src, const int32_t* seg_ptr, int32_t n_segments, float* out, xeq_stream_t stream) {
   XEQ_CHECK_ARG(seg_ptr && out && n_segments >= 0, "segment_sum: bad arguments");
@@ -71,7 +77,7 @@ int xeq_segment_sum(const float* src, const int32_t* seg_ptr, int32_t n_segments
   XEQ_CHECK_ARG(src, "segment_sum: src is NULL");
   const int blocks = (int)(((size_t)n_segments * 32 + 255) / 256);
   segment_sum_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(src, seg_ptr, n_segments, out);
-  XEQ_LAUNCH_CHECK();
+  XEQ_LAUNCHED(1);
   return XEQ_OK;
 }
 
@@ -83,7 +89,7 @@ int xeq_layout_convert(const float* src, float* dst, int32_t n_nodes, const xeq_
   if (total == 0) return XEQ_OK;
   layout_convert_kernel<<<(unsigned)((total + 255) / 256), 256, 0, (cudaStream_t)stream>>>(src, dst, n_nodes, dims->mul0,
                                                                                          dims->mul1, dims->mul2, direction);
-  XEQ_LAUNCH_CHECK();
+  XEQ_LAUNCHED(1);
   return XEQ_OK;
 }
 

@@ -102,7 +102,7 @@ static int exclusive_scan(const int* in, int* out, int n, int* scratch, cudaStre
   scan_blocks_kernel<<<nblocks, SCAN_THREADS, 0, st>>>(in, out, scratch, n);
   scan_totals_kernel<<<1, SCAN_THREADS, 0, st>>>(scratch, nblocks, out + n);
   if (nblocks > 1) add_offsets_kernel<<<(n + 255) / 256, 256, 0, st>>>(out, scratch, n);
-  XEQ_LAUNCH_CHECK();
+  XEQ_LAUNCHED(nblocks > 1 ? 3 : 2);
   return XEQ_OK;
 }
 
@@ -374,7 +374,7 @@ int xeq_radius_graph_count(const float* pos, int32_t n, const int32_t* graph_ptr
     graph_scan_kernel<false, false><<<blocks, 256, 0, st>>>(pos, nullptr, graph_ptr, node_graph, nullptr, pp, cutoff, n,
                                                             deg, nullptr, nullptr, nullptr, nullptr, nullptr, 0);
   }
-  XEQ_LAUNCH_CHECK();
+  XEQ_LAUNCHED(periodic ? 2 : 1);
   return exclusive_scan(deg, rowptr, n, scratch, st);
 }
 
@@ -414,7 +414,7 @@ int xeq_radius_graph_fill(const float* pos, int32_t n, const int32_t* graph_ptr,
                                                            nullptr, rowptr, col, nullptr, (long long*)edge_index, nullptr,
                                                            n_edges);
   }
-  XEQ_LAUNCH_CHECK();
+  XEQ_LAUNCHED(periodic ? 2 : 1);
   return XEQ_OK;
 }
 
@@ -429,7 +429,7 @@ int xeq_csr_from_sorted_coo(const int64_t* edge_index, const float* cell_offsets
   XEQ_CHECK_ARG(edge_index && col, "csr_from_sorted_coo: NULL edge_index/col");
   coo_to_csr_kernel<<<(n_edges + 255) / 256, 256, 0, st>>>((const long long*)edge_index, cell_offsets, n_nodes, n_edges,
                                                            rowptr, col, offsets);
-  XEQ_LAUNCH_CHECK();
+  XEQ_LAUNCHED(1);
   return XEQ_OK;
 }
 
@@ -450,6 +450,7 @@ int xeq_csr_transpose(const int32_t* rowptr, const int32_t* col, int32_t n_nodes
   if (n_edges > 0) {
     XEQ_CHECK_ARG(col && t_row && t_eid, "csr_transpose: NULL col/t_row/t_eid");
     count_cols_kernel<<<(n_edges + 255) / 256, 256, 0, st>>>(col, n_edges, cnt);
+    XEQ_LAUNCHED(1);
   }
   int rc = exclusive_scan(cnt, t_rowptr, n_nodes, scratch, st);
   if (rc) return rc;
@@ -457,6 +458,7 @@ int xeq_csr_transpose(const int32_t* rowptr, const int32_t* col, int32_t n_nodes
     XEQ_CUDA(cudaMemsetAsync(cnt, 0, sizeof(int) * (size_t)(n_nodes + 1), st));
     fill_transposed_kernel<<<(n_nodes + 127) / 128, 128, 0, st>>>(rowptr, col, n_nodes, t_rowptr, cnt, t_row, t_eid);
     sort_transposed_rows_kernel<<<(n_nodes + 127) / 128, 128, 0, st>>>(t_rowptr, n_nodes, t_row, t_eid);
+    XEQ_LAUNCHED(2);
   }
   XEQ_LAUNCH_CHECK();
   return XEQ_OK;

@@ -44,6 +44,14 @@ class NeighborGraph:
         _lib.check(lib.xeq_csr_transpose(_lib.ptr(self.rowptr), _lib.ptr(self.col), N, E, _lib.ptr(self.t_rowptr),
                                          _lib.ptr(self.t_row), _lib.ptr(self.t_eid), _lib.ptr(ws), nbytes,
                                          _lib.stream()), "xeq_csr_transpose")
+        # node-aligned work tiles of both structures
+        tc, tn = lib.xeq_center_tile_edges(), lib.xeq_neighbor_tile_edges()
+        self.tile_ptr = torch.empty(E // tc + 2, dtype=torch.int32, device=dev)
+        self.t_tile_ptr = torch.empty(E // tn + 2, dtype=torch.int32, device=dev)
+        _lib.check(lib.xeq_csr_tile_bounds(_lib.ptr(self.rowptr), N, E, tc, _lib.ptr(self.tile_ptr), _lib.stream()),
+                   "xeq_csr_tile_bounds")
+        _lib.check(lib.xeq_csr_tile_bounds(_lib.ptr(self.t_rowptr), N, E, tn, _lib.ptr(self.t_tile_ptr), _lib.stream()),
+                   "xeq_csr_tile_bounds")
 
     @property
     def struct(self) -> _lib.XeqGraph:
@@ -55,6 +63,7 @@ class NeighborGraph:
             g.offsets = self.offsets.data_ptr() if self.offsets is not None else None
             g.cell = self.cell.data_ptr() if self.cell is not None else None
             g.node_graph = self.node_graph.data_ptr() if self.node_graph is not None else None
+            g.tile_ptr, g.t_tile_ptr = self.tile_ptr.data_ptr(), self.t_tile_ptr.data_ptr()
             self._struct = g
         return self._struct
 

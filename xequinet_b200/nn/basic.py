@@ -9,7 +9,7 @@ from typing import Dict, List, Optional
 
 import torch
 
-from .. import keys
+from .. import keys, ops
 from ..graph import NeighborGraph, graph_from_edge_index
 
 
@@ -45,8 +45,9 @@ def compute_edge_data(data: Dict[str, torch.Tensor], compute_forces: bool = True
 def compute_forces_only(energy: torch.Tensor, pos: torch.Tensor, training: bool = True) -> torch.Tensor:
     """nn/basic.py:143-159: the backward pass runs K2b (and records K2bb when training)."""
     grad_outputs: List[Optional[torch.Tensor]] = [torch.ones_like(energy)]
-    pos_grad = torch.autograd.grad(outputs=[energy], inputs=[pos], grad_outputs=grad_outputs, retain_graph=training,
-                                   create_graph=training, allow_unused=True)[0]
+    with ops.param_grads(False):  # only d/dpos is requested here
+        pos_grad = torch.autograd.grad(outputs=[energy], inputs=[pos], grad_outputs=grad_outputs,
+                                       retain_graph=training, create_graph=training, allow_unused=True)[0]
     if pos_grad is None:
         pos_grad = torch.zeros_like(pos)
     return -1.0 * pos_grad

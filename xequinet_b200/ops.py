@@ -52,6 +52,60 @@ def _workspace(nbytes: int, device) -> torch.Tensor:
     return torch.empty(max(int(nbytes), 256), dtype=torch.uint8, device=device)
 
 
+class _ParamGradState:
+    """`ctx.needs_input_grad` is static, so a custom backward cannot see that
+    torch.autograd.grad(E, [pos]) (the force computation, nn/basic.py:150-156) does not ask for
+    parameter gradients.  compute_forces_only() narrows it with this switch so that the
+    force pass runs the cheaper weight-gradient-free K2b instantiation."""
+
+    wanted = True
+
+
+class param_grads:
+    def __init__(self, wanted: bool):
+        self.wanted = wanted
+
+    def __enter__(self):
+        self.prev = _ParamGradState.wanted
+        _ParamGradState.wanted = self.wanted
+
+    def __exit__(self, *exc):
+        _ParamGradState.wanted = self.prev
+
+
+class KernelTimer:
+    """Optional CUDA-event timing of the edge kernels on the launching stream (bench.py's
+    roofline leg).  Disabled by default: no events are recorded on the product path."""
+
+    enabled = False
+    records = []  # (kind, n_nodes, n_edges, start_event, end_event)
+
+    @classmethod
+    def start(cls):
+        if not cls.enabled:
+            return None
+        ev = torch.cuda.Event(enable_timing=True)
+        ev.record()
+        return ev
+
+    @classmethod
+    def stop(cls, ev, kind, graph):
+        if ev is None:
+            return
+        end = torch.cuda.Event(enable_timing=True)
+        end.record()
+        cls.records.append((kind, graph.n_nodes, graph.n_edges, ev, end))
+
+    @classmethod
+    def summary(cls):
+        """{kind: (launches, mean ms, n_nodes, n_edges)} -- call after torch.cuda.synchronize()."""
+        out = {}
+        for kind, n, e, a, b in cls.records:
+            cnt, tot, _, _ = out.get(kind, (0, 0.0, n, e))
+            out[kind] = (cnt + 1, tot + a.elapsed_time(b), n, e)
+        return {k: (c, t / c, n, e) for k, (c, t, n, e) in out.items()}
+
+
 # ------------------------------------------------------------------------------------------
 # raw kernel calls (no autograd)
 # ------------------------------------------------------------------------------------------
@@ -61,9 +115,11 @@ def edge_message_fwd_raw(graph: NeighborGraph, dims: Dims, pos, s, v, x_in, V_in
     x_out = torch.empty((N, dims.node_dim), dtype=torch.float32, device=s.device)
     V_out = torch.empty((N, dims.D), dtype=torch.float32, device=s.device)
     d = dims.struct()
+    ev = KernelTimer.start()
     _lib.check(lib.xeq_edge_message_fwd(graph.struct, d, _lib.ptr(pos), _lib.ptr(s), _lib.ptr(v), _lib.ptr(x_in),
                                         _lib.ptr(V_in), _lib.ptr(W), _lib.ptr(b), _lib.ptr(freq), _lib.ptr(x_out),
                                         _lib.ptr(V_out), _lib.stream()), "xeq_edge_message_fwd")
+    KernelTimer.stop(ev, "edge_fwd", graph)
     return x_out, V_out
 
 
@@ -81,10 +137,12 @@ def edge_message_bwd_raw(graph: NeighborGraph, dims: Dims, pos, s, v, W, b, freq
     d = dims.struct()
     nbytes = lib.xeq_edge_message_bwd_workspace_bytes(graph.struct, d, int(need_w))
     ws = _workspace(nbytes, dev)
+    ev = KernelTimer.start()
     _lib.check(lib.xeq_edge_message_bwd(graph.struct, d, _lib.ptr(pos), _lib.ptr(s), _lib.ptr(v), _lib.ptr(W),
                                         _lib.ptr(b), _lib.ptr(freq), _lib.ptr(gx), _lib.ptr(gV), _lib.ptr(gs),
                                         _lib.ptr(gv), _lib.ptr(gpos), _lib.ptr(gW), _lib.ptr(gb), _lib.ptr(gf),
                                         _lib.ptr(ws), nbytes, _lib.stream()), "xeq_edge_message_bwd")
+    KernelTimer.stop(ev, "edge_bwd_wgrad" if need_w else "edge_bwd", graph)
     return gs, gv, gpos, gW, gb, gf
 
 
@@ -104,11 +162,13 @@ def edge_message_bwdbwd_raw(graph: NeighborGraph, dims: Dims, pos, s, v, W, b, f
     d = dims.struct()
     nbytes = lib.xeq_edge_message_bwdbwd_workspace_bytes(graph.struct, d, int(need_w))
     ws = _workspace(nbytes, dev)
+    ev = KernelTimer.start()
     _lib.check(lib.xeq_edge_message_bwdbwd(graph.struct, d, _lib.ptr(pos), _lib.ptr(s), _lib.ptr(v), _lib.ptr(W),
                                            _lib.ptr(b), _lib.ptr(freq), _lib.ptr(gx), _lib.ptr(gV), _lib.ptr(a_s),
                                            _lib.ptr(a_v), _lib.ptr(a_pos), _lib.ptr(o_gx), _lib.ptr(o_gV), _lib.ptr(o_s),
                                            _lib.ptr(o_v), _lib.ptr(o_pos), _lib.ptr(o_W), _lib.ptr(o_b), _lib.ptr(o_f),
                                            _lib.ptr(ws), nbytes, _lib.stream()), "xeq_edge_message_bwdbwd")
+    KernelTimer.stop(ev, "edge_bwdbwd", graph)
     return o_gx, o_gV, o_s, o_v, o_pos, o_W, o_b, o_f
 
 
@@ -165,7 +225,7 @@ class _EdgeMessage(torch.autograd.Function):
             gx = torch.zeros((s.shape[0], ctx.dims.node_dim), dtype=s.dtype, device=s.device)
         if gV is None:
             gV = torch.zeros((s.shape[0], ctx.dims.D), dtype=s.dtype, device=s.device)
-        need_w = ni[5] or ni[6] or ni[7]
+        need_w = (ni[5] or ni[6] or ni[7]) and _ParamGradState.wanted
         needs = (ni[2], ni[3], ni[4], need_w)
         gs = gv = gpos = gW = gb = gf = None
         if any(needs):
