@@ -110,7 +110,14 @@ int xeq_radius_graph_fill(const float* pos, int32_t n_nodes,
                           int8_t* offsets /* [E,4] out or NULL */,
                           int64_t* edge_index /* [2,E] out or NULL */,
                           float* cell_offsets /* [E,3] out or NULL */,
+                          int32_t edge_capacity /* > 0: capacity mode, see below; 0: outputs sized from rowptr[N] */,
+                          int32_t* overflow /* device flag set to 1 when E > edge_capacity, or NULL */,
                           void* workspace, size_t workspace_bytes, xeq_stream_t stream);
+/* Capacity mode (CUDA-graph replay, MD loops): the caller allocates col/offsets/t_row/t_eid for
+ * `edge_capacity` edges once, passes n_edges = edge_capacity everywhere (xeq_graph_t.n_edges,
+ * xeq_csr_transpose, xeq_csr_tile_bounds) and never reads the edge count back: every kernel takes
+ * the live count from rowptr[N] on the device, tiles past it are empty.  The COO output then uses
+ * row stride `edge_capacity`. */
 
 /* CSR from a caller-supplied COO edge list that is already sorted by center
  * (edge_index[0] non-decreasing): rowptr from segment boundaries, col = int32(edge_index[1]),

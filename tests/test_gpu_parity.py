@@ -293,3 +293,41 @@ def test_param_grads_match_reference(name, use_forces):
     assert checked > 50
     if not use_forces:
         assert well_conditioned  # first-order training gradients are always well conditioned
+
+
+# ---------------------------------------------------------------------------------------
+# capacity mode (CUDA-graph replay / MD loops): same structure, edge count stays on the device
+# ---------------------------------------------------------------------------------------
+@pytest.mark.parametrize("periodic", [False, True])
+def test_static_graph_builder_matches_dynamic(periodic):
+    from xequinet_b200.graph import StaticGraphBuilder
+
+    if periodic:
+        datas = [orc.make_small_pbc(14, 6.5, seed=s, triclinic=True) for s in (3, 4)]
+    else:
+        datas = [orc.make_aspirin_batch(6, seed=s, with_edges=False) for s in (0, 1)]
+    d0 = _dev(datas[0])
+    builder = StaticGraphBuilder(d0["pos"].shape[0], d0["ptr"], 5.0, edge_capacity=4096 if periodic else 3000,
+                                 cell=d0.get("cell"), pbc=d0.get("pbc"))
+    model = _model(orc.CONFIG_DEFAULT, 1234)
+    for data in datas:  # the same builder (and buffers) serves every structure of that shape
+        d = _dev(data)
+        g_dyn, _, _ = build_graph(d["pos"], 5.0, ptr=d["ptr"], batch=d["batch"], cell=d.get("cell"), pbc=d.get("pbc"))
+        g = builder.build(d["pos"])
+        E = g_dyn.n_edges
+        assert int(builder.overflow.item()) == 0 and int(g.rowptr[-1].item()) == E
+        assert torch.equal(g.rowptr, g_dyn.rowptr) and torch.equal(g.col[:E], g_dyn.col[:E])
+        assert torch.equal(g.t_rowptr, g_dyn.t_rowptr) and torch.equal(g.t_eid[:E], g_dyn.t_eid[:E])
+        if periodic:
+            assert torch.equal(g.offsets[:E], g_dyn.offsets[:E])
+        outs = []
+        for graph in (g_dyn, g):
+            dd = {k: v for k, v in d.items() if k not in ("pbc",)}
+            dd[keys.GRAPH] = graph
+            dd["pos"] = d["pos"].clone()
+            outs.append(model(dd, compute_forces=True))
+        assert torch.equal(outs[0]["energy"], outs[1]["energy"]) and torch.equal(outs[0]["forces"], outs[1]["forces"])
+    # overflow is flagged, not silently truncated into garbage
+    small = StaticGraphBuilder(d0["pos"].shape[0], d0["ptr"], 5.0, edge_capacity=64, cell=d0.get("cell"), pbc=d0.get("pbc"))
+    small.build(d0["pos"])
+    assert int(small.overflow.item()) == 1

@@ -35,7 +35,7 @@ _SIGNATURES = {
                                        POINTER(c_int32), c_float, c_void_p, c_void_p, c_size_t, c_void_p]),
     "xeq_radius_graph_fill": (c_int, [c_void_p, c_int32, c_void_p, c_void_p, c_int32, c_void_p, POINTER(c_int32),
                                       POINTER(c_int32), c_float, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
-                                      c_void_p, c_size_t, c_void_p]),
+                                      c_int32, c_void_p, c_void_p, c_size_t, c_void_p]),
     "xeq_csr_from_sorted_coo": (c_int, [c_void_p, c_void_p, c_int32, c_int32, c_void_p, c_void_p, c_void_p, c_void_p]),
     "xeq_csr_transpose_workspace_bytes": (c_size_t, [c_int32, c_int32]),
     "xeq_csr_transpose": (c_int, [c_void_p, c_void_p, c_int32, c_int32, c_void_p, c_void_p, c_void_p, c_void_p,

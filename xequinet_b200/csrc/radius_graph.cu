@@ -186,7 +186,8 @@ __global__ void __launch_bounds__(256) graph_scan_kernel(const float* __restrict
                                                           PbcParams pp, float r, int n, int* __restrict__ deg,
                                                           const int* __restrict__ rowptr, int* __restrict__ col,
                                                           int8_t* __restrict__ offsets, long long* __restrict__ edge_index,
-                                                          float* __restrict__ cell_offsets, long long n_edges) {
+                                                          float* __restrict__ cell_offsets, long long coo_stride,
+                                                          int capacity, int* __restrict__ overflow) {
   const int a = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
   if (a >= n) return;
@@ -225,8 +226,11 @@ __global__ void __launch_bounds__(256) graph_scan_kernel(const float* __restrict
       pass = edge_test<PERIODIC>(pa, pb, c, ox, oy, oz, r, r2, a == b);
     }
     const unsigned m = __ballot_sync(0xffffffffu, pass);
-    if (FILL && pass) {
-      const int e = base + running + __popc(m & ((1u << lane) - 1u));
+    const int e_slot = base + running + __popc(m & ((1u << lane) - 1u));
+    if (FILL && pass && e_slot >= capacity) {
+      if (overflow) *overflow = 1;  // caller-supplied capacity exceeded: edge dropped, flag raised
+    } else if (FILL && pass) {
+      const int e = e_slot;
       col[e] = b;
       int fx = ox, fy = oy, fz = oz;
       if (PERIODIC) {  // refer offsets to the unwrapped positions (data/radius_graph.py:186-190)
@@ -247,7 +251,7 @@ __global__ void __launch_bounds__(256) graph_scan_kernel(const float* __restrict
       }
       if (edge_index) {
         edge_index[e] = a;
-        edge_index[n_edges + e] = b;
+        edge_index[coo_stride + e] = b;
       }
     }
     running += __popc(m);
@@ -276,17 +280,19 @@ __global__ void coo_to_csr_kernel(const long long* __restrict__ ei, const float*
   }
 }
 
-__global__ void count_cols_kernel(const int* __restrict__ col, int n_edges, int* __restrict__ cnt) {
+// n_edges_dev points at rowptr[n_nodes]: the edge count stays on the device (capacity mode)
+__global__ void count_cols_kernel(const int* __restrict__ col, const int* __restrict__ n_edges_dev, int capacity,
+                                  int* __restrict__ cnt) {
   const int e = blockIdx.x * blockDim.x + threadIdx.x;
-  if (e < n_edges) atomicAdd(&cnt[col[e]], 1);
+  if (e < min(*n_edges_dev, capacity)) atomicAdd(&cnt[col[e]], 1);
 }
 
 __global__ void fill_transposed_kernel(const int* __restrict__ rowptr, const int* __restrict__ col, int n_nodes,
-                                       const int* __restrict__ t_rowptr, int* __restrict__ cursor, int* __restrict__ t_row,
-                                       int* __restrict__ t_eid) {
+                                       int capacity, const int* __restrict__ t_rowptr, int* __restrict__ cursor,
+                                       int* __restrict__ t_row, int* __restrict__ t_eid) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n_nodes) return;
-  for (int e = rowptr[i]; e < rowptr[i + 1]; ++e) {
+  for (int e = rowptr[i]; e < min(rowptr[i + 1], capacity); ++e) {
     const int j = col[e];
     const int slot = t_rowptr[j] + atomicAdd(&cursor[j], 1);
     t_row[slot] = i;
@@ -369,10 +375,10 @@ int xeq_radius_graph_count(const float* pos, int32_t n, const int32_t* graph_ptr
     int* shift = cv.take<int>(3 * (size_t)n);
     wrap_positions_kernel<<<(n + 255) / 256, 256, 0, st>>>(pos, node_graph, cell, pp, n, pw, shift);
     graph_scan_kernel<true, false><<<blocks, 256, 0, st>>>(pw, shift, graph_ptr, node_graph, cell, pp, cutoff, n, deg,
-                                                           nullptr, nullptr, nullptr, nullptr, nullptr, 0);
+                                                           nullptr, nullptr, nullptr, nullptr, nullptr, 0, 0, nullptr);
   } else {
     graph_scan_kernel<false, false><<<blocks, 256, 0, st>>>(pos, nullptr, graph_ptr, node_graph, nullptr, pp, cutoff, n,
-                                                            deg, nullptr, nullptr, nullptr, nullptr, nullptr, 0);
+                                                            deg, nullptr, nullptr, nullptr, nullptr, nullptr, 0, 0, nullptr);
   }
   XEQ_LAUNCHED(periodic ? 2 : 1);
   return exclusive_scan(deg, rowptr, n, scratch, st);
@@ -381,7 +387,7 @@ int xeq_radius_graph_count(const float* pos, int32_t n, const int32_t* graph_ptr
 int xeq_radius_graph_fill(const float* pos, int32_t n, const int32_t* graph_ptr, const int32_t* node_graph, int32_t G,
                           const float* cell, const int32_t* pbc_host, const int32_t* rep_host, float cutoff,
                           const int32_t* rowptr, int32_t* col, int8_t* offsets, int64_t* edge_index, float* cell_offsets,
-                          void* ws, size_t ws_bytes, xeq_stream_t stream) {
+                          int32_t edge_capacity, int32_t* overflow, void* ws, size_t ws_bytes, xeq_stream_t stream) {
   cudaStream_t st = (cudaStream_t)stream;
   bool periodic;
   PbcParams pp;
@@ -391,8 +397,9 @@ int xeq_radius_graph_fill(const float* pos, int32_t n, const int32_t* graph_ptr,
   if (n == 0) return XEQ_OK;
   // n_edges is needed for the COO layout; the caller sized the outputs from rowptr[n], re-read it here
   // only when the COO output is requested (tiny D2H; the Python layer already synchronised on it).
-  long long n_edges = 0;
-  if (edge_index) {
+  long long n_edges = edge_capacity;  // COO row stride; capacity mode keeps the edge count on the device
+  const int cap = edge_capacity > 0 ? edge_capacity : 0x7fffffff;
+  if (edge_index && edge_capacity <= 0) {
     int e32 = 0;
     XEQ_CUDA(cudaMemcpyAsync(&e32, rowptr + n, sizeof(int), cudaMemcpyDeviceToHost, st));
     XEQ_CUDA(cudaStreamSynchronize(st));
@@ -408,11 +415,11 @@ int xeq_radius_graph_fill(const float* pos, int32_t n, const int32_t* graph_ptr,
     wrap_positions_kernel<<<(n + 255) / 256, 256, 0, st>>>(pos, node_graph, cell, pp, n, pw, shift);
     graph_scan_kernel<true, true><<<blocks, 256, 0, st>>>(pw, shift, graph_ptr, node_graph, cell, pp, cutoff, n, nullptr,
                                                           rowptr, col, offsets, (long long*)edge_index, cell_offsets,
-                                                          n_edges);
+                                                          n_edges, cap, overflow);
   } else {
     graph_scan_kernel<false, true><<<blocks, 256, 0, st>>>(pos, nullptr, graph_ptr, node_graph, nullptr, pp, cutoff, n,
                                                            nullptr, rowptr, col, nullptr, (long long*)edge_index, nullptr,
-                                                           n_edges);
+                                                           n_edges, cap, overflow);
   }
   XEQ_LAUNCHED(periodic ? 2 : 1);
   return XEQ_OK;
@@ -449,14 +456,15 @@ int xeq_csr_transpose(const int32_t* rowptr, const int32_t* col, int32_t n_nodes
   XEQ_CUDA(cudaMemsetAsync(cnt, 0, sizeof(int) * (size_t)(n_nodes + 1), st));
   if (n_edges > 0) {
     XEQ_CHECK_ARG(col && t_row && t_eid, "csr_transpose: NULL col/t_row/t_eid");
-    count_cols_kernel<<<(n_edges + 255) / 256, 256, 0, st>>>(col, n_edges, cnt);
+    count_cols_kernel<<<(n_edges + 255) / 256, 256, 0, st>>>(col, rowptr + n_nodes, n_edges, cnt);
     XEQ_LAUNCHED(1);
   }
   int rc = exclusive_scan(cnt, t_rowptr, n_nodes, scratch, st);
   if (rc) return rc;
   if (n_edges > 0 && n_nodes > 0) {
     XEQ_CUDA(cudaMemsetAsync(cnt, 0, sizeof(int) * (size_t)(n_nodes + 1), st));
-    fill_transposed_kernel<<<(n_nodes + 127) / 128, 128, 0, st>>>(rowptr, col, n_nodes, t_rowptr, cnt, t_row, t_eid);
+    fill_transposed_kernel<<<(n_nodes + 127) / 128, 128, 0, st>>>(rowptr, col, n_nodes, n_edges, t_rowptr, cnt, t_row,
+                                                                  t_eid);
     sort_transposed_rows_kernel<<<(n_nodes + 127) / 128, 128, 0, st>>>(t_rowptr, n_nodes, t_row, t_eid);
     XEQ_LAUNCHED(2);
   }

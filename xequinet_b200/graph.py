@@ -19,35 +19,41 @@ from . import _lib, keys
 class NeighborGraph:
     """Device-resident CSR (by center) + transposed CSR (by neighbor) of one batch."""
 
-    def __init__(self, n_nodes: int, n_graphs: int, rowptr, col, offsets=None, cell=None, node_graph=None):
+    def __init__(self, n_nodes: int, n_graphs: int, rowptr, col, offsets=None, cell=None, node_graph=None,
+                 capacity: Optional[int] = None):
         self.n_nodes = int(n_nodes)
         self.n_graphs = int(n_graphs)
         self.rowptr = rowptr
         self.col = col
-        self.n_edges = int(col.numel())
+        # capacity mode: n_edges is the allocated capacity, the live count stays in rowptr[N] on the device
+        self.capacity = capacity
+        self.n_edges = int(capacity) if capacity else int(col.numel())
         self.offsets = offsets  # int8 [E,4] or None
         self.cell = cell  # float32 [G,3,3] or None
         self.node_graph = node_graph  # int32 [N] or None
-        self.t_rowptr = self.t_row = self.t_eid = None
         self._struct = None
-        self._transpose()
-
-    def _transpose(self):
         lib = _lib.get()
         dev = self.rowptr.device
         N, E = self.n_nodes, self.n_edges
         self.t_rowptr = torch.empty(N + 1, dtype=torch.int32, device=dev)
         self.t_row = torch.empty(max(E, 1), dtype=torch.int32, device=dev)
         self.t_eid = torch.empty(max(E, 1), dtype=torch.int32, device=dev)
-        nbytes = lib.xeq_csr_transpose_workspace_bytes(N, E)
-        ws = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+        self._t_ws = torch.empty(lib.xeq_csr_transpose_workspace_bytes(N, E), dtype=torch.uint8, device=dev)
+        tc, tn = lib.xeq_center_tile_edges(), lib.xeq_neighbor_tile_edges()
+        self.tile_ptr = torch.empty(E // tc + 2, dtype=torch.int32, device=dev)
+        self.t_tile_ptr = torch.empty(E // tn + 2, dtype=torch.int32, device=dev)
+        self.transpose()
+
+    def transpose(self):
+        """(Re)derive the transposed CSR and the work tiles from rowptr/col; launches only."""
+        lib = _lib.get()
+        N, E = self.n_nodes, self.n_edges
+        ws, nbytes = self._t_ws, self._t_ws.numel()
         _lib.check(lib.xeq_csr_transpose(_lib.ptr(self.rowptr), _lib.ptr(self.col), N, E, _lib.ptr(self.t_rowptr),
                                          _lib.ptr(self.t_row), _lib.ptr(self.t_eid), _lib.ptr(ws), nbytes,
                                          _lib.stream()), "xeq_csr_transpose")
         # node-aligned work tiles of both structures
         tc, tn = lib.xeq_center_tile_edges(), lib.xeq_neighbor_tile_edges()
-        self.tile_ptr = torch.empty(E // tc + 2, dtype=torch.int32, device=dev)
-        self.t_tile_ptr = torch.empty(E // tn + 2, dtype=torch.int32, device=dev)
         _lib.check(lib.xeq_csr_tile_bounds(_lib.ptr(self.rowptr), N, E, tc, _lib.ptr(self.tile_ptr), _lib.stream()),
                    "xeq_csr_tile_bounds")
         _lib.check(lib.xeq_csr_tile_bounds(_lib.ptr(self.t_rowptr), N, E, tn, _lib.ptr(self.t_tile_ptr), _lib.stream()),
@@ -152,11 +158,65 @@ def build_graph(pos: torch.Tensor, cutoff: float, ptr: Optional[torch.Tensor] = 
     _lib.check(lib.xeq_radius_graph_fill(_lib.ptr(pos32), N, _lib.ptr(ptr32), _lib.ptr(node_graph), G,
                                          _lib.ptr(cell32), pbc_arr, rep_arr, float(cutoff), _lib.ptr(rowptr),
                                          _lib.ptr(col), _lib.ptr(offsets), _lib.ptr(ei) if E else None,
-                                         _lib.ptr(co) if (co is not None and E) else None, _lib.ptr(ws), nbytes, st),
+                                         _lib.ptr(co) if (co is not None and E) else None, 0, None, _lib.ptr(ws), nbytes,
+                                         st),
                "xeq_radius_graph_fill")
     g = NeighborGraph(N, G, rowptr, col[:E] if E else col[:0], offsets[:E] if (periodic and E) else (offsets[:0] if periodic else None),
                       cell32, node_graph if (periodic and G > 1) else None)
     return g, ei, co
+
+
+class StaticGraphBuilder:
+    """Capacity-mode K1 for CUDA-graph replay and MD loops: all arrays are allocated once for
+    (n_nodes, n_graphs, edge_capacity); build() only launches kernels (no allocation, no host
+    sync) and always returns the same NeighborGraph, whose live edge count stays on the device.
+    `overflow` (device int32) is raised when a structure has more than `edge_capacity` edges."""
+
+    def __init__(self, n_nodes: int, ptr: torch.Tensor, cutoff: float, edge_capacity: int, cell=None, pbc=None):
+        lib = _lib.get()
+        dev = ptr.device
+        self.cutoff = float(cutoff)
+        self.N = int(n_nodes)
+        self.ptr32 = ptr.to(torch.int32).contiguous()
+        self.G = self.ptr32.numel() - 1
+        self.cap = int(edge_capacity)
+        self.node_graph = (torch.repeat_interleave(torch.arange(self.G, device=dev, dtype=torch.int32),
+                                                   (self.ptr32[1:] - self.ptr32[:-1]).long())
+                           if self.G > 1 else None)
+        self.periodic = cell is not None
+        self.pbc_arr = (ctypes.c_int32 * 3)(0, 0, 0)
+        self.rep_arr = (ctypes.c_int32 * 3)(0, 0, 0)
+        self.cell32 = None
+        if self.periodic:
+            self.cell32 = cell.detach().to(device=dev, dtype=torch.float32).reshape(-1, 3, 3).contiguous()
+            pbc_l = [True, True, True] if pbc is None else [bool(v) for v in torch.as_tensor(pbc).reshape(-1, 3)[0].tolist()]
+            reps = _image_repeats(self.cell32, pbc_l, self.cutoff)  # fixed cell: computed once
+            for k in range(3):
+                self.pbc_arr[k], self.rep_arr[k] = int(pbc_l[k]), reps[k]
+        self.nbytes = lib.xeq_radius_graph_workspace_bytes(self.N, self.G, int(self.periodic))
+        self.ws = torch.empty(self.nbytes, dtype=torch.uint8, device=dev)
+        self.rowptr = torch.zeros(self.N + 1, dtype=torch.int32, device=dev)
+        self.col = torch.zeros(self.cap, dtype=torch.int32, device=dev)
+        self.offsets = torch.zeros((self.cap, 4), dtype=torch.int8, device=dev) if self.periodic else None
+        self.overflow = torch.zeros(1, dtype=torch.int32, device=dev)
+        self.graph = NeighborGraph(self.N, self.G, self.rowptr, self.col, self.offsets, self.cell32,
+                                   self.node_graph if (self.periodic and self.G > 1) else None, capacity=self.cap)
+
+    def build(self, pos: torch.Tensor) -> "NeighborGraph":
+        lib = _lib.get()
+        pos32 = pos.detach()
+        st = _lib.stream()
+        _lib.check(lib.xeq_radius_graph_count(_lib.ptr(pos32), self.N, _lib.ptr(self.ptr32), _lib.ptr(self.node_graph),
+                                              self.G, _lib.ptr(self.cell32), self.pbc_arr, self.rep_arr, self.cutoff,
+                                              _lib.ptr(self.rowptr), _lib.ptr(self.ws), self.nbytes, st),
+                   "xeq_radius_graph_count")
+        _lib.check(lib.xeq_radius_graph_fill(_lib.ptr(pos32), self.N, _lib.ptr(self.ptr32), _lib.ptr(self.node_graph),
+                                             self.G, _lib.ptr(self.cell32), self.pbc_arr, self.rep_arr, self.cutoff,
+                                             _lib.ptr(self.rowptr), _lib.ptr(self.col), _lib.ptr(self.offsets), None, None,
+                                             self.cap, _lib.ptr(self.overflow), _lib.ptr(self.ws), self.nbytes, st),
+                   "xeq_radius_graph_fill")
+        self.graph.transpose()
+        return self.graph
 
 
 def graph_from_edge_index(edge_index: torch.Tensor, n_nodes: int, n_graphs: int = 1,
