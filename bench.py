@@ -399,10 +399,16 @@ def run_gpu(args):
     h2d = sum(host[0][k].numel() * host[0][k].element_size() for k in h2d_keys)
     d2h = 4 if train else energy_host.numel() * 4
 
+    def hard_exit():
+        # NCCL teardown with captured graphs alive can hang; all timed work is done, so leave
+        # without running destructors (rank 0 still has the CPU baseline and the print to do).
+        sys.stdout.flush()
+        sys.stderr.flush()
+        os._exit(0)
+
     if rank != 0:
-        if world > 1:
-            dist.destroy_process_group()
-        return
+        torch.cuda.synchronize()
+        hard_exit()
 
     # roofline of the dominant hand-written kernel (by share of the step)
     peak, peak_src = measured_hbm_peak()
@@ -449,7 +455,7 @@ def run_gpu(args):
     }
     print(json.dumps(line), flush=True)
     if world > 1:
-        dist.destroy_process_group()
+        hard_exit()
 
 
 def run_reference(args):
