@@ -67,6 +67,12 @@ typedef struct {
   const int32_t* node_graph;/* [N]    graph id per node (needed when cell && G > 1)   */
   const int32_t* tile_ptr;  /* [E/Tc+2] node bounds of Tc-edge tiles of the CSR (xeq_csr_tile_bounds, Tc = xeq_center_tile_edges())   */
   const int32_t* t_tile_ptr;/* [E/Tn+2] same for the transposed CSR, Tn = xeq_neighbor_tile_edges()                                */
+  int32_t n_tiles;          /* tiles described by tile_ptr   (entries = n_tiles + 1)                                                */
+  int32_t t_n_tiles;        /* tiles described by t_tile_ptr                                                                       */
+  int32_t tile_mode;        /* 0: edge-block tiles (xeq_csr_tile_bounds).  1: molecule tiles -- tile_ptr = t_tile_ptr = the batch  */
+                            /*    `ptr` array, every neighbor of a tile's nodes lies inside the tile: the kernels then stage the   */
+                            /*    tile's rows in shared memory once instead of gathering them per edge                             */
+  int32_t _pad2;
 } xeq_graph_t;
 
 int xeq_version(void);

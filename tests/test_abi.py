@@ -43,7 +43,7 @@ def test_struct_layout_matches_header():
     from xequinet_b200 import _lib
 
     assert ctypes.sizeof(_lib.XeqDims) == 24
-    assert ctypes.sizeof(_lib.XeqGraph) == 16 + 10 * 8
+    assert ctypes.sizeof(_lib.XeqGraph) == 16 + 10 * 8 + 16
     assert _lib.XeqGraph.rowptr.offset == 16
 
 

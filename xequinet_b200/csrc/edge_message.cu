@@ -123,6 +123,25 @@ __device__ __forceinline__ void lds_row(const float* __restrict__ src, float* ds
   }
 }
 
+// Explicit shared-space accessors for the dynamically sized row window (keeps the addressing in
+// 32-bit shared space; a generic pointer would re-derive the shared window base per access).
+__device__ __forceinline__ void sts_f32(uint32_t addr, float v) {
+  asm volatile("st.shared.f32 [%0], %1;" ::"r"(addr), "f"(v) : "memory");
+}
+__device__ __forceinline__ float lds_f32(uint32_t addr) {
+  float v;
+  asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(addr) : "memory");
+  return v;
+}
+extern __shared__ __align__(16) unsigned char xeq_dyn_smem[];
+
+// Rows a CTA can stage per tile ("window").  With molecule tiles (tile_mode 1) every neighbor of a
+// tile's nodes lies inside the tile's own node range, so the CTA copies those rows to shared memory
+// once (each thread only ever touches its own columns -> no barrier) and the per-edge gathers become
+// shared-memory reads: HBM/L2 traffic drops from E rows to N rows.
+template <int C, bool JVP> struct CenterWin { static constexpr int value = (C == 128) ? 21 : 0; };  // fwd: 2 CTAs/SM
+template <int C> struct NbrWin { static constexpr int value = (C == 128) ? 24 : 0; };
+
 // ------------------------------------------------------------------------------------------
 // shared-memory geometry records and the two geometry stages
 // ------------------------------------------------------------------------------------------
@@ -254,7 +273,7 @@ __device__ __noinline__ void geo_stage_a2(const GeoArgs& A, int cnt, const GeoA<
 // ==========================================================================================
 // center kernel
 // ==========================================================================================
-template <bool JVP> struct CenterChunk { static constexpr int value = JVP ? 48 : CT; };  // 48 KB static smem
+template <bool JVP> struct CenterChunk { static constexpr int value = JVP ? 48 : 32; };  // smem budget (2 CTAs/SM fwd)
 
 template <bool JVP>
 struct CenterSmem {
@@ -326,7 +345,42 @@ __device__ __forceinline__ void center_role(const CenterArgs& A, CenterSmem<JVP>
   };
 
   ChunkCursor<TC> cur_it;
-  cur_it.init(g.rowptr, g.tile_ptr, g.n_edges / CT + 1);
+  cur_it.init(g.rowptr, g.tile_ptr, g.n_tiles);
+  // staged window: [row][column][thread-of-role] floats, role regions side by side
+  constexpr int WMAX = CenterWin<C, JVP>::value;
+  constexpr int NCOL = (L == 0 ? 4 : (L == 1 ? 5 : 7)) * (JVP ? 2 : 1);  // s-columns + v-components (+ tangents)
+  constexpr int ROWF = (C * 4 + M1 * 5 + M2 * 7) * (JVP ? 2 : 1);
+  constexpr int NTHR = (L == 0) ? C : (L == 1 ? M1 : M2);
+  constexpr int ROLE_OFF = (L == 0 ? 0 : (L == 1 ? C * 4 : C * 4 + M1 * 5)) * (JVP ? 2 : 1);
+  const int tt = (L == 0) ? t : (L == 1 ? t - C : t - C - M1);
+  const uint32_t win0 = (uint32_t)__cvta_generic_to_shared(xeq_dyn_smem) + 4u * (ROLE_OFF + tt);
+  bool staged = false;
+  int win_lo = 0;
+  auto stage_window = [&](int n0, int n1) {
+#pragma unroll 2
+    for (int j = n0; j < n1; ++j) {
+      const uint32_t a = win0 + 4u * (uint32_t)((j - n0) * ROWF);
+      const float* sj = A.s + (size_t)j * H;
+      const float* vj = A.v + (size_t)j * D + vbase;
+      float vals[NCOL];
+      int c = 0;
+      vals[c++] = sj[q];
+      vals[c++] = sj[M + q];
+      if (L == 0) vals[c++] = sj[2 * M + q];
+#pragma unroll
+      for (int m = 0; m < NC; ++m) vals[c++] = vj[m * vstride];
+      if (JVP) {
+        const float* aj = A.a_s ? A.a_s + (size_t)j * H : nullptr;
+        vals[c++] = aj ? aj[q] : 0.f;
+        vals[c++] = aj ? aj[M + q] : 0.f;
+        if (L == 0) vals[c++] = aj ? aj[2 * M + q] : 0.f;
+#pragma unroll
+        for (int m = 0; m < NC; ++m) vals[c++] = A.a_v ? A.a_v[(size_t)j * D + vbase + m * vstride] : 0.f;
+      }
+#pragma unroll
+      for (int k = 0; k < NCOL; ++k) sts_f32(a + 4u * (uint32_t)(k * NTHR), vals[k]);
+    }
+  };
   float base_x = 0.f, base_V[NC];
 #pragma unroll
   for (int m = 0; m < NC; ++m) base_V[m] = 0.f;
@@ -352,7 +406,12 @@ __device__ __forceinline__ void center_role(const CenterArgs& A, CenterSmem<JVP>
     const GeoA<TC, false, JVP>& sa = sm.a[c % 3];
     const GeoB<TC, JVP, false, false, false>& sb = sm.b[c & 1];
     const int cnt = d0.cnt;
-    if (d0.first) cur = -1;
+    if (d0.first) {
+      cur = -1;
+      staged = WMAX > 0 && g.tile_mode == 1 && (d0.n1 - d0.n0) <= WMAX;
+      win_lo = d0.n0;
+      if (staged) stage_window(d0.n0, d0.n1);
+    }
     auto fetch_base = [&](int node) {
 #pragma unroll
       for (int m = 0; m < NC; ++m) base_V[m] = A.V_in ? A.V_in[(size_t)node * D + vbase + m * vstride] : 0.f;
@@ -363,8 +422,7 @@ __device__ __forceinline__ void center_role(const CenterArgs& A, CenterSmem<JVP>
       for (int m = 0; m < NC; ++m) A.V_out[(size_t)node * D + vbase + m * vstride] = base_V[m] + th.accV[m];
       if (L == 0) A.x_out[(size_t)node * C + t] = base_x + th.accx;
     };
-    auto body = [&](int ee, const Gathered& gc, Gathered& gn) {
-      if (ee + 2 < cnt) gather(sa, ee + 2, gn);
+    auto body = [&](int ee, const Gathered& gc) {
       const int i = sa.own[ee];
       if (i != cur) {
         if (cur >= 0) emit_acc(cur);
@@ -391,13 +449,41 @@ __device__ __forceinline__ void center_role(const CenterArgs& A, CenterSmem<JVP>
                gc.sdx, gc.vd);
       }
     };
-    Gathered g0, g1, g2;
-    if (cnt > 0) gather(sa, 0, g0);
-    if (cnt > 1) gather(sa, 1, g1);
-    for (int ee = 0; ee < cnt; ee += 3) {
-      body(ee, g0, g2);
-      if (ee + 1 < cnt) body(ee + 1, g1, g0);
-      if (ee + 2 < cnt) body(ee + 2, g2, g1);
+    if (staged) {  // neighbor rows come from the shared-memory window
+      for (int ee = 0; ee < cnt; ++ee) {
+        const uint32_t a = win0 + 4u * (uint32_t)((sa.gat[ee] - win_lo) * ROWF);
+        Gathered gc;
+        int c = 0;
+        gc.ss = lds_f32(a + 4u * (uint32_t)(NTHR * c++));
+        gc.se = lds_f32(a + 4u * (uint32_t)(NTHR * c++));
+        gc.sx = (L == 0) ? lds_f32(a + 4u * (uint32_t)(NTHR * c++)) : 0.f;
+#pragma unroll
+        for (int m = 0; m < NC; ++m) gc.v[m] = lds_f32(a + 4u * (uint32_t)(NTHR * c++));
+        if (JVP) {
+          gc.sds = lds_f32(a + 4u * (uint32_t)(NTHR * c++));
+          gc.sde = lds_f32(a + 4u * (uint32_t)(NTHR * c++));
+          gc.sdx = (L == 0) ? lds_f32(a + 4u * (uint32_t)(NTHR * c++)) : 0.f;
+#pragma unroll
+          for (int m = 0; m < NC; ++m) gc.vd[m] = lds_f32(a + 4u * (uint32_t)(NTHR * c++));
+        }
+        body(ee, gc);
+      }
+    } else {  // direct gathers from L2/HBM, prefetched two edges ahead (modulo-3 register renaming)
+      Gathered g0, g1, g2;
+      if (cnt > 0) gather(sa, 0, g0);
+      if (cnt > 1) gather(sa, 1, g1);
+      for (int ee = 0; ee < cnt; ee += 3) {
+        if (ee + 2 < cnt) gather(sa, ee + 2, g2);
+        body(ee, g0);
+        if (ee + 1 < cnt) {
+          if (ee + 3 < cnt) gather(sa, ee + 3, g0);
+          body(ee + 1, g1);
+        }
+        if (ee + 2 < cnt) {
+          if (ee + 4 < cnt) gather(sa, ee + 4, g1);
+          body(ee + 2, g2);
+        }
+      }
     }
     if (d0.last) {
       if (cur >= 0) emit_acc(cur);
@@ -411,7 +497,7 @@ __device__ __forceinline__ void center_role(const CenterArgs& A, CenterSmem<JVP>
 }
 
 template <int C, int M1, int M2, bool JVP>
-__global__ void __launch_bounds__(C + M1 + M2) center_kernel(const CenterArgs A) {
+__global__ void __launch_bounds__(C + M1 + M2, (C == 128 && !JVP) ? 2 : 1) center_kernel(const CenterArgs A) {
   __shared__ CenterSmem<JVP> sm;
   const int t = threadIdx.x;
   if (t < C) center_role<0, C, M1, M2, JVP>(A, sm);
@@ -510,7 +596,28 @@ __device__ __forceinline__ void nbr_main_role(const NeighborArgs& A, NbrMainSmem
   };
 
   ChunkCursor<TC> cur_it;
-  cur_it.init(g.t_rowptr, g.t_tile_ptr, E / NT + 1);  // tiles are NT-edge, chunks TC-edge
+  cur_it.init(g.t_rowptr, g.t_tile_ptr, g.t_n_tiles);
+  constexpr int WMAX = NbrWin<C>::value;
+  constexpr int NCOL = (L == 0) ? 2 : (L == 1 ? 3 : 5);  // gV components (+ gx for l = 0)
+  constexpr int ROWF = C * 2 + M1 * 3 + M2 * 5;
+  constexpr int NTHR = (L == 0) ? C : (L == 1 ? M1 : M2);
+  constexpr int ROLE_OFF = (L == 0) ? 0 : (L == 1 ? C * 2 : C * 2 + M1 * 3);
+  const int tt = (L == 0) ? t : (L == 1 ? t - C : t - C - M1);
+  const uint32_t win0 = (uint32_t)__cvta_generic_to_shared(xeq_dyn_smem) + 4u * (ROLE_OFF + tt);
+  bool staged = false;
+  int win_lo = 0;
+  auto stage_window = [&](int n0, int n1) {
+#pragma unroll 4
+    for (int i = n0; i < n1; ++i) {
+      const uint32_t a = win0 + 4u * (uint32_t)((i - n0) * ROWF);
+      float vals[NCOL];
+#pragma unroll
+      for (int m = 0; m < NC; ++m) vals[m] = A.gV[(size_t)i * D + vbase + m * vstride];
+      if (L == 0) vals[NC] = A.gx[(size_t)i * C + q];
+#pragma unroll
+      for (int k = 0; k < NCOL; ++k) sts_f32(a + 4u * (uint32_t)(k * NTHR), vals[k]);
+    }
+  };
   ChunkDesc d0 = cur_it.next(), d1 = cur_it.next(), d2, dprev;
   dprev.cnt = -1;
   if (d0.cnt >= 0) geo_stage_a1<TC, true, true, SECOND>(A.geo, d0, sm.a[0]);
@@ -538,10 +645,14 @@ __device__ __forceinline__ void nbr_main_role(const NeighborArgs& A, NbrMainSmem
       const GeoA<TC, true, SECOND>& sa = sm.a[c % 3];
       const GeoB<TC, true, SECOND, false, false>& sb = sm.b[c & 1];
       const int cnt = d0.cnt, rs = c & 1;
-      if (d0.first) cur = -1;
+      if (d0.first) {
+        cur = -1;
+        staged = WMAX > 0 && g.tile_mode == 1 && (d0.n1 - d0.n0) <= WMAX;
+        win_lo = d0.n0;
+        if (staged) stage_window(d0.n0, d0.n1);
+      }
       if (t < cnt) sm.red_eid[rs][t] = sa.eid[t];
-      auto body = [&](int ee, const Gathered& gc, Gathered& gn) {
-        if (ee + 2 < cnt) gather(sa, ee + 2, gn);
+      auto body = [&](int ee, const Gathered& gc) {
         const int j = sa.own[ee];
         if (j != cur) {
           if (cur >= 0) emit(cur, true);
@@ -580,13 +691,25 @@ __device__ __forceinline__ void nbr_main_role(const NeighborArgs& A, NbrMainSmem
           sm.red[rs][ee][warp][0] = pr[0]; sm.red[rs][ee][warp][1] = pr[1]; sm.red[rs][ee][warp][2] = pr[2];
         }
       };
-      Gathered g0, g1, g2;
-      if (cnt > 0) gather(sa, 0, g0);
-      if (cnt > 1) gather(sa, 1, g1);
-      for (int ee = 0; ee < cnt; ++ee) {  // (a modulo-3 unrolled variant tripled the code and ran 2x slower)
-        body(ee, g0, g2);
-        g0 = g1;
-        g1 = g2;
+      if (staged) {
+        for (int ee = 0; ee < cnt; ++ee) {
+          const uint32_t a = win0 + 4u * (uint32_t)((sa.gat[ee] - win_lo) * ROWF);
+          Gathered gc;
+#pragma unroll
+          for (int m = 0; m < NC; ++m) gc.g[m] = lds_f32(a + 4u * (uint32_t)(NTHR * m));
+          gc.gx = (L == 0) ? lds_f32(a + 4u * (uint32_t)(NTHR * NC)) : 0.f;
+          body(ee, gc);
+        }
+      } else {
+        Gathered g0, g1, g2;
+        if (cnt > 0) gather(sa, 0, g0);
+        if (cnt > 1) gather(sa, 1, g1);
+        for (int ee = 0; ee < cnt; ++ee) {  // (a modulo-3 unrolled variant tripled the code and ran 2x slower)
+          if (ee + 2 < cnt) gather(sa, ee + 2, g2);
+          body(ee, g0);
+          g0 = g1;
+          g1 = g2;
+        }
       }
       if (d0.last) {
         if (cur >= 0) emit(cur, true);
@@ -601,7 +724,7 @@ __device__ __forceinline__ void nbr_main_role(const NeighborArgs& A, NbrMainSmem
 }
 
 template <int C, int M1, int M2, int ORDER>
-__global__ void __launch_bounds__(C + M1 + M2) nbr_main_kernel(const NeighborArgs A) {
+__global__ void __launch_bounds__(C + M1 + M2, (C == 128 && ORDER == 1) ? 2 : 1) nbr_main_kernel(const NeighborArgs A) {
   __shared__ NbrMainSmem<ORDER, (C + M1 + M2) / 32> sm;
   const int t = threadIdx.x;
   if (t < C) nbr_main_role<0, C, M1, M2, ORDER>(A, sm);
@@ -648,7 +771,7 @@ __device__ __forceinline__ void nbr_wgrad_role(const NeighborArgs& A, NbrWgradSm
   };
 
   ChunkCursor<NT> cur_it;
-  cur_it.init(g.t_rowptr, g.t_tile_ptr, g.n_edges / NT + 1);
+  cur_it.init(g.t_rowptr, g.t_tile_ptr, g.t_n_tiles);
   ChunkDesc d0 = cur_it.next(), d1 = cur_it.next(), d2;
   if (d0.cnt >= 0) geo_stage_a1<NT, true, false, SECOND>(A.geo, d0, sm.a[0]);
   __syncthreads();
@@ -802,7 +925,8 @@ static int check_dims(const xeq_dims_t* d, int* cfg) {
 static int check_graph(const xeq_graph_t* g, bool need_t) {
   XEQ_CHECK_ARG(g && g->rowptr && g->n_nodes >= 0 && g->n_edges >= 0, "graph: bad arguments");
   XEQ_CHECK_ARG(g->n_edges == 0 || g->col, "graph: col is NULL");
-  XEQ_CHECK_ARG(g->tile_ptr, "graph: tile_ptr missing (xeq_csr_tile_bounds)");
+  XEQ_CHECK_ARG(g->tile_ptr && g->n_tiles >= 1, "graph: tile_ptr missing (xeq_csr_tile_bounds)");
+  XEQ_CHECK_ARG(!need_t || g->t_n_tiles >= 1, "graph: t_n_tiles missing");
   XEQ_CHECK_ARG(!need_t || (g->t_rowptr && g->t_tile_ptr && (g->n_edges == 0 || (g->t_row && g->t_eid))),
                 "graph: transposed CSR missing");
   XEQ_CHECK_ARG((g->offsets == nullptr) == (g->cell == nullptr), "graph: offsets and cell must be given together");
@@ -820,10 +944,18 @@ static int set_smem(Kernel k, size_t bytes) {
 
 template <int C, int M1, int M2, bool JVP>
 static int launch_center(const CenterArgs& A, cudaStream_t st) {
-  const int n_tiles = A.geo.g.n_edges / CT + 1;
-  const int grid = min(n_tiles, num_sms() * (C == 128 ? 2 : 1));
+  const int n_tiles = A.geo.g.n_tiles;
   static_assert(sizeof(CenterSmem<JVP>) <= 48 * 1024, "static shared memory limit");
-  center_kernel<C, M1, M2, JVP><<<grid, C + M1 + M2, 0, st>>>(A);
+  const bool window = CenterWin<C, JVP>::value > 0 && A.geo.g.tile_mode == 1;
+  const size_t dyn = window ? (size_t)CenterWin<C, JVP>::value * (C * 4 + M1 * 5 + M2 * 7) * (JVP ? 2 : 1) * 4 : 0;
+  static bool attr_set = false;
+  if (dyn && !attr_set) {
+    int rc = set_smem(center_kernel<C, M1, M2, JVP>, dyn);
+    if (rc) return rc;
+    attr_set = true;
+  }
+  const int grid = min(n_tiles, num_sms() * ((C == 128 && (!window || !JVP)) ? 2 : 1));
+  center_kernel<C, M1, M2, JVP><<<grid, C + M1 + M2, dyn, st>>>(A);
   XEQ_LAUNCHED(1);
   return XEQ_OK;
 }
@@ -841,7 +973,7 @@ static int run_center(const xeq_graph_t* g, const xeq_dims_t* dims, CenterArgs& 
   return jvp ? launch_center<256, 128, 64, true>(A, st) : launch_center<256, 128, 64, false>(A, st);
 }
 
-static int wgrad_grid_x(const xeq_graph_t* g) { return min(g->n_edges / NT + 1, num_sms() * 2); }
+static int wgrad_grid_x(const xeq_graph_t* g) { return min(g->t_n_tiles, num_sms() * 2); }
 
 static size_t neighbor_ws_bytes(const xeq_graph_t* g, const xeq_dims_t* d, int want_wgrad) {
   const int H = dims_H(d);
@@ -858,10 +990,18 @@ static int launch_neighbor(NeighborArgs& A, bool main, bool wgrad, int gx, cudaS
   constexpr int M = C + M1 + M2, H = C + 2 * M;
   static_assert(H % WTHREADS == 0, "channel slices must tile H");
   if (main) {
-    const int n_tiles = A.geo.g.n_edges / NT + 1;
-    const int grid = min(n_tiles, num_sms() * ((C == 128 && ORDER == 1) ? 2 : 1));
+    const int n_tiles = A.geo.g.t_n_tiles;
     static_assert(sizeof(NbrMainSmem<ORDER, M / 32>) <= 48 * 1024, "static shared memory limit");
-    nbr_main_kernel<C, M1, M2, ORDER><<<grid, M, 0, st>>>(A);
+    const bool window = NbrWin<C>::value > 0 && A.geo.g.tile_mode == 1;
+    const size_t dyn = window ? (size_t)NbrWin<C>::value * (C * 2 + M1 * 3 + M2 * 5) * 4 : 0;
+    static bool attr_set = false;
+    if (dyn && !attr_set) {
+      int rc = set_smem(nbr_main_kernel<C, M1, M2, ORDER>, dyn);
+      if (rc) return rc;
+      attr_set = true;
+    }
+    const int grid = min(n_tiles, num_sms() * ((C == 128 && ORDER == 1) ? 2 : 1));
+    nbr_main_kernel<C, M1, M2, ORDER><<<grid, M, dyn, st>>>(A);
     XEQ_LAUNCHED(1);
   }
   if (wgrad) {

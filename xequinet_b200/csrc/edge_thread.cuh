@@ -15,12 +15,20 @@ namespace xeq {
 
 template <int L> struct YOff { static constexpr int value = (L == 1) ? 0 : 3; };  // offset into Y[8]
 
+// NK-term dot product as three interleaved partial sums: the dependent-FMA chain is a third as
+// long, which is what bounds a lightly occupied SM (few warps, 4-cycle FMA latency).
 template <int NK, typename T>
 XEQ_HD T dot_nk(const T* __restrict__ w, const T* __restrict__ p) {
-  T acc = T(0);
+  T a0 = T(0), a1 = T(0), a2 = T(0);
 #pragma unroll
-  for (int k = 0; k < NK; ++k) acc += w[k] * p[k];
-  return acc;
+  for (int k = 0; k + 2 < NK; k += 3) {
+    a0 += w[k] * p[k];
+    a1 += w[k + 1] * p[k + 1];
+    a2 += w[k + 2] * p[k + 2];
+  }
+#pragma unroll
+  for (int k = NK - NK % 3; k < NK; ++k) a0 += w[k] * p[k];
+  return (a0 + a1) + a2;
 }
 
 // ------------------------------------------------------------------------------------------

@@ -19,8 +19,10 @@ from . import _lib, keys
 class NeighborGraph:
     """Device-resident CSR (by center) + transposed CSR (by neighbor) of one batch."""
 
+    MOLECULE_TILE_MAX_NODES = 64  # graphs up to this size become one work tile each (staged rows)
+
     def __init__(self, n_nodes: int, n_graphs: int, rowptr, col, offsets=None, cell=None, node_graph=None,
-                 capacity: Optional[int] = None):
+                 capacity: Optional[int] = None, mol_ptr: Optional[torch.Tensor] = None):
         self.n_nodes = int(n_nodes)
         self.n_graphs = int(n_graphs)
         self.rowptr = rowptr
@@ -40,8 +42,17 @@ class NeighborGraph:
         self.t_eid = torch.empty(max(E, 1), dtype=torch.int32, device=dev)
         self._t_ws = torch.empty(lib.xeq_csr_transpose_workspace_bytes(N, E), dtype=torch.uint8, device=dev)
         tc, tn = lib.xeq_center_tile_edges(), lib.xeq_neighbor_tile_edges()
-        self.tile_ptr = torch.empty(E // tc + 2, dtype=torch.int32, device=dev)
-        self.t_tile_ptr = torch.empty(E // tn + 2, dtype=torch.int32, device=dev)
+        # work tiles: one per molecule when the caller vouches that every graph is small (mol_ptr = the
+        # batch `ptr` array, int32), else node-aligned blocks of tc / tn edges
+        self.mol_ptr = mol_ptr
+        if mol_ptr is not None:
+            self.tile_ptr = self.t_tile_ptr = mol_ptr
+            self.n_tiles = self.t_n_tiles = int(mol_ptr.numel()) - 1
+            self.tile_mode = 1
+        else:
+            self.tile_ptr = torch.empty(E // tc + 2, dtype=torch.int32, device=dev)
+            self.t_tile_ptr = torch.empty(E // tn + 2, dtype=torch.int32, device=dev)
+            self.n_tiles, self.t_n_tiles, self.tile_mode = E // tc + 1, E // tn + 1, 0
         self.transpose()
 
     def transpose(self):
@@ -52,6 +63,8 @@ class NeighborGraph:
         _lib.check(lib.xeq_csr_transpose(_lib.ptr(self.rowptr), _lib.ptr(self.col), N, E, _lib.ptr(self.t_rowptr),
                                          _lib.ptr(self.t_row), _lib.ptr(self.t_eid), _lib.ptr(ws), nbytes,
                                          _lib.stream()), "xeq_csr_transpose")
+        if self.tile_mode == 1:
+            return
         # node-aligned work tiles of both structures
         tc, tn = lib.xeq_center_tile_edges(), lib.xeq_neighbor_tile_edges()
         _lib.check(lib.xeq_csr_tile_bounds(_lib.ptr(self.rowptr), N, E, tc, _lib.ptr(self.tile_ptr), _lib.stream()),
@@ -70,6 +83,7 @@ class NeighborGraph:
             g.cell = self.cell.data_ptr() if self.cell is not None else None
             g.node_graph = self.node_graph.data_ptr() if self.node_graph is not None else None
             g.tile_ptr, g.t_tile_ptr = self.tile_ptr.data_ptr(), self.t_tile_ptr.data_ptr()
+            g.n_tiles, g.t_n_tiles, g.tile_mode = self.n_tiles, self.t_n_tiles, self.tile_mode
             self._struct = g
         return self._struct
 
@@ -150,7 +164,9 @@ def build_graph(pos: torch.Tensor, cutoff: float, ptr: Optional[torch.Tensor] = 
     _lib.check(lib.xeq_radius_graph_count(_lib.ptr(pos32), N, _lib.ptr(ptr32), _lib.ptr(node_graph), G,
                                           _lib.ptr(cell32), pbc_arr, rep_arr, float(cutoff), _lib.ptr(rowptr),
                                           _lib.ptr(ws), nbytes, st), "xeq_radius_graph_count")
-    E = int(rowptr[-1].item())  # the one host sync of the neighbour search: sizes the edge arrays
+    sizes = (ptr32[1:] - ptr32[:-1]).max() if N else ptr32[0]
+    E, max_nodes = torch.stack([rowptr[-1], sizes]).tolist()  # the one host sync: sizes the edge arrays
+    mol_ptr = ptr32 if (0 < max_nodes <= NeighborGraph.MOLECULE_TILE_MAX_NODES) else None
     col = torch.empty(max(E, 1), dtype=torch.int32, device=dev)
     offsets = torch.empty((max(E, 1), 4), dtype=torch.int8, device=dev) if periodic else None
     ei = torch.empty((2, E), dtype=torch.int64, device=dev) if want_coo else None
@@ -162,7 +178,7 @@ def build_graph(pos: torch.Tensor, cutoff: float, ptr: Optional[torch.Tensor] = 
                                          st),
                "xeq_radius_graph_fill")
     g = NeighborGraph(N, G, rowptr, col[:E] if E else col[:0], offsets[:E] if (periodic and E) else (offsets[:0] if periodic else None),
-                      cell32, node_graph if (periodic and G > 1) else None)
+                      cell32, node_graph if (periodic and G > 1) else None, mol_ptr=mol_ptr)
     return g, ei, co
 
 
@@ -199,8 +215,11 @@ class StaticGraphBuilder:
         self.col = torch.zeros(self.cap, dtype=torch.int32, device=dev)
         self.offsets = torch.zeros((self.cap, 4), dtype=torch.int8, device=dev) if self.periodic else None
         self.overflow = torch.zeros(1, dtype=torch.int32, device=dev)
+        max_nodes = int((self.ptr32[1:] - self.ptr32[:-1]).max().item()) if self.N else 0
+        mol_ptr = self.ptr32 if (0 < max_nodes <= NeighborGraph.MOLECULE_TILE_MAX_NODES) else None
         self.graph = NeighborGraph(self.N, self.G, self.rowptr, self.col, self.offsets, self.cell32,
-                                   self.node_graph if (self.periodic and self.G > 1) else None, capacity=self.cap)
+                                   self.node_graph if (self.periodic and self.G > 1) else None, capacity=self.cap,
+                                   mol_ptr=mol_ptr)
 
     def build(self, pos: torch.Tensor) -> "NeighborGraph":
         lib = _lib.get()
@@ -221,7 +240,7 @@ class StaticGraphBuilder:
 
 def graph_from_edge_index(edge_index: torch.Tensor, n_nodes: int, n_graphs: int = 1,
                           cell_offsets: Optional[torch.Tensor] = None, cell: Optional[torch.Tensor] = None,
-                          batch: Optional[torch.Tensor] = None) -> NeighborGraph:
+                          batch: Optional[torch.Tensor] = None, ptr: Optional[torch.Tensor] = None) -> NeighborGraph:
     """CSR structure for a caller-supplied COO edge list (any order; nn/basic.py:67 takes
     `edge_index` from the data dict).  Unsorted lists are first put in canonical order."""
     lib = _lib.get()
@@ -252,7 +271,13 @@ def graph_from_edge_index(edge_index: torch.Tensor, n_nodes: int, n_graphs: int 
         if batch is None:
             raise ValueError("batch is required for multi-graph periodic input")
         node_graph = batch.to(device=dev, dtype=torch.int32).contiguous()
-    g = NeighborGraph(n_nodes, n_graphs, rowptr, col[:E], offsets[:E] if periodic else None, cell32, node_graph)
+    mol_ptr = None
+    if ptr is not None and n_nodes > 0:
+        ptr32 = ptr.to(device=dev, dtype=torch.int32).contiguous()
+        if int((ptr32[1:] - ptr32[:-1]).max().item()) <= NeighborGraph.MOLECULE_TILE_MAX_NODES:
+            mol_ptr = ptr32
+    g = NeighborGraph(n_nodes, n_graphs, rowptr, col[:E], offsets[:E] if periodic else None, cell32, node_graph,
+                      mol_ptr=mol_ptr)
     g.sorted_edge_index = ei
     return g
 

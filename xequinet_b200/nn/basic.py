@@ -35,6 +35,7 @@ def compute_edge_data(data: Dict[str, torch.Tensor], compute_forces: bool = True
             cell_offsets=data.get(keys.CELL_OFFSETS) if has_cell else None,
             cell=data[keys.CELL] if has_cell else None,
             batch=data[keys.BATCH],
+            ptr=data[keys.BATCH_PTR],
         )
         data[keys.GRAPH] = graph
     if compute_forces:
