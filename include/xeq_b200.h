@@ -209,6 +209,98 @@ int xeq_segment_sum(const float* src, const int32_t* seg_ptr /* [G+1] */, int32_
 int xeq_layout_convert(const float* src, float* dst, int32_t n_nodes, const xeq_dims_t* dims,
                        int direction, xeq_stream_t stream);
 
+/* ------------------------------------------------------------------------------------
+ * K3  node-side dense contractions on tcgen05 tensor cores (3xTF32 split, fp32 accumulate in
+ * TMEM; fp32-level accuracy).  One launch evaluates a GROUP of independent problems
+ *     C = act( alpha * op(A) op(B) + bias )        op(A): [m,k]   op(B): [k,n]   C: [m,n]
+ * Storage: a_trans = 0 -> A is [m,k] row-major (lda), 1 -> A is [k,m] row-major;
+ *          b_trans = 0 -> B is [k,n] row-major (ldb), 1 -> B is [n,k] row-major (the
+ *          nn.Linear weight form).  bias [n] or NULL; act 0 = none, 1 = SiLU.
+ * Replaces: nn.Linear in scalar_mlp / update_mlp / dot_lin / embedding / out_mlp
+ * (nn/xpainn.py:44-47,111-115,190,195-199; nn/output.py:107-111), the per-l blocks of
+ * e3nn o3.Linear update_U / update_V (nn/xpainn.py:186-187,211-212: one problem per (l, m)
+ * on the cm layout, alpha = 1/sqrt(mul_l)), and the grad-input / grad-weight products of
+ * their first and second derivatives (grad-weight: a_trans = 1, b_trans = 0, k = N nodes,
+ * split_k > 1: partials in the workspace are reduced in fixed order => deterministic).
+ * Consecutive problems that name the same output (c, m, n, ldc) ACCUMULATE into it (the 2l+1
+ * component blocks of one o3.Linear weight block): their partial slabs and the split-K slabs go
+ * through the workspace and one fixed-order reduction kernel.
+ * Constraints: pointers 16-byte aligned, leading dimensions % 4 == 0, the contiguous
+ * extent of each operand % 4 == 0; <= 20 problems per launch; act needs split_k == 1
+ * and no shared outputs.
+ * ---------------------------------------------------------------------------------- */
+typedef struct {
+  const float* a;
+  const float* b;
+  const float* bias;
+  float* c;
+  int32_t m, n, k;
+  int32_t lda, ldb, ldc;
+  int32_t a_trans, b_trans;
+  float alpha;
+  int32_t act;
+} xeq_gemm_t;
+
+size_t xeq_gemm_workspace_bytes(const xeq_gemm_t* problems_host, int32_t n_problems, int32_t split_k);
+int xeq_gemm_tf32x3(const xeq_gemm_t* problems_host, int32_t n_problems, int32_t split_k,
+                    void* workspace, size_t workspace_bytes, xeq_stream_t stream);
+
+/* ------------------------------------------------------------------------------------
+ * Node-side normalisations, fused, with first and second derivatives.
+ * EquivariantLayerNorm (nn/o3layer.py:145-171, called at nn/xpainn.py:131,209) on the cm layout and
+ * nn.LayerNorm(node_dim) (nn/xpainn.py:123,130,201,208), which is the same map for irreps "Cx0e"
+ * (mul1 = mul2 = 0):
+ *     z = x with the mul0 scalars centred;  rho = rsqrt(sum z^2 / (mul0+mul1+mul2) + eps)
+ *     y_i = gamma[irrep(i)] z_i rho + (i < mul0 ? beta[i] : 0)
+ * bwd:    g = dL/dy  ->  gx [N,D]; ggamma [M], gbeta [mul0] (either NULL = skipped)
+ * bwdbwd: cotangent a of gx -> dx = d<a,gx>/dx, dg = d<a,gx>/dg, dgamma [M]  (outputs may be NULL)
+ * One warp per row; parameter gradients via per-CTA partial rows in the workspace and a fixed-order
+ * reduction (deterministic).  Row widths D in {32,64,128,256,288,480,960}; mul* multiples of 32.
+ * ---------------------------------------------------------------------------------- */
+size_t xeq_irreps_norm_workspace_bytes(int32_t n_rows, int32_t mul0, int32_t mul1, int32_t mul2);
+int xeq_irreps_norm_fwd(const float* x, const float* gamma, const float* beta, int32_t n_rows,
+                        int32_t mul0, int32_t mul1, int32_t mul2, float eps, float* y, xeq_stream_t stream);
+int xeq_irreps_norm_bwd(const float* x, const float* gamma, const float* g, int32_t n_rows,
+                        int32_t mul0, int32_t mul1, int32_t mul2, float eps,
+                        float* gx, float* ggamma, float* gbeta,
+                        void* workspace, size_t workspace_bytes, xeq_stream_t stream);
+int xeq_irreps_norm_bwdbwd(const float* x, const float* gamma, const float* g, const float* a, int32_t n_rows,
+                           int32_t mul0, int32_t mul1, int32_t mul2, float eps,
+                           float* dx, float* dg, float* dgamma,
+                           void* workspace, size_t workspace_bytes, xeq_stream_t stream);
+
+/* ------------------------------------------------------------------------------------
+ * Node-side per-irrep maps of XPainnUpdate.forward (nn/xpainn.py:206-231) on the cm layout and the
+ * SiLU of the MLPs, fused, each with first (bwd) and second (bwdbwd) derivatives.
+ *   invariant_dot : nrm[n,q] = sqrt(sum_m W^2 + 1e-10) - 1e-5   (Invariant, nn/o3layer.py:40-44)
+ *                   t0[n,q]  = sum_m U W                         (EquivariantDot, nn/o3layer.py:104-109)
+ *                   nrm has row stride ld_nrm (>= M) so it can land inside the [N, C+M] MLP input.
+ *   gate_residual : x' = x + a_sv*t + a_ss ;  V'[(q,m)] = V[(q,m)] + a_vv[q] U[(q,m)]
+ *                   with a = [a_vv (M) | a_sv (C) | a_ss (C)] (nn/xpainn.py:218-229), C = mul0.
+ *                   bwd returns d/da, d/dU, d/dt (d/dx = gx, d/dV = gV are the identity).
+ *   silu          : y = u * sigmoid(u)  (nn/basic.py:255-256)
+ * bwdbwd takes cotangents of the bwd outputs and returns the derivatives with respect to the
+ * bwd inputs.  NULL input gradients are treated as zero, NULL outputs are skipped where noted.
+ * ---------------------------------------------------------------------------------- */
+int xeq_invariant_dot_fwd(const float* U, const float* W, int32_t n, int32_t mul0, int32_t mul1, int32_t mul2,
+                          float* nrm, int32_t ld_nrm, float* t0, xeq_stream_t stream);
+int xeq_invariant_dot_bwd(const float* U, const float* W, const float* gn, int32_t ld_gn, const float* gt, int32_t n,
+                          int32_t mul0, int32_t mul1, int32_t mul2, float* gU, float* gW, xeq_stream_t stream);
+int xeq_invariant_dot_bwdbwd(const float* U, const float* W, const float* gn, int32_t ld_gn, const float* gt,
+                             const float* aU, const float* aW, int32_t n, int32_t mul0, int32_t mul1, int32_t mul2,
+                             float* d_gn, float* d_gt, float* dU, float* dW, xeq_stream_t stream);
+int xeq_gate_residual_fwd(const float* a, const float* U, const float* t, const float* x, const float* V, int32_t n,
+                          int32_t mul0, int32_t mul1, int32_t mul2, float* x_out, float* V_out, xeq_stream_t stream);
+int xeq_gate_residual_bwd(const float* a, const float* U, const float* t, const float* gx, const float* gV, int32_t n,
+                          int32_t mul0, int32_t mul1, int32_t mul2, float* ga, float* gU, float* gt, xeq_stream_t stream);
+int xeq_gate_residual_bwdbwd(const float* a, const float* U, const float* t, const float* gx, const float* gV,
+                             const float* c_a, const float* c_U, const float* c_t, int32_t n,
+                             int32_t mul0, int32_t mul1, int32_t mul2,
+                             float* d_gx, float* d_gV, float* d_a, float* d_U, float* d_t, xeq_stream_t stream);
+int xeq_silu_fwd(const float* u, size_t n, float* y, xeq_stream_t stream);
+int xeq_silu_bwd(const float* u, const float* g, size_t n, float* gu, xeq_stream_t stream);
+int xeq_silu_bwdbwd(const float* u, const float* g, const float* c, size_t n, float* dg, float* du, xeq_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -51,34 +51,62 @@ def test_defaults_and_unsupported_options():
         xb.resolve_model("xpainn", rbf_kernel="gaussian")
 
 
+@pytest.mark.gpu
 def test_cm_blocks_match_oracle():
-    cfg = orc.XPaiNNConfig(node_dim=16, muls=(16, 8, 4))
+    """EquivariantLayerNorm / Invariant / gate expansion on the cm layout (fused kernels) vs the oracle."""
+    cfg = orc.XPaiNNConfig(node_dim=32, muls=(32, 32, 32))
     g = torch.Generator().manual_seed(0)
-    N = 7
+    N = 70
     V = torch.randn(N, cfg.D, generator=g, dtype=torch.float64)  # e3nn layout
-    Vc = orc.to_cm(V, cfg)
-    gam, bet = torch.randn(cfg.M, generator=g, dtype=torch.float64), torch.randn(16, generator=g, dtype=torch.float64)
-    ln = EquivariantLayerNorm(cfg.muls).double()
-    ln.affine_weight.data, ln.affine_bias.data = gam, bet
-    torch.testing.assert_close(orc.from_cm(ln(Vc), cfg), orc.equivariant_layer_norm(V, gam, bet, cfg))
-    torch.testing.assert_close(Invariant(cfg.muls)(Vc), orc.invariant(V, cfg))
-    lin = O3Linear(cfg.muls).double()
-    lin.bias.data = torch.randn(16, generator=g, dtype=torch.float64)
-    torch.testing.assert_close(orc.from_cm(lin(Vc), cfg), orc.o3_linear(V, lin.weight, lin.bias, cfg))
+    Vc = orc.to_cm(V, cfg).float().cuda()
+    gam, bet = torch.randn(cfg.M, generator=g, dtype=torch.float64), torch.randn(32, generator=g, dtype=torch.float64)
+    ln = EquivariantLayerNorm(cfg.muls)
+    ln.affine_weight.data, ln.affine_bias.data = gam.float(), bet.float()
+    ln = ln.cuda()
+    back = lambda t: orc.from_cm(t.detach().cpu().double(), cfg)
+    torch.testing.assert_close(back(ln(Vc)), orc.equivariant_layer_norm(V, gam, bet, cfg), rtol=1e-5, atol=1e-5)
+    torch.testing.assert_close(Invariant(cfg.muls)(Vc).cpu().double(), orc.invariant(V, cfg), rtol=1e-5, atol=1e-5)
     gate = torch.randn(N, cfg.M, generator=g, dtype=torch.float64)
-    torch.testing.assert_close(orc.from_cm(cm.expand_gate(gate, cfg.muls) * Vc, cfg), orc.expand_gate(gate, cfg) * V)
+    torch.testing.assert_close(orc.from_cm(cm.expand_gate(gate, cfg.muls) * Vc.cpu().double(), cfg), orc.expand_gate(gate, cfg) * V)
 
 
+def test_dense_blocks_have_no_cpu_path():
+    """The dense contractions (K3) run on the tcgen05 kernels only: host tensors must raise."""
+    lin = O3Linear((16, 8, 4))
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        lin(torch.randn(3, 16 + 24 + 20))
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        EquivariantLayerNorm((32, 32, 32))(torch.randn(3, 32 * 9))
+    from xequinet_b200.nn.layers import Linear
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        Linear(8, 8)(torch.randn(3, 8))
+
+
+@pytest.mark.gpu
+def test_o3_linear_matches_oracle():
+    cfg = orc.XPaiNNConfig(node_dim=32, muls=(32, 32, 32))
+    g = torch.Generator().manual_seed(0)
+    V = torch.randn(300, cfg.D, generator=g, dtype=torch.float64)  # e3nn layout
+    lin = O3Linear(cfg.muls)
+    lin.bias.data = torch.randn(32, generator=g)
+    ref = orc.o3_linear(V, lin.weight.double(), lin.bias.double(), cfg)
+    out = lin.cuda()(orc.to_cm(V, cfg).float().cuda())
+    torch.testing.assert_close(orc.from_cm(out.cpu().double(), cfg), ref, rtol=0, atol=2e-5)
+
+
+@pytest.mark.gpu
 def test_update_block_matches_oracle_layer():
-    """XPainnUpdate (cm layout, CPU-runnable: no E-sized work) against the oracle's update math."""
+    """XPainnUpdate (cm layout, tcgen05 GEMMs) against the oracle's update math in fp64."""
     cfg = orc.XPaiNNConfig(node_dim=32, muls=(32, 32, 32), action_blocks=1)
     sd = orc.synthetic_state_dict(cfg, 7, torch.float64)
-    upd = XPainnUpdate(node_dim=32, node_irreps=cfg.irreps_str).double()
-    upd.load_state_dict({k[len("mods.update_0."):]: v for k, v in sd.items() if k.startswith("mods.update_0.")}, strict=False)
+    upd = XPainnUpdate(node_dim=32, node_irreps=cfg.irreps_str)
+    upd.load_state_dict({k[len("mods.update_0."):]: v.float() for k, v in sd.items() if k.startswith("mods.update_0.")}, strict=False)
+    upd = upd.cuda()
     g = torch.Generator().manual_seed(1)
     x = torch.randn(5, 32, generator=g, dtype=torch.float64)
     V = torch.randn(5, cfg.D, generator=g, dtype=torch.float64)
-    out = upd({keys.NODE_INVARIANT: x, keys.NODE_EQUIVARIANT: orc.to_cm(V, cfg)})
+    out = upd({keys.NODE_INVARIANT: x.float().cuda(), keys.NODE_EQUIVARIANT: orc.to_cm(V, cfg).float().cuda()})
+    out = {k: v.detach().cpu().double() for k, v in out.items()}
     import torch.nn.functional as F
     p = "mods.update_0."
     xn = F.layer_norm(x, (32,), sd[p + "norm.weight"], sd[p + "norm.bias"], 1e-5)
@@ -90,5 +118,5 @@ def test_update_block_matches_oracle_layer():
     M, C = cfg.M, 32
     x_ref = x + a[:, M:M + C] * F.linear(orc.irrep_dot(U, W, cfg), sd[p + "dot_lin.weight"]) + a[:, M + C:]
     V_ref = V + U * orc.expand_gate(a[:, :M], cfg)
-    torch.testing.assert_close(out[keys.NODE_INVARIANT], x_ref)
-    torch.testing.assert_close(orc.from_cm(out[keys.NODE_EQUIVARIANT], cfg), V_ref)
+    torch.testing.assert_close(out[keys.NODE_INVARIANT], x_ref, rtol=1e-5, atol=2e-5)
+    torch.testing.assert_close(orc.from_cm(out[keys.NODE_EQUIVARIANT], cfg), V_ref, rtol=1e-5, atol=2e-5)

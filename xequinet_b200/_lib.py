@@ -26,6 +26,12 @@ class XeqGraph(ctypes.Structure):
                 ("n_tiles", c_int32), ("t_n_tiles", c_int32), ("tile_mode", c_int32), ("_pad2", c_int32)]
 
 
+class XeqGemm(ctypes.Structure):
+    _fields_ = [("a", c_void_p), ("b", c_void_p), ("bias", c_void_p), ("c", c_void_p),
+                ("m", c_int32), ("n", c_int32), ("k", c_int32), ("lda", c_int32), ("ldb", c_int32), ("ldc", c_int32),
+                ("a_trans", c_int32), ("b_trans", c_int32), ("alpha", c_float), ("act", c_int32)]
+
+
 _SIGNATURES = {
     "xeq_version": (c_int, []),
     "xeq_last_error": (c_char_p, []),
@@ -50,6 +56,21 @@ _SIGNATURES = {
     "xeq_edge_message_bwdbwd_workspace_bytes": (c_size_t, [POINTER(XeqGraph), POINTER(XeqDims), c_int]),
     "xeq_edge_message_bwdbwd": (c_int, [POINTER(XeqGraph), POINTER(XeqDims)] + [c_void_p] * 19 + [c_void_p, c_size_t, c_void_p]),
     "xeq_segment_sum": (c_int, [c_void_p, c_void_p, c_int32, c_void_p, c_void_p]),
+    "xeq_gemm_workspace_bytes": (c_size_t, [POINTER(XeqGemm), c_int32, c_int32]),
+    "xeq_gemm_tf32x3": (c_int, [POINTER(XeqGemm), c_int32, c_int32, c_void_p, c_size_t, c_void_p]),
+    "xeq_irreps_norm_workspace_bytes": (c_size_t, [c_int32] * 4),
+    "xeq_irreps_norm_fwd": (c_int, [c_void_p] * 3 + [c_int32] * 4 + [c_float, c_void_p, c_void_p]),
+    "xeq_irreps_norm_bwd": (c_int, [c_void_p] * 3 + [c_int32] * 4 + [c_float] + [c_void_p] * 3 + [c_void_p, c_size_t, c_void_p]),
+    "xeq_irreps_norm_bwdbwd": (c_int, [c_void_p] * 4 + [c_int32] * 4 + [c_float] + [c_void_p] * 3 + [c_void_p, c_size_t, c_void_p]),
+    "xeq_invariant_dot_fwd": (c_int, [c_void_p] * 2 + [c_int32] * 4 + [c_void_p, c_int32, c_void_p, c_void_p]),
+    "xeq_invariant_dot_bwd": (c_int, [c_void_p] * 3 + [c_int32, c_void_p] + [c_int32] * 4 + [c_void_p] * 3),
+    "xeq_invariant_dot_bwdbwd": (c_int, [c_void_p] * 3 + [c_int32] + [c_void_p] * 3 + [c_int32] * 4 + [c_void_p] * 5),
+    "xeq_gate_residual_fwd": (c_int, [c_void_p] * 5 + [c_int32] * 4 + [c_void_p] * 3),
+    "xeq_gate_residual_bwd": (c_int, [c_void_p] * 5 + [c_int32] * 4 + [c_void_p] * 4),
+    "xeq_gate_residual_bwdbwd": (c_int, [c_void_p] * 8 + [c_int32] * 4 + [c_void_p] * 6),
+    "xeq_silu_fwd": (c_int, [c_void_p, c_size_t, c_void_p, c_void_p]),
+    "xeq_silu_bwd": (c_int, [c_void_p, c_void_p, c_size_t, c_void_p, c_void_p]),
+    "xeq_silu_bwdbwd": (c_int, [c_void_p, c_void_p, c_void_p, c_size_t, c_void_p, c_void_p, c_void_p]),
     "xeq_layout_convert": (c_int, [c_void_p, c_void_p, c_int32, POINTER(XeqDims), c_int, c_void_p]),
 }
 

@@ -15,19 +15,46 @@ import torch
 import torch.nn as nn
 import torch.nn.functional as F
 
+from .. import gemm, nodeops
 from . import cm
 from .irreps import irreps_dim, num_irreps
 
 _DATA = Path(__file__).resolve().parent.parent / "data"
 
 
+class SiLU(nn.SiLU):
+    """SiLU as one fused kernel per derivative order (csrc/node_update.cu)."""
+
+    def forward(self, x: torch.Tensor) -> torch.Tensor:
+        return nodeops.silu(x)
+
+
+class LayerNorm(nn.LayerNorm):
+    """nn.LayerNorm(C) (same parameters) on the fused irreps-norm kernel: it is the "Cx0e" case of
+    EquivariantLayerNorm (csrc/node_norm.cu)."""
+
+    def forward(self, x: torch.Tensor) -> torch.Tensor:
+        return nodeops.layer_norm(x, self.weight, self.bias, self.eps)
+
+
 def resolve_activation(activation: str) -> nn.Module:
     """xequinet/nn/basic.py:241-262; only SiLU is on the XPaiNN path (basic.py:255-256)."""
-    table = {"silu": nn.SiLU, "relu": nn.ReLU, "leakyrelu": nn.LeakyReLU, "softplus": nn.Softplus,
+    table = {"silu": SiLU, "relu": nn.ReLU, "leakyrelu": nn.LeakyReLU, "softplus": nn.Softplus,
              "sigmoid": nn.Sigmoid, "tanh": nn.Tanh, "identity": nn.Identity}
     if activation.lower() not in table:
         raise NotImplementedError(f"Unsupported activation function {activation}")
     return table[activation.lower()]()
+
+
+class Linear(nn.Linear):
+    """nn.Linear (same parameters / state_dict names) evaluated by the tcgen05 GEMM kernel (K3,
+    csrc/node_gemm.cu) together with all of its derivatives.  Widths that are not multiples of 4
+    (only the 64 -> 1 energy read-out, nn/output.py:107-111) stay a torch op."""
+
+    def forward(self, x: torch.Tensor) -> torch.Tensor:
+        if self.in_features % 4 or self.out_features % 4 or x.dim() != 2:
+            return F.linear(x, self.weight, self.bias)
+        return gemm.linear(x, self.weight, self.bias)
 
 
 class _E3nnBuffers(nn.Module):
@@ -92,8 +119,9 @@ class Invariant(_TPHolder):
         self.muls, self.squared, self.eps = tuple(muls), squared, eps
 
     def forward(self, x: torch.Tensor) -> torch.Tensor:
-        q = cm.irrep_dot(x, x, self.muls)
-        return q if self.squared else torch.sqrt(q + self.eps**2) - self.eps
+        if self.squared:
+            return nodeops.invariant_dot(x, x, self.muls)[1]
+        return nodeops.invariant_dot(x, x, self.muls)[0]
 
 
 class EquivariantDot(_TPHolder):
@@ -102,7 +130,7 @@ class EquivariantDot(_TPHolder):
         self.muls = tuple(muls)
 
     def forward(self, a: torch.Tensor, b: torch.Tensor) -> torch.Tensor:
-        return cm.irrep_dot(a, b, self.muls)
+        return nodeops.invariant_dot(a, b, self.muls)[1]
 
 
 class EquivariantLayerNorm(nn.Module):
@@ -128,13 +156,7 @@ class EquivariantLayerNorm(nn.Module):
 
     def forward(self, V: torch.Tensor) -> torch.Tensor:
         assert V.shape[-1] == self.dim, "Input tensor must have the same last dimension as the irreps"
-        m0 = self.num_scalar
-        scal = V[:, :m0]
-        z = torch.cat([scal - scal.mean(dim=1, keepdim=True), V[:, m0:]], dim=1)
-        q = cm.irrep_dot(z, z, self.muls)
-        rho = torch.reciprocal(torch.sqrt(q.mean(dim=1, keepdim=True) + self.eps))
-        out = z * rho * cm.expand_gate(self.affine_weight.unsqueeze(0), self.muls)
-        return torch.cat([out[:, :m0] + self.affine_bias.unsqueeze(0), out[:, m0:]], dim=1)
+        return nodeops.irreps_norm(V, self.affine_weight, self.affine_bias, self.muls, self.eps)
 
 
 class O3Linear(nn.Module):
@@ -155,10 +177,5 @@ class O3Linear(nn.Module):
                 w[m0 * m0 + m1 * m1 :].view(m2, m2))
 
     def forward(self, V: torch.Tensor) -> torch.Tensor:
-        m0, m1, m2 = self.muls
-        W0, W1, W2 = self.blocks()
-        v0, v1, v2 = cm.split(V, self.muls)
-        o0 = torch.addmm(self.bias, v0, W0, alpha=1.0 / math.sqrt(m0)) if self.bias.numel() else (v0 @ W0) / math.sqrt(m0)
-        o1 = torch.matmul(v1, W1) * (1.0 / math.sqrt(m1)) if m1 else v1
-        o2 = torch.matmul(v2, W2) * (1.0 / math.sqrt(m2)) if m2 else v2
-        return cm.join(o0, o1, o2)
+        # one grouped tcgen05 launch: a problem per (l, m) block of the cm layout
+        return gemm.irreps_linear(V, self.weight, self.bias if self.bias.numel() else None, self.muls)

@@ -7,7 +7,7 @@ import torch
 import torch.nn as nn
 
 from .. import keys, ops
-from .layers import resolve_activation
+from .layers import Linear, resolve_activation
 
 
 class OutputModule(nn.Module):
@@ -19,10 +19,10 @@ class EnergyOut(OutputModule):
                  node_scale: float = 1.0, **kwargs) -> None:
         super().__init__()
         self.node_dim, self.hidden_dim = node_dim, hidden_dim
-        final_linear = nn.Linear(self.hidden_dim, 1)
+        final_linear = Linear(self.hidden_dim, 1)
         final_linear.weight.data *= node_scale  # nn/output.py:104-106: baked in at construction
         nn.init.constant_(final_linear.bias, node_shift)
-        self.out_mlp = nn.Sequential(nn.Linear(self.node_dim, self.hidden_dim), resolve_activation(activation),
+        self.out_mlp = nn.Sequential(Linear(self.node_dim, self.hidden_dim), resolve_activation(activation),
                                      final_linear)
         self.extra_properties = [keys.TOTAL_ENERGY, keys.ATOMIC_ENERGIES]
 

@@ -9,10 +9,10 @@ from typing import Dict, Iterable
 import torch
 import torch.nn as nn
 
-from .. import keys, ops
+from .. import keys, nodeops, ops
 from . import cm
 from .irreps import irreps_dim, num_irreps, parse_irreps
-from .layers import (CosineCutoff, EquivariantDot, EquivariantLayerNorm, Int2c1eEmbedding, Invariant, O3Linear,
+from .layers import (CosineCutoff, LayerNorm, Linear, EquivariantDot, EquivariantLayerNorm, Int2c1eEmbedding, Invariant, O3Linear,
                      SphericalBesselj0, _E3nnBuffers, resolve_activation)
 
 
@@ -28,7 +28,7 @@ class XEmbedding(nn.Module):
             self.embedding = nn.Embedding(100, self.node_dim, padding_idx=0)
         else:
             int2c1e = Int2c1eEmbedding(embed_basis, aux_basis)
-            self.embedding = nn.Sequential(int2c1e, nn.Linear(int2c1e.embed_dim, self.node_dim))
+            self.embedding = nn.Sequential(int2c1e, Linear(int2c1e.embed_dim, self.node_dim))
             nn.init.zeros_(self.embedding[1].bias)
         if rbf_kernel != "bessel" or cutoff_fn != "cosine":
             raise NotImplementedError("the B200 edge kernel implements the bessel basis with the cosine cutoff "
@@ -58,13 +58,13 @@ class XPainnMessage(nn.Module):
         self.hidden_dim = self.node_dim + self.node_num_irreps * 2
         self.num_basis = num_basis
         self.scalar_mlp = nn.Sequential(
-            nn.Linear(self.node_dim, self.node_dim),
+            Linear(self.node_dim, self.node_dim),
             resolve_activation(activation),
-            nn.Linear(self.node_dim, self.hidden_dim),
+            Linear(self.node_dim, self.hidden_dim),
         )
-        self.rbf_lin = nn.Linear(self.num_basis, self.hidden_dim, bias=True)
+        self.rbf_lin = Linear(self.num_basis, self.hidden_dim, bias=True)
         self.rsh_conv = _E3nnBuffers(irreps_dim(self.muls))
-        self.norm = nn.LayerNorm(self.node_dim) if layer_norm else nn.Identity()
+        self.norm = LayerNorm(self.node_dim) if layer_norm else nn.Identity()
         self.o3norm = EquivariantLayerNorm(self.muls) if layer_norm else nn.Identity()
         self._dims = None
 
@@ -94,14 +94,14 @@ class XPainnUpdate(nn.Module):
         self.update_V = O3Linear(self.muls, biases=True)
         self.invariant = Invariant(self.muls)
         self.equidot = EquivariantDot(self.muls)
-        self.dot_lin = nn.Linear(self.node_num_irreps, self.node_dim, bias=False)
+        self.dot_lin = Linear(self.node_num_irreps, self.node_dim, bias=False)
         self.rsh_conv = _E3nnBuffers(irreps_dim(self.muls))
         self.update_mlp = nn.Sequential(
-            nn.Linear(self.node_dim + self.node_num_irreps, self.node_dim),
+            Linear(self.node_dim + self.node_num_irreps, self.node_dim),
             resolve_activation(activation),
-            nn.Linear(self.node_dim, self.hidden_dim),
+            Linear(self.node_dim, self.hidden_dim),
         )
-        self.norm = nn.LayerNorm(self.node_dim) if layer_norm else nn.Identity()
+        self.norm = LayerNorm(self.node_dim) if layer_norm else nn.Identity()
         self.o3norm = EquivariantLayerNorm(self.muls) if layer_norm else nn.Identity()
 
     def forward(self, data: Dict[str, torch.Tensor]) -> Dict[str, torch.Tensor]:
@@ -111,11 +111,9 @@ class XPainnUpdate(nn.Module):
         vn = self.o3norm(V)
         U = self.update_U(vn)
         W = self.update_V(vn)
-        n = self.invariant(W)
-        a = self.update_mlp(torch.cat([xn, n], dim=-1))
-        a_vv, a_sv, a_ss = a[:, :M], a[:, M : M + C], a[:, M + C :]
-        dV = U * cm.expand_gate(a_vv, self.muls)
-        t = self.dot_lin(self.equidot(U, W))
-        data[keys.NODE_INVARIANT] = x + (a_sv * t + a_ss)
-        data[keys.NODE_EQUIVARIANT] = V + dV
+        n, t0 = nodeops.invariant_dot(U, W, self.muls)  # Invariant(W), EquivariantDot(U, W): one kernel
+        a = self.update_mlp(torch.cat([xn, n], dim=-1))  # [a_vv | a_sv | a_ss]
+        t = self.dot_lin(t0)
+        # x + a_sv * t + a_ss ,  V + expand(a_vv) * U : one kernel
+        data[keys.NODE_INVARIANT], data[keys.NODE_EQUIVARIANT] = nodeops.gate_residual(a, U, t, x, V, self.muls)
         return data
