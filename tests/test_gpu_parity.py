@@ -68,6 +68,23 @@ def test_radius_graph_pbc_water_golden():
     assert np.array_equal(co.cpu().numpy().astype(np.int8), z["cell_offsets"])
 
 
+@pytest.mark.parametrize("shear", [0.0, 0.35])
+def test_radius_graph_cell_list_matches_oracle(shear):
+    """Large fully periodic box -> the cell-list path of K1 (csrc/radius_graph.cu); bit-exact against the
+    restated reference search (data/radius_graph.py:35-192), cubic and triclinic cells, unwrapped input."""
+    d = orc.make_water_box(8, seed=3)  # 1536 atoms
+    cell = d["cell"].clone()
+    if shear:
+        cell[0, 1, 0] = shear * cell[0, 0, 0]
+        cell[0, 2, 1] = -0.5 * shear * cell[0, 1, 1]
+    n = torch.tensor([d["pos"].shape[0]])
+    ei_ref, co_ref = orc.radius_graph_pbc(d["pos"], n, d["pbc"], cell, 5.0)
+    ei_ref, co_ref = orc.canonical_sort(ei_ref, co_ref)
+    ei, co = xb.radius_graph_pbc(d["pos"].to(DEV), n.to(DEV), d["pbc"].to(DEV), cell.to(DEV), 5.0)
+    assert torch.equal(ei.cpu(), ei_ref)
+    assert torch.equal(co.cpu(), co_ref)
+
+
 def test_graph_from_unsorted_edge_index():
     d = orc.make_molecule_batch(5, (4, 12), seed=9)
     ei = d["edge_index"]

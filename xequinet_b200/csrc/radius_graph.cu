@@ -260,6 +260,183 @@ __global__ void __launch_bounds__(256) graph_scan_kernel(const float* __restrict
 }
 
 // ------------------------------------------------------------------------------------------
+// cell list for one large fully periodic graph (the MD-style box of BASELINE.json configs[4]):
+// atoms are binned on the fractional axes into nb_x * nb_y * nb_z cells whose perpendicular width is
+// >= r (so with image repeat 1 every pair within r lies in the 27 adjacent cells, the wrap of the
+// cell index giving the image offset); one warp per center atom scans those cells with the SAME
+// distance arithmetic as the brute-force scan, and a per-row rank sort restores the canonical
+// (neighbor, ox, oy, oz) order => bit-identical output, O(N) instead of O(27 N^2) candidates.
+// ------------------------------------------------------------------------------------------
+struct CellGrid {  // lives in the workspace (device side only: no host round trip)
+  int nb[3];
+  int total;
+  float inv[9];
+};
+
+__global__ void cell_setup_kernel(const float* __restrict__ cell, float r, int max_bins, CellGrid* __restrict__ grid) {
+  if (threadIdx.x != 0 || blockIdx.x != 0) return;
+  const float* c = cell;
+  float inv[9];
+  inv3x3(c, inv);
+  const float a[3][3] = {{c[0], c[1], c[2]}, {c[3], c[4], c[5]}, {c[6], c[7], c[8]}};
+  const float vol = fabsf(a[0][0] * (a[1][1] * a[2][2] - a[1][2] * a[2][1]) - a[0][1] * (a[1][0] * a[2][2] - a[1][2] * a[2][0]) +
+                          a[0][2] * (a[1][0] * a[2][1] - a[1][1] * a[2][0]));
+  int nb[3];
+  for (int x = 0; x < 3; ++x) {
+    const float* u = a[(x + 1) % 3];
+    const float* v = a[(x + 2) % 3];
+    const float cx = u[1] * v[2] - u[2] * v[1], cy = u[2] * v[0] - u[0] * v[2], cz = u[0] * v[1] - u[1] * v[0];
+    const float width = vol / sqrtf(cx * cx + cy * cy + cz * cz);  // perpendicular width of the cell along axis x
+    nb[x] = max(1, (int)floorf(width / r * 0.999f));               // a hair wider than r: rounding safety
+  }
+  while ((long long)nb[0] * nb[1] * nb[2] > max_bins) {
+    int big = 0;
+    if (nb[1] > nb[big]) big = 1;
+    if (nb[2] > nb[big]) big = 2;
+    nb[big] -= 1;
+  }
+  grid->nb[0] = nb[0]; grid->nb[1] = nb[1]; grid->nb[2] = nb[2];
+  grid->total = nb[0] * nb[1] * nb[2];
+  for (int k = 0; k < 9; ++k) grid->inv[k] = inv[k];
+}
+
+__device__ __forceinline__ void bin_coords(const float* __restrict__ pw, int a, const CellGrid& G, int* b) {
+  const float p[3] = {pw[3 * a], pw[3 * a + 1], pw[3 * a + 2]};
+#pragma unroll
+  for (int x = 0; x < 3; ++x) {
+    float f = p[0] * G.inv[x] + p[1] * G.inv[3 + x] + p[2] * G.inv[6 + x];
+    f -= floorf(f);
+    b[x] = min(G.nb[x] - 1, max(0, (int)(f * (float)G.nb[x])));
+  }
+}
+
+__global__ void bin_count_kernel(const float* __restrict__ pw, int n, const CellGrid* __restrict__ grid, int* __restrict__ cnt,
+                                 int* __restrict__ atom_bin) {
+  const int a = blockIdx.x * blockDim.x + threadIdx.x;
+  if (a >= n) return;
+  const CellGrid G = *grid;
+  int b[3];
+  bin_coords(pw, a, G, b);
+  const int id = (b[0] * G.nb[1] + b[1]) * G.nb[2] + b[2];
+  atom_bin[a] = id;
+  atomicAdd(&cnt[id], 1);
+}
+
+__global__ void bin_fill_kernel(const int* __restrict__ atom_bin, int n, const int* __restrict__ bin_start, int* __restrict__ cursor,
+                                int* __restrict__ bin_atoms) {
+  const int a = blockIdx.x * blockDim.x + threadIdx.x;
+  if (a >= n) return;
+  const int id = atom_bin[a];
+  bin_atoms[bin_start[id] + atomicAdd(&cursor[id], 1)] = a;
+}
+
+// FILL = false: deg[a] = number of edges.  FILL = true: keys (b * 27 + image code) into keys[rowptr[a] ...],
+// in cell-traversal order (made canonical by row_sort_decode_kernel).
+template <bool FILL>
+__global__ void __launch_bounds__(256) cell_scan_kernel(const float* __restrict__ pw, const float* __restrict__ cell, float r, int n,
+                                                         const CellGrid* __restrict__ grid, const int* __restrict__ atom_bin,
+                                                         const int* __restrict__ bin_start, const int* __restrict__ bin_atoms,
+                                                         int* __restrict__ deg, const int* __restrict__ rowptr,
+                                                         int* __restrict__ keys, int capacity, int* __restrict__ overflow) {
+  const int a = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (a >= n) return;
+  const CellGrid G = *grid;
+  float c[9];
+#pragma unroll
+  for (int k = 0; k < 9; ++k) c[k] = cell[k];
+  const float r2 = __fmul_rn(r, r);
+  const float pa[3] = {pw[3 * a], pw[3 * a + 1], pw[3 * a + 2]};
+  const int id = atom_bin[a];
+  const int bz = id % G.nb[2], by = (id / G.nb[2]) % G.nb[1], bx = id / (G.nb[2] * G.nb[1]);
+  int running = 0;
+  const int base = FILL ? rowptr[a] : 0;
+  for (int dd = 0; dd < 27; ++dd) {
+    const int dx = dd / 9 - 1, dy = (dd / 3) % 3 - 1, dz = dd % 3 - 1;
+    int cx = bx + dx, cy = by + dy, cz = bz + dz, ox = 0, oy = 0, oz = 0;
+    if (cx < 0) { cx += G.nb[0]; ox = -1; } else if (cx >= G.nb[0]) { cx -= G.nb[0]; ox = 1; }
+    if (cy < 0) { cy += G.nb[1]; oy = -1; } else if (cy >= G.nb[1]) { cy -= G.nb[1]; oy = 1; }
+    if (cz < 0) { cz += G.nb[2]; oz = -1; } else if (cz >= G.nb[2]) { cz -= G.nb[2]; oz = 1; }
+    const int cid = (cx * G.nb[1] + cy) * G.nb[2] + cz;
+    const int s0 = bin_start[cid], s1 = bin_start[cid + 1];
+    for (int it = s0; it < s1; it += 32) {
+      const int sl = it + lane;
+      bool pass = false;
+      int b = 0;
+      if (sl < s1) {
+        b = bin_atoms[sl];
+        const float pb[3] = {pw[3 * b], pw[3 * b + 1], pw[3 * b + 2]};
+        pass = edge_test<true>(pa, pb, c, ox, oy, oz, r, r2, a == b);
+      }
+      const unsigned m = __ballot_sync(0xffffffffu, pass);
+      if (FILL && pass) {
+        const int e = base + running + __popc(m & ((1u << lane) - 1u));
+        if (e >= capacity) {
+          if (overflow) *overflow = 1;
+        } else {
+          keys[e] = b * 27 + (ox + 1) * 9 + (oy + 1) * 3 + (oz + 1);
+        }
+      }
+      running += __popc(m);
+    }
+  }
+  if (!FILL && lane == 0) deg[a] = running;
+}
+
+// one warp per row: rank sort of the (unique) keys, then decode into the output arrays
+constexpr int ROW_SORT_MAX = 192;
+__global__ void __launch_bounds__(256) row_sort_decode_kernel(const int* __restrict__ rowptr, int n, const int* __restrict__ shift,
+                                                               int capacity, int* __restrict__ col, int8_t* __restrict__ offsets,
+                                                               long long* __restrict__ edge_index, float* __restrict__ cell_offsets,
+                                                               long long coo_stride) {
+  __shared__ int skeys[8][ROW_SORT_MAX];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int a = blockIdx.x * 8 + warp;
+  if (a >= n) return;
+  const int e0 = min(rowptr[a], capacity), e1 = min(rowptr[a + 1], capacity);
+  const int deg = e1 - e0;
+  if (deg <= 0) return;
+  if (deg <= ROW_SORT_MAX) {
+    for (int i = lane; i < deg; i += 32) skeys[warp][i] = col[e0 + i];
+    __syncwarp();
+    for (int i = lane; i < deg; i += 32) {
+      const int key = skeys[warp][i];
+      int rank = 0;
+      for (int k = 0; k < deg; ++k) rank += skeys[warp][k] < key;
+      col[e0 + rank] = key;
+    }
+    __syncwarp();
+  } else if (lane == 0) {  // very dense rows: in-place insertion sort
+    for (int i = e0 + 1; i < e1; ++i) {
+      const int key = col[i];
+      int k = i - 1;
+      while (k >= e0 && col[k] > key) { col[k + 1] = col[k]; --k; }
+      col[k + 1] = key;
+    }
+  }
+  __syncwarp();
+  for (int e = e0 + lane; e < e1; e += 32) {
+    const int key = col[e];
+    const int b = key / 27, code = key % 27;
+    const int fx = code / 9 - 1 + shift[3 * a] - shift[3 * b];
+    const int fy = (code / 3) % 3 - 1 + shift[3 * a + 1] - shift[3 * b + 1];
+    const int fz = code % 3 - 1 + shift[3 * a + 2] - shift[3 * b + 2];
+    col[e] = b;
+    if (offsets) {
+      offsets[4 * (size_t)e] = (int8_t)fx; offsets[4 * (size_t)e + 1] = (int8_t)fy;
+      offsets[4 * (size_t)e + 2] = (int8_t)fz; offsets[4 * (size_t)e + 3] = 0;
+    }
+    if (cell_offsets) {
+      cell_offsets[3 * (size_t)e] = (float)fx; cell_offsets[3 * (size_t)e + 1] = (float)fy; cell_offsets[3 * (size_t)e + 2] = (float)fz;
+    }
+    if (edge_index) {
+      edge_index[e] = a;
+      edge_index[coo_stride + e] = b;
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------
 // COO -> CSR for center-sorted edge lists, and the transposed structure
 // ------------------------------------------------------------------------------------------
 __global__ void coo_to_csr_kernel(const long long* __restrict__ ei, const float* __restrict__ co, int n_nodes, int n_edges,
@@ -325,6 +502,41 @@ using namespace xeq;
 
 extern "C" {
 
+static inline size_t cell_max_bins(int n_nodes) { return (size_t)(n_nodes > 64 ? n_nodes : 64); }
+constexpr int CELL_LIST_MIN_ATOMS = 256;
+
+struct CellWs {
+  CellGrid* grid;
+  int *cnt, *bin_start, *scratch, *atom_bin, *bin_atoms;
+  int max_bins;
+};
+
+// bins the wrapped positions (count -> scan -> fill); everything stays on the device
+static int build_cells(Carver& cv, const float* pw, const float* cell, float cutoff, int n, CellWs* W, cudaStream_t st) {
+  W->max_bins = (int)cell_max_bins(n);
+  W->grid = cv.take<CellGrid>(1);
+  W->cnt = cv.take<int>(W->max_bins + 1);
+  W->bin_start = cv.take<int>(W->max_bins + 1);
+  W->scratch = cv.take<int>(scan_scratch_ints(W->max_bins + 1));
+  W->atom_bin = cv.take<int>(n);
+  W->bin_atoms = cv.take<int>(n);
+  cell_setup_kernel<<<1, 32, 0, st>>>(cell, cutoff, W->max_bins, W->grid);
+  XEQ_CUDA(cudaMemsetAsync(W->cnt, 0, sizeof(int) * (size_t)(W->max_bins + 1), st));
+  bin_count_kernel<<<(n + 255) / 256, 256, 0, st>>>(pw, n, W->grid, W->cnt, W->atom_bin);
+  XEQ_LAUNCHED(2);
+  int rc = exclusive_scan(W->cnt, W->bin_start, W->max_bins, W->scratch, st);
+  if (rc) return rc;
+  XEQ_CUDA(cudaMemsetAsync(W->cnt, 0, sizeof(int) * (size_t)(W->max_bins + 1), st));
+  bin_fill_kernel<<<(n + 255) / 256, 256, 0, st>>>(W->atom_bin, n, W->bin_start, W->cnt, W->bin_atoms);
+  XEQ_LAUNCHED(1);
+  return XEQ_OK;
+}
+
+static bool use_cell_list(bool periodic, int n, int G, const PbcParams& pp) {
+  return periodic && G == 1 && n >= CELL_LIST_MIN_ATOMS && pp.pbc[0] && pp.pbc[1] && pp.pbc[2] && pp.rep[0] == 1 &&
+         pp.rep[1] == 1 && pp.rep[2] == 1;
+}
+
 size_t xeq_radius_graph_workspace_bytes(int32_t n_nodes, int32_t n_graphs, int periodic) {
   (void)n_graphs;
   size_t b = 256;
@@ -333,6 +545,11 @@ size_t xeq_radius_graph_workspace_bytes(int32_t n_nodes, int32_t n_graphs, int p
   if (periodic) {
     b += align_up(sizeof(float) * 3 * (size_t)n_nodes, 256);               // wrapped positions
     b += align_up(sizeof(int) * 3 * (size_t)n_nodes, 256);                 // integer shifts
+    const size_t mb = cell_max_bins(n_nodes);                              // cell list (large fully periodic graphs)
+    b += align_up(sizeof(CellGrid), 256);
+    b += 2 * align_up(sizeof(int) * (mb + 1), 256);                        // bin counts / cursors, bin starts
+    b += align_up(sizeof(int) * scan_scratch_ints((int)mb + 1), 256);
+    b += 2 * align_up(sizeof(int) * (size_t)n_nodes, 256);                 // bin of each atom, atoms by bin
   }
   return b;
 }
@@ -374,8 +591,16 @@ int xeq_radius_graph_count(const float* pos, int32_t n, const int32_t* graph_ptr
     float* pw = cv.take<float>(3 * (size_t)n);
     int* shift = cv.take<int>(3 * (size_t)n);
     wrap_positions_kernel<<<(n + 255) / 256, 256, 0, st>>>(pos, node_graph, cell, pp, n, pw, shift);
-    graph_scan_kernel<true, false><<<blocks, 256, 0, st>>>(pw, shift, graph_ptr, node_graph, cell, pp, cutoff, n, deg,
-                                                           nullptr, nullptr, nullptr, nullptr, nullptr, 0, 0, nullptr);
+    if (use_cell_list(periodic, n, G, pp)) {
+      CellWs W;
+      rc = build_cells(cv, pw, cell, cutoff, n, &W, st);
+      if (rc) return rc;
+      cell_scan_kernel<false><<<blocks, 256, 0, st>>>(pw, cell, cutoff, n, W.grid, W.atom_bin, W.bin_start, W.bin_atoms, deg,
+                                                      nullptr, nullptr, 0, nullptr);
+    } else {
+      graph_scan_kernel<true, false><<<blocks, 256, 0, st>>>(pw, shift, graph_ptr, node_graph, cell, pp, cutoff, n, deg,
+                                                             nullptr, nullptr, nullptr, nullptr, nullptr, 0, 0, nullptr);
+    }
   } else {
     graph_scan_kernel<false, false><<<blocks, 256, 0, st>>>(pos, nullptr, graph_ptr, node_graph, nullptr, pp, cutoff, n,
                                                             deg, nullptr, nullptr, nullptr, nullptr, nullptr, 0, 0, nullptr);
@@ -413,9 +638,20 @@ int xeq_radius_graph_fill(const float* pos, int32_t n, const int32_t* graph_ptr,
     float* pw = cv.take<float>(3 * (size_t)n);
     int* shift = cv.take<int>(3 * (size_t)n);
     wrap_positions_kernel<<<(n + 255) / 256, 256, 0, st>>>(pos, node_graph, cell, pp, n, pw, shift);
-    graph_scan_kernel<true, true><<<blocks, 256, 0, st>>>(pw, shift, graph_ptr, node_graph, cell, pp, cutoff, n, nullptr,
-                                                          rowptr, col, offsets, (long long*)edge_index, cell_offsets,
-                                                          n_edges, cap, overflow);
+    if (use_cell_list(periodic, n, G, pp)) {
+      CellWs W;
+      rc = build_cells(cv, pw, cell, cutoff, n, &W, st);
+      if (rc) return rc;
+      cell_scan_kernel<true><<<blocks, 256, 0, st>>>(pw, cell, cutoff, n, W.grid, W.atom_bin, W.bin_start, W.bin_atoms, nullptr,
+                                                     rowptr, col, cap, overflow);
+      row_sort_decode_kernel<<<(n + 7) / 8, 256, 0, st>>>(rowptr, n, shift, cap, col, offsets, (long long*)edge_index,
+                                                          cell_offsets, n_edges);
+      XEQ_LAUNCHED(1);
+    } else {
+      graph_scan_kernel<true, true><<<blocks, 256, 0, st>>>(pw, shift, graph_ptr, node_graph, cell, pp, cutoff, n, nullptr,
+                                                            rowptr, col, offsets, (long long*)edge_index, cell_offsets,
+                                                            n_edges, cap, overflow);
+    }
   } else {
     graph_scan_kernel<false, true><<<blocks, 256, 0, st>>>(pos, nullptr, graph_ptr, node_graph, nullptr, pp, cutoff, n,
                                                            nullptr, rowptr, col, nullptr, (long long*)edge_index, nullptr,
