@@ -10,7 +10,8 @@ One "step" is one pass of the hot path over one batch of synthetic molecules:
      all-reduce (N > 1), AdamW -- on 256 molecules per GPU (weak scaling).
   c1: E+F inference, 64 x 18 atoms.   c2: energy-only training, 256 x 18 atoms.
   c4: E+F inference, 256 channels, 128 drug-like molecules (30..70 atoms) per GPU.
-  c5: periodic water box (~10k atoms), E+F inference incl. neighbour rebuild (replicas for N > 1).
+  c5: periodic water box (~10k atoms), E+F inference incl. neighbour rebuild; N > 1 = spatial slabs with
+      halo exchange (xequinet_b200/domain.py), strong scaling of one box; value counts water molecules.
 
 Output: ONE JSON line (rank 0).  `value` = whole-job molecules/s with the inputs resident in
 HBM; `e2e` = the same through the public API with pinned-host inputs copied in and the loss /
@@ -108,9 +109,8 @@ def cpu_step_fn(workload: str, n_mol: int):
             opt.step()
         return out
 
-    mols = batch["ptr"].numel() - 1
-    frac = 1.0 if workload != "c5" else batch["pos"].shape[0] / 10125.0
-    return step, mols * frac, f"{mols} molecule(s), {batch['pos'].shape[0]} atoms per step"
+    mols = batch["ptr"].numel() - 1 if workload != "c5" else batch["pos"].shape[0] // 3  # c5 counts water molecules
+    return step, float(mols), f"{mols} molecule(s), {batch['pos'].shape[0]} atoms per step"
 
 
 def time_cpu(workload: str, n_mol: int, steps: int, warmup: int):
@@ -234,7 +234,35 @@ def run_gpu(args):
     loss_host = torch.zeros(1).pin_memory()
     energy_host = torch.zeros(host[0]["ptr"].numel() - 1).pin_memory()
 
+    sharded = args.workload == "c5" and world > 1
+    if sharded:
+        # spatial domain sharding with halo exchange (xequinet_b200/domain.py): strong scaling of ONE box
+        from xequinet_b200 import domain
+        own_host = []
+        for d in host:
+            o = domain.shard_atoms({k: v for k, v in d.items() if torch.is_tensor(v)}, rank, world)
+            own_host.append({k: v.pin_memory() for k, v in o.items()})
+        own_res = [{k: v.to(dev) for k, v in o.items()} for o in own_host]
+        for a, b in zip(host, own_host):
+            a["_owned"] = b
+        for a, b in zip(resident, own_res):
+            a["_owned"] = b
+        energy_host = torch.zeros(1).pin_memory()
+
+    def step_sharded(batch, e2e: bool):
+        o = batch["_owned"]
+        if e2e:
+            o = {k: o[k].to(dev, non_blocking=True) for k in ("pos", "atomic_numbers", "cell")}
+        out = domain.energy_forces_sharded(model, o, rank, world)
+        e_tot = out["energy"].detach().sum().reshape(1)
+        dist.all_reduce(e_tot)  # total energy of the box (forces stay sharded)
+        if e2e:
+            energy_host.copy_(e_tot, non_blocking=True)
+        return e_tot
+
     def step(batch, e2e: bool):
+        if sharded:
+            return step_sharded(batch, e2e)
         if e2e:
             d = {k: batch[k].to(dev, non_blocking=True) for k in h2d_keys}
         else:
@@ -270,7 +298,7 @@ def run_gpu(args):
     # a captured graph needs one static batch structure: workloads whose batches differ in size (c4:
     # 30..70 atoms per molecule) are replayed eagerly
     same_shape = all(d["pos"].shape == resident[0]["pos"].shape and torch.equal(d["ptr"], resident[0]["ptr"]) for d in resident)
-    use_graph = (not args.eager) and same_shape
+    use_graph = (not args.eager) and same_shape and not sharded  # the halo plan has host-synchronised counts
     graph_step = None
     if use_graph:
         from xequinet_b200.graph import StaticGraphBuilder, build_graph
@@ -395,11 +423,17 @@ def run_gpu(args):
         sampler.stop_flag.set()
         sampler.join(timeout=2)
 
-    mols_per_step = n_mol * world
+    if args.workload == "c5":
+        n_units = host[0]["pos"].shape[0] // 3  # water molecules in the box
+        mols_per_step = n_units if sharded else n_units * world
+    else:
+        mols_per_step = n_mol * world
     ms_per_step = total_ms / args.steps
     value = mols_per_step / (ms_per_step * 1e-3)
     e2e_value = mols_per_step / (e2e_ms / args.steps * 1e-3)
     h2d = sum(host[0][k].numel() * host[0][k].element_size() for k in h2d_keys)
+    if sharded:
+        h2d = sum(host[0]["_owned"][k].numel() * host[0]["_owned"][k].element_size() for k in ("pos", "atomic_numbers", "cell"))
     d2h = 4 if train else energy_host.numel() * 4
 
     def hard_exit():
@@ -442,11 +476,12 @@ def run_gpu(args):
 
     line = {
         "metric": METRIC, "value": round(value, 2), "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-        "ms_per_step": round(ms_per_step, 4), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "ms_per_step": round(ms_per_step, 4), "higher_is_better": True, "scaling": "strong" if sharded else "weak", "vs_baseline": None,
         "dtype": "f32", "data": "synthetic (seeded generators of SURVEY.md 8d), random-init weights",
         "config": {"workload": f"{args.workload}: {w['desc']}", "molecules_per_gpu": n_mol,
                    "atoms_per_gpu": int(host[0]["pos"].shape[0]), "l2": "flushed between timed steps (256 MB write, untimed)",
-                   "parallelism": f"dp{world}" if args.workload != "c5" else f"replicas{world}",
+                   "parallelism": (f"dp{world}" if args.workload != "c5" else
+                                   (f"spatial slabs x{world} + halo exchange (NCCL all-to-all)" if sharded else "single GPU")),
                    "execution": "whole step replayed as one CUDA graph (K1 in capacity mode)" if use_graph else
                                 ("eager launches" if args.eager else "eager launches (batch shapes vary: no static graph)")},
         "e2e": {"value": round(e2e_value, 2), "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h)},

@@ -1,0 +1,86 @@
+"""torchrun --nproc-per-node N tests/domain_gpu_worker.py [n_side] (driven by tests/test_domain_gpu.py) : sharded E+F of a periodic water box vs the
+single-GPU result (every rank also runs the full box as the reference)."""
+import os, sys
+from pathlib import Path
+sys.path.insert(0, str(Path(__file__).resolve().parent.parent))
+os.chdir(Path(__file__).resolve().parent.parent)
+import torch, torch.distributed as dist
+import xequinet_b200 as xb
+from xequinet_b200 import domain, keys
+from oracle import xpainn_oracle as orc
+rank, world = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"])
+torch.cuda.set_device(int(os.environ["LOCAL_RANK"])); dev = torch.device("cuda", int(os.environ["LOCAL_RANK"]))
+dist.init_process_group("nccl", device_id=dev)
+cfg = orc.CONFIG_DEFAULT
+model = xb.resolve_model("xpainn", **cfg.model_kwargs())
+model.load_state_dict(orc.synthetic_state_dict(cfg, 1234), strict=False)
+model = model.to(dev).eval()
+for p in model.parameters(): p.requires_grad_(False)
+n_side = int(sys.argv[1]) if len(sys.argv) > 1 else 6
+box = {k: (v.to(dev) if torch.is_tensor(v) else v) for k, v in orc.make_water_box(n_side, seed=1).items()}
+# reference: whole box on this GPU (positions wrapped into the cell first, as the sharded path does, so that both
+# evaluate the same fp32 edge vectors up to the rounding of the ghost shift)
+box["pos"] = domain.wrap_into_cell(box["pos"], box["cell"].reshape(3, 3)).contiguous()
+d = xb.NeighborTransform(cfg.cutoff)({k: box[k] for k in ["pos", "atomic_numbers", "batch", "ptr", "cell", "pbc"]})
+ref = model(d, compute_forces=True)
+E_ref, F_ref = ref["energy"].detach().double().sum(), ref["forces"].detach()
+owned = domain.shard_atoms(box, rank, world)
+out = domain.energy_forces_sharded(model, owned, rank, world)
+E = out["energy"].detach().double().sum(); dist.all_reduce(E)
+F_err = (out["forces"] - F_ref[owned["global_index"]]).abs().max(); dist.all_reduce(F_err, op=dist.ReduceOp.MAX)
+Ea_err = (out["atomic_energies"].detach() - ref["atomic_energies"].detach()[owned["global_index"]]).abs().max()
+dist.all_reduce(Ea_err, op=dist.ReduceOp.MAX)
+# fp64 oracle on the host (rank 0 computes, everyone receives): separates real errors from fp32 noise
+import numpy as np
+F64 = torch.zeros_like(F_ref, dtype=torch.float64)
+if rank == 0:
+    sd64 = orc.synthetic_state_dict(cfg, 1234, torch.float64)
+    table = torch.from_numpy(np.load("xequinet_b200/data/gfn2-xtb_aux56.npy"))
+    b64 = {k: (v.cpu().double() if (torch.is_tensor(v) and v.is_floating_point()) else (v.cpu() if torch.is_tensor(v) else v)) for k, v in box.items()}
+    b64["edge_index"], b64["cell_offsets"] = d["edge_index"].cpu(), d["cell_offsets"].cpu().double()
+    r64 = orc.xpainn_energy_forces(sd64, table, b64, cfg)
+    F64 = r64["forces"].to(dev)
+    sd32 = {k: v.float() for k, v in sd64.items()}
+    b32 = {k: (v.float() if (torch.is_tensor(v) and v.is_floating_point()) else v) for k, v in b64.items()}
+    r32 = orc.xpainn_energy_forces(sd32, table.float(), b32, cfg)
+    e32 = (r32["forces"].double() - r64["forces"]).abs().max(dim=1)[0]
+    print(f"oracle fp32 (torch CPU, the reference's arithmetic) vs fp64: max {float(e32.max()):.2e}, atoms > 1e-4: {int((e32 > 1e-4).sum())}", flush=True)
+    print(f"fp64 oracle: E {float(r64['energy'].sum()):.6f}", flush=True)
+dist.broadcast(F64, 0)
+e_single = (F_ref.double() - F64).abs().max(); e_shard = (out["forces"].double() - F64[owned["global_index"]]).abs().max()
+dist.all_reduce(e_shard, op=dist.ReduceOp.MAX)
+es = (F_ref.double() - F64).abs().max(dim=1)[0]
+if rank == 0: print(f"single-GPU atoms > 1e-4: {int((es > 1e-4).sum())}", flush=True)
+esh = (out["forces"].double() - F64[owned["global_index"]]).abs().max(dim=1)[0]
+rms_sh = (out["forces"].double() - F64[owned["global_index"]]).pow(2).sum(); dist.all_reduce(rms_sh)
+if rank == 0: print(f"rms |F - F64| sharded {float((rms_sh / F64.numel()).sqrt()):.2e}", flush=True)
+print(f"[rank {rank}] sharded atoms > 1e-4 vs fp64: {int((esh > 1e-4).sum())}; of those also > 1e-4 on single GPU: {int(((esh > 1e-4) & (es[owned['global_index']] > 1e-4)).sum())}", flush=True)
+if rank == 0: print(f"max |F - F64|: single-GPU {float(e_single):.2e}   sharded {float(e_shard):.2e}", flush=True)
+errv = (out["forces"] - F_ref[owned["global_index"]]).abs().max(dim=1)[0]
+f0 = domain.fractional(owned["pos"], box["cell"].reshape(3, 3))[:, 0] * world - rank   # position inside the slab, 0..1
+bad = errv > 1e-4
+print(f"[rank {rank}] max|F_ref| {float(F_ref.abs().max()):.3f}  bad atoms {int(bad.sum())}/{bad.numel()}  slab-coordinate of bad atoms: "
+      f"min {float(f0[bad].min()) if bad.any() else -1:.3f} max {float(f0[bad].max()) if bad.any() else -1:.3f}; "
+      f"worst at f0={float(f0[errv.argmax()]):.3f}; sumF sharded {out['forces'].sum(0).tolist()} ", flush=True)
+srt = torch.argsort(errv, descending=True)[:8]
+print(f"[rank {rank}] worst errs {errv[srt].tolist()} at slab coords {f0[srt].tolist()}", flush=True)
+if rank == 0:
+    print(f"world {world} atoms {box['pos'].shape[0]}: E {float(E):.6f} vs {float(E_ref):.6f} rel {abs(float(E - E_ref)) / abs(float(E_ref)):.2e}; "
+          f"max |dEa| {float(Ea_err):.2e}; max |dF| {float(F_err):.2e}", flush=True)
+    rms_single = float((F_ref.double() - F64).pow(2).mean().sqrt())
+    print(f"rms |F - F64| single-GPU {rms_single:.2e}", flush=True)
+    assert abs(float(E - E_ref)) <= 1e-5 * abs(float(E_ref)), "sharded energy differs"
+    assert float(e_shard) <= max(1e-4, 4 * float(e32.max())), "sharded forces differ beyond the fp32 noise floor of the reference arithmetic"
+    print("SHARDED OK", flush=True)
+# timing
+def tm(f, n=5):
+    f(); torch.cuda.synchronize(); dist.barrier(); a = torch.cuda.Event(enable_timing=True); b = torch.cuda.Event(enable_timing=True); a.record()
+    for _ in range(n): f()
+    b.record(); torch.cuda.synchronize(); return a.elapsed_time(b) / n
+t_sh = tm(lambda: domain.energy_forces_sharded(model, owned, rank, world))
+def full():
+    dd = xb.NeighborTransform(cfg.cutoff)({k: box[k] for k in ["pos", "atomic_numbers", "batch", "ptr", "cell", "pbc"]})
+    return model(dd, compute_forces=True)
+t_full = tm(full)
+if rank == 0: print(f"ms/step sharded {t_sh:.2f}  single-GPU full box {t_full:.2f}", flush=True)
+torch.cuda.synchronize(); sys.stdout.flush(); os._exit(0)

@@ -22,8 +22,12 @@ class NeighborGraph:
     MOLECULE_TILE_MAX_NODES = 64  # graphs up to this size become one work tile each (staged rows)
 
     def __init__(self, n_nodes: int, n_graphs: int, rowptr, col, offsets=None, cell=None, node_graph=None,
-                 capacity: Optional[int] = None, mol_ptr: Optional[torch.Tensor] = None):
+                 capacity: Optional[int] = None, mol_ptr: Optional[torch.Tensor] = None,
+                 n_centers: Optional[int] = None):
         self.n_nodes = int(n_nodes)
+        # nodes that can be centers (rows of the CSR that are walked); the rest (ghost atoms of a spatially
+        # sharded run, xequinet_b200/domain.py) only ever appear as neighbours
+        self.n_centers = int(n_centers) if n_centers is not None else int(n_nodes)
         self.n_graphs = int(n_graphs)
         self.rowptr = rowptr
         self.col = col
@@ -67,7 +71,7 @@ class NeighborGraph:
             return
         # node-aligned work tiles of both structures
         tc, tn = lib.xeq_center_tile_edges(), lib.xeq_neighbor_tile_edges()
-        _lib.check(lib.xeq_csr_tile_bounds(_lib.ptr(self.rowptr), N, E, tc, _lib.ptr(self.tile_ptr), _lib.stream()),
+        _lib.check(lib.xeq_csr_tile_bounds(_lib.ptr(self.rowptr), self.n_centers, E, tc, _lib.ptr(self.tile_ptr), _lib.stream()),
                    "xeq_csr_tile_bounds")
         _lib.check(lib.xeq_csr_tile_bounds(_lib.ptr(self.t_rowptr), N, E, tn, _lib.ptr(self.t_tile_ptr), _lib.stream()),
                    "xeq_csr_tile_bounds")

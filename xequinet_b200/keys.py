@@ -25,3 +25,4 @@ VIRIAL = "virial"
 GRAPH = "_xeq_graph"
 RBF_FREQ = "_xeq_rbf_freq"
 RBF_CUTOFF = "_xeq_rbf_cutoff"
+HALO = "_xeq_halo"  # domain.HaloPlan of a spatially sharded run (xequinet_b200/domain.py)

@@ -75,6 +75,21 @@ class XPainnMessage(nn.Module):
             self._dims = ops.Dims(self.node_dim, *self.muls, self.num_basis, cutoff)
         s = self.scalar_mlp(self.norm(x))
         v = self.o3norm(V)
+        plan = data.get(keys.HALO)
+        if plan is not None:
+            # spatially sharded run (xequinet_b200/domain.py): the rows of boundary atoms travel to the ranks
+            # that ghost them -- one exchange of [s | v] per layer; node-side work stays on owned atoms
+            from ..domain import halo_gather
+            H = s.shape[1]
+            sv = halo_gather(torch.cat([s, v], dim=1), plan)
+            s, v = sv[:, :H], sv[:, H:]
+            pad = (0, 0, 0, plan.n_ghost)
+            x_loc, V_loc = torch.nn.functional.pad(x, pad), torch.nn.functional.pad(V, pad)
+            x_new, V_new = ops.edge_message(x_loc, V_loc, s, v, data[keys.POSITIONS], self.rbf_lin.weight,
+                                            self.rbf_lin.bias, data[keys.RBF_FREQ], data[keys.GRAPH], self._dims)
+            data[keys.NODE_INVARIANT] = x_new[: plan.n_owned]
+            data[keys.NODE_EQUIVARIANT] = V_new[: plan.n_owned]
+            return data
         x_new, V_new = ops.edge_message(x, V, s, v, data[keys.POSITIONS], self.rbf_lin.weight, self.rbf_lin.bias,
                                         data[keys.RBF_FREQ], data[keys.GRAPH], self._dims)
         data[keys.NODE_INVARIANT] = x_new
