@@ -16,259 +16,11 @@
 // memory by a 3-stage software pipeline (geometry of chunk c+2 / radial terms of chunk c+1 /
 // message of chunk c) with ONE __syncthreads per chunk; nothing E-sized except the 12-byte
 // d/dr record ever touches HBM.
-#include "common.cuh"
-#include "edge_thread.cuh"
+#include <stdlib.h>
+
+#include "edge_geo.cuh"
 
 namespace xeq {
-
-constexpr int NB_ = 20;       // num_basis instantiated
-constexpr int NK_ = NB_ + 1;  // + bias/cutoff term
-constexpr int CT = 64;        // edges per chunk, center kernels
-constexpr int NT = 32;        // slots per chunk, neighbor kernels
-constexpr int WTHREADS = 288; // nbr_wgrad: filter channels per CTA; grid.y = H / 288 slices
-
-// ------------------------------------------------------------------------------------------
-// chunk stream: the (tile, chunk) work items of one CTA, in order
-// ------------------------------------------------------------------------------------------
-struct ChunkDesc {
-  int n0, n1;  // node range of the tile this chunk belongs to
-  int eb;      // first edge/slot of the chunk
-  int cnt;     // edges in the chunk (0 for an edge-less tile), -1 = end of stream
-  int first;   // first chunk of its tile
-  int last;    // last chunk of its tile
-};
-
-template <int T>
-struct ChunkCursor {
-  const int* __restrict__ rowptr;
-  const int* __restrict__ tile_ptr;
-  int n_tiles, tile, n0, n1, e0, e1, eb;
-  bool valid;
-
-  __device__ __forceinline__ void load_tile() {
-    valid = false;
-    while (tile < n_tiles) {
-      n0 = tile_ptr[tile];
-      n1 = tile_ptr[tile + 1];
-      if (n0 < n1) {
-        e0 = rowptr[n0];
-        e1 = rowptr[n1];
-        eb = e0;
-        valid = true;
-        return;
-      }
-      tile += gridDim.x;
-    }
-  }
-  __device__ __forceinline__ void init(const int* rp, const int* tp, int nt) {
-    rowptr = rp; tile_ptr = tp; n_tiles = nt; tile = blockIdx.x;
-    load_tile();
-  }
-  __device__ __forceinline__ ChunkDesc next() {
-    ChunkDesc d;
-    if (!valid) {
-      d.n0 = d.n1 = d.eb = 0; d.cnt = -1; d.first = d.last = 0;
-      return d;
-    }
-    d.n0 = n0; d.n1 = n1; d.eb = eb;
-    d.cnt = min(T, e1 - eb);
-    d.first = (eb == e0);
-    d.last = (eb + T >= e1);
-    eb += T;
-    if (eb >= e1) {
-      tile += gridDim.x;
-      load_tile();
-    }
-    return d;
-  }
-};
-
-// node that owns edge/slot e inside [n0, n1): rowptr[i] <= e < rowptr[i+1]
-__device__ __forceinline__ int owner_of(const int* __restrict__ rowptr, int n0, int n1, int e) {
-  int lo = n0, hi = n1;
-  while (lo < hi) {
-    const int mid = (lo + hi) >> 1;
-    if (rowptr[mid] <= e) lo = mid + 1; else hi = mid;
-  }
-  return lo - 1;
-}
-
-__device__ __forceinline__ void edge_vector(const xeq_graph_t& g, const float* __restrict__ pos, int i, int j, int eid,
-                                            float r[3]) {
-  r[0] = pos[3 * i] - pos[3 * j];
-  r[1] = pos[3 * i + 1] - pos[3 * j + 1];
-  r[2] = pos[3 * i + 2] - pos[3 * j + 2];
-  if (g.offsets != nullptr) {  // nn/basic.py:119-128: vectors -= cell_offsets @ cell[graph(neighbor)]
-    const char4 o = reinterpret_cast<const char4*>(g.offsets)[eid];
-    const float* c = g.cell + 9 * (g.node_graph ? g.node_graph[j] : 0);
-    const float ox = (float)o.x, oy = (float)o.y, oz = (float)o.z;
-#pragma unroll
-    for (int x = 0; x < 3; ++x) r[x] -= ox * c[x] + oy * c[3 + x] + oz * c[6 + x];
-  }
-}
-
-__device__ __forceinline__ void load_wrow(const float* __restrict__ W, const float* __restrict__ b, int h, float* row) {
-  row[0] = b[h];
-#pragma unroll
-  for (int k = 0; k < NB_; ++k) row[k + 1] = W[(size_t)h * NB_ + k];
-#pragma unroll
-  for (int k = NK_; k < NBP; ++k) row[k] = 0.f;
-}
-
-__device__ __forceinline__ void lds_row(const float* __restrict__ src, float* dst) {
-#pragma unroll
-  for (int k = 0; k < NBP / 4; ++k) {
-    const float4 p = reinterpret_cast<const float4*>(src)[k];
-    dst[4 * k] = p.x; dst[4 * k + 1] = p.y; dst[4 * k + 2] = p.z; dst[4 * k + 3] = p.w;
-  }
-}
-
-// Explicit shared-space accessors for the dynamically sized row window (keeps the addressing in
-// 32-bit shared space; a generic pointer would re-derive the shared window base per access).
-__device__ __forceinline__ void sts_f32(uint32_t addr, float v) {
-  asm volatile("st.shared.f32 [%0], %1;" ::"r"(addr), "f"(v) : "memory");
-}
-__device__ __forceinline__ float lds_f32(uint32_t addr) {
-  float v;
-  asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(addr) : "memory");
-  return v;
-}
-extern __shared__ __align__(16) unsigned char xeq_dyn_smem[];
-
-// Rows a CTA can stage per tile ("window").  With molecule tiles (tile_mode 1) every neighbor of a
-// tile's nodes lies inside the tile's own node range, so the CTA copies those rows to shared memory
-// once (each thread only ever touches its own columns -> no barrier) and the per-edge gathers become
-// shared-memory reads: HBM/L2 traffic drops from E rows to N rows.
-template <int C, bool JVP> struct CenterWin { static constexpr int value = (C == 128) ? 21 : 0; };  // fwd: 2 CTAs/SM
-template <int C> struct NbrWin { static constexpr int value = (C == 128) ? 24 : 0; };
-
-// ------------------------------------------------------------------------------------------
-// shared-memory geometry records and the two geometry stages
-// ------------------------------------------------------------------------------------------
-template <int T, bool NEED_G, bool SECOND>
-struct alignas(16) GeoA {  // stage A1: one thread per edge
-  float Y[T][8];
-  float u[T][4];
-  float d[T];
-  float chi[T][3];
-  int gat[T];  // node whose rows are gathered (neighbor j for center kernels, center i for neighbor kernels)
-  int own[T];  // node that owns the row being walked
-  int eid[T];  // canonical edge id
-  float G[NEED_G ? T : 1][24];
-  float Hm[(NEED_G && SECOND) ? T : 1][24];
-  float Ydot[SECOND ? T : 1][8];
-  float rp[SECOND ? T : 1][4];
-  float ddot[SECOND ? T : 1];
-};
-
-template <int T, bool D1, bool D2, bool XI, bool DXI>
-struct alignas(16) GeoB {  // stage A2: one thread per (edge, k)
-  float psi[T][NBP];
-  float dpsi[D1 ? T : 1][NBP];
-  float ddpsi[D2 ? T : 1][NBP];
-  float xi[XI ? T : 1][NBP];
-  float dxi[DXI ? T : 1][NBP];
-};
-
-struct GeoArgs {
-  xeq_graph_t g;
-  const float* pos;
-  const float* a_pos;  // tangent of pos (second order) or NULL
-  const float* freq;
-  float rc;
-};
-
-// TRANSPOSED = false: walk CSR rows (owner = center i, gathered = neighbor j = col[e], eid = e)
-// TRANSPOSED = true : walk transposed rows (owner = neighbor j, gathered = center i = t_row[sl], eid = t_eid[sl])
-template <int T, bool TRANSPOSED, bool NEED_G, bool SECOND>
-__device__ __noinline__ void geo_stage_a1(const GeoArgs& A, const ChunkDesc d, GeoA<T, NEED_G, SECOND>& sa) {
-  const int t = threadIdx.x;
-  if (t >= d.cnt) return;
-  const xeq_graph_t& g = A.g;
-  const int sl = d.eb + t;
-  int i, j, e, owner;
-  if (!TRANSPOSED) {
-    owner = owner_of(g.rowptr, d.n0, d.n1, sl);
-    i = owner; j = g.col[sl]; e = sl;
-    sa.gat[t] = j;
-  } else {
-    owner = owner_of(g.t_rowptr, d.n0, d.n1, sl);
-    j = owner; i = g.t_row[sl]; e = g.t_eid[sl];
-    sa.gat[t] = i;
-  }
-  sa.own[t] = owner;
-  sa.eid[t] = e;
-  float r[3], dist, u[3];
-  edge_vector(g, A.pos, i, j, e, r);
-  unit_vector(r, dist, u);
-  if (!NEED_G && !SECOND) {
-    sph_harm(u, sa.Y[t]);
-  } else {
-    float G[3][8];
-    angular_first(u, dist, sa.Y[t], G);
-    if (NEED_G) {
-#pragma unroll
-      for (int x = 0; x < 3; ++x)
-#pragma unroll
-        for (int m = 0; m < 8; ++m) sa.G[t][x * 8 + m] = G[x][m];
-    }
-    if (SECOND) {
-      float Hm[3][8], rp[3], rdot[3] = {0.f, 0.f, 0.f}, dd;
-      if (A.a_pos) {
-#pragma unroll
-        for (int x = 0; x < 3; ++x) rdot[x] = A.a_pos[3 * i + x] - A.a_pos[3 * j + x];
-      }
-      angular_second(u, dist, rdot, G, dd, rp, sa.Ydot[t], Hm);
-      sa.ddot[t] = dd;
-#pragma unroll
-      for (int x = 0; x < 3; ++x) {
-        sa.rp[t][x] = rp[x];
-        if (NEED_G) {
-#pragma unroll
-          for (int m = 0; m < 8; ++m) sa.Hm[t][x * 8 + m] = Hm[x][m];
-        }
-      }
-    }
-  }
-#pragma unroll
-  for (int x = 0; x < 3; ++x) sa.u[t][x] = u[x];
-  const Cutoff<float> c = cutoff_terms(dist, A.rc);
-  sa.d[t] = dist;
-  sa.chi[t][0] = c.chi; sa.chi[t][1] = c.dchi; sa.chi[t][2] = c.ddchi;
-}
-
-template <int T, int THREADS, bool NEED_G, bool SECOND, bool D1, bool D2, bool XI, bool DXI>
-__device__ __noinline__ void geo_stage_a2(const GeoArgs& A, int cnt, const GeoA<T, NEED_G, SECOND>& sa,
-                                          GeoB<T, D1, D2, XI, DXI>& sb) {
-  const int t = threadIdx.x;
-  for (int idx = t; idx < cnt * NK_; idx += THREADS) {
-    const int ee = idx / NK_, k = idx - ee * NK_;
-    Cutoff<float> c;
-    c.chi = sa.chi[ee][0]; c.dchi = sa.chi[ee][1]; c.ddchi = sa.chi[ee][2];
-    if (k == 0) {  // bias / cutoff term, plus the zero padding of the row
-      sb.psi[ee][0] = c.chi;
-      if (D1) sb.dpsi[ee][0] = c.dchi;
-      if (D2) sb.ddpsi[ee][0] = c.ddchi;
-      if (XI) sb.xi[ee][0] = 0.f;
-      if (DXI) sb.dxi[ee][0] = 0.f;
-#pragma unroll
-      for (int kk = NK_; kk < NBP; ++kk) {
-        sb.psi[ee][kk] = 0.f;
-        if (D1) sb.dpsi[ee][kk] = 0.f;
-        if (D2) sb.ddpsi[ee][kk] = 0.f;
-        if (XI) sb.xi[ee][kk] = 0.f;
-        if (DXI) sb.dxi[ee][kk] = 0.f;
-      }
-    } else {
-      const Radial<float> rr = radial_term(sa.d[ee], A.freq[k - 1], A.rc, c);
-      sb.psi[ee][k] = rr.psi;
-      if (D1) sb.dpsi[ee][k] = rr.dpsi;
-      if (D2) sb.ddpsi[ee][k] = rr.ddpsi;
-      if (XI) sb.xi[ee][k] = rr.xi;
-      if (DXI) sb.dxi[ee][k] = rr.dxi;
-    }
-  }
-}
 
 // ==========================================================================================
 // center kernel
@@ -280,13 +32,6 @@ struct CenterSmem {
   static constexpr int TC = CenterChunk<JVP>::value;
   GeoA<TC, false, JVP> a[3];
   GeoB<TC, JVP, false, false, false> b[2];
-};
-
-struct CenterArgs {
-  GeoArgs geo;
-  const float *s, *v, *x_in, *V_in, *W, *b;
-  const float *a_s, *a_v;  // JVP only
-  float *x_out, *V_out;
 };
 
 template <int L, int C, int M1, int M2, bool JVP>
@@ -388,16 +133,16 @@ __device__ __forceinline__ void center_role(const CenterArgs& A, CenterSmem<JVP>
   ChunkDesc d0 = cur_it.next();  // chunk being processed
   ChunkDesc d1 = cur_it.next();  // chunk whose radial terms are produced
   ChunkDesc d2;                  // chunk whose geometry is produced
-  if (d0.cnt >= 0) geo_stage_a1<TC, false, false, JVP>(A.geo, d0, sm.a[0]);
+  if (d0.cnt >= 0) geo_stage_a1<TC, false, false, JVP>(A.geo, d0, sm.a[0], threadIdx.x);
   __syncthreads();
-  if (d1.cnt >= 0) geo_stage_a1<TC, false, false, JVP>(A.geo, d1, sm.a[1]);
+  if (d1.cnt >= 0) geo_stage_a1<TC, false, false, JVP>(A.geo, d1, sm.a[1], threadIdx.x);
   if (d0.cnt >= 0) geo_stage_a2<TC, THREADS>(A.geo, d0.cnt, sm.a[0], sm.b[0]);
   __syncthreads();
 
   int cur = -1;
   for (int c = 0; d0.cnt >= 0; ++c) {
     d2 = cur_it.next();
-    if (d2.cnt >= 0) geo_stage_a1<TC, false, false, JVP>(A.geo, d2, sm.a[(c + 2) % 3]);
+    if (d2.cnt >= 0) geo_stage_a1<TC, false, false, JVP>(A.geo, d2, sm.a[(c + 2) % 3], threadIdx.x);
     if (d1.cnt >= 0) geo_stage_a2<TC, THREADS>(A.geo, d1.cnt, sm.a[(c + 1) % 3], sm.b[(c + 1) & 1]);
 
     // ---- message accumulation over chunk c.  Gathers run two edges ahead of their use; the
@@ -519,15 +264,6 @@ struct NbrMainSmem {
   int red_eid[2][TC];
 };
 
-struct NeighborArgs {
-  GeoArgs geo;
-  const float *s, *v, *W, *b, *gx, *gV;
-  const float *a_s, *a_v;  // ORDER 2 only
-  float *o_s, *o_v;        // [N,H], [N,D]
-  float* gr;               // [slices, E, 3] per-edge d/dr
-  float* wpart;            // [gridDim.x, H, 2*NBP] weight-gradient partials (wgrad kernel)
-};
-
 template <int L, int C, int M1, int M2, int ORDER>
 __device__ __forceinline__ void nbr_main_role(const NeighborArgs& A, NbrMainSmem<ORDER, (C + M1 + M2) / 32>& sm) {
   constexpr int M = C + M1 + M2, D = C + 3 * M1 + 5 * M2, H = C + 2 * M, NC = 2 * L + 1;
@@ -620,9 +356,9 @@ __device__ __forceinline__ void nbr_main_role(const NeighborArgs& A, NbrMainSmem
   };
   ChunkDesc d0 = cur_it.next(), d1 = cur_it.next(), d2, dprev;
   dprev.cnt = -1;
-  if (d0.cnt >= 0) geo_stage_a1<TC, true, true, SECOND>(A.geo, d0, sm.a[0]);
+  if (d0.cnt >= 0) geo_stage_a1<TC, true, true, SECOND>(A.geo, d0, sm.a[0], threadIdx.x);
   __syncthreads();
-  if (d1.cnt >= 0) geo_stage_a1<TC, true, true, SECOND>(A.geo, d1, sm.a[1]);
+  if (d1.cnt >= 0) geo_stage_a1<TC, true, true, SECOND>(A.geo, d1, sm.a[1], threadIdx.x);
   if (d0.cnt >= 0) geo_stage_a2<TC, THREADS>(A.geo, d0.cnt, sm.a[0], sm.b[0]);
   __syncthreads();
 
@@ -639,7 +375,7 @@ __device__ __forceinline__ void nbr_main_role(const NeighborArgs& A, NbrMainSmem
     }
     if (d0.cnt >= 0) {
       d2 = cur_it.next();
-      if (d2.cnt >= 0) geo_stage_a1<TC, true, true, SECOND>(A.geo, d2, sm.a[(c + 2) % 3]);
+      if (d2.cnt >= 0) geo_stage_a1<TC, true, true, SECOND>(A.geo, d2, sm.a[(c + 2) % 3], threadIdx.x);
       if (d1.cnt >= 0) geo_stage_a2<TC, THREADS>(A.geo, d1.cnt, sm.a[(c + 1) % 3], sm.b[(c + 1) & 1]);
 
       const GeoA<TC, true, SECOND>& sa = sm.a[c % 3];
@@ -773,16 +509,16 @@ __device__ __forceinline__ void nbr_wgrad_role(const NeighborArgs& A, NbrWgradSm
   ChunkCursor<NT> cur_it;
   cur_it.init(g.t_rowptr, g.t_tile_ptr, g.t_n_tiles);
   ChunkDesc d0 = cur_it.next(), d1 = cur_it.next(), d2;
-  if (d0.cnt >= 0) geo_stage_a1<NT, true, false, SECOND>(A.geo, d0, sm.a[0]);
+  if (d0.cnt >= 0) geo_stage_a1<NT, true, false, SECOND>(A.geo, d0, sm.a[0], threadIdx.x);
   __syncthreads();
-  if (d1.cnt >= 0) geo_stage_a1<NT, true, false, SECOND>(A.geo, d1, sm.a[1]);
+  if (d1.cnt >= 0) geo_stage_a1<NT, true, false, SECOND>(A.geo, d1, sm.a[1], threadIdx.x);
   if (d0.cnt >= 0) geo_stage_a2<NT, WTHREADS>(A.geo, d0.cnt, sm.a[0], sm.b[0]);
   __syncthreads();
 
   int cur = -1;
   for (int c = 0; d0.cnt >= 0; ++c) {
     d2 = cur_it.next();
-    if (d2.cnt >= 0) geo_stage_a1<NT, true, false, SECOND>(A.geo, d2, sm.a[(c + 2) % 3]);
+    if (d2.cnt >= 0) geo_stage_a1<NT, true, false, SECOND>(A.geo, d2, sm.a[(c + 2) % 3], threadIdx.x);
     if (d1.cnt >= 0) geo_stage_a2<NT, WTHREADS>(A.geo, d1.cnt, sm.a[(c + 1) % 3], sm.b[(c + 1) & 1]);
     const GeoA<NT, false, SECOND>& sa = sm.a[c % 3];
     const auto& sb = sm.b[c & 1];
@@ -960,6 +696,15 @@ static int launch_center(const CenterArgs& A, cudaStream_t st) {
   return XEQ_OK;
 }
 
+// tensor-core variants (edge_message_mma.cu), default widths only
+int launch_center_mma(const CenterArgs& A, bool jvp, cudaStream_t st);
+
+// XEQ_EDGE_SIMT=1 forces the SIMT filter contraction for the default widths too (A/B timing)
+static bool use_mma() {
+  static const bool simt = [] { const char* e = getenv("XEQ_EDGE_SIMT"); return e && e[0] == '1'; }();
+  return !simt;
+}
+
 static int run_center(const xeq_graph_t* g, const xeq_dims_t* dims, CenterArgs& A, bool jvp, cudaStream_t st) {
   int cfg;
   int rc = check_dims(dims, &cfg);
@@ -969,6 +714,7 @@ static int run_center(const xeq_graph_t* g, const xeq_dims_t* dims, CenterArgs& 
   if (g->n_nodes == 0) return XEQ_OK;
   A.geo.g = *g;
   A.geo.rc = dims->cutoff;
+  if (cfg == 0 && use_mma()) return launch_center_mma(A, jvp, st);
   if (cfg == 0) return jvp ? launch_center<128, 64, 32, true>(A, st) : launch_center<128, 64, 32, false>(A, st);
   return jvp ? launch_center<256, 128, 64, true>(A, st) : launch_center<256, 128, 64, false>(A, st);
 }

@@ -47,35 +47,47 @@ struct CenterThread {
     accx = T(0);
   }
 
-  // forward message of one edge: psi[NBP], Y[8]; s_* are s[j, .] of the neighbor, v its v[j, (q, m)]
-  XEQ_HD void fwd(const T* psi, const T* Y, T s_state, T s_edge, T s_x, const T* v) {
-    const T gs = s_state * dot_nk<NK>(Ws, psi);
-    const T ge = s_edge * dot_nk<NK>(We, psi);
+  // forward message of one edge given the filter values w = [b|W_rbf] . psi of this thread's rows
+  // (the tcgen05 kernels read them from TMEM); s_* are s[j, .] of the neighbor, v its v[j, (q, m)]
+  XEQ_HD void fwd_w(T ws, T we, T wx, const T* Y, T s_state, T s_edge, T s_x, const T* v) {
+    const T gs = s_state * ws;
+    const T ge = s_edge * we;
     if (L == 0) {
       accV[0] += gs * v[0] + ge;
-      accx += s_x * dot_nk<NK>(Wx, psi);
+      accx += s_x * wx;
     } else {
 #pragma unroll
       for (int m = 0; m < NC; ++m) accV[m] += gs * v[m] + ge * Y[YOff<L>::value + m];
     }
   }
 
-  // tangent of the forward message along (sdot, vdot, rdot): d/deps of fwd()
-  XEQ_HD void jvp(const T* psi, const T* dpsi, const T* Y, const T* Ydot, T ddot, T s_state, T s_edge,
-                  T s_x, const T* v, T sd_state, T sd_edge, T sd_x, const T* vd) {
-    const T ws = dot_nk<NK>(Ws, psi), we = dot_nk<NK>(We, psi);
-    const T dws = dot_nk<NK>(Ws, dpsi) * ddot, dwe = dot_nk<NK>(We, dpsi) * ddot;
+  // forward message of one edge: psi[NBP], Y[8]
+  XEQ_HD void fwd(const T* psi, const T* Y, T s_state, T s_edge, T s_x, const T* v) {
+    fwd_w(dot_nk<NK>(Ws, psi), dot_nk<NK>(We, psi), (L == 0) ? dot_nk<NK>(Wx, psi) : T(0), Y, s_state, s_edge, s_x, v);
+  }
+
+  // tangent of the forward message along (sdot, vdot, rdot): d/deps of fwd_w(); dw* = [b|W_rbf] . dpsi
+  XEQ_HD void jvp_w(T ws, T we, T wx, T dws_, T dwe_, T dwx_, const T* Y, const T* Ydot, T ddot, T s_state, T s_edge,
+                    T s_x, const T* v, T sd_state, T sd_edge, T sd_x, const T* vd) {
+    const T dws = dws_ * ddot, dwe = dwe_ * ddot;
     const T gs = s_state * ws, ge = s_edge * we;
     const T gsd = sd_state * ws + s_state * dws;
     const T ged = sd_edge * we + s_edge * dwe;
     if (L == 0) {
       accV[0] += gsd * v[0] + gs * vd[0] + ged;
-      accx += sd_x * dot_nk<NK>(Wx, psi) + s_x * dot_nk<NK>(Wx, dpsi) * ddot;
+      accx += sd_x * wx + s_x * dwx_ * ddot;
     } else {
 #pragma unroll
       for (int m = 0; m < NC; ++m)
         accV[m] += gsd * v[m] + gs * vd[m] + ged * Y[YOff<L>::value + m] + ge * Ydot[YOff<L>::value + m];
     }
+  }
+
+  XEQ_HD void jvp(const T* psi, const T* dpsi, const T* Y, const T* Ydot, T ddot, T s_state, T s_edge,
+                  T s_x, const T* v, T sd_state, T sd_edge, T sd_x, const T* vd) {
+    jvp_w(dot_nk<NK>(Ws, psi), dot_nk<NK>(We, psi), (L == 0) ? dot_nk<NK>(Wx, psi) : T(0), dot_nk<NK>(Ws, dpsi),
+          dot_nk<NK>(We, dpsi), (L == 0) ? dot_nk<NK>(Wx, dpsi) : T(0), Y, Ydot, ddot, s_state, s_edge, s_x, v, sd_state,
+          sd_edge, sd_x, vd);
   }
 };
 
@@ -128,8 +140,10 @@ struct NeighborThread {
   // First derivatives.  g = gV[i,(q,:)] (state/edge roles) or gx[i,c] (scalar role).
   // pr[3] receives this thread's share of dPhi/dr_e.
   XEQ_HD void first(const NbrEdge<T>& e, const T* g, T pr[3]) {
-    const T w = MAIN ? dot_nk<NK>(Wt, e.psi) : T(0);
-    const T dw = MAIN ? dot_nk<NK>(Wt, e.dpsi) : T(0);
+    first_w(e, g, pr, MAIN ? dot_nk<NK>(Wt, e.psi) : T(0), MAIN ? dot_nk<NK>(Wt, e.dpsi) : T(0));
+  }
+  // same with the filter values w = Wt . psi, dw = Wt . dpsi supplied (tcgen05 kernels: from TMEM)
+  XEQ_HD void first_w(const NbrEdge<T>& e, const T* g, T pr[3], const T w, const T dw) {
     T pw;  // dPhi/dw_e[h]
     T cy[NC];
     if (ROLE == ROLE_STATE) {
@@ -185,9 +199,10 @@ struct NeighborThread {
 
   // Second derivatives: gradient of Psi_e (the tangent of Phi_e along (sd, vd, rdot)).
   XEQ_HD void second(const NbrEdge<T>& e, const T* g, T pr[3]) {
-    const T w = MAIN ? dot_nk<NK>(Wt, e.psi) : T(0);
-    const T dw = MAIN ? dot_nk<NK>(Wt, e.dpsi) : T(0);
-    const T ddw = MAIN ? dot_nk<NK>(Wt, e.ddpsi) : T(0);
+    second_w(e, g, pr, MAIN ? dot_nk<NK>(Wt, e.psi) : T(0), MAIN ? dot_nk<NK>(Wt, e.dpsi) : T(0),
+             MAIN ? dot_nk<NK>(Wt, e.ddpsi) : T(0));
+  }
+  XEQ_HD void second_w(const NbrEdge<T>& e, const T* g, T pr[3], const T w, const T dw, const T ddw) {
     const T dwd = dw * e.ddot;  // tangent of w
     T alpha, beta;
     T cy[NC], cz[NC];
