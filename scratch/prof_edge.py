@@ -9,7 +9,7 @@ reps = int(sys.argv[2]) if len(sys.argv) > 2 else 2
 cfg = orc.CONFIG_DEFAULT
 d = orc.make_aspirin_batch(n_mol, seed=0, with_edges=False)
 dev = 'cuda'
-g, _, _ = xb.build_graph(d['pos'].to(dev), 5.0, batch=d['batch'].to(dev))
+g, _, _ = xb.build_graph(d["pos"].to(dev), 5.0, ptr=d["ptr"].to(dev), batch=d["batch"].to(dev))
 N = g.n_nodes
 dims = ops.Dims(cfg.node_dim, *cfg.muls, cfg.num_basis, cfg.cutoff)
 r = lambda *s: torch.randn(*s, device=dev)

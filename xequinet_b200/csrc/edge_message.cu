@@ -698,6 +698,7 @@ static int launch_center(const CenterArgs& A, cudaStream_t st) {
 
 // tensor-core variants (edge_message_mma.cu), default widths only
 int launch_center_mma(const CenterArgs& A, bool jvp, cudaStream_t st);
+int launch_wgrad_mma(const NeighborArgs& A, int order, int grid, cudaStream_t st);
 
 // XEQ_EDGE_SIMT=1 forces the SIMT filter contraction for the default widths too (A/B timing)
 static bool use_mma() {
@@ -773,7 +774,8 @@ static int run_neighbor(const xeq_graph_t* g, const xeq_dims_t* dims, NeighborAr
   if (g->n_nodes == 0) return XEQ_OK;
   Carver cv(ws);
   float* gr = cv.take<float>(3 * (size_t)(g->n_edges > 0 ? g->n_edges : 1));
-  const int gx = wgrad_grid_x(g);
+  const bool mma = cfg == 0 && use_mma();
+  const int gx = mma ? min(g->t_n_tiles, num_sms()) : wgrad_grid_x(g);  // per-CTA partial slabs
   float *wpart = nullptr, *ftot = nullptr;
   if (wgrad) {
     wpart = cv.take<float>((size_t)gx * H * 2 * NBP);
@@ -783,7 +785,10 @@ static int run_neighbor(const xeq_graph_t* g, const xeq_dims_t* dims, NeighborAr
   A.geo.rc = dims->cutoff;
   A.gr = o_pos ? gr : nullptr;
   A.wpart = wpart;
-  if (cfg == 0) rc = order == 1 ? launch_neighbor<128, 64, 32, 1>(A, main, wgrad, gx, st) : launch_neighbor<128, 64, 32, 2>(A, main, wgrad, gx, st);
+  if (mma) {
+    rc = order == 1 ? launch_neighbor<128, 64, 32, 1>(A, main, false, gx, st) : launch_neighbor<128, 64, 32, 2>(A, main, false, gx, st);
+    if (!rc && wgrad) rc = launch_wgrad_mma(A, order, gx, st);
+  } else if (cfg == 0) rc = order == 1 ? launch_neighbor<128, 64, 32, 1>(A, main, wgrad, gx, st) : launch_neighbor<128, 64, 32, 2>(A, main, wgrad, gx, st);
   else rc = order == 1 ? launch_neighbor<256, 128, 64, 1>(A, main, wgrad, gx, st) : launch_neighbor<256, 128, 64, 2>(A, main, wgrad, gx, st);
   if (rc) return rc;
   if (o_pos) {

@@ -36,6 +36,14 @@ __device__ __forceinline__ void split_tf32(float x, uint32_t& hi, uint32_t& lo) 
   asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(lo) : "f"(r));
 }
 
+// Same split on the integer / FMA pipes for the per-edge hot paths (cvt.rna runs on the quarter-rate
+// conversion pipe): hi = x rounded to 10 mantissa bits by an integer add, lo = x - hi exactly; the
+// tensor core ignores the 13 low mantissa bits of lo, a relative error of 2^-21 of x.
+__device__ __forceinline__ void split_fast(float x, uint32_t& hi, uint32_t& lo) {
+  hi = (__float_as_uint(x) + 0x1000u) & 0xffffe000u;
+  lo = __float_as_uint(x - __uint_as_float(hi));
+}
+
 // K-major SWIZZLE_128B shared-memory matrix descriptor (same encoding as node_gemm.cu)
 __device__ __forceinline__ uint64_t smem_desc(uint32_t addr) {
   return (uint64_t)((addr >> 4) & 0x3FFFu) | (1ull << 16) | ((uint64_t)(1024 >> 4) << 32) | (1ull << 46) | (2ull << 61);
@@ -99,6 +107,10 @@ __device__ __forceinline__ void proxy_fence() { asm volatile("fence.proxy.async.
 __device__ __forceinline__ void tmem_st8(uint32_t taddr, const uint32_t (&r)[8]) {
   asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"r"(taddr), "r"(r[0]), "r"(r[1]),
                "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7])
+               : "memory");
+}
+__device__ __forceinline__ void tmem_st4(uint32_t taddr, const uint32_t (&r)[4]) {
+  asm volatile("tcgen05.st.sync.aligned.32x32b.x4.b32 [%0], {%1, %2, %3, %4};" ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3])
                : "memory");
 }
 __device__ __forceinline__ void tmem_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
@@ -172,7 +184,7 @@ __device__ __noinline__ void geo_stage_b(const GeoArgs& A, int cnt, const GeoA<T
 #pragma unroll
     for (int o = 0; o < NOUT; ++o) {
       uint32_t hi, lo;
-      split_tf32(val[o], hi, lo);
+      split_fast(val[o], hi, lo);
       asm volatile("st.shared.b32 [%0], %1;" ::"r"(tiles + (2 * o) * b_tile_bytes<T>() + off), "r"(hi) : "memory");
       asm volatile("st.shared.b32 [%0], %1;" ::"r"(tiles + (2 * o + 1) * b_tile_bytes<T>() + off), "r"(lo) : "memory");
     }

@@ -197,6 +197,56 @@ struct NeighborThread {
     }
   }
 
+  // dPhi/dw_e[h] of this thread's filter row (first order) -- the left operand of the weight-gradient
+  // GEMM  GW[h, k] = sum_e pw[h, e] psi_k(e),  GF[h, k] = sum_e pw[h, e] xi_k(e)  (tcgen05 kernels)
+  XEQ_HD T pw_first(const T* Y, const T* g) const {
+    if (ROLE == ROLE_STATE) {
+      T A = T(0);
+#pragma unroll
+      for (int m = 0; m < NC; ++m) A += g[m] * v[m];
+      return A * s;
+    } else if (ROLE == ROLE_EDGE) {
+      T B = T(0);
+      if (L == 0) {
+        B = g[0];
+      } else {
+#pragma unroll
+        for (int m = 0; m < NC; ++m) B += g[m] * Y[YO + m];
+      }
+      return B * s;
+    }
+    return g[0] * s;
+  }
+  // second order: GW += alpha psi + (beta ddot) dpsi,  GF += alpha xi + (beta ddot) dxi
+  XEQ_HD void ab_second(const T* Y, const T* Ydot, const T* g, T& alpha, T& beta) const {
+    if (ROLE == ROLE_STATE) {
+      T A = T(0), Ad = T(0);
+#pragma unroll
+      for (int m = 0; m < NC; ++m) {
+        A += g[m] * v[m];
+        Ad += g[m] * vd[m];
+      }
+      alpha = sd * A + s * Ad;
+      beta = s * A;
+    } else if (ROLE == ROLE_EDGE) {
+      T B = T(0), Bd = T(0);
+      if (L == 0) {
+        B = g[0];
+      } else {
+#pragma unroll
+        for (int m = 0; m < NC; ++m) {
+          B += g[m] * Y[YO + m];
+          Bd += g[m] * Ydot[YO + m];
+        }
+      }
+      alpha = sd * B + s * Bd;
+      beta = s * B;
+    } else {
+      alpha = g[0] * sd;
+      beta = g[0] * s;
+    }
+  }
+
   // Second derivatives: gradient of Psi_e (the tangent of Phi_e along (sd, vd, rdot)).
   XEQ_HD void second(const NbrEdge<T>& e, const T* g, T pr[3]) {
     second_w(e, g, pr, MAIN ? dot_nk<NK>(Wt, e.psi) : T(0), MAIN ? dot_nk<NK>(Wt, e.dpsi) : T(0),
