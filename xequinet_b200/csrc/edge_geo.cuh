@@ -236,9 +236,11 @@ struct GeoArgs {
 template <int T, bool TRANSPOSED, bool NEED_G, bool SECOND>
 __device__ __noinline__ void geo_stage_a1(const GeoArgs& A, const ChunkDesc d, GeoA<T, NEED_G, SECOND>& sa,
                                           const int t /* edge slot of this thread: threadIdx.x, or the lane of a producer warp */) {
-  if (t >= d.cnt) return;
+  // RowCursor chunks: the slots past the end of the row piece repeat its last edge, so the per-edge loops of the
+  // tcgen05 kernels can run whole groups without bounds checks (their filter values are exact zeros)
+  if (t >= d.cnt && (d.owner < 0 || d.cnt <= 0 || t >= T)) return;
   const xeq_graph_t& g = A.g;
-  const int sl = d.eb + t;
+  const int sl = d.eb + min(t, d.cnt - 1);
   int i, j, e, owner;
   if (!TRANSPOSED) {
     owner = d.owner >= 0 ? d.owner : owner_of(g.rowptr, d.n0, d.n1, sl);

@@ -699,6 +699,7 @@ static int launch_center(const CenterArgs& A, cudaStream_t st) {
 // tensor-core variants (edge_message_mma.cu), default widths only
 int launch_center_mma(const CenterArgs& A, bool jvp, cudaStream_t st);
 int launch_wgrad_mma(const NeighborArgs& A, int order, int grid, cudaStream_t st);
+int launch_nbr_mma(const NeighborArgs& A, int order, cudaStream_t st);
 
 // XEQ_EDGE_SIMT=1 forces the SIMT filter contraction for the default widths too (A/B timing)
 static bool use_mma() {
@@ -786,7 +787,7 @@ static int run_neighbor(const xeq_graph_t* g, const xeq_dims_t* dims, NeighborAr
   A.gr = o_pos ? gr : nullptr;
   A.wpart = wpart;
   if (mma) {
-    rc = order == 1 ? launch_neighbor<128, 64, 32, 1>(A, main, false, gx, st) : launch_neighbor<128, 64, 32, 2>(A, main, false, gx, st);
+    if (main) rc = launch_nbr_mma(A, order, st);
     if (!rc && wgrad) rc = launch_wgrad_mma(A, order, gx, st);
   } else if (cfg == 0) rc = order == 1 ? launch_neighbor<128, 64, 32, 1>(A, main, wgrad, gx, st) : launch_neighbor<128, 64, 32, 2>(A, main, wgrad, gx, st);
   else rc = order == 1 ? launch_neighbor<256, 128, 64, 1>(A, main, wgrad, gx, st) : launch_neighbor<256, 128, 64, 2>(A, main, wgrad, gx, st);

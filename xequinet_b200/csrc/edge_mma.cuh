@@ -164,15 +164,16 @@ __device__ __forceinline__ void store_a_row(uint32_t lane_base, int tile, const 
 template <int T> __device__ __forceinline__ constexpr uint32_t b_tile_bytes() { return T * 128; }
 
 // Geometry stage B: radial terms of a chunk, split and written straight into the B tiles
-// (output 0 = psi, 1 = dpsi, 2 = ddpsi).  One thread per (edge, k); rows >= cnt stay unwritten (their
-// accumulator columns are never read).
+// (output 0 = psi, 1 = dpsi, 2 = ddpsi).  One thread per (edge, k); rows >= cnt are zero-filled, so the filter
+// values of the slots past the end of a row piece are exact zeros.
 template <int T, int THREADS, int NOUT, bool NEED_G, bool SECOND>
 __device__ __noinline__ void geo_stage_b(const GeoArgs& A, int cnt, const GeoA<T, NEED_G, SECOND>& sa, uint32_t tiles) {
   const int t = threadIdx.x;
-  for (int idx = t; idx < cnt * NBP; idx += THREADS) {
+  for (int idx = t; idx < T * NBP; idx += THREADS) {
     const int ee = idx / NBP, k = idx - ee * NBP;
     float val[3] = {0.f, 0.f, 0.f};
-    if (k == 0) {
+    if (ee >= cnt) {
+    } else if (k == 0) {
       val[0] = sa.chi[ee][0]; val[1] = sa.chi[ee][1]; val[2] = sa.chi[ee][2];
     } else if (k <= NB_) {
       Cutoff<float> c;

@@ -143,7 +143,11 @@ struct NeighborThread {
     first_w(e, g, pr, MAIN ? dot_nk<NK>(Wt, e.psi) : T(0), MAIN ? dot_nk<NK>(Wt, e.dpsi) : T(0));
   }
   // same with the filter values w = Wt . psi, dw = Wt . dpsi supplied (tcgen05 kernels: from TMEM)
-  XEQ_HD void first_w(const NbrEdge<T>& e, const T* g, T pr[3], const T w, const T dw) {
+  // RADIAL_ONLY (rows without an angular term: l = 0, or the state / scalar roles): return the coefficient
+  // of u in dPhi/dr_e instead of the 3-vector, so that the cross-channel reduction moves one value.
+  template <bool RADIAL_ONLY = false>
+  XEQ_HD void first_w(const NbrEdge<T>& e, const T* g, T pr[3], const T w, const T dw, T* radial = nullptr) {
+    static_assert(!RADIAL_ONLY || !(ROLE == ROLE_EDGE && L > 0), "row has an angular term");
     T pw;  // dPhi/dw_e[h]
     T cy[NC];
     if (ROLE == ROLE_STATE) {
@@ -176,7 +180,9 @@ struct NeighborThread {
       pw = g[0] * s;
       if (MAIN) acc_s += g[0] * w;
     }
-    if (MAIN) {
+    if (MAIN && RADIAL_ONLY) {
+      radial[0] = pw * dw;
+    } else if (MAIN) {
       const T dpart = pw * dw;
 #pragma unroll
       for (int x = 0; x < 3; ++x) {
@@ -252,7 +258,10 @@ struct NeighborThread {
     second_w(e, g, pr, MAIN ? dot_nk<NK>(Wt, e.psi) : T(0), MAIN ? dot_nk<NK>(Wt, e.dpsi) : T(0),
              MAIN ? dot_nk<NK>(Wt, e.ddpsi) : T(0));
   }
-  XEQ_HD void second_w(const NbrEdge<T>& e, const T* g, T pr[3], const T w, const T dw, const T ddw) {
+  // RADIAL_ONLY: radial[0] = coefficient of u, radial[1] = coefficient of rp in dPsi/dr_e
+  template <bool RADIAL_ONLY = false>
+  XEQ_HD void second_w(const NbrEdge<T>& e, const T* g, T pr[3], const T w, const T dw, const T ddw, T* radial = nullptr) {
+    static_assert(!RADIAL_ONLY || !(ROLE == ROLE_EDGE && L > 0), "row has an angular term");
     const T dwd = dw * e.ddot;  // tangent of w
     T alpha, beta;
     T cy[NC], cz[NC];
@@ -299,7 +308,10 @@ struct NeighborThread {
       beta = g[0] * s;
       if (MAIN) acc_s += g[0] * dwd;
     }
-    if (MAIN) {
+    if (MAIN && RADIAL_ONLY) {
+      radial[0] = alpha * dw + e.ddot * beta * ddw;
+      radial[1] = beta * dw;
+    } else if (MAIN) {
       const T P = alpha * dw + e.ddot * beta * ddw;
       const T R1 = beta * dw;
 #pragma unroll
