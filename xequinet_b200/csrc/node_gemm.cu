@@ -31,7 +31,7 @@ constexpr int A_TILE_BYTES = TILE_M * 128;
 constexpr int B_TILE_BYTES = MAX_PASS_N * 128;
 constexpr int STAGE_BYTES = 2 * A_TILE_BYTES + 2 * B_TILE_BYTES;  // hi + lo of both operands
 constexpr int GEMM_SMEM = 2 * STAGE_BYTES + 1024 /* alignment slack */ + 64 /* barriers, tmem slot */ + MAX_PASS_N * 4 /* bias */;
-constexpr int TMEM_COLS = 512;  // [0,256): sum of a_hi*b_hi;  [256,512): sum of the correction terms
+// TMEM: [0, pn): sum of a_hi*b_hi;  [pn, 2 pn): sum of the correction terms (pn = columns of the pass)
 constexpr int MAX_PROBLEMS = 20;
 
 struct Problem {
@@ -70,10 +70,22 @@ struct ReduceArgs {
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
-__device__ __forceinline__ void split_tf32(float x, uint32_t& hi, uint32_t& lo) {
-  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(hi) : "f"(x));
-  const float r = x - __uint_as_float(hi);
-  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(lo) : "f"(r));
+// per-element split on the integer / FMA pipes (cvt.rna is quarter rate): hi = x rounded to 10 mantissa
+// bits by an integer add, lo = x - hi exactly; the tensor core ignores the 13 low mantissa bits of lo
+__device__ __forceinline__ void split_fast(float x, uint32_t& hi, uint32_t& lo) {
+  hi = (__float_as_uint(x) + 0x1000u) & 0xffffe000u;
+  lo = __float_as_uint(x - __uint_as_float(hi));
+}
+__device__ __forceinline__ uint32_t elect_one() {  // one lane of a converged warp
+  uint32_t pred;
+  asm volatile(
+      "{\n\t"
+      ".reg .pred P;\n\t"
+      "elect.sync _|P, 0xffffffff;\n\t"
+      "selp.u32 %0, 1, 0, P;\n\t"
+      "}\n"
+      : "=r"(pred));
+  return pred;
 }
 
 __device__ __forceinline__ void sts_v4(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
@@ -111,10 +123,10 @@ __device__ __forceinline__ void store_k_contig(uint32_t s_hi, uint32_t s_lo, int
     const int r = c >> 3, kc = c & 7;
     if (r < tile_rows) {
       uint32_t h0, h1, h2, h3, l0, l1, l2, l3;
-      split_tf32(f[it].x, h0, l0);
-      split_tf32(f[it].y, h1, l1);
-      split_tf32(f[it].z, h2, l2);
-      split_tf32(f[it].w, h3, l3);
+      split_fast(f[it].x, h0, l0);
+      split_fast(f[it].y, h1, l1);
+      split_fast(f[it].z, h2, l2);
+      split_fast(f[it].w, h3, l3);
       const uint32_t off = (uint32_t)(r * 128 + ((kc ^ (r & 7)) << 4));
       sts_v4(s_hi + off, h0, h1, h2, h3);
       sts_v4(s_lo + off, l0, l1, l2, l3);
@@ -149,7 +161,7 @@ __device__ __forceinline__ void store_k_strided(uint32_t s_hi, uint32_t s_lo, in
       for (int i = 0; i < 4; ++i) {
         const int r = 4 * j + i;
         uint32_t h, l;
-        split_tf32(vals[i], h, l);
+        split_fast(vals[i], h, l);
         const uint32_t off = (uint32_t)(r * 128 + (((lane >> 2) ^ (r & 7)) << 4) + (lane & 3) * 4);
         sts_b32(s_hi + off, h);
         sts_b32(s_lo + off, l);
@@ -241,8 +253,11 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tf32x3_kernel(const __gr
     const float bv = (P.bias && !args.use_partials && col < P.n) ? __ldg(P.bias + col) : 0.f;
     asm volatile("st.shared.f32 [%0], %1;" ::"r"(bias_s + 4u * tid), "f"(bv) : "memory");
   }
+  // two accumulators of pn columns each; allocations are powers of two >= 32
+  uint32_t tmem_cols = 32;
+  while ((int)tmem_cols < 2 * pn) tmem_cols <<= 1;
   if (warp == 0) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "n"(TMEM_COLS) : "memory");
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"(tmem_cols) : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
   }
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -277,7 +292,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tf32x3_kernel(const __gr
     if (i + 2 < nkb) load_block(i + 2, fa, fb);
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy stores -> visible to the tensor core
     __syncthreads();
-    if (tid == 0) {
+    if (warp == 0 && elect_one()) {  // warp 0 is converged here (elect.sync lets ptxas issue the MMAs back to back)
       asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
       const int nks = min(KB / 8, (P.k - k0 + 7) / 8);
       for (int ks = 0; ks < nks; ++ks) {
@@ -285,8 +300,8 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tf32x3_kernel(const __gr
         const uint64_t db_hi = smem_desc(sb_hi + ks * 32), db_lo = smem_desc(sb_lo + ks * 32);
         // the correction terms (2^-11 of the main term) get their own accumulator, so the rounding of the
         // large running sum happens once per k step instead of three times; the epilogue adds the two
-        mma_tf32(tmem_base + MAX_PASS_N, da_lo, db_hi, idesc, (i | ks) ? 1u : 0u);
-        mma_tf32(tmem_base + MAX_PASS_N, da_hi, db_lo, idesc, 1u);
+        mma_tf32(tmem_base + pn, da_lo, db_hi, idesc, (i | ks) ? 1u : 0u);
+        mma_tf32(tmem_base + pn, da_hi, db_lo, idesc, 1u);
         mma_tf32(tmem_base, da_hi, db_hi, idesc, (i | ks) ? 1u : 0u);
       }
       umma_commit(bar0 + 8 * s);  // implies tcgen05.fence::before_thread_sync
@@ -315,7 +330,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tf32x3_kernel(const __gr
     const uint32_t taddr = tmem_base + ((uint32_t)(32 * (warp & 3)) << 16) + (uint32_t)(ch * 16);
     if (nkb > 0) {
       tmem_ld16(taddr, r);
-      tmem_ld16(taddr + MAX_PASS_N, rc);
+      tmem_ld16(taddr + pn, rc);
       asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 #pragma unroll
       for (int j = 0; j < 16; ++j) r[j] = __float_as_uint(__uint_as_float(r[j]) + __uint_as_float(rc[j]));
@@ -350,7 +365,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tf32x3_kernel(const __gr
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
   if (warp == 0) {
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(TMEM_COLS) : "memory");
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(tmem_cols) : "memory");
   }
 }
 
