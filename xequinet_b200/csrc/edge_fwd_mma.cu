@@ -1,0 +1,344 @@
+// K2 forward message, warp-specialised: the kernel of edge_message_mma.cu (filter contraction on tcgen05,
+// filter rows resident in TMEM, thread per irrep channel, register-resident segment sums) with the
+// per-chunk work split over three kinds of warps so that the channel threads do nothing but the edge loop:
+//
+//   warps 0-6  (224 threads) consumers : one thread per irrep channel; wait for the accumulators of chunk c,
+//                                        read them with tcgen05.ld, gather / multiply / accumulate, write rows
+//   warp  7                  cursor    : walks the row-aligned chunk stream ahead of the consumers (descriptor +
+//                                        per-edge geometry, one lane per edge, software-pipelined over chunks
+//                                        so no dependent global load is waited for where it is issued) and issues
+//                                        the MMAs of chunk c+1 while the consumers are on chunk c (accumulators
+//                                        double buffered: 2 x 80 TMEM columns at 16 edges per chunk)
+//   warps 8-15 (256 threads) radial    : chi * phi_k of chunk c+2 -> 3xTF32 split -> SWIZZLE_128B tiles (three
+//                                        stages) and the generic->async proxy fence, off the consumers' path
+//
+// One __syncthreads per chunk joins the three groups; the ring depths (descriptors/geometry 4, radial tiles 3,
+// accumulators 2) make every buffer written in iteration c distinct from the ones read in it.
+// Replaces nn/xpainn.py:66-74, 140-159 + nn/basic.py:114-131 (forward values); contract: xeq_edge_message_fwd.
+#include <type_traits>
+
+#include "edge_mma.cuh"
+
+namespace xeq {
+
+using namespace fm;
+
+namespace {
+
+constexpr int FW_TC = 16;                   // edges per chunk = MMA N
+constexpr int FW_STAGE = 2 * FW_TC * 128;   // radial tiles of one chunk: hi + lo
+constexpr int FW_NSTAGE = 3;
+constexpr int FW_WIN = 21;                  // rows of the shared-memory window (aspirin: 21 atoms)
+constexpr int FW_CONS = 224, FW_RADIAL = 256, FW_THREADS = FW_CONS + 32 + FW_RADIAL;
+constexpr int FW_DCOLS = TILES * FW_TC;     // accumulator columns of one chunk (80)
+
+struct FwdSmem {
+  GeoA<FW_TC, false, false> a[4];
+  ChunkDesc desc[8];
+  uint64_t full[2];  // accumulator buffer s holds the filter values of its chunk (tcgen05.commit arrives)
+  uint32_t slot;
+};
+
+template <int L, int C, int M1, int M2>
+__device__ __forceinline__ void fwd_consumer(const CenterArgs& A, FwdSmem& sm, const uint32_t tmem, const uint32_t win_base) {
+  constexpr int M = C + M1 + M2, D = C + 3 * M1 + 5 * M2, H = C + 2 * M, NC = 2 * L + 1;
+  constexpr int TC = FW_TC;
+  constexpr int TS = (L == 0) ? 0 : 3, TE = (L == 0) ? 1 : 4, TX = 2;  // row tiles of this thread's filter rows
+  const int t = threadIdx.x, warp = t >> 5;
+  const int q = t;
+  const int vbase = (L == 0) ? t : (L == 1 ? C + (t - C) : C + 3 * M1 + (t - C - M1));
+  constexpr int vstride = (L == 0) ? 0 : (L == 1 ? M1 : M2);
+  const xeq_graph_t& g = A.geo.g;
+  const uint32_t lane_base = tmem + ((uint32_t)(32 * (warp & 3)) << 16);
+
+  {  // filter rows -> TMEM (once per CTA)
+    float row[NBP];
+    load_wrow(A.W, A.b, q, row);
+    store_a_row(lane_base, TS, row);
+    load_wrow(A.W, A.b, M + q, row);
+    store_a_row(lane_base, TE, row);
+    if (L == 0) {
+      load_wrow(A.W, A.b, 2 * M + q, row);
+      store_a_row(lane_base, TX, row);
+    }
+    tmem_wait_st();
+  }
+
+  CenterThread<float, L, NK_> th;  // accumulators only (the filter rows live in TMEM)
+  th.reset();
+
+  struct Gathered {
+    float ss, se, sx, v[NC];
+  };
+  auto gather = [&](int j, Gathered& o) {
+    const float* sj = A.s + (size_t)j * H;
+    o.ss = sj[q];
+    o.se = sj[M + q];
+    o.sx = (L == 0) ? sj[2 * M + q] : 0.f;
+    const float* vj = A.v + (size_t)j * D + vbase;
+#pragma unroll
+    for (int m = 0; m < NC; ++m) o.v[m] = vj[m * vstride];
+  };
+  // staged window: [row][column][thread-of-role] floats, role regions side by side
+  constexpr int ROWF = C * 4 + M1 * 5 + M2 * 7;
+  constexpr int NTHR = (L == 0) ? C : (L == 1 ? M1 : M2);
+  constexpr int ROLE_OFF = (L == 0) ? 0 : (L == 1 ? C * 4 : C * 4 + M1 * 5);
+  const int tt = (L == 0) ? t : (L == 1 ? t - C : t - C - M1);
+  const uint32_t win0 = win_base + 4u * (ROLE_OFF + tt);
+  bool staged = false;
+  int win_lo = 0;
+  auto stage_window = [&](int n0, int n1) {
+#pragma unroll 2
+    for (int j = n0; j < n1; ++j) {
+      const uint32_t a = win0 + 4u * (uint32_t)((j - n0) * ROWF);
+      Gathered gc;
+      gather(j, gc);
+      int c = 0;
+      sts_f32(a + 4u * (uint32_t)(NTHR * c++), gc.ss);
+      sts_f32(a + 4u * (uint32_t)(NTHR * c++), gc.se);
+      if (L == 0) sts_f32(a + 4u * (uint32_t)(NTHR * c++), gc.sx);
+#pragma unroll
+      for (int m = 0; m < NC; ++m) sts_f32(a + 4u * (uint32_t)(NTHR * c++), gc.v[m]);
+    }
+  };
+  auto gather_window = [&](int j, Gathered& o) {
+    const uint32_t a = win0 + 4u * (uint32_t)((j - win_lo) * ROWF);
+    int c = 0;
+    o.ss = lds_f32(a + 4u * (uint32_t)(NTHR * c++));
+    o.se = lds_f32(a + 4u * (uint32_t)(NTHR * c++));
+    o.sx = (L == 0) ? lds_f32(a + 4u * (uint32_t)(NTHR * c++)) : 0.f;
+#pragma unroll
+    for (int m = 0; m < NC; ++m) o.v[m] = lds_f32(a + 4u * (uint32_t)(NTHR * c++));
+  };
+
+  float base_x = 0.f, base_V[NC];
+#pragma unroll
+  for (int m = 0; m < NC; ++m) base_V[m] = 0.f;
+
+  tc_fence_before();
+  __syncthreads();  // (P1) cursor: descriptors + geometry of chunks 0..2
+  __syncthreads();  // (P2) radial: tiles of chunks 0, 1
+  uint32_t ph[2] = {0u, 0u};
+  for (int c = 0;; ++c) {
+    const ChunkDesc d0 = sm.desc[c & 7];
+    if (d0.cnt < 0) break;
+    const GeoA<TC, false, false>& sa = sm.a[c & 3];
+    const int cnt = d0.cnt, node = d0.owner, buf = c & 1;
+    if (d0.first) {
+      staged = g.tile_mode == 1 && (d0.n1 - d0.n0) <= FW_WIN;
+      win_lo = d0.n0;
+      if (staged) stage_window(d0.n0, d0.n1);
+    }
+    if (d0.rfirst) {  // residual row of the node: requested now, consumed when its row ends
+#pragma unroll
+      for (int m = 0; m < NC; ++m) base_V[m] = A.V_in ? A.V_in[(size_t)node * D + vbase + m * vstride] : 0.f;
+      if (L == 0) base_x = A.x_in ? A.x_in[(size_t)node * C + t] : 0.f;
+      th.reset();
+    }
+    if (cnt > 0) {
+      mbar_wait(smem_u32(&sm.full[buf]), ph[buf]);
+      ph[buf] ^= 1u;
+      tc_fence_after();
+    }
+    // the edges of this piece of the row, four at a time; no row switch and no bounds checks inside (the slots
+    // past cnt repeat the last edge with exactly zero filter values)
+    const uint32_t dbase = lane_base + D_COL + buf * FW_DCOLS;
+    auto run_chunk = [&](auto staged_c) {
+      constexpr bool ST = decltype(staged_c)::value;
+#pragma unroll 1
+      for (int g0 = 0; g0 < cnt; g0 += 4) {
+        float ws[4], we[4], wx[4] = {0.f, 0.f, 0.f, 0.f};
+        tmem_ld4(dbase + TS * TC + g0, ws);
+        tmem_ld4(dbase + TE * TC + g0, we);
+        if (L == 0) tmem_ld4(dbase + TX * TC + g0, wx);
+        Gathered gc[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          if (ST) gather_window(sa.gat[g0 + j], gc[j]);
+          else gather(sa.gat[g0 + j], gc[j]);
+        }
+        tmem_wait_ld();
+        pin(ws); pin(we);
+        if (L == 0) pin(wx);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          float Yl[NC];
+          if (L > 0) {
+#pragma unroll
+            for (int m = 0; m < NC; ++m) Yl[m] = sa.Y[g0 + j][YOff<L>::value + m];
+          }
+          th.fwd_w(ws[j], we[j], wx[j], Yl - YOff<L>::value, gc[j].ss, gc[j].se, gc[j].sx, gc[j].v);
+        }
+      }
+    };
+    if (staged) run_chunk(std::true_type{});
+    else run_chunk(std::false_type{});
+    if (d0.rlast) {
+#pragma unroll
+      for (int m = 0; m < NC; ++m) A.V_out[(size_t)node * D + vbase + m * vstride] = base_V[m] + th.accV[m];
+      if (L == 0) A.x_out[(size_t)node * C + t] = base_x + th.accx;
+    }
+    tc_fence_before();
+    __syncthreads();
+  }
+}
+
+// MMAs of `chunk` into accumulator buffer chunk & 1 from radial stage chunk % 3 (one elected lane of a converged warp)
+__device__ __forceinline__ void fwd_issue(FwdSmem& sm, const uint32_t tmem, const uint32_t tiles, int chunk) {
+  if (elect_one()) {
+    const uint32_t idesc = idesc_tf32(FW_TC);
+    const uint32_t b_hi = tiles + (uint32_t)(chunk % FW_NSTAGE) * FW_STAGE, b_lo = b_hi + FW_TC * 128;
+    const uint32_t d0 = tmem + D_COL + (uint32_t)(chunk & 1) * FW_DCOLS;
+#pragma unroll
+    for (int ks = 0; ks < NBP / 8; ++ks) {
+      const uint64_t db_hi = smem_desc(b_hi + ks * 32), db_lo = smem_desc(b_lo + ks * 32);
+#pragma unroll
+      for (int tile = 0; tile < TILES; ++tile) {
+        const uint32_t d = d0 + tile * FW_TC;
+        mma_ts(d, tmem + A_LO + tile * NBP + ks * 8, db_hi, idesc, ks ? 1u : 0u);
+        mma_ts(d, tmem + A_HI + tile * NBP + ks * 8, db_lo, idesc, 1u);
+        mma_ts(d, tmem + A_HI + tile * NBP + ks * 8, db_hi, idesc, 1u);
+      }
+    }
+    umma_commit(smem_u32(&sm.full[chunk & 1]));
+  }
+  __syncwarp();
+}
+
+// cursor warp: issues the MMAs of chunk c+1 and runs the per-edge geometry as a three-stage software pipeline
+// over consecutive chunks, so that none of its dependent global loads (rowptr -> col -> pos) is waited for in
+// the iteration that issued it:   A(c+5) descriptor + neighbour index load | B(c+4) edge vector (position
+// loads) | C(c+3) distances, harmonics, cutoff -> shared memory.
+__device__ __forceinline__ void fwd_cursor(const CenterArgs& A, FwdSmem& sm, const uint32_t tmem, const uint32_t tiles) {
+  const int lane = threadIdx.x & 31;
+  const xeq_graph_t& g = A.geo.g;
+  RowCursor<FW_TC> cur_it;
+  cur_it.init(g.rowptr, g.tile_ptr, g.n_tiles);
+
+  // pipeline registers
+  ChunkDesc dB, dC;      // chunks entering stages B and C
+  int colB = 0, jC = 0;  // neighbour index of this lane's slot
+  float piC[3] = {0.f, 0.f, 0.f}, pjC[3] = {0.f, 0.f, 0.f}, shC[3] = {0.f, 0.f, 0.f};  // raw loads, consumed one step later
+  dB.cnt = dC.cnt = -1;
+  dB.eb = dC.eb = 0; dB.owner = dC.owner = 0;
+
+  auto stage_a = [&](int k) {
+    const ChunkDesc d = cur_it.next();
+    if (lane == 0) sm.desc[k & 7] = d;
+    dB = d;
+    colB = (d.cnt > 0 && lane < FW_TC) ? g.col[d.eb + min(lane, d.cnt - 1)] : 0;
+  };
+  auto stage_b = [&]() {
+    dC = dB;
+    jC = colB;
+    if (dB.cnt > 0 && lane < FW_TC) {
+      const int i = dB.owner, j = colB;
+#pragma unroll
+      for (int x = 0; x < 3; ++x) {  // loads only: the subtraction happens in stage C, after the latency has passed
+        piC[x] = A.geo.pos[3 * i + x];
+        pjC[x] = A.geo.pos[3 * j + x];
+        shC[x] = 0.f;
+      }
+      if (g.offsets != nullptr) {  // nn/basic.py:119-128: vectors -= cell_offsets @ cell[graph(neighbor)]
+        const char4 o = reinterpret_cast<const char4*>(g.offsets)[dB.eb + min(lane, dB.cnt - 1)];
+        const float* cl = g.cell + 9 * (g.node_graph ? g.node_graph[j] : 0);
+        const float ox = (float)o.x, oy = (float)o.y, oz = (float)o.z;
+#pragma unroll
+        for (int x = 0; x < 3; ++x) shC[x] = ox * cl[x] + oy * cl[3 + x] + oz * cl[6 + x];
+      }
+    }
+  };
+  auto stage_c = [&](int k) {
+    if (dC.cnt > 0 && lane < FW_TC) {
+      GeoA<FW_TC, false, false>& sa = sm.a[k & 3];
+      float dist, u[3], rC[3];
+#pragma unroll
+      for (int x = 0; x < 3; ++x) rC[x] = (piC[x] - pjC[x]) - shC[x];
+      unit_vector(rC, dist, u);
+      sph_harm(u, sa.Y[lane]);
+#pragma unroll
+      for (int x = 0; x < 3; ++x) sa.u[lane][x] = u[x];
+      const Cutoff<float> c = cutoff_terms(dist, A.geo.rc);
+      sa.d[lane] = dist;
+      sa.chi[lane][0] = c.chi; sa.chi[lane][1] = c.dchi; sa.chi[lane][2] = c.ddchi;
+      sa.gat[lane] = jC;
+      sa.own[lane] = dC.owner;
+      sa.eid[lane] = dC.eb + min(lane, dC.cnt - 1);
+    }
+  };
+  auto step = [&](int c) {  // geometry work of iteration c
+    if (c + 3 >= 0) stage_c(c + 3);
+    if (c + 4 >= 0) stage_b();
+    stage_a(c + 5);
+    __syncwarp();
+  };
+  for (int c = -5; c < 0; ++c) step(c);  // fill: geometry of chunks 0..2 in shared memory, 3 and 4 in flight
+  __syncthreads();  // (P1)
+  __syncthreads();  // (P2) tiles of chunks 0, 1 written and fenced; filter rows are in TMEM
+  tc_fence_after();
+  if (sm.desc[0].cnt > 0) fwd_issue(sm, tmem, tiles, 0);
+  for (int c = 0; sm.desc[c & 7].cnt >= 0; ++c) {
+    tc_fence_after();
+    if (sm.desc[(c + 1) & 7].cnt > 0) fwd_issue(sm, tmem, tiles, c + 1);
+    step(c);
+    __syncthreads();
+  }
+}
+
+// radial warps: tiles of chunk c+2
+// radial warps: tiles of chunk c+2
+__device__ __forceinline__ void fwd_radial(const CenterArgs& A, FwdSmem& sm, const uint32_t tiles) {
+  const int rt = threadIdx.x - (FW_CONS + 32);
+  __syncthreads();  // (P1)
+#pragma unroll
+  for (int i = 0; i < 2; ++i) {
+    const int cnt = sm.desc[i].cnt;
+    if (cnt > 0) geo_stage_b<FW_TC, FW_RADIAL, 1>(A.geo, cnt, sm.a[i], tiles + (uint32_t)i * FW_STAGE, rt);
+  }
+  proxy_fence();
+  __syncthreads();  // (P2)
+  for (int c = 0;; ++c) {
+    if (sm.desc[c & 7].cnt < 0) break;
+    const int cnt = sm.desc[(c + 2) & 7].cnt;
+    if (cnt > 0) {
+      geo_stage_b<FW_TC, FW_RADIAL, 1>(A.geo, cnt, sm.a[(c + 2) & 3], tiles + (uint32_t)((c + 2) % FW_NSTAGE) * FW_STAGE, rt);
+      proxy_fence();
+    }
+    __syncthreads();
+  }
+}
+
+template <int C, int M1, int M2>
+__global__ void __launch_bounds__(FW_THREADS, 1) center_fwd_kernel(const CenterArgs A) {
+  static_assert(C == 128 && M1 + M2 <= 96 && M1 % 32 == 0 && M2 % 32 == 0 && C + M1 + M2 == FW_CONS, "row-tile mapping");
+  __shared__ FwdSmem sm;
+  const uint32_t tmem = tmem_setup(&sm.slot, sm.full, 2);
+  const uint32_t tiles = (smem_u32(xeq_dyn_smem) + 1023u) & ~1023u;
+  const uint32_t win_base = tiles + FW_NSTAGE * FW_STAGE;
+  const int t = threadIdx.x;
+  if (t < C) fwd_consumer<0, C, M1, M2>(A, sm, tmem, win_base);
+  else if (t < C + M1) fwd_consumer<1, C, M1, M2>(A, sm, tmem, win_base);
+  else if (t < FW_CONS) fwd_consumer<2, C, M1, M2>(A, sm, tmem, win_base);
+  else if (t < FW_CONS + 32) fwd_cursor(A, sm, tmem, tiles);
+  else fwd_radial(A, sm, tiles);
+  tmem_teardown(tmem);
+}
+
+}  // namespace
+
+int launch_center_fwd_ws(const CenterArgs& A, cudaStream_t st) {
+  constexpr int C = 128, M1 = 64, M2 = 32;
+  static_assert(sizeof(FwdSmem) <= 16 * 1024, "static shared memory budget");
+  const size_t dyn = 1024 + (size_t)FW_NSTAGE * FW_STAGE + (size_t)FW_WIN * (C * 4 + M1 * 5 + M2 * 7) * 4;
+  static bool attr_set = false;
+  if (!attr_set) {
+    XEQ_CUDA(cudaFuncSetAttribute(center_fwd_kernel<C, M1, M2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn));
+    attr_set = true;
+  }
+  const int grid = min(A.geo.g.n_tiles, num_sms());
+  center_fwd_kernel<C, M1, M2><<<grid, FW_THREADS, dyn, st>>>(A);
+  XEQ_LAUNCHED(1);
+  return XEQ_OK;
+}
+
+}  // namespace xeq

@@ -700,6 +700,7 @@ static int launch_center(const CenterArgs& A, cudaStream_t st) {
 int launch_center_mma(const CenterArgs& A, bool jvp, cudaStream_t st);
 int launch_wgrad_mma(const NeighborArgs& A, int order, int grid, cudaStream_t st);
 int launch_nbr_mma(const NeighborArgs& A, int order, cudaStream_t st);
+int launch_center_fwd_ws(const CenterArgs& A, cudaStream_t st);  // edge_fwd_mma.cu: warp-specialised forward
 
 // XEQ_EDGE_SIMT=1 forces the SIMT filter contraction for the default widths too (A/B timing)
 static bool use_mma() {
@@ -716,7 +717,10 @@ static int run_center(const xeq_graph_t* g, const xeq_dims_t* dims, CenterArgs& 
   if (g->n_nodes == 0) return XEQ_OK;
   A.geo.g = *g;
   A.geo.rc = dims->cutoff;
-  if (cfg == 0 && use_mma()) return launch_center_mma(A, jvp, st);
+  if (cfg == 0 && use_mma()) {
+    static const bool ws = [] { const char* e = getenv("XEQ_FWD_WS"); return !(e && e[0] == '0'); }();  // A/B switch
+    return (!jvp && ws) ? launch_center_fwd_ws(A, st) : launch_center_mma(A, jvp, st);
+  }
   if (cfg == 0) return jvp ? launch_center<128, 64, 32, true>(A, st) : launch_center<128, 64, 32, false>(A, st);
   return jvp ? launch_center<256, 128, 64, true>(A, st) : launch_center<256, 128, 64, false>(A, st);
 }

@@ -151,7 +151,7 @@ __device__ __forceinline__ void center_mma_role(const CenterArgs& A, CenterMmaSm
   // pipeline prologue (the producer warp has described and measured chunks 0 and 1)
   __syncthreads();
   ChunkDesc d0 = sm.desc[0], d1 = sm.desc[1];
-  if (d0.cnt > 0) geo_stage_b<TC, THREADS, NOUT>(A.geo, d0.cnt, sm.a[0], tiles);
+  if (d0.cnt > 0) geo_stage_b<TC, THREADS, NOUT>(A.geo, d0.cnt, sm.a[0], tiles, threadIdx.x);
   proxy_fence();
   tc_fence_before();
   __syncthreads();
@@ -161,7 +161,7 @@ __device__ __forceinline__ void center_mma_role(const CenterArgs& A, CenterMmaSm
     const bool has = d0.cnt > 0;
     // radial terms of the next chunk -> B tiles, in the shadow of this chunk's MMAs
     if (d1.cnt > 0) {
-      geo_stage_b<TC, THREADS, NOUT>(A.geo, d1.cnt, sm.a[(c + 1) % 3], tiles + (uint32_t)((c + 1) & 1) * STAGE);
+      geo_stage_b<TC, THREADS, NOUT>(A.geo, d1.cnt, sm.a[(c + 1) % 3], tiles + (uint32_t)((c + 1) & 1) * STAGE, threadIdx.x);
       proxy_fence();
     }
 
@@ -460,7 +460,7 @@ __device__ __forceinline__ void nbr_mma_role(const NeighborArgs& A, NbrMmaSmem<O
   // pipeline prologue (the producer warp has described and measured chunks 0 and 1)
   __syncthreads();
   ChunkDesc d0 = sm.desc[0], d1 = sm.desc[1];
-  if (d0.cnt > 0) geo_stage_b<TC, THREADS, NOUT>(A.geo, d0.cnt, sm.a[0], tiles);
+  if (d0.cnt > 0) geo_stage_b<TC, THREADS, NOUT>(A.geo, d0.cnt, sm.a[0], tiles, threadIdx.x);
   proxy_fence();
   tc_fence_before();
   __syncthreads();
@@ -471,7 +471,7 @@ __device__ __forceinline__ void nbr_mma_role(const NeighborArgs& A, NbrMmaSmem<O
     const bool has = d0.cnt > 0;
     flush_red((c + 1) & 1, prev_cnt);  // chunk c-1
     if (d1.cnt > 0) {  // radial terms of the next chunk -> B tiles, in the shadow of this chunk's MMAs
-      geo_stage_b<TC, THREADS, NOUT>(A.geo, d1.cnt, sm.a[(c + 1) % 3], tiles + (uint32_t)((c + 1) & 1) * STAGE);
+      geo_stage_b<TC, THREADS, NOUT>(A.geo, d1.cnt, sm.a[(c + 1) % 3], tiles + (uint32_t)((c + 1) & 1) * STAGE, threadIdx.x);
       proxy_fence();
     }
     const GeoA<TC, true, SECOND>& sa = sm.a[c % 3];

@@ -167,8 +167,8 @@ template <int T> __device__ __forceinline__ constexpr uint32_t b_tile_bytes() { 
 // (output 0 = psi, 1 = dpsi, 2 = ddpsi).  One thread per (edge, k); rows >= cnt are zero-filled, so the filter
 // values of the slots past the end of a row piece are exact zeros.
 template <int T, int THREADS, int NOUT, bool NEED_G, bool SECOND>
-__device__ __noinline__ void geo_stage_b(const GeoArgs& A, int cnt, const GeoA<T, NEED_G, SECOND>& sa, uint32_t tiles) {
-  const int t = threadIdx.x;
+__device__ __noinline__ void geo_stage_b(const GeoArgs& A, int cnt, const GeoA<T, NEED_G, SECOND>& sa, uint32_t tiles,
+                                         const int t /* dense index of this thread among the THREADS writers */) {
   for (int idx = t; idx < T * NBP; idx += THREADS) {
     const int ee = idx / NBP, k = idx - ee * NBP;
     float val[3] = {0.f, 0.f, 0.f};
