@@ -181,6 +181,17 @@ def algorithmic_bytes(kind: str, cfg: orc.XPaiNNConfig, N: int, E: int, periodic
     raise KeyError(kind)
 
 
+# DRAM bytes per launch (dram__bytes_read.sum + dram__bytes_write.sum) of the kernels behind each timed op, from
+# the committed `ncu --set full` capture profiles/r01_edge_mma_ncu_full.md (c3 shape: N = 5376, E = 106068).
+# Only valid for that shape; other workloads report traffic = null.
+NCU_TRAFFIC_C3 = {
+    "edge_fwd": 36.42e6 + 0.43e6,
+    "edge_bwd": 36.87e6 + 2.22e6,
+    "edge_bwd_wgrad": (36.87e6 + 2.22e6) + (36.78e6 + 0.60e6),
+    "edge_bwdbwd": (46.14e6 + 0.91e6) + (59.67e6 + 7.72e6) + (59.6e6 + 5.3e6),
+}
+
+
 def measured_hbm_peak():
     p = ROOT / "MEASURED_PEAKS.json"
     if p.exists():
@@ -463,8 +474,9 @@ def run_gpu(args):
     if dom is not None:
         cnt, mean_ms, N, E = kern[dom]
         achieved = algorithmic_bytes(dom, cfg, N, E, periodic) / (mean_ms * 1e-3) / 1e9
+        traffic = NCU_TRAFFIC_C3.get(dom) if (args.workload == "c3" and N == 5376) else None
         roofline = {"kernel": dom, "bound": "hbm", "achieved": round(achieved, 2), "peak": peak, "unit": "GB/s",
-                    "frac": round(achieved / peak, 5), "traffic": None, "peak_source": peak_src,
+                    "frac": round(achieved / peak, 5), "traffic": traffic, "peak_source": peak_src,
                     "n_nodes": N, "n_edges": E, "mean_launch_ms": round(mean_ms, 5)}
 
     # CPU oracle on the host cores, bounded sample
