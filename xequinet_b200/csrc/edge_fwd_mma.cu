@@ -215,61 +215,14 @@ __device__ __forceinline__ void fwd_cursor(const CenterArgs& A, FwdSmem& sm, con
   RowCursor<FW_TC> cur_it;
   cur_it.init(g.rowptr, g.tile_ptr, g.n_tiles);
 
-  // pipeline registers
-  ChunkDesc dB, dC;      // chunks entering stages B and C
-  int colB = 0, jC = 0;  // neighbour index of this lane's slot
-  float piC[3] = {0.f, 0.f, 0.f}, pjC[3] = {0.f, 0.f, 0.f}, shC[3] = {0.f, 0.f, 0.f};  // raw loads, consumed one step later
-  dB.cnt = dC.cnt = -1;
-  dB.eb = dC.eb = 0; dB.owner = dC.owner = 0;
-
-  auto stage_a = [&](int k) {
+  GeoPipe<FW_TC, false, false, false> gp;
+  gp.init();
+  auto step = [&](int c) {  // geometry pipeline of iteration c: C(c+3) -> shared memory, B(c+4), A(c+5)
+    if (c + 3 >= 0) gp.stage_c(A.geo, sm.a[(c + 3) & 3], lane);
+    if (c + 4 >= 0) gp.stage_b(A.geo, lane);
     const ChunkDesc d = cur_it.next();
-    if (lane == 0) sm.desc[k & 7] = d;
-    dB = d;
-    colB = (d.cnt > 0 && lane < FW_TC) ? g.col[d.eb + min(lane, d.cnt - 1)] : 0;
-  };
-  auto stage_b = [&]() {
-    dC = dB;
-    jC = colB;
-    if (dB.cnt > 0 && lane < FW_TC) {
-      const int i = dB.owner, j = colB;
-#pragma unroll
-      for (int x = 0; x < 3; ++x) {  // loads only: the subtraction happens in stage C, after the latency has passed
-        piC[x] = A.geo.pos[3 * i + x];
-        pjC[x] = A.geo.pos[3 * j + x];
-        shC[x] = 0.f;
-      }
-      if (g.offsets != nullptr) {  // nn/basic.py:119-128: vectors -= cell_offsets @ cell[graph(neighbor)]
-        const char4 o = reinterpret_cast<const char4*>(g.offsets)[dB.eb + min(lane, dB.cnt - 1)];
-        const float* cl = g.cell + 9 * (g.node_graph ? g.node_graph[j] : 0);
-        const float ox = (float)o.x, oy = (float)o.y, oz = (float)o.z;
-#pragma unroll
-        for (int x = 0; x < 3; ++x) shC[x] = ox * cl[x] + oy * cl[3 + x] + oz * cl[6 + x];
-      }
-    }
-  };
-  auto stage_c = [&](int k) {
-    if (dC.cnt > 0 && lane < FW_TC) {
-      GeoA<FW_TC, false, false>& sa = sm.a[k & 3];
-      float dist, u[3], rC[3];
-#pragma unroll
-      for (int x = 0; x < 3; ++x) rC[x] = (piC[x] - pjC[x]) - shC[x];
-      unit_vector(rC, dist, u);
-      sph_harm(u, sa.Y[lane]);
-#pragma unroll
-      for (int x = 0; x < 3; ++x) sa.u[lane][x] = u[x];
-      const Cutoff<float> c = cutoff_terms(dist, A.geo.rc);
-      sa.d[lane] = dist;
-      sa.chi[lane][0] = c.chi; sa.chi[lane][1] = c.dchi; sa.chi[lane][2] = c.ddchi;
-      sa.gat[lane] = jC;
-      sa.own[lane] = dC.owner;
-      sa.eid[lane] = dC.eb + min(lane, dC.cnt - 1);
-    }
-  };
-  auto step = [&](int c) {  // geometry work of iteration c
-    if (c + 3 >= 0) stage_c(c + 3);
-    if (c + 4 >= 0) stage_b();
-    stage_a(c + 5);
+    if (lane == 0) sm.desc[(c + 5) & 7] = d;
+    gp.stage_a(A.geo, d, lane);
     __syncwarp();
   };
   for (int c = -5; c < 0; ++c) step(c);  // fill: geometry of chunks 0..2 in shared memory, 3 and 4 in flight

@@ -231,30 +231,15 @@ struct GeoArgs {
   float rc;
 };
 
-// TRANSPOSED = false: walk CSR rows (owner = center i, gathered = neighbor j = col[e], eid = e)
-// TRANSPOSED = true : walk transposed rows (owner = neighbor j, gathered = center i = t_row[sl], eid = t_eid[sl])
-template <int T, bool TRANSPOSED, bool NEED_G, bool SECOND>
-__device__ __noinline__ void geo_stage_a1(const GeoArgs& A, const ChunkDesc d, GeoA<T, NEED_G, SECOND>& sa,
-                                          const int t /* edge slot of this thread: threadIdx.x, or the lane of a producer warp */) {
-  // RowCursor chunks: the slots past the end of the row piece repeat its last edge, so the per-edge loops of the
-  // tcgen05 kernels can run whole groups without bounds checks (their filter values are exact zeros)
-  if (t >= d.cnt && (d.owner < 0 || d.cnt <= 0 || t >= T)) return;
-  const xeq_graph_t& g = A.g;
-  const int sl = d.eb + min(t, d.cnt - 1);
-  int i, j, e, owner;
-  if (!TRANSPOSED) {
-    owner = d.owner >= 0 ? d.owner : owner_of(g.rowptr, d.n0, d.n1, sl);
-    i = owner; j = g.col[sl]; e = sl;
-    sa.gat[t] = j;
-  } else {
-    owner = d.owner >= 0 ? d.owner : owner_of(g.t_rowptr, d.n0, d.n1, sl);
-    j = owner; i = g.t_row[sl]; e = g.t_eid[sl];
-    sa.gat[t] = i;
-  }
+// Geometry record of one edge slot t from its edge vector r (and, second order, the tangent rdot of r):
+// distances, harmonics (+ dY/dr, Hessian . rdot), cutoff terms, indices.
+template <int T, bool NEED_G, bool SECOND>
+__device__ __forceinline__ void geo_record(const GeoArgs& A, GeoA<T, NEED_G, SECOND>& sa, const int t, const int gat,
+                                           const int owner, const int e, const float r[3], const float rdot[3]) {
+  sa.gat[t] = gat;
   sa.own[t] = owner;
   sa.eid[t] = e;
-  float r[3], dist, u[3];
-  edge_vector(g, A.pos, i, j, e, r);
+  float dist, u[3];
   unit_vector(r, dist, u);
   if (!NEED_G && !SECOND) {
     sph_harm(u, sa.Y[t]);
@@ -268,11 +253,7 @@ __device__ __noinline__ void geo_stage_a1(const GeoArgs& A, const ChunkDesc d, G
         for (int m = 0; m < 8; ++m) sa.G[t][x * 8 + m] = G[x][m];
     }
     if (SECOND) {
-      float Hm[3][8], rp[3], rdot[3] = {0.f, 0.f, 0.f}, dd;
-      if (A.a_pos) {
-#pragma unroll
-        for (int x = 0; x < 3; ++x) rdot[x] = A.a_pos[3 * i + x] - A.a_pos[3 * j + x];
-      }
+      float Hm[3][8], rp[3], dd;
       angular_second(u, dist, rdot, G, dd, rp, sa.Ydot[t], Hm);
       sa.ddot[t] = dd;
 #pragma unroll
@@ -291,6 +272,93 @@ __device__ __noinline__ void geo_stage_a1(const GeoArgs& A, const ChunkDesc d, G
   sa.d[t] = dist;
   sa.chi[t][0] = c.chi; sa.chi[t][1] = c.dchi; sa.chi[t][2] = c.ddchi;
 }
+
+// TRANSPOSED = false: walk CSR rows (owner = center i, gathered = neighbor j = col[e], eid = e)
+// TRANSPOSED = true : walk transposed rows (owner = neighbor j, gathered = center i = t_row[sl], eid = t_eid[sl])
+template <int T, bool TRANSPOSED, bool NEED_G, bool SECOND>
+__device__ __noinline__ void geo_stage_a1(const GeoArgs& A, const ChunkDesc d, GeoA<T, NEED_G, SECOND>& sa,
+                                          const int t /* edge slot of this thread: threadIdx.x, or the lane of a producer warp */) {
+  // RowCursor chunks: the slots past the end of the row piece repeat its last edge, so the per-edge loops of the
+  // tcgen05 kernels can run whole groups without bounds checks (their filter values are exact zeros)
+  if (t >= d.cnt && (d.owner < 0 || d.cnt <= 0 || t >= T)) return;
+  const xeq_graph_t& g = A.g;
+  const int sl = d.eb + min(t, d.cnt - 1);
+  int i, j, e, owner;
+  if (!TRANSPOSED) {
+    owner = d.owner >= 0 ? d.owner : owner_of(g.rowptr, d.n0, d.n1, sl);
+    i = owner; j = g.col[sl]; e = sl;
+  } else {
+    owner = d.owner >= 0 ? d.owner : owner_of(g.t_rowptr, d.n0, d.n1, sl);
+    j = owner; i = g.t_row[sl]; e = g.t_eid[sl];
+  }
+  float r[3], rdot[3] = {0.f, 0.f, 0.f};
+  edge_vector(g, A.pos, i, j, e, r);
+  if (SECOND && A.a_pos) {
+#pragma unroll
+    for (int x = 0; x < 3; ++x) rdot[x] = A.a_pos[3 * i + x] - A.a_pos[3 * j + x];
+  }
+  geo_record<T, NEED_G, SECOND>(A, sa, t, TRANSPOSED ? i : j, owner, e, r, rdot);
+}
+
+// The same per-edge geometry as a three-stage software pipeline inside ONE producer warp (one lane per edge slot
+// of a RowCursor chunk), so that none of the dependent global loads  rowptr -> col / t_row, t_eid -> pos  is waited
+// for in the step that issued it:  A(k+2) indices | B(k+1) raw position loads | C(k) arithmetic -> shared memory.
+template <int T, bool TRANSPOSED, bool NEED_G, bool SECOND>
+struct GeoPipe {
+  ChunkDesc dB, dC;
+  int iB, jB, eB, iC, jC, eC;
+  float pi[3], pj[3], sh[3], ai[3], aj[3];
+
+  __device__ __forceinline__ void init() {
+    dB.cnt = dC.cnt = -1;
+    dB.owner = dC.owner = 0;
+    iB = jB = eB = iC = jC = eC = 0;
+#pragma unroll
+    for (int x = 0; x < 3; ++x) pi[x] = pj[x] = sh[x] = ai[x] = aj[x] = 0.f;
+  }
+  __device__ __forceinline__ void stage_a(const GeoArgs& A, const ChunkDesc& d, const int lane) {
+    dB = d;
+    if (d.cnt > 0 && lane < T) {
+      const int sl = d.eb + min(lane, d.cnt - 1);
+      if (!TRANSPOSED) { iB = d.owner; jB = A.g.col[sl]; eB = sl; }
+      else { jB = d.owner; iB = A.g.t_row[sl]; eB = A.g.t_eid[sl]; }
+    }
+  }
+  __device__ __forceinline__ void stage_b(const GeoArgs& A, const int lane) {
+    dC = dB; iC = iB; jC = jB; eC = eB;
+    if (dB.cnt > 0 && lane < T) {
+      const xeq_graph_t& g = A.g;
+#pragma unroll
+      for (int x = 0; x < 3; ++x) {  // loads only: the arithmetic happens in stage C, after the latency has passed
+        pi[x] = A.pos[3 * iB + x];
+        pj[x] = A.pos[3 * jB + x];
+        sh[x] = 0.f;
+        if (SECOND) {
+          ai[x] = A.a_pos ? A.a_pos[3 * iB + x] : 0.f;
+          aj[x] = A.a_pos ? A.a_pos[3 * jB + x] : 0.f;
+        }
+      }
+      if (g.offsets != nullptr) {  // nn/basic.py:119-128: vectors -= cell_offsets @ cell[graph(neighbor)]
+        const char4 o = reinterpret_cast<const char4*>(g.offsets)[eB];
+        const float* cl = g.cell + 9 * (g.node_graph ? g.node_graph[jB] : 0);
+        const float ox = (float)o.x, oy = (float)o.y, oz = (float)o.z;
+#pragma unroll
+        for (int x = 0; x < 3; ++x) sh[x] = ox * cl[x] + oy * cl[3 + x] + oz * cl[6 + x];
+      }
+    }
+  }
+  __device__ __forceinline__ void stage_c(const GeoArgs& A, GeoA<T, NEED_G, SECOND>& sa, const int lane) {
+    if (dC.cnt > 0 && lane < T) {
+      float r[3], rdot[3];
+#pragma unroll
+      for (int x = 0; x < 3; ++x) {
+        r[x] = (pi[x] - pj[x]) - sh[x];
+        rdot[x] = SECOND ? ai[x] - aj[x] : 0.f;
+      }
+      geo_record<T, NEED_G, SECOND>(A, sa, lane, TRANSPOSED ? iC : jC, dC.owner, eC, r, rdot);
+    }
+  }
+};
 
 template <int T, int THREADS, bool NEED_G, bool SECOND, bool D1, bool D2, bool XI, bool DXI>
 __device__ __noinline__ void geo_stage_a2(const GeoArgs& A, int cnt, const GeoA<T, NEED_G, SECOND>& sa,

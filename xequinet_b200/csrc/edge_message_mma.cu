@@ -37,7 +37,7 @@ template <bool JVP> struct CenterMma {
 template <bool JVP>
 struct CenterMmaSmem {
   GeoA<CenterMma<JVP>::TC, false, JVP> a[3];
-  ChunkDesc desc[3];  // written by the producer warp, one chunk ahead of the geometry it describes
+  ChunkDesc desc[8];  // ring written by the producer warp, ahead of the geometry it describes
   uint64_t bar;
   uint32_t slot;
 };
@@ -243,7 +243,7 @@ __device__ __forceinline__ void center_mma_role(const CenterArgs& A, CenterMmaSm
     tc_fence_before();
     __syncthreads();
     d0 = d1;
-    d1 = sm.desc[(c + 2) % 3];
+    d1 = sm.desc[(c + 2) & 7];
   }
 }
 
@@ -258,27 +258,30 @@ __device__ __forceinline__ void center_mma_producer(const CenterArgs& A, CenterM
   const uint32_t bar = smem_u32(&sm.bar);
   RowCursor<TC> cur_it;
   cur_it.init(g.rowptr, g.tile_ptr, g.n_tiles);
-  ChunkDesc d0 = cur_it.next(), d1 = cur_it.next(), d2;
-  if (lane == 0) { sm.desc[0] = d0; sm.desc[1] = d1; }
-  if (d0.cnt > 0) geo_stage_a1<TC, false, false, JVP>(A.geo, d0, sm.a[0], lane);
-  if (d1.cnt > 0) geo_stage_a1<TC, false, false, JVP>(A.geo, d1, sm.a[1], lane);
+  GeoPipe<TC, false, false, JVP> gp;
+  gp.init();
+  auto step = [&](int c) {  // geometry pipeline of iteration c: C(c+2) -> shared memory, B(c+3), A(c+4)
+    if (c + 2 >= 0) gp.stage_c(A.geo, sm.a[(c + 2) % 3], lane);
+    if (c + 3 >= 0) gp.stage_b(A.geo, lane);
+    const ChunkDesc d = cur_it.next();
+    if (lane == 0) sm.desc[(c + 4) & 7] = d;
+    gp.stage_a(A.geo, d, lane);
+    __syncwarp();
+  };
+  for (int c = -4; c < 0; ++c) step(c);  // fill: geometry of chunks 0, 1 in shared memory, 2 and 3 in flight
   __syncthreads();
   __syncthreads();  // the consumers have written the B tiles of chunk 0
-  for (int c = 0; d0.cnt >= 0; ++c) {
+  for (int c = 0; sm.desc[c & 7].cnt >= 0; ++c) {
     tc_fence_after();
-    if (d0.cnt > 0) {
+    if (sm.desc[c & 7].cnt > 0) {
       if (elect_one()) {
         issue_chunk<TC, NOUT>(tmem, tiles + (uint32_t)(c & 1) * STAGE);
         umma_commit(bar);
       }
       __syncwarp();
     }
-    d2 = cur_it.next();
-    if (lane == 0) sm.desc[(c + 2) % 3] = d2;
-    if (d2.cnt > 0) geo_stage_a1<TC, false, false, JVP>(A.geo, d2, sm.a[(c + 2) % 3], lane);
+    step(c);
     __syncthreads();
-    d0 = d1;
-    d1 = d2;
   }
 }
 
@@ -311,7 +314,7 @@ template <int ORDER> struct NbrMma {
 template <int ORDER>
 struct NbrMmaSmem {
   GeoA<NbrMma<ORDER>::TC, true, ORDER == 2> a[3];
-  ChunkDesc desc[3];
+  ChunkDesc desc[8];
   float red[2][NbrMma<ORDER>::TC][NbrMma<ORDER>::NW][3];
   int red_eid[2][NbrMma<ORDER>::TC];
   uint64_t bar;
@@ -577,7 +580,7 @@ __device__ __forceinline__ void nbr_mma_role(const NeighborArgs& A, NbrMmaSmem<O
     __syncthreads();
     prev_cnt = cnt;
     d0 = d1;
-    d1 = sm.desc[(c + 2) % 3];
+    d1 = sm.desc[(c + 2) & 7];
     if (d0.cnt < 0) flush_red(c & 1, prev_cnt);  // last chunk
   }
 }
@@ -592,27 +595,30 @@ __device__ __forceinline__ void nbr_mma_producer(const NeighborArgs& A, NbrMmaSm
   const uint32_t bar = smem_u32(&sm.bar);
   RowCursor<TC> cur_it;
   cur_it.init(g.t_rowptr, g.t_tile_ptr, g.t_n_tiles);
-  ChunkDesc d0 = cur_it.next(), d1 = cur_it.next(), d2;
-  if (lane == 0) { sm.desc[0] = d0; sm.desc[1] = d1; }
-  if (d0.cnt > 0) geo_stage_a1<TC, true, true, SECOND>(A.geo, d0, sm.a[0], lane);
-  if (d1.cnt > 0) geo_stage_a1<TC, true, true, SECOND>(A.geo, d1, sm.a[1], lane);
+  GeoPipe<TC, true, true, SECOND> gp;
+  gp.init();
+  auto step = [&](int c) {  // geometry pipeline of iteration c: C(c+2) -> shared memory, B(c+3), A(c+4)
+    if (c + 2 >= 0) gp.stage_c(A.geo, sm.a[(c + 2) % 3], lane);
+    if (c + 3 >= 0) gp.stage_b(A.geo, lane);
+    const ChunkDesc d = cur_it.next();
+    if (lane == 0) sm.desc[(c + 4) & 7] = d;
+    gp.stage_a(A.geo, d, lane);
+    __syncwarp();
+  };
+  for (int c = -4; c < 0; ++c) step(c);
   __syncthreads();
   __syncthreads();  // the consumers have written the B tiles of chunk 0
-  for (int c = 0; d0.cnt >= 0; ++c) {
+  for (int c = 0; sm.desc[c & 7].cnt >= 0; ++c) {
     tc_fence_after();
-    if (d0.cnt > 0) {
+    if (sm.desc[c & 7].cnt > 0) {
       if (elect_one()) {
         issue_chunk<TC, NOUT>(tmem, tiles + (uint32_t)(c & 1) * STAGE);
         umma_commit(bar);
       }
       __syncwarp();
     }
-    d2 = cur_it.next();
-    if (lane == 0) sm.desc[(c + 2) % 3] = d2;
-    if (d2.cnt > 0) geo_stage_a1<TC, true, true, SECOND>(A.geo, d2, sm.a[(c + 2) % 3], lane);
+    step(c);
     __syncthreads();
-    d0 = d1;
-    d1 = d2;
   }
 }
 
@@ -655,7 +661,7 @@ template <int ORDER> struct WgradMma {
 template <int ORDER>
 struct WgradMmaSmem {
   GeoA<WgradMma<ORDER>::KE, false, ORDER == 2> a[3];
-  ChunkDesc desc[3];
+  ChunkDesc desc[8];
   uint64_t bar;
   uint32_t slot;
 };
@@ -883,7 +889,7 @@ __device__ __forceinline__ void wgrad_mma_role(const NeighborArgs& A, WgradMmaSm
     tc_fence_before();
     __syncthreads();
     pending = has;
-    d0 = sm.desc[(c + 1) % 3];
+    d0 = sm.desc[(c + 1) & 7];
   }
   if (pending) {
     mbar_wait(bar, phase);
@@ -921,13 +927,21 @@ __device__ __forceinline__ void wgrad_mma_producer(const NeighborArgs& A, WgradM
   const uint32_t bar = smem_u32(&sm.bar);
   RowCursor<KE> cur_it;
   cur_it.init(g.t_rowptr, g.t_tile_ptr, g.t_n_tiles);
-  ChunkDesc d0 = cur_it.next(), d1;
-  if (lane == 0) sm.desc[0] = d0;
-  if (d0.cnt > 0) geo_stage_a1<KE, true, false, SECOND>(A.geo, d0, sm.a[0], lane);
+  GeoPipe<KE, true, false, SECOND> gp;
+  gp.init();
+  auto step = [&](int c) {  // geometry pipeline of iteration c: C(c+1) -> shared memory, B(c+2), A(c+3)
+    if (c + 1 >= 0) gp.stage_c(A.geo, sm.a[(c + 1) % 3], lane);
+    if (c + 2 >= 0) gp.stage_b(A.geo, lane);
+    const ChunkDesc d = cur_it.next();
+    if (lane == 0) sm.desc[(c + 3) & 7] = d;
+    gp.stage_a(A.geo, d, lane);
+    __syncwarp();
+  };
+  for (int c = -3; c < 0; ++c) step(c);  // fill: geometry of chunk 0 in shared memory, 1 and 2 in flight
   __syncthreads();
-  bool prev = false, issued = false;
+  bool issued = false;
   for (int c = 0;; ++c) {
-    if (prev) {  // MMAs of chunk c-1 (operands complete at the barrier that ended its iteration)
+    if (c > 0 && sm.desc[(c - 1) & 7].cnt > 0) {  // MMAs of chunk c-1 (operands complete at the barrier that ended its iteration)
       tc_fence_after();
       if (elect_one()) {
         issue_wgrad<ORDER>(tmem, tiles + (uint32_t)((c - 1) & 1) * STAGE, !issued);
@@ -936,13 +950,9 @@ __device__ __forceinline__ void wgrad_mma_producer(const NeighborArgs& A, WgradM
       __syncwarp();
       issued = true;
     }
-    if (d0.cnt < 0) break;
-    d1 = cur_it.next();
-    if (lane == 0) sm.desc[(c + 1) % 3] = d1;
-    if (d1.cnt > 0) geo_stage_a1<KE, true, false, SECOND>(A.geo, d1, sm.a[(c + 1) % 3], lane);
+    if (sm.desc[c & 7].cnt < 0) break;
+    step(c);
     __syncthreads();
-    prev = d0.cnt > 0;
-    d0 = d1;
   }
 }
 
