@@ -427,9 +427,11 @@ def run_gpu(args):
         kern_steps = min(args.steps, 5)
     else:
         total_ms, launches = timed(False, args.steps, args.warmup, True)
+        kern = ops.KernelTimer.summary()  # before the next timed() call clears the records
         e2e_ms, _ = timed(True, args.steps, max(3, args.warmup // 2), False)
         kern_steps = args.steps
-    kern = ops.KernelTimer.summary()
+    if use_graph:
+        kern = ops.KernelTimer.summary()
     if sampler:
         sampler.stop_flag.set()
         sampler.join(timeout=2)

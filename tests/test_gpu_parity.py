@@ -349,3 +349,56 @@ def test_static_graph_builder_matches_dynamic(periodic):
     small = StaticGraphBuilder(d0["pos"].shape[0], d0["ptr"], 5.0, edge_capacity=64, cell=d0.get("cell"), pbc=d0.get("pbc"))
     small.build(d0["pos"])
     assert int(small.overflow.item()) == 1
+
+
+# ---------------------------------------------------------------------------------------
+# the two implementations of the filter contraction (tcgen05 / SIMT) agree
+# ---------------------------------------------------------------------------------------
+_SIMT_SCRIPT = r"""
+import sys, torch
+sys.path.insert(0, {root!r}); sys.path.insert(0, {tests!r})
+from test_gpu_parity import _edge_outputs
+torch.save(_edge_outputs({n_mol}, {staged}), {out!r})
+"""
+
+
+def _edge_outputs(n_mol, staged):
+    """All edge-kernel outputs (values, first and second derivatives) on an aspirin-shaped batch; `staged`
+    selects molecule tiles (shared-memory row window) or edge-block tiles (direct gathers)."""
+    cfg = orc.CONFIG_DEFAULT
+    d = orc.make_aspirin_batch(n_mol, seed=11, with_edges=False)
+    kw = dict(ptr=d["ptr"].to(DEV)) if staged else {}
+    g, _, _ = build_graph(d["pos"].to(DEV), cfg.cutoff, batch=d["batch"].to(DEV), **kw)
+    N = g.n_nodes
+    dims = ops.Dims(cfg.node_dim, *cfg.muls, cfg.num_basis, cfg.cutoff)
+    gen = torch.Generator().manual_seed(5)
+    r = lambda *s: torch.randn(*s, generator=gen).to(DEV)
+    pos = d["pos"].to(DEV)
+    s, v, x, V = r(N, dims.H), r(N, dims.D), r(N, dims.node_dim), r(N, dims.D)
+    W, b = 0.3 * r(dims.H, 20), 0.3 * r(dims.H)
+    freq = (torch.pi * torch.arange(1, 21) / 5.0).float().to(DEV)
+    gx, gV, a_s, a_v, a_p = r(N, dims.node_dim), r(N, dims.D), r(N, dims.H), r(N, dims.D), r(N, 3)
+    out = list(ops.edge_message_fwd_raw(g, dims, pos, s, v, x, V, W, b, freq))
+    out += list(ops.edge_message_bwd_raw(g, dims, pos, s, v, W, b, freq, gx, gV, need_w=True))
+    out += list(ops.edge_message_bwdbwd_raw(g, dims, pos, s, v, W, b, freq, gx, gV, a_s, a_v, a_p))
+    torch.cuda.synchronize()
+    return [o.cpu() for o in out]
+
+
+@pytest.mark.parametrize("staged", [True, False], ids=["molecule-tiles", "edge-block-tiles"])
+def test_tcgen05_and_simt_edge_kernels_agree(staged, tmp_path):
+    """The tensor-core kernels (edge_message_mma.cu, edge_fwd_mma.cu) against the SIMT kernels (edge_message.cu,
+    run in a subprocess with XEQ_EDGE_SIMT=1): same results to fp32 round-off on every output."""
+    import os, subprocess, sys
+    from pathlib import Path
+
+    root = Path(__file__).resolve().parent.parent
+    ref_file = tmp_path / "simt.pt"
+    script = _SIMT_SCRIPT.format(root=str(root), tests=str(root / "tests"), n_mol=12, staged=staged, out=str(ref_file))
+    env = dict(os.environ, XEQ_EDGE_SIMT="1")
+    subprocess.run([sys.executable, "-c", script], check=True, env=env, timeout=300)
+    ref = torch.load(ref_file)
+    got = _edge_outputs(12, staged)
+    assert len(got) == len(ref) == 16
+    for i, (a, bref) in enumerate(zip(got, ref)):
+        assert _rel(a, bref) < 1e-5, f"output {i}"
