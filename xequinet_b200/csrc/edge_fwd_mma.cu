@@ -45,8 +45,8 @@ __device__ __forceinline__ void fwd_consumer(const CenterArgs& A, FwdSmem& sm, c
   constexpr int TC = FW_TC;
   constexpr int TS = (L == 0) ? 0 : 3, TE = (L == 0) ? 1 : 4, TX = 2;  // row tiles of this thread's filter rows
   const int t = threadIdx.x, warp = t >> 5;
-  const int q = t;
-  const int vbase = (L == 0) ? t : (L == 1 ? C + (t - C) : C + 3 * M1 + (t - C - M1));
+  const int q = slice_channel<L, C, M1>(t, blockIdx.y);  // irrep channel of this thread
+  const int vbase = (L == 0) ? q : (L == 1 ? C + (q - C) : C + 3 * M1 + (q - C - M1));
   constexpr int vstride = (L == 0) ? 0 : (L == 1 ? M1 : M2);
   const xeq_graph_t& g = A.geo.g;
   const uint32_t lane_base = tmem + ((uint32_t)(32 * (warp & 3)) << 16);
@@ -80,10 +80,10 @@ __device__ __forceinline__ void fwd_consumer(const CenterArgs& A, FwdSmem& sm, c
     for (int m = 0; m < NC; ++m) o.v[m] = vj[m * vstride];
   };
   // staged window: [row][column][thread-of-role] floats, role regions side by side
-  constexpr int ROWF = C * 4 + M1 * 5 + M2 * 7;
-  constexpr int NTHR = (L == 0) ? C : (L == 1 ? M1 : M2);
-  constexpr int ROLE_OFF = (L == 0) ? 0 : (L == 1 ? C * 4 : C * 4 + M1 * 5);
-  const int tt = (L == 0) ? t : (L == 1 ? t - C : t - C - M1);
+  constexpr int ROWF = SL_C * 4 + SL_M1 * 5 + SL_M2 * 7;
+  constexpr int NTHR = (L == 0) ? SL_C : (L == 1 ? SL_M1 : SL_M2);
+  constexpr int ROLE_OFF = (L == 0) ? 0 : (L == 1 ? SL_C * 4 : SL_C * 4 + SL_M1 * 5);
+  const int tt = (L == 0) ? t : (L == 1 ? t - SL_C : t - SL_C - SL_M1);
   const uint32_t win0 = win_base + 4u * (ROLE_OFF + tt);
   bool staged = false;
   int win_lo = 0;
@@ -132,7 +132,7 @@ __device__ __forceinline__ void fwd_consumer(const CenterArgs& A, FwdSmem& sm, c
     if (d0.rfirst) {  // residual row of the node: requested now, consumed when its row ends
 #pragma unroll
       for (int m = 0; m < NC; ++m) base_V[m] = A.V_in ? A.V_in[(size_t)node * D + vbase + m * vstride] : 0.f;
-      if (L == 0) base_x = A.x_in ? A.x_in[(size_t)node * C + t] : 0.f;
+      if (L == 0) base_x = A.x_in ? A.x_in[(size_t)node * C + q] : 0.f;
       th.reset();
     }
     if (cnt > 0) {
@@ -176,7 +176,7 @@ __device__ __forceinline__ void fwd_consumer(const CenterArgs& A, FwdSmem& sm, c
     if (d0.rlast) {
 #pragma unroll
       for (int m = 0; m < NC; ++m) A.V_out[(size_t)node * D + vbase + m * vstride] = base_V[m] + th.accV[m];
-      if (L == 0) A.x_out[(size_t)node * C + t] = base_x + th.accx;
+      if (L == 0) A.x_out[(size_t)node * C + q] = base_x + th.accx;
     }
     tc_fence_before();
     __syncthreads();
@@ -263,14 +263,14 @@ __device__ __forceinline__ void fwd_radial(const CenterArgs& A, FwdSmem& sm, con
 
 template <int C, int M1, int M2>
 __global__ void __launch_bounds__(FW_THREADS, 1) center_fwd_kernel(const CenterArgs A) {
-  static_assert(C == 128 && M1 + M2 <= 96 && M1 % 32 == 0 && M2 % 32 == 0 && C + M1 + M2 == FW_CONS, "row-tile mapping");
+  static_assert(C % SL_C == 0 && M1 == C / 2 && M2 == C / 4 && SL_M == FW_CONS, "channel slices of edge_mma.cuh");
   __shared__ FwdSmem sm;
   const uint32_t tmem = tmem_setup(&sm.slot, sm.full, 2);
   const uint32_t tiles = (smem_u32(xeq_dyn_smem) + 1023u) & ~1023u;
   const uint32_t win_base = tiles + FW_NSTAGE * FW_STAGE;
   const int t = threadIdx.x;
-  if (t < C) fwd_consumer<0, C, M1, M2>(A, sm, tmem, win_base);
-  else if (t < C + M1) fwd_consumer<1, C, M1, M2>(A, sm, tmem, win_base);
+  if (t < SL_C) fwd_consumer<0, C, M1, M2>(A, sm, tmem, win_base);
+  else if (t < SL_C + SL_M1) fwd_consumer<1, C, M1, M2>(A, sm, tmem, win_base);
   else if (t < FW_CONS) fwd_consumer<2, C, M1, M2>(A, sm, tmem, win_base);
   else if (t < FW_CONS + 32) fwd_cursor(A, sm, tmem, tiles);
   else fwd_radial(A, sm, tiles);
@@ -279,19 +279,25 @@ __global__ void __launch_bounds__(FW_THREADS, 1) center_fwd_kernel(const CenterA
 
 }  // namespace
 
-int launch_center_fwd_ws(const CenterArgs& A, cudaStream_t st) {
-  constexpr int C = 128, M1 = 64, M2 = 32;
+template <int C>
+static int launch_center_fwd_t(const CenterArgs& A, cudaStream_t st) {
+  constexpr int M1 = C / 2, M2 = C / 4, SLICES = C / SL_C;
   static_assert(sizeof(FwdSmem) <= 16 * 1024, "static shared memory budget");
-  const size_t dyn = 1024 + (size_t)FW_NSTAGE * FW_STAGE + (size_t)FW_WIN * (C * 4 + M1 * 5 + M2 * 7) * 4;
+  const size_t dyn = 1024 + (size_t)FW_NSTAGE * FW_STAGE + (size_t)FW_WIN * (SL_C * 4 + SL_M1 * 5 + SL_M2 * 7) * 4;
   static bool attr_set = false;
   if (!attr_set) {
     XEQ_CUDA(cudaFuncSetAttribute(center_fwd_kernel<C, M1, M2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn));
     attr_set = true;
   }
-  const int grid = min(A.geo.g.n_tiles, num_sms());
-  center_fwd_kernel<C, M1, M2><<<grid, FW_THREADS, dyn, st>>>(A);
+  const int grid = max(1, min(A.geo.g.n_tiles, num_sms() / SLICES));
+  center_fwd_kernel<C, M1, M2><<<dim3(grid, SLICES), FW_THREADS, dyn, st>>>(A);
   XEQ_LAUNCHED(1);
   return XEQ_OK;
+}
+
+// `wide`: 256x0e + 128x1o + 64x2e (two channel slices per tile of edges, grid.y = 2)
+int launch_center_fwd_ws(const CenterArgs& A, bool wide, cudaStream_t st) {
+  return wide ? launch_center_fwd_t<256>(A, st) : launch_center_fwd_t<128>(A, st);
 }
 
 }  // namespace xeq

@@ -585,17 +585,24 @@ __global__ void __launch_bounds__(WTHREADS) nbr_wgrad_kernel(const NeighborArgs 
   else nbr_wgrad_role<0, ROLE_SCALAR, C, M1, M2, ORDER>(A, sm);
 }
 
-// gpos[n] = sum_{e in row n} gr[e] - sum_{slot in t-row n} gr[t_eid[slot]]
-__global__ void pos_grad_kernel(xeq_graph_t g, const float* __restrict__ gr, float* __restrict__ gpos) {
+// gpos[n] = sum_{e in row n} gr[e] - sum_{slot in t-row n} gr[t_eid[slot]],  gr[e] = sum over the slice slabs (fixed order)
+__global__ void pos_grad_kernel(xeq_graph_t g, const float* __restrict__ gr, int n_slabs, float* __restrict__ gpos) {
   const int n = blockIdx.x * blockDim.x + threadIdx.x;
   if (n >= g.n_nodes) return;
+  const size_t slab = 3 * (size_t)g.n_edges;
   float a0 = 0.f, a1 = 0.f, a2 = 0.f;
   for (int e = g.rowptr[n]; e < g.rowptr[n + 1]; ++e) {
-    a0 += gr[3 * (size_t)e]; a1 += gr[3 * (size_t)e + 1]; a2 += gr[3 * (size_t)e + 2];
+    for (int k = 0; k < n_slabs; ++k) {
+      const float* p = gr + k * slab + 3 * (size_t)e;
+      a0 += p[0]; a1 += p[1]; a2 += p[2];
+    }
   }
   for (int s = g.t_rowptr[n]; s < g.t_rowptr[n + 1]; ++s) {
     const size_t e = g.t_eid[s];
-    a0 -= gr[3 * e]; a1 -= gr[3 * e + 1]; a2 -= gr[3 * e + 2];
+    for (int k = 0; k < n_slabs; ++k) {
+      const float* p = gr + k * slab + 3 * e;
+      a0 -= p[0]; a1 -= p[1]; a2 -= p[2];
+    }
   }
   gpos[3 * n] = a0; gpos[3 * n + 1] = a1; gpos[3 * n + 2] = a2;
 }
@@ -697,10 +704,10 @@ static int launch_center(const CenterArgs& A, cudaStream_t st) {
 }
 
 // tensor-core variants (edge_message_mma.cu), default widths only
-int launch_center_mma(const CenterArgs& A, bool jvp, cudaStream_t st);
-int launch_wgrad_mma(const NeighborArgs& A, int order, int grid, cudaStream_t st);
-int launch_nbr_mma(const NeighborArgs& A, int order, cudaStream_t st);
-int launch_center_fwd_ws(const CenterArgs& A, cudaStream_t st);  // edge_fwd_mma.cu: warp-specialised forward
+int launch_center_mma(const CenterArgs& A, bool jvp, bool wide, cudaStream_t st);
+int launch_wgrad_mma(const NeighborArgs& A, int order, bool wide, int grid, cudaStream_t st);
+int launch_nbr_mma(const NeighborArgs& A, int order, bool wide, cudaStream_t st);
+int launch_center_fwd_ws(const CenterArgs& A, bool wide, cudaStream_t st);  // edge_fwd_mma.cu: warp-specialised forward
 
 // XEQ_EDGE_SIMT=1 forces the SIMT filter contraction for the default widths too (A/B timing)
 static bool use_mma() {
@@ -717,9 +724,9 @@ static int run_center(const xeq_graph_t* g, const xeq_dims_t* dims, CenterArgs& 
   if (g->n_nodes == 0) return XEQ_OK;
   A.geo.g = *g;
   A.geo.rc = dims->cutoff;
-  if (cfg == 0 && use_mma()) {
+  if (use_mma()) {
     static const bool ws = [] { const char* e = getenv("XEQ_FWD_WS"); return !(e && e[0] == '0'); }();  // A/B switch
-    return (!jvp && ws) ? launch_center_fwd_ws(A, st) : launch_center_mma(A, jvp, st);
+    return (!jvp && ws) ? launch_center_fwd_ws(A, cfg == 1, st) : launch_center_mma(A, jvp, cfg == 1, st);
   }
   if (cfg == 0) return jvp ? launch_center<128, 64, 32, true>(A, st) : launch_center<128, 64, 32, false>(A, st);
   return jvp ? launch_center<256, 128, 64, true>(A, st) : launch_center<256, 128, 64, false>(A, st);
@@ -729,7 +736,7 @@ static int wgrad_grid_x(const xeq_graph_t* g) { return min(g->t_n_tiles, num_sms
 
 static size_t neighbor_ws_bytes(const xeq_graph_t* g, const xeq_dims_t* d, int want_wgrad) {
   const int H = dims_H(d);
-  size_t b = 256 + align_up(sizeof(float) * 3 * (size_t)(g->n_edges > 0 ? g->n_edges : 1), 256);
+  size_t b = 256 + align_up(sizeof(float) * 2 * 3 * (size_t)(g->n_edges > 0 ? g->n_edges : 1), 256);
   if (want_wgrad) {
     b += align_up(sizeof(float) * (size_t)wgrad_grid_x(g) * H * 2 * NBP, 256);
     b += align_up(sizeof(float) * (size_t)H * NB_, 256);
@@ -778,9 +785,10 @@ static int run_neighbor(const xeq_graph_t* g, const xeq_dims_t* dims, NeighborAr
   const int H = dims_H(dims);
   if (g->n_nodes == 0) return XEQ_OK;
   Carver cv(ws);
-  float* gr = cv.take<float>(3 * (size_t)(g->n_edges > 0 ? g->n_edges : 1));
-  const bool mma = cfg == 0 && use_mma();
-  const int gx = mma ? min(g->t_n_tiles, num_sms()) : wgrad_grid_x(g);  // per-CTA partial slabs
+  float* gr = cv.take<float>(2 * 3 * (size_t)(g->n_edges > 0 ? g->n_edges : 1));  // up to two slice slabs
+  const bool mma = use_mma();
+  const int slices = mma ? (cfg == 1 ? 2 : 1) : 1;  // channel slices of the tcgen05 kernels: one d/dr slab each
+  const int gx = mma ? max(1, min(g->t_n_tiles, num_sms() / slices)) : wgrad_grid_x(g);  // per-CTA partial slabs
   float *wpart = nullptr, *ftot = nullptr;
   if (wgrad) {
     wpart = cv.take<float>((size_t)gx * H * 2 * NBP);
@@ -791,13 +799,13 @@ static int run_neighbor(const xeq_graph_t* g, const xeq_dims_t* dims, NeighborAr
   A.gr = o_pos ? gr : nullptr;
   A.wpart = wpart;
   if (mma) {
-    if (main) rc = launch_nbr_mma(A, order, st);
-    if (!rc && wgrad) rc = launch_wgrad_mma(A, order, gx, st);
+    if (main) rc = launch_nbr_mma(A, order, cfg == 1, st);
+    if (!rc && wgrad) rc = launch_wgrad_mma(A, order, cfg == 1, gx, st);
   } else if (cfg == 0) rc = order == 1 ? launch_neighbor<128, 64, 32, 1>(A, main, wgrad, gx, st) : launch_neighbor<128, 64, 32, 2>(A, main, wgrad, gx, st);
   else rc = order == 1 ? launch_neighbor<256, 128, 64, 1>(A, main, wgrad, gx, st) : launch_neighbor<256, 128, 64, 2>(A, main, wgrad, gx, st);
   if (rc) return rc;
   if (o_pos) {
-    pos_grad_kernel<<<(g->n_nodes + 127) / 128, 128, 0, st>>>(*g, gr, o_pos);
+    pos_grad_kernel<<<(g->n_nodes + 127) / 128, 128, 0, st>>>(*g, gr, slices, o_pos);
     XEQ_LAUNCHED(1);
   }
   if (wgrad) {

@@ -46,12 +46,12 @@ template <int L, int C, int M1, int M2, bool JVP>
 __device__ __forceinline__ void center_mma_role(const CenterArgs& A, CenterMmaSmem<JVP>& sm, const uint32_t tmem,
                                                 const uint32_t tiles, const uint32_t win_base) {
   constexpr int M = C + M1 + M2, D = C + 3 * M1 + 5 * M2, H = C + 2 * M, NC = 2 * L + 1;
-  constexpr int THREADS = M;
+  constexpr int THREADS = SL_M;
   constexpr int TC = CenterMma<JVP>::TC, NOUT = CenterMma<JVP>::NOUT, STAGE = CenterMma<JVP>::STAGE;
   constexpr int TS = (L == 0) ? 0 : 3, TE = (L == 0) ? 1 : 4, TX = 2;  // row tiles of this thread's filter rows
   const int t = threadIdx.x, warp = t >> 5;
-  const int q = t;
-  const int vbase = (L == 0) ? t : (L == 1 ? C + (t - C) : C + 3 * M1 + (t - C - M1));
+  const int q = slice_channel<L, C, M1>(t, blockIdx.y);  // irrep channel of this thread
+  const int vbase = (L == 0) ? q : (L == 1 ? C + (q - C) : C + 3 * M1 + (q - C - M1));
   constexpr int vstride = (L == 0) ? 0 : (L == 1 ? M1 : M2);
   const xeq_graph_t& g = A.geo.g;
   const uint32_t lane_base = tmem + ((uint32_t)(32 * (warp & 3)) << 16);
@@ -99,10 +99,10 @@ __device__ __forceinline__ void center_mma_role(const CenterArgs& A, CenterMmaSm
 
   // staged window: [row][column][thread-of-role] floats, role regions side by side (as in edge_message.cu)
   constexpr int WMAX = CenterMma<JVP>::WIN;
-  constexpr int ROWF = (C * 4 + M1 * 5 + M2 * 7) * (JVP ? 2 : 1);
-  constexpr int NTHR = (L == 0) ? C : (L == 1 ? M1 : M2);
-  constexpr int ROLE_OFF = (L == 0 ? 0 : (L == 1 ? C * 4 : C * 4 + M1 * 5)) * (JVP ? 2 : 1);
-  const int tt = (L == 0) ? t : (L == 1 ? t - C : t - C - M1);
+  constexpr int ROWF = (SL_C * 4 + SL_M1 * 5 + SL_M2 * 7) * (JVP ? 2 : 1);
+  constexpr int NTHR = (L == 0) ? SL_C : (L == 1 ? SL_M1 : SL_M2);
+  constexpr int ROLE_OFF = (L == 0 ? 0 : (L == 1 ? SL_C * 4 : SL_C * 4 + SL_M1 * 5)) * (JVP ? 2 : 1);
+  const int tt = (L == 0) ? t : (L == 1 ? t - SL_C : t - SL_C - SL_M1);
   const uint32_t win0 = win_base + 4u * (ROLE_OFF + tt);
   bool staged = false;
   int win_lo = 0;
@@ -175,7 +175,7 @@ __device__ __forceinline__ void center_mma_role(const CenterArgs& A, CenterMmaSm
     if (d0.rfirst) {  // residual row of the node: requested now, consumed when its row ends
 #pragma unroll
       for (int m = 0; m < NC; ++m) base_V[m] = A.V_in ? A.V_in[(size_t)node * D + vbase + m * vstride] : 0.f;
-      if (L == 0) base_x = A.x_in ? A.x_in[(size_t)node * C + t] : 0.f;
+      if (L == 0) base_x = A.x_in ? A.x_in[(size_t)node * C + q] : 0.f;
       th.reset();
     }
     if (has) {
@@ -238,7 +238,7 @@ __device__ __forceinline__ void center_mma_role(const CenterArgs& A, CenterMmaSm
     if (d0.rlast) {
 #pragma unroll
       for (int m = 0; m < NC; ++m) A.V_out[(size_t)node * D + vbase + m * vstride] = base_V[m] + th.accV[m];
-      if (L == 0) A.x_out[(size_t)node * C + t] = base_x + th.accx;
+      if (L == 0) A.x_out[(size_t)node * C + q] = base_x + th.accx;
     }
     tc_fence_before();
     __syncthreads();
@@ -286,16 +286,16 @@ __device__ __forceinline__ void center_mma_producer(const CenterArgs& A, CenterM
 }
 
 template <int C, int M1, int M2, bool JVP>
-__global__ void __launch_bounds__(C + M1 + M2 + 32, 1) center_mma_kernel(const CenterArgs A) {
-  static_assert(C == 128 && M1 + M2 <= 96 && M1 % 32 == 0 && M2 % 32 == 0, "row-tile mapping of edge_mma.cuh");
+__global__ void __launch_bounds__(SL_M + 32, 1) center_mma_kernel(const CenterArgs A) {
+  static_assert(C % SL_C == 0 && M1 == C / 2 && M2 == C / 4, "channel slices of edge_mma.cuh");
   __shared__ CenterMmaSmem<JVP> sm;
   const uint32_t tmem = tmem_setup(&sm.slot, &sm.bar, 1);
   const uint32_t tiles = (smem_u32(xeq_dyn_smem) + 1023u) & ~1023u;
   const uint32_t win_base = tiles + 2u * CenterMma<JVP>::STAGE;
   const int t = threadIdx.x;
-  if (t < C) center_mma_role<0, C, M1, M2, JVP>(A, sm, tmem, tiles, win_base);
-  else if (t < C + M1) center_mma_role<1, C, M1, M2, JVP>(A, sm, tmem, tiles, win_base);
-  else if (t < C + M1 + M2) center_mma_role<2, C, M1, M2, JVP>(A, sm, tmem, tiles, win_base);
+  if (t < SL_C) center_mma_role<0, C, M1, M2, JVP>(A, sm, tmem, tiles, win_base);
+  else if (t < SL_C + SL_M1) center_mma_role<1, C, M1, M2, JVP>(A, sm, tmem, tiles, win_base);
+  else if (t < SL_M) center_mma_role<2, C, M1, M2, JVP>(A, sm, tmem, tiles, win_base);
   else center_mma_producer<C, M1, M2, JVP>(A, sm, tmem, tiles);
   tmem_teardown(tmem);
 }
@@ -350,13 +350,13 @@ template <int L, int C, int M1, int M2, int ORDER>
 __device__ __forceinline__ void nbr_mma_role(const NeighborArgs& A, NbrMmaSmem<ORDER>& sm, const uint32_t tmem,
                                              const uint32_t tiles, const uint32_t win_base) {
   constexpr int M = C + M1 + M2, D = C + 3 * M1 + 5 * M2, H = C + 2 * M, NC = 2 * L + 1;
-  constexpr int THREADS = M, NW = NbrMma<ORDER>::NW;
+  constexpr int THREADS = SL_M, NW = NbrMma<ORDER>::NW;
   constexpr bool SECOND = ORDER == 2;
   constexpr int TC = NbrMma<ORDER>::TC, NOUT = NbrMma<ORDER>::NOUT, STAGE = NbrMma<ORDER>::STAGE;
   constexpr int TS = (L == 0) ? 0 : 3, TE = (L == 0) ? 1 : 4, TX = 2;
   const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
-  const int q = t;
-  const int vbase = (L == 0) ? t : (L == 1 ? C + (t - C) : C + 3 * M1 + (t - C - M1));
+  const int q = slice_channel<L, C, M1>(t, blockIdx.y);  // irrep channel of this thread
+  const int vbase = (L == 0) ? q : (L == 1 ? C + (q - C) : C + 3 * M1 + (q - C - M1));
   constexpr int vstride = (L == 0) ? 0 : (L == 1 ? M1 : M2);
   const xeq_graph_t& g = A.geo.g;
   const uint32_t lane_base = tmem + ((uint32_t)(32 * (warp & 3)) << 16);
@@ -425,10 +425,10 @@ __device__ __forceinline__ void nbr_mma_role(const NeighborArgs& A, NbrMmaSmem<O
     o.gx = (L == 0) ? A.gx[(size_t)i * C + q] : 0.f;
   };
   constexpr int WMAX = NbrMma<ORDER>::WIN;
-  constexpr int ROWF = C * 2 + M1 * 3 + M2 * 5;
-  constexpr int NTHR = (L == 0) ? C : (L == 1 ? M1 : M2);
-  constexpr int ROLE_OFF = (L == 0) ? 0 : (L == 1 ? C * 2 : C * 2 + M1 * 3);
-  const int tt = (L == 0) ? t : (L == 1 ? t - C : t - C - M1);
+  constexpr int ROWF = SL_C * 2 + SL_M1 * 3 + SL_M2 * 5;
+  constexpr int NTHR = (L == 0) ? SL_C : (L == 1 ? SL_M1 : SL_M2);
+  constexpr int ROLE_OFF = (L == 0) ? 0 : (L == 1 ? SL_C * 2 : SL_C * 2 + SL_M1 * 3);
+  const int tt = (L == 0) ? t : (L == 1 ? t - SL_C : t - SL_C - SL_M1);
   const uint32_t win0 = win_base + 4u * (ROLE_OFF + tt);
   bool staged = false;
   int win_lo = 0;
@@ -455,7 +455,7 @@ __device__ __forceinline__ void nbr_mma_role(const NeighborArgs& A, NbrMmaSmem<O
       float a0 = 0.f, a1 = 0.f, a2 = 0.f;
 #pragma unroll
       for (int w = 0; w < NW; ++w) { a0 += sm.red[rs][t][w][0]; a1 += sm.red[rs][t][w][1]; a2 += sm.red[rs][t][w][2]; }
-      float* dst = A.gr + (size_t)sm.red_eid[rs][t] * 3;
+      float* dst = A.gr + ((size_t)blockIdx.y * g.n_edges + sm.red_eid[rs][t]) * 3;
       dst[0] = a0; dst[1] = a1; dst[2] = a2;
     }
   };
@@ -623,17 +623,17 @@ __device__ __forceinline__ void nbr_mma_producer(const NeighborArgs& A, NbrMmaSm
 }
 
 template <int C, int M1, int M2, int ORDER>
-__global__ void __launch_bounds__(C + M1 + M2 + 32, 1) nbr_mma_kernel(const NeighborArgs A) {
-  static_assert(C == 128 && M1 + M2 <= 96 && M1 % 32 == 0 && M2 % 32 == 0, "row-tile mapping of edge_mma.cuh");
-  static_assert((C + M1 + M2) / 32 == NbrMma<ORDER>::NW, "consumer warps");
+__global__ void __launch_bounds__(SL_M + 32, 1) nbr_mma_kernel(const NeighborArgs A) {
+  static_assert(C % SL_C == 0 && M1 == C / 2 && M2 == C / 4, "channel slices of edge_mma.cuh");
+  static_assert(SL_M / 32 == NbrMma<ORDER>::NW, "consumer warps");
   __shared__ NbrMmaSmem<ORDER> sm;
   const uint32_t tmem = tmem_setup(&sm.slot, &sm.bar, 1);
   const uint32_t tiles = (smem_u32(xeq_dyn_smem) + 1023u) & ~1023u;
   const uint32_t win_base = tiles + 2u * NbrMma<ORDER>::STAGE;
   const int t = threadIdx.x;
-  if (t < C) nbr_mma_role<0, C, M1, M2, ORDER>(A, sm, tmem, tiles, win_base);
-  else if (t < C + M1) nbr_mma_role<1, C, M1, M2, ORDER>(A, sm, tmem, tiles, win_base);
-  else if (t < C + M1 + M2) nbr_mma_role<2, C, M1, M2, ORDER>(A, sm, tmem, tiles, win_base);
+  if (t < SL_C) nbr_mma_role<0, C, M1, M2, ORDER>(A, sm, tmem, tiles, win_base);
+  else if (t < SL_C + SL_M1) nbr_mma_role<1, C, M1, M2, ORDER>(A, sm, tmem, tiles, win_base);
+  else if (t < SL_M) nbr_mma_role<2, C, M1, M2, ORDER>(A, sm, tmem, tiles, win_base);
   else nbr_mma_producer<C, M1, M2, ORDER>(A, sm, tmem, tiles);
   tmem_teardown(tmem);
 }
@@ -724,14 +724,14 @@ template <int L, int C, int M1, int M2, int ORDER>
 __device__ __forceinline__ void wgrad_mma_role(const NeighborArgs& A, WgradMmaSmem<ORDER>& sm, const uint32_t tmem,
                                                const uint32_t tiles, const uint32_t win_base) {
   constexpr int M = C + M1 + M2, D = C + 3 * M1 + 5 * M2, H = C + 2 * M, NC = 2 * L + 1;
-  constexpr int THREADS = M;
+  constexpr int THREADS = SL_M;
   constexpr bool SECOND = ORDER == 2;
   constexpr int KE = WgradMma<ORDER>::KE, NB = WgradMma<ORDER>::NB, A0 = WgradMma<ORDER>::A0, STAGE = WgradMma<ORDER>::STAGE;
   constexpr int TS = (L == 0) ? 0 : 3, TE = (L == 0) ? 1 : 4, TX = 2;
   constexpr int NROW = (L == 0) ? 3 : 2;
   const int t = threadIdx.x, warp = t >> 5;
-  const int q = t;
-  const int vbase = (L == 0) ? t : (L == 1 ? C + (t - C) : C + 3 * M1 + (t - C - M1));
+  const int q = slice_channel<L, C, M1>(t, blockIdx.y);  // irrep channel of this thread
+  const int vbase = (L == 0) ? q : (L == 1 ? C + (q - C) : C + 3 * M1 + (q - C - M1));
   constexpr int vstride = (L == 0) ? 0 : (L == 1 ? M1 : M2);
   const xeq_graph_t& g = A.geo.g;
   const uint32_t lane_base = tmem + ((uint32_t)(32 * (warp & 3)) << 16);
@@ -774,10 +774,10 @@ __device__ __forceinline__ void wgrad_mma_role(const NeighborArgs& A, WgradMmaSm
   };
   // window of gV / gx rows (layout of edge_message.cu's neighbor kernels)
   constexpr int WMAX = WgradMma<ORDER>::WIN;
-  constexpr int ROWF = C * 2 + M1 * 3 + M2 * 5;
-  constexpr int NTHR = (L == 0) ? C : (L == 1 ? M1 : M2);
-  constexpr int ROLE_OFF = (L == 0) ? 0 : (L == 1 ? C * 2 : C * 2 + M1 * 3);
-  const int tt = (L == 0) ? t : (L == 1 ? t - C : t - C - M1);
+  constexpr int ROWF = SL_C * 2 + SL_M1 * 3 + SL_M2 * 5;
+  constexpr int NTHR = (L == 0) ? SL_C : (L == 1 ? SL_M1 : SL_M2);
+  constexpr int ROLE_OFF = (L == 0) ? 0 : (L == 1 ? SL_C * 2 : SL_C * 2 + SL_M1 * 3);
+  const int tt = (L == 0) ? t : (L == 1 ? t - SL_C : t - SL_C - SL_M1);
   const uint32_t win0 = win_base + 4u * (ROLE_OFF + tt);
   bool staged = false;
   int win_lo = 0;
@@ -957,16 +957,16 @@ __device__ __forceinline__ void wgrad_mma_producer(const NeighborArgs& A, WgradM
 }
 
 template <int C, int M1, int M2, int ORDER>
-__global__ void __launch_bounds__(C + M1 + M2 + 32, 1) wgrad_mma_kernel(const NeighborArgs A) {
-  static_assert(C == 128 && M1 + M2 <= 96 && M1 % 32 == 0 && M2 % 32 == 0, "row-tile mapping of edge_mma.cuh");
+__global__ void __launch_bounds__(SL_M + 32, 1) wgrad_mma_kernel(const NeighborArgs A) {
+  static_assert(C % SL_C == 0 && M1 == C / 2 && M2 == C / 4, "channel slices of edge_mma.cuh");
   __shared__ WgradMmaSmem<ORDER> sm;
   const uint32_t tmem = tmem_setup(&sm.slot, &sm.bar, 1);
   const uint32_t tiles = (smem_u32(xeq_dyn_smem) + 1023u) & ~1023u;
   const uint32_t win_base = tiles + 2u * WgradMma<ORDER>::STAGE;
   const int t = threadIdx.x;
-  if (t < C) wgrad_mma_role<0, C, M1, M2, ORDER>(A, sm, tmem, tiles, win_base);
-  else if (t < C + M1) wgrad_mma_role<1, C, M1, M2, ORDER>(A, sm, tmem, tiles, win_base);
-  else if (t < C + M1 + M2) wgrad_mma_role<2, C, M1, M2, ORDER>(A, sm, tmem, tiles, win_base);
+  if (t < SL_C) wgrad_mma_role<0, C, M1, M2, ORDER>(A, sm, tmem, tiles, win_base);
+  else if (t < SL_C + SL_M1) wgrad_mma_role<1, C, M1, M2, ORDER>(A, sm, tmem, tiles, win_base);
+  else if (t < SL_M) wgrad_mma_role<2, C, M1, M2, ORDER>(A, sm, tmem, tiles, win_base);
   else wgrad_mma_producer<C, M1, M2, ORDER>(A, sm, tmem, tiles);
   tmem_teardown(tmem);
 }
@@ -977,72 +977,74 @@ static int set_smem(Kernel k, size_t bytes) {
   return XEQ_OK;
 }
 
-template <bool JVP>
+// Launchers.  `wide` selects the 256x0e + 128x1o + 64x2e instantiation (two channel slices per tile of edges:
+// grid.y = 2, half as many CTAs along x so that all CTAs are resident at once).
+template <int C, bool JVP>
 static int launch_center_mma_t(const CenterArgs& A, cudaStream_t st) {
-  constexpr int C = 128, M1 = 64, M2 = 32;
+  constexpr int M1 = C / 2, M2 = C / 4, SLICES = C / SL_C;
   static_assert(sizeof(CenterMmaSmem<JVP>) <= 24 * 1024, "static shared memory budget");
   const size_t dyn = 1024 + 2 * (size_t)CenterMma<JVP>::STAGE +
-                     (size_t)CenterMma<JVP>::WIN * (C * 4 + M1 * 5 + M2 * 7) * (JVP ? 2 : 1) * 4;
+                     (size_t)CenterMma<JVP>::WIN * (SL_C * 4 + SL_M1 * 5 + SL_M2 * 7) * (JVP ? 2 : 1) * 4;
   static bool attr_set = false;
   if (!attr_set) {
     int rc = set_smem(center_mma_kernel<C, M1, M2, JVP>, dyn);
     if (rc) return rc;
     attr_set = true;
   }
-  const int grid = min(A.geo.g.n_tiles, num_sms());
-  center_mma_kernel<C, M1, M2, JVP><<<grid, C + M1 + M2 + 32, dyn, st>>>(A);
+  const int grid = max(1, min(A.geo.g.n_tiles, num_sms() / SLICES));
+  center_mma_kernel<C, M1, M2, JVP><<<dim3(grid, SLICES), SL_M + 32, dyn, st>>>(A);
   XEQ_LAUNCHED(1);
   return XEQ_OK;
 }
 
-int launch_center_mma(const CenterArgs& A, bool jvp, cudaStream_t st) {
-  return jvp ? launch_center_mma_t<true>(A, st) : launch_center_mma_t<false>(A, st);
+int launch_center_mma(const CenterArgs& A, bool jvp, bool wide, cudaStream_t st) {
+  if (wide) return jvp ? launch_center_mma_t<256, true>(A, st) : launch_center_mma_t<256, false>(A, st);
+  return jvp ? launch_center_mma_t<128, true>(A, st) : launch_center_mma_t<128, false>(A, st);
 }
 
-}  // namespace xeq
-
-namespace xeq {
-
-template <int ORDER>
+template <int C, int ORDER>
 static int launch_wgrad_mma_t(const NeighborArgs& A, int grid, cudaStream_t st) {
-  constexpr int C = 128, M1 = 64, M2 = 32;
+  constexpr int M1 = C / 2, M2 = C / 4, SLICES = C / SL_C;
   static_assert(sizeof(WgradMmaSmem<ORDER>) <= 24 * 1024, "static shared memory budget");
-  const size_t dyn = 1024 + 2 * (size_t)WgradMma<ORDER>::STAGE + (size_t)WgradMma<ORDER>::WIN * (C * 2 + M1 * 3 + M2 * 5) * 4;
+  const size_t dyn = 1024 + 2 * (size_t)WgradMma<ORDER>::STAGE + (size_t)WgradMma<ORDER>::WIN * (SL_C * 2 + SL_M1 * 3 + SL_M2 * 5) * 4;
   static bool attr_set = false;
   if (!attr_set) {
     int rc = set_smem(wgrad_mma_kernel<C, M1, M2, ORDER>, dyn);
     if (rc) return rc;
     attr_set = true;
   }
-  wgrad_mma_kernel<C, M1, M2, ORDER><<<grid, C + M1 + M2 + 32, dyn, st>>>(A);
+  wgrad_mma_kernel<C, M1, M2, ORDER><<<dim3(grid, SLICES), SL_M + 32, dyn, st>>>(A);
   XEQ_LAUNCHED(1);
   return XEQ_OK;
 }
 
-template <int ORDER>
+template <int C, int ORDER>
 static int launch_nbr_mma_t(const NeighborArgs& A, cudaStream_t st) {
-  constexpr int C = 128, M1 = 64, M2 = 32;
+  constexpr int M1 = C / 2, M2 = C / 4, SLICES = C / SL_C;
   static_assert(sizeof(NbrMmaSmem<ORDER>) <= 40 * 1024, "static shared memory budget");
-  const size_t dyn = 1024 + 2 * (size_t)NbrMma<ORDER>::STAGE + (size_t)NbrMma<ORDER>::WIN * (C * 2 + M1 * 3 + M2 * 5) * 4;
+  const size_t dyn = 1024 + 2 * (size_t)NbrMma<ORDER>::STAGE + (size_t)NbrMma<ORDER>::WIN * (SL_C * 2 + SL_M1 * 3 + SL_M2 * 5) * 4;
   static bool attr_set = false;
   if (!attr_set) {
     int rc = set_smem(nbr_mma_kernel<C, M1, M2, ORDER>, dyn);
     if (rc) return rc;
     attr_set = true;
   }
-  const int grid = min(A.geo.g.t_n_tiles, num_sms());
-  nbr_mma_kernel<C, M1, M2, ORDER><<<grid, C + M1 + M2 + 32, dyn, st>>>(A);
+  const int grid = max(1, min(A.geo.g.t_n_tiles, num_sms() / SLICES));
+  nbr_mma_kernel<C, M1, M2, ORDER><<<dim3(grid, SLICES), SL_M + 32, dyn, st>>>(A);
   XEQ_LAUNCHED(1);
   return XEQ_OK;
 }
 
-int launch_nbr_mma(const NeighborArgs& A, int order, cudaStream_t st) {
-  return order == 1 ? launch_nbr_mma_t<1>(A, st) : launch_nbr_mma_t<2>(A, st);
+// A.gr holds one [E, 3] slab of per-edge d/dr partials per channel slice (pos_grad_kernel sums them)
+int launch_nbr_mma(const NeighborArgs& A, int order, bool wide, cudaStream_t st) {
+  if (wide) return order == 1 ? launch_nbr_mma_t<256, 1>(A, st) : launch_nbr_mma_t<256, 2>(A, st);
+  return order == 1 ? launch_nbr_mma_t<128, 1>(A, st) : launch_nbr_mma_t<128, 2>(A, st);
 }
 
-// grid = number of per-CTA partial slabs written to A.wpart ([grid, H, 48])
-int launch_wgrad_mma(const NeighborArgs& A, int order, int grid, cudaStream_t st) {
-  return order == 1 ? launch_wgrad_mma_t<1>(A, grid, st) : launch_wgrad_mma_t<2>(A, grid, st);
+// grid = number of per-CTA partial slabs written to A.wpart ([grid, H, 48]; the slices write disjoint rows)
+int launch_wgrad_mma(const NeighborArgs& A, int order, bool wide, int grid, cudaStream_t st) {
+  if (wide) return order == 1 ? launch_wgrad_mma_t<256, 1>(A, grid, st) : launch_wgrad_mma_t<256, 2>(A, grid, st);
+  return order == 1 ? launch_wgrad_mma_t<128, 1>(A, grid, st) : launch_wgrad_mma_t<128, 2>(A, grid, st);
 }
 
 }  // namespace xeq

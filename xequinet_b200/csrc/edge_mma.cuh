@@ -22,7 +22,16 @@
 namespace xeq {
 namespace fm {
 
+// One CTA handles a SLICE of 128 l=0 + 64 l=1 + 32 l=2 channels (576 filter rows = 5 row tiles); wider models
+// (256x0e + 128x1o + 64x2e: c4) run C / 128 slices per tile of edges (blockIdx.y), each with the filter rows of
+// its own channels in TMEM -- the geometry of an edge is recomputed per slice, the feature traffic is not.
+constexpr int SL_C = 128, SL_M1 = 64, SL_M2 = 32, SL_M = SL_C + SL_M1 + SL_M2;
 constexpr int TILES = 5;
+// irrep channel of consumer thread t (< 224) of slice sl
+template <int L, int C, int M1>
+__device__ __forceinline__ int slice_channel(int t, int sl) {
+  return (L == 0) ? sl * SL_C + t : (L == 1 ? C + sl * SL_M1 + (t - SL_C) : C + M1 + sl * SL_M2 + (t - SL_C - SL_M1));
+}
 constexpr int A_HI = 0;                  // TMEM columns [0, 120): hi parts, tile-major, 24 per tile
 constexpr int A_LO = TILES * NBP;        // [120, 240): lo parts
 constexpr int D_COL = 2 * TILES * NBP;   // [240, ...): accumulators, (output, tile)-major, T columns each
