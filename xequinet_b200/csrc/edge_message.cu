@@ -591,17 +591,14 @@ __global__ void pos_grad_kernel(xeq_graph_t g, const float* __restrict__ gr, int
   if (n >= g.n_nodes) return;
   const size_t slab = 3 * (size_t)g.n_edges;
   float a0 = 0.f, a1 = 0.f, a2 = 0.f;
-  for (int e = g.rowptr[n]; e < g.rowptr[n + 1]; ++e) {
-    for (int k = 0; k < n_slabs; ++k) {
-      const float* p = gr + k * slab + 3 * (size_t)e;
-      a0 += p[0]; a1 += p[1]; a2 += p[2];
+  for (int k = 0; k < n_slabs; ++k) {
+    const float* grk = gr + k * slab;
+    for (int e = g.rowptr[n]; e < g.rowptr[n + 1]; ++e) {
+      a0 += grk[3 * (size_t)e]; a1 += grk[3 * (size_t)e + 1]; a2 += grk[3 * (size_t)e + 2];
     }
-  }
-  for (int s = g.t_rowptr[n]; s < g.t_rowptr[n + 1]; ++s) {
-    const size_t e = g.t_eid[s];
-    for (int k = 0; k < n_slabs; ++k) {
-      const float* p = gr + k * slab + 3 * e;
-      a0 -= p[0]; a1 -= p[1]; a2 -= p[2];
+    for (int s = g.t_rowptr[n]; s < g.t_rowptr[n + 1]; ++s) {
+      const size_t e = g.t_eid[s];
+      a0 -= grk[3 * e]; a1 -= grk[3 * e + 1]; a2 -= grk[3 * e + 2];
     }
   }
   gpos[3 * n] = a0; gpos[3 * n + 1] = a1; gpos[3 * n + 2] = a2;
