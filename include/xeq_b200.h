@@ -204,6 +204,12 @@ int xeq_edge_message_bwdbwd(const xeq_graph_t* g, const xeq_dims_t* dims, const 
 int xeq_segment_sum(const float* src, const int32_t* seg_ptr /* [G+1] */, int32_t n_segments,
                     float* out, xeq_stream_t stream);
 
+/* out[c] = sum over rows of src[r, c] (row stride ld floats): the bias gradient of an nn.Linear = the sum of the
+ * output gradient over the nodes (autograd of nn/xpainn.py:111-115, 195-199; torch: grad_output.sum(0)).
+ * Deterministic (fixed summation order). */
+int xeq_colsum(const float* src, int32_t n_rows, int32_t n_cols, int32_t ld, float* out /* [n_cols] */,
+               xeq_stream_t stream);
+
 /* e3nn (mul-major, m-fastest) <-> cm (component-major) layout of [N, D] tensors.
  * direction 0: e3nn -> cm, 1: cm -> e3nn. */
 int xeq_layout_convert(const float* src, float* dst, int32_t n_nodes, const xeq_dims_t* dims,

@@ -168,3 +168,22 @@ def test_norm_parameter_gradients():
     for a, r in zip(G1, G2):
         assert _rel(a, r) < 2e-5
     assert torch.equal(G1[0], torch.autograd.grad((nodeops.irreps_norm(Vc, gc, bc, muls) ** 3).sum(), [gc])[0]), "not deterministic"
+
+
+@pytest.mark.parametrize("shape", [(5376, 576), (1000, 130), (3, 7), (0, 64), (4097, 128)])
+def test_colsum_matches_torch(shape):
+    """Bias-gradient column sum (xeq_colsum): values, row-strided views, determinism, broadcast derivative."""
+    from xequinet_b200 import gemm
+
+    g = torch.randn(shape, device=DEV)
+    out = gemm.colsum_raw(g)
+    ref = g.double().sum(0)
+    assert float((out.double() - ref).abs().max() if shape[1] else 0.0) <= 1e-5 * max(1.0, float(ref.abs().max()) if shape[0] else 1.0)
+    assert torch.equal(out, gemm.colsum_raw(g))
+    if shape[1] >= 8 and shape[0] > 0:
+        view = g[:, 2 : shape[1] - 3]
+        assert torch.allclose(gemm.colsum_raw(view), view.sum(0), rtol=1e-5, atol=1e-4)
+        x = g.clone().requires_grad_(True)
+        w = torch.randn(shape[1], device=DEV)
+        (gemm.colsum(x) * w).sum().backward()
+        assert torch.allclose(x.grad, w.expand_as(x))

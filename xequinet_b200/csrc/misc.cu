@@ -4,6 +4,8 @@
 
 #include <atomic>
 
+#include <cooperative_groups.h>
+
 #include "common.cuh"
 
 namespace xeq {
@@ -46,6 +48,51 @@ __global__ void segment_sum_kernel(const float* __restrict__ src, const int* __r
   if (lane == 0) out[seg] = acc;
 }
 
+// out[c] = sum_r src[r, c].  A cluster of 8 CTAs owns 32 columns: CTA k sums its eighth of the rows (lane =
+// column: 128-byte coalesced reads, four rows in flight per warp, the 16 warp partials added in fixed order),
+// then CTA 0 adds the 8 partials through distributed shared memory in fixed order => deterministic, one launch,
+// no workspace.  Bias gradients of the Linear layers (sum of the output gradient over the nodes).
+constexpr int COLSUM_CLUSTER = 8, COLSUM_WARPS = 16;
+__global__ void __cluster_dims__(1, COLSUM_CLUSTER, 1) __launch_bounds__(COLSUM_WARPS * 32)
+    colsum_kernel(const float* __restrict__ src, int n_rows, int n_cols, int ld, float* __restrict__ out) {
+  namespace cg = cooperative_groups;
+  __shared__ float part[COLSUM_WARPS][33];
+  __shared__ float tot[32];
+  cg::cluster_group cluster = cg::this_cluster();
+  const int rank = (int)cluster.block_rank();
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int col = blockIdx.x * 32 + lane;
+  const int chunk = (n_rows + COLSUM_CLUSTER - 1) / COLSUM_CLUSTER;
+  const int r_end = min(n_rows, (rank + 1) * chunk);
+  float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+  if (col < n_cols) {
+    int r = rank * chunk + warp;
+    for (; r + 3 * COLSUM_WARPS < r_end; r += 4 * COLSUM_WARPS) {
+      a0 += src[(size_t)r * ld + col];
+      a1 += src[(size_t)(r + COLSUM_WARPS) * ld + col];
+      a2 += src[(size_t)(r + 2 * COLSUM_WARPS) * ld + col];
+      a3 += src[(size_t)(r + 3 * COLSUM_WARPS) * ld + col];
+    }
+    for (; r < r_end; r += COLSUM_WARPS) a0 += src[(size_t)r * ld + col];
+  }
+  part[warp][lane] = (a0 + a1) + (a2 + a3);
+  __syncthreads();
+  if (warp == 0) {
+    float acc = 0.f;
+#pragma unroll
+    for (int w = 0; w < COLSUM_WARPS; ++w) acc += part[w][lane];
+    tot[lane] = acc;
+  }
+  cluster.sync();
+  if (rank == 0 && warp == 0 && col < n_cols) {
+    float acc = 0.f;
+#pragma unroll
+    for (int k = 0; k < COLSUM_CLUSTER; ++k) acc += *cluster.map_shared_rank(&tot[lane], k);
+    out[col] = acc;
+  }
+  cluster.sync();  // the partials of the other CTAs stay alive until CTA 0 has read them
+}
+
 __global__ void layout_convert_kernel(const float* __restrict__ src, float* __restrict__ dst, int n, int m0, int m1,
                                       int m2, int direction) {
   const int D = m0 + 3 * m1 + 5 * m2;
@@ -77,6 +124,15 @@ int xeq_segment_sum(const float* src, const int32_t* seg_ptr, int32_t n_segments
   XEQ_CHECK_ARG(src, "segment_sum: src is NULL");
   const int blocks = (int)(((size_t)n_segments * 32 + 255) / 256);
   segment_sum_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(src, seg_ptr, n_segments, out);
+  XEQ_LAUNCHED(1);
+  return XEQ_OK;
+}
+
+int xeq_colsum(const float* src, int32_t n_rows, int32_t n_cols, int32_t ld, float* out, xeq_stream_t stream) {
+  XEQ_CHECK_ARG(out && n_rows >= 0 && n_cols >= 0 && ld >= n_cols, "colsum: bad arguments");
+  if (n_cols == 0) return XEQ_OK;
+  XEQ_CHECK_ARG(src || n_rows == 0, "colsum: src is NULL");
+  colsum_kernel<<<dim3((n_cols + 31) / 32, COLSUM_CLUSTER), COLSUM_WARPS * 32, 0, (cudaStream_t)stream>>>(src, n_rows, n_cols, ld, out);
   XEQ_LAUNCHED(1);
   return XEQ_OK;
 }

@@ -88,6 +88,36 @@ def mm_raw(A: torch.Tensor, B: torch.Tensor, ta: bool, tb: bool, bias: Optional[
     return C
 
 
+def colsum_raw(g: torch.Tensor) -> torch.Tensor:
+    """g.sum(0) of a 2-D fp32 CUDA tensor with unit inner stride (a row-strided view is fine)."""
+    if g.dtype != torch.float32 or not g.is_cuda or g.dim() != 2:
+        raise RuntimeError("colsum: 2-D fp32 CUDA tensor expected (there is no CPU fallback)")
+    if g.stride(1) != 1 or g.stride(0) < g.shape[1]:
+        g = g.contiguous()
+    out = torch.empty(g.shape[1], dtype=torch.float32, device=g.device)
+    lib = _lib.get()
+    src = ctypes.c_void_p(g.data_ptr()) if g.numel() else None  # row-strided views are addressed through ld
+    _lib.check(lib.xeq_colsum(src, g.shape[0], g.shape[1], max(g.stride(0), g.shape[1]), _lib.ptr(out), _lib.stream()), "xeq_colsum")
+    return out
+
+
+class _ColSum(torch.autograd.Function):
+    """Bias gradient g.sum(0) as one deterministic kernel; its own derivative is a broadcast."""
+
+    @staticmethod
+    def forward(ctx, g):
+        ctx.n_rows = g.shape[0]
+        return colsum_raw(g)
+
+    @staticmethod
+    def backward(ctx, gout):
+        return gout.unsqueeze(0).expand(ctx.n_rows, -1)
+
+
+def colsum(g: torch.Tensor) -> torch.Tensor:
+    return _ColSum.apply(g)
+
+
 class _MM(torch.autograd.Function):
     @staticmethod
     def forward(ctx, A, B, bias, ta, tb, alpha):
@@ -105,7 +135,7 @@ class _MM(torch.autograd.Function):
         if ctx.needs_input_grad[1]:
             gB = mm(A, gC, not ta, False, alpha=alpha) if not tb else mm(gC, A, True, ta, alpha=alpha)
         if ctx.needs_input_grad[2]:
-            gbias = gC.sum(0)
+            gbias = colsum(gC)
         return gA, gB, gbias, None, None, None
 
 
@@ -193,7 +223,7 @@ class _IrrepsLinear(torch.autograd.Function):
         if ctx.needs_input_grad[1]:
             gw = _IrrepsWgrad.apply(V, g, muls) if not transposed else _IrrepsWgrad.apply(g, V, muls)
         if ctx.needs_input_grad[2]:
-            gb = g[:, : muls[0]].sum(0)
+            gb = colsum(g[:, : muls[0]])
         return gV, gw, gb, None, None
 
 
