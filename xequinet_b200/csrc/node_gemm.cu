@@ -376,8 +376,17 @@ __global__ void gemm_reduce_kernel(const __grid_constant__ ReduceArgs args) {
   const size_t total = (size_t)G.m * G.n;
   for (size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (size_t)gridDim.x * blockDim.x) {
     const int row = (int)(idx / G.n), col = (int)(idx % G.n);
-    float acc = 0.f;
-    for (int z = 0; z < G.slabs; ++z) acc += G.part[(size_t)z * total + idx];
+    // four interleaved partial sums (fixed order): four slab reads in flight instead of one
+    float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+    int z = 0;
+    for (; z + 3 < G.slabs; z += 4) {
+      a0 += G.part[(size_t)z * total + idx];
+      a1 += G.part[(size_t)(z + 1) * total + idx];
+      a2 += G.part[(size_t)(z + 2) * total + idx];
+      a3 += G.part[(size_t)(z + 3) * total + idx];
+    }
+    for (; z < G.slabs; ++z) a0 += G.part[(size_t)z * total + idx];
+    float acc = (a0 + a1) + (a2 + a3);
     if (G.bias) acc += G.bias[col];
     G.c[(size_t)row * G.ldc + col] = acc;
   }
