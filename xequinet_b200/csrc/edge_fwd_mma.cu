@@ -162,12 +162,9 @@ __device__ __forceinline__ void fwd_consumer(const CenterArgs& A, FwdSmem& sm, c
         if (L == 0) pin(wx);
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
-          float Yl[NC];
-          if (L > 0) {
-#pragma unroll
-            for (int m = 0; m < NC; ++m) Yl[m] = sa.Y[g0 + j][YOff<L>::value + m];
-          }
-          th.fwd_w(ws[j], we[j], wx[j], Yl - YOff<L>::value, gc[j].ss, gc[j].se, gc[j].sx, gc[j].v);
+          float Yr[8];
+          load_rows8<L, 1>(sa.Y[g0 + j], Yr);  // 128-bit loads of the entries this irrep type uses
+          th.fwd_w(ws[j], we[j], wx[j], Yr, gc[j].ss, gc[j].se, gc[j].sx, gc[j].v);
         }
       }
     };

@@ -216,18 +216,13 @@ __device__ __forceinline__ void center_mma_role(const CenterArgs& A, CenterMmaSm
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
           const int e = g0 + j;
-          float Yl[NC], Yd[NC];
-          if (L > 0) {
-#pragma unroll
-            for (int m = 0; m < NC; ++m) {
-              Yl[m] = sa.Y[e][YOff<L>::value + m];
-              Yd[m] = JVP ? sa.Ydot[e][YOff<L>::value + m] : 0.f;
-            }
-          }
+          float Yl[8], Yd[8];
+          load_rows8<L, 1>(sa.Y[e], Yl);  // 128-bit loads of the entries this irrep type uses
+          if (JVP) load_rows8<L, 1>(sa.Ydot[e], Yd);
           if (!JVP) {
-            th.fwd_w(ws[j], we[j], wx[j], Yl - YOff<L>::value, gc[j].ss, gc[j].se, gc[j].sx, gc[j].v);
+            th.fwd_w(ws[j], we[j], wx[j], Yl, gc[j].ss, gc[j].se, gc[j].sx, gc[j].v);
           } else {
-            th.jvp_w(ws[j], we[j], wx[j], dws[j], dwe[j], dwx[j], Yl - YOff<L>::value, Yd - YOff<L>::value, sa.ddot[e],
+            th.jvp_w(ws[j], we[j], wx[j], dws[j], dwe[j], dwx[j], Yl, Yd, sa.ddot[e],
                      gc[j].ss, gc[j].se, gc[j].sx, gc[j].v, gc[j].sds, gc[j].sde, gc[j].sdx, gc[j].vd);
           }
         }
@@ -525,11 +520,21 @@ __device__ __forceinline__ void nbr_mma_role(const NeighborArgs& A, NbrMmaSmem<O
           const int e = g0 + j;
           NbrEdge<float> ne;
           ne.psi = nullptr; ne.dpsi = nullptr; ne.ddpsi = nullptr; ne.xi = nullptr; ne.dxi = nullptr;
-          ne.Y = sa.Y[e]; ne.G = sa.G[e];
-          ne.Hm = SECOND ? sa.Hm[e] : nullptr;
-          ne.Ydot = SECOND ? sa.Ydot[e] : nullptr;
-          ne.u = sa.u[e];
-          ne.rp = SECOND ? sa.rp[e] : nullptr;
+          // geometry rows -> registers with 128-bit loads (only the entries this irrep type uses)
+          float Yr[8], Gr[24], Hr[24], Ydr[8], ur[3], rpr[3];
+          load_rows8<L, 1>(sa.Y[e], Yr);
+          load_rows8<L, 3>(sa.G[e], Gr);
+          load_vec3(sa.u[e], ur);
+          if (SECOND) {
+            load_rows8<L, 3>(sa.Hm[e], Hr);
+            load_rows8<L, 1>(sa.Ydot[e], Ydr);
+            load_vec3(sa.rp[e], rpr);
+          }
+          ne.Y = Yr; ne.G = Gr;
+          ne.Hm = SECOND ? Hr : nullptr;
+          ne.Ydot = SECOND ? Ydr : nullptr;
+          ne.u = ur;
+          ne.rp = SECOND ? rpr : nullptr;
           ne.ddot = SECOND ? sa.ddot[e] : 0.f;
           if constexpr (L == 0) {
             float ra[2] = {0.f, 0.f}, rb[2] = {0.f, 0.f}, rc[2] = {0.f, 0.f};

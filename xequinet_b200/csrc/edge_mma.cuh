@@ -169,6 +169,30 @@ __device__ __forceinline__ void store_a_row(uint32_t lane_base, int tile, const 
   }
 }
 
+// Per-edge geometry rows of GeoA, fetched with 128-bit shared-memory loads into registers: only the entries the
+// thread's irrep type uses (l = 1: m = 0..2, l = 2: m = 3..7 of each 8-wide row), a third of the scalar loads.
+// dst keeps the row's own indexing so that edge_thread.cuh can address it unchanged.
+template <int L, int ROWS>
+__device__ __forceinline__ void load_rows8(const float* __restrict__ src, float* dst) {
+  if constexpr (L > 0) {
+#pragma unroll
+    for (int x = 0; x < ROWS; ++x) {
+      if (L == 1) {
+        const float4 v = *reinterpret_cast<const float4*>(src + x * 8);
+        dst[x * 8] = v.x; dst[x * 8 + 1] = v.y; dst[x * 8 + 2] = v.z;
+      } else {
+        const float4 v = *reinterpret_cast<const float4*>(src + x * 8 + 4);
+        dst[x * 8 + 3] = src[x * 8 + 3];
+        dst[x * 8 + 4] = v.x; dst[x * 8 + 5] = v.y; dst[x * 8 + 6] = v.z; dst[x * 8 + 7] = v.w;
+      }
+    }
+  }
+}
+__device__ __forceinline__ void load_vec3(const float* __restrict__ src /* [4], 16-byte aligned */, float* dst) {
+  const float4 v = *reinterpret_cast<const float4*>(src);
+  dst[0] = v.x; dst[1] = v.y; dst[2] = v.z;
+}
+
 // Shared-memory B tiles of one chunk: [output o][hi, lo][T rows x 128 bytes].
 template <int T> __device__ __forceinline__ constexpr uint32_t b_tile_bytes() { return T * 128; }
 
