@@ -674,9 +674,8 @@ struct WgradMmaSmem {
 // radial terms of a chunk, transposed: row n = k (psi_k) / 24 + k (xi_k), column = edge slot; dead slots = 0
 template <int ORDER, int THREADS>
 __device__ __noinline__ void geo_stage_bt(const GeoArgs& A, int cnt, const GeoA<WgradMma<ORDER>::KE, false, ORDER == 2>& sa,
-                                          uint32_t tiles) {
+                                          uint32_t tiles, const int t /* dense index among the THREADS writers */) {
   constexpr int KE = WgradMma<ORDER>::KE, BT = WgradMma<ORDER>::BT;
-  const int t = threadIdx.x;
   for (int idx = t; idx < NBP * KE; idx += THREADS) {
     const int k = idx / KE, ee = idx - k * KE;
     float psi = 0.f, xi = 0.f, dpsi = 0.f, dxi = 0.f;
@@ -729,12 +728,17 @@ template <int L, int C, int M1, int M2, int ORDER>
 __device__ __forceinline__ void wgrad_mma_role(const NeighborArgs& A, WgradMmaSmem<ORDER>& sm, const uint32_t tmem,
                                                const uint32_t tiles, const uint32_t win_base) {
   constexpr int M = C + M1 + M2, D = C + 3 * M1 + 5 * M2, H = C + 2 * M, NC = 2 * L + 1;
-  constexpr int THREADS = SL_M;
+  constexpr int THREADS = 2 * SL_M;  // two consumer groups write the radial tiles together
   constexpr bool SECOND = ORDER == 2;
   constexpr int KE = WgradMma<ORDER>::KE, NB = WgradMma<ORDER>::NB, A0 = WgradMma<ORDER>::A0, STAGE = WgradMma<ORDER>::STAGE;
   constexpr int TS = (L == 0) ? 0 : 3, TE = (L == 0) ? 1 : 4, TX = 2;
   constexpr int NROW = (L == 0) ? 3 : 2;
-  const int t = threadIdx.x, warp = t >> 5;
+  // Two consumer groups (threads 0-223 and 256-479; warp 7 is the producer) own the same channels and split the
+  // 4-edge groups of every chunk between them: twice the warps for the latency-bound per-edge work with the same
+  // tensor-memory footprint (their rows of the A operand land in disjoint K slots).
+  const int grp = (threadIdx.x >= SL_M + 32) ? 1 : 0;
+  const int t = threadIdx.x - grp * (SL_M + 32), warp = t >> 5;  // index inside the group
+  const int t2 = t + grp * SL_M;                                  // dense index over both groups
   const int q = slice_channel<L, C, M1>(t, blockIdx.y);  // irrep channel of this thread
   const int vbase = (L == 0) ? q : (L == 1 ? C + (q - C) : C + 3 * M1 + (q - C - M1));
   constexpr int vstride = (L == 0) ? 0 : (L == 1 ? M1 : M2);
@@ -783,7 +787,7 @@ __device__ __forceinline__ void wgrad_mma_role(const NeighborArgs& A, WgradMmaSm
   constexpr int NTHR = (L == 0) ? SL_C : (L == 1 ? SL_M1 : SL_M2);
   constexpr int ROLE_OFF = (L == 0) ? 0 : (L == 1 ? SL_C * 2 : SL_C * 2 + SL_M1 * 3);
   const int tt = (L == 0) ? t : (L == 1 ? t - SL_C : t - SL_C - SL_M1);
-  const uint32_t win0 = win_base + 4u * (ROLE_OFF + tt);
+  const uint32_t win0 = win_base + (uint32_t)grp * (4u * WMAX * ROWF) + 4u * (ROLE_OFF + tt);  // one window per group
   bool staged = false;
   int win_lo = 0;
   auto stage_window = [&](int n0, int n1) {
@@ -821,7 +825,7 @@ __device__ __forceinline__ void wgrad_mma_role(const NeighborArgs& A, WgradMmaSm
     if (has) {
       // radial terms of this chunk, transposed -> B tiles (stage c & 1 was last read by the MMAs of chunk c-2);
       // runs in the shadow of the previous chunk's MMAs
-      geo_stage_bt<ORDER, THREADS>(A.geo, cnt, sa, tiles + (uint32_t)(c & 1) * STAGE);
+      geo_stage_bt<ORDER, THREADS>(A.geo, cnt, sa, tiles + (uint32_t)(c & 1) * STAGE, t2);
       proxy_fence();
     }
     if (pending) {  // the MMAs of the previous chunk have read the A operand
@@ -834,7 +838,7 @@ __device__ __forceinline__ void wgrad_mma_role(const NeighborArgs& A, WgradMmaSm
       // rows of the A operand, four edge slots at a time: registers -> TMEM (hi and lo); slots past cnt = 0
       const uint32_t col_s = lane_base + A0 + TS * 16, col_e = lane_base + A0 + TE * 16, col_x = lane_base + A0 + TX * 16;
 #pragma unroll 1
-      for (int j0 = 0; j0 < KE; j0 += 4) {
+      for (int j0 = 4 * grp; j0 < KE; j0 += 8) {
         uint32_t hs[4] = {0u, 0u, 0u, 0u}, ls[4] = {0u, 0u, 0u, 0u}, he[4] = {0u, 0u, 0u, 0u}, le[4] = {0u, 0u, 0u, 0u};
         uint32_t hx[4] = {0u, 0u, 0u, 0u}, lx[4] = {0u, 0u, 0u, 0u};
         uint32_t hs2[4] = {0u, 0u, 0u, 0u}, ls2[4] = {0u, 0u, 0u, 0u}, he2[4] = {0u, 0u, 0u, 0u}, le2[4] = {0u, 0u, 0u, 0u};
@@ -901,7 +905,7 @@ __device__ __forceinline__ void wgrad_mma_role(const NeighborArgs& A, WgradMmaSm
     phase ^= 1u;
   }
   tc_fence_after();
-  // accumulators -> per-CTA partials [gridDim.x, H, 48]
+  // accumulators -> per-CTA partials [gridDim.x, H, 48] (the groups take alternate 4-column pieces)
   {
     constexpr int tiles_of[3] = {TS, TE, TX};
     const int rows_of[3] = {q, M + q, 2 * M + q};
@@ -909,7 +913,7 @@ __device__ __forceinline__ void wgrad_mma_role(const NeighborArgs& A, WgradMmaSm
     for (int r = 0; r < NROW; ++r) {
       float* dst = A.wpart + ((size_t)blockIdx.x * H + rows_of[r]) * NB;
 #pragma unroll
-      for (int c4 = 0; c4 < NB / 4; ++c4) {
+      for (int c4 = grp; c4 < NB / 4; c4 += 2) {
         float v4[4] = {0.f, 0.f, 0.f, 0.f};
         if (any) {
           tmem_ld4(lane_base + tiles_of[r] * NB + c4 * 4, v4);
@@ -962,17 +966,18 @@ __device__ __forceinline__ void wgrad_mma_producer(const NeighborArgs& A, WgradM
 }
 
 template <int C, int M1, int M2, int ORDER>
-__global__ void __launch_bounds__(SL_M + 32, 1) wgrad_mma_kernel(const NeighborArgs A) {
+__global__ void __launch_bounds__(2 * SL_M + 32, 1) wgrad_mma_kernel(const NeighborArgs A) {
   static_assert(C % SL_C == 0 && M1 == C / 2 && M2 == C / 4, "channel slices of edge_mma.cuh");
   __shared__ WgradMmaSmem<ORDER> sm;
   const uint32_t tmem = tmem_setup(&sm.slot, &sm.bar, 1);
   const uint32_t tiles = (smem_u32(xeq_dyn_smem) + 1023u) & ~1023u;
   const uint32_t win_base = tiles + 2u * WgradMma<ORDER>::STAGE;
   const int t = threadIdx.x;
-  if (t < SL_C) wgrad_mma_role<0, C, M1, M2, ORDER>(A, sm, tmem, tiles, win_base);
-  else if (t < SL_C + SL_M1) wgrad_mma_role<1, C, M1, M2, ORDER>(A, sm, tmem, tiles, win_base);
-  else if (t < SL_M) wgrad_mma_role<2, C, M1, M2, ORDER>(A, sm, tmem, tiles, win_base);
-  else wgrad_mma_producer<C, M1, M2, ORDER>(A, sm, tmem, tiles);
+  const int tg = (t >= SL_M + 32) ? t - (SL_M + 32) : t;  // index inside a consumer group; threads SL_M..SL_M+31 = producer
+  if (t >= SL_M && t < SL_M + 32) wgrad_mma_producer<C, M1, M2, ORDER>(A, sm, tmem, tiles);
+  else if (tg < SL_C) wgrad_mma_role<0, C, M1, M2, ORDER>(A, sm, tmem, tiles, win_base);
+  else if (tg < SL_C + SL_M1) wgrad_mma_role<1, C, M1, M2, ORDER>(A, sm, tmem, tiles, win_base);
+  else wgrad_mma_role<2, C, M1, M2, ORDER>(A, sm, tmem, tiles, win_base);
   tmem_teardown(tmem);
 }
 
@@ -1011,14 +1016,14 @@ template <int C, int ORDER>
 static int launch_wgrad_mma_t(const NeighborArgs& A, int grid, cudaStream_t st) {
   constexpr int M1 = C / 2, M2 = C / 4, SLICES = C / SL_C;
   static_assert(sizeof(WgradMmaSmem<ORDER>) <= 24 * 1024, "static shared memory budget");
-  const size_t dyn = 1024 + 2 * (size_t)WgradMma<ORDER>::STAGE + (size_t)WgradMma<ORDER>::WIN * (SL_C * 2 + SL_M1 * 3 + SL_M2 * 5) * 4;
+  const size_t dyn = 1024 + 2 * (size_t)WgradMma<ORDER>::STAGE + 2 * (size_t)WgradMma<ORDER>::WIN * (SL_C * 2 + SL_M1 * 3 + SL_M2 * 5) * 4;
   static bool attr_set = false;
   if (!attr_set) {
     int rc = set_smem(wgrad_mma_kernel<C, M1, M2, ORDER>, dyn);
     if (rc) return rc;
     attr_set = true;
   }
-  wgrad_mma_kernel<C, M1, M2, ORDER><<<dim3(grid, SLICES), SL_M + 32, dyn, st>>>(A);
+  wgrad_mma_kernel<C, M1, M2, ORDER><<<dim3(grid, SLICES), 2 * SL_M + 32, dyn, st>>>(A);
   XEQ_LAUNCHED(1);
   return XEQ_OK;
 }
