@@ -477,7 +477,11 @@ def run_gpu(args):
         cnt, mean_ms, N, E = kern[dom]
         achieved = algorithmic_bytes(dom, cfg, N, E, periodic) / (mean_ms * 1e-3) / 1e9
         traffic = NCU_TRAFFIC_C3.get(dom) if (args.workload == "c3" and N == 5376) else None
-        roofline = {"kernel": dom, "bound": "hbm", "achieved": round(achieved, 2), "peak": peak, "unit": "GB/s",
+        launch_of = {"edge_fwd": "xeq_edge_message_fwd: center_fwd_kernel",
+                     "edge_bwd": "xeq_edge_message_bwd: nbr_mma_kernel<1> + pos_grad",
+                     "edge_bwd_wgrad": "xeq_edge_message_bwd with weight gradients: nbr_mma_kernel<1> + wgrad_mma_kernel<1> + reductions",
+                     "edge_bwdbwd": "xeq_edge_message_bwdbwd: center_mma_kernel<jvp> + nbr_mma_kernel<2> + wgrad_mma_kernel<2> + reductions"}
+        roofline = {"kernel": dom, "launch": launch_of.get(dom), "bound": "hbm", "achieved": round(achieved, 2), "peak": peak, "unit": "GB/s",
                     "frac": round(achieved / peak, 5), "traffic": traffic, "peak_source": peak_src,
                     "n_nodes": N, "n_edges": E, "mean_launch_ms": round(mean_ms, 5)}
 

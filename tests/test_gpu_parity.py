@@ -103,6 +103,9 @@ def _edge_case(kind, cfg):
     if kind == "mol":
         d = orc.make_molecule_batch(24, (6, 22), seed=2)
         ei, co, cell = d["edge_index"], None, None
+    elif kind == "iso":  # many single atoms (rows and whole tiles without edges) next to small molecules
+        d = orc.make_molecule_batch(40, (1, 4), seed=7)
+        ei, co, cell = d["edge_index"], None, None
     elif kind == "pbc":
         d = orc.make_small_pbc(14, 6.5, seed=3, triclinic=True)
         ei, co = orc.radius_graph_pbc(d["pos"], torch.tensor([14]), d["pbc"], d["cell"], 5.0)
@@ -125,7 +128,7 @@ def _rel(got, ref):
     return float((got.double().cpu() - ref).abs().max() / (ref.abs().max() + 1e-30))
 
 
-@pytest.mark.parametrize("kind", ["mol", "pbc", "pbc2"])
+@pytest.mark.parametrize("kind", ["mol", "pbc", "pbc2", "iso"])
 @pytest.mark.parametrize("cfg", [orc.CONFIG_DEFAULT, orc.CONFIG_C4], ids=["c128", "c256"])
 def test_edge_kernels_match_oracle_autograd(kind, cfg):
     d, ei, co, cell, t = _edge_case(kind, cfg)
@@ -363,10 +366,11 @@ torch.save(_edge_outputs({n_mol}, {staged}), {out!r})
 
 
 def _edge_outputs(n_mol, staged):
-    """All edge-kernel outputs (values, first and second derivatives) on an aspirin-shaped batch; `staged`
-    selects molecule tiles (shared-memory row window) or edge-block tiles (direct gathers)."""
+    """All edge-kernel outputs (values, first and second derivatives) on a batch of molecules of 1..21 atoms
+    (single atoms = rows and tiles without edges); `staged` selects molecule tiles (shared-memory row window)
+    or edge-block tiles (direct gathers)."""
     cfg = orc.CONFIG_DEFAULT
-    d = orc.make_aspirin_batch(n_mol, seed=11, with_edges=False)
+    d = orc.make_molecule_batch(n_mol, (1, 21), seed=11, with_edges=False)
     kw = dict(ptr=d["ptr"].to(DEV)) if staged else {}
     g, _, _ = build_graph(d["pos"].to(DEV), cfg.cutoff, batch=d["batch"].to(DEV), **kw)
     N = g.n_nodes
@@ -394,11 +398,11 @@ def test_tcgen05_and_simt_edge_kernels_agree(staged, tmp_path):
 
     root = Path(__file__).resolve().parent.parent
     ref_file = tmp_path / "simt.pt"
-    script = _SIMT_SCRIPT.format(root=str(root), tests=str(root / "tests"), n_mol=12, staged=staged, out=str(ref_file))
+    script = _SIMT_SCRIPT.format(root=str(root), tests=str(root / "tests"), n_mol=40, staged=staged, out=str(ref_file))
     env = dict(os.environ, XEQ_EDGE_SIMT="1")
     subprocess.run([sys.executable, "-c", script], check=True, env=env, timeout=300)
     ref = torch.load(ref_file)
-    got = _edge_outputs(12, staged)
+    got = _edge_outputs(40, staged)
     assert len(got) == len(ref) == 16
     for i, (a, bref) in enumerate(zip(got, ref)):
         assert _rel(a, bref) < 1e-5, f"output {i}"
