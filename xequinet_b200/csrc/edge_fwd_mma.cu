@@ -9,7 +9,9 @@
 //                                        so no dependent global load is waited for where it is issued) and issues
 //                                        the MMAs of chunk c+1 while the consumers are on chunk c (accumulators
 //                                        double buffered: 2 x 80 TMEM columns at 16 edges per chunk)
-//   warps 8-15 (256 threads) radial    : chi * phi_k of chunk c+2 -> 3xTF32 split -> SWIZZLE_128B tiles (three
+//   warp  8                  MMA       : issues the MMAs of chunk c+1 (measured: the cursor warp was the last to
+//                                        reach the barrier in every iteration while it also issued the 45 MMAs)
+//   warps 9-20 (384 threads) radial    : chi * phi_k of chunk c+2 -> 3xTF32 split -> SWIZZLE_128B tiles (three
 //                                        stages) and the generic->async proxy fence, off the consumers' path
 //
 // One __syncthreads per chunk joins the three groups; the ring depths (descriptors/geometry 4, radial tiles 3,
@@ -23,13 +25,24 @@ namespace xeq {
 
 using namespace fm;
 
+#ifdef XEQ_TRACE
+// Debug timeline (scratch/trace_fwd.py): cycle stamps of every warp of CTA 0 at the per-chunk barrier.
+__device__ long long g_trace[21][2][256];
+#define XEQ_TRACE_STAMP(which, c)                                                                           \
+  do {                                                                                                      \
+    if (blockIdx.x == 0 && blockIdx.y == 0 && (threadIdx.x & 31) == 0 && (c) < 256) g_trace[threadIdx.x >> 5][which][c] = clock64(); \
+  } while (0)
+#else
+#define XEQ_TRACE_STAMP(which, c) do { } while (0)
+#endif
+
 namespace {
 
 constexpr int FW_TC = 16;                   // edges per chunk = MMA N
 constexpr int FW_STAGE = 2 * FW_TC * 128;   // radial tiles of one chunk: hi + lo
 constexpr int FW_NSTAGE = 3;
 constexpr int FW_WIN = 21;                  // rows of the shared-memory window (aspirin: 21 atoms)
-constexpr int FW_CONS = 224, FW_RADIAL = 256, FW_THREADS = FW_CONS + 32 + FW_RADIAL;
+constexpr int FW_CONS = 224, FW_RADIAL = 384, FW_THREADS = FW_CONS + 64 + FW_RADIAL;  // + cursor warp + MMA warp
 constexpr int FW_DCOLS = TILES * FW_TC;     // accumulator columns of one chunk (80)
 
 struct FwdSmem {
@@ -122,6 +135,7 @@ __device__ __forceinline__ void fwd_consumer(const CenterArgs& A, FwdSmem& sm, c
   for (int c = 0;; ++c) {
     const ChunkDesc d0 = sm.desc[c & 7];
     if (d0.cnt < 0) break;
+    XEQ_TRACE_STAMP(0, c);
     const GeoA<TC, false, false>& sa = sm.a[c & 3];
     const int cnt = d0.cnt, node = d0.owner, buf = c & 1;
     if (d0.first) {
@@ -176,6 +190,7 @@ __device__ __forceinline__ void fwd_consumer(const CenterArgs& A, FwdSmem& sm, c
       if (L == 0) A.x_out[(size_t)node * C + q] = base_x + th.accx;
     }
     tc_fence_before();
+    XEQ_TRACE_STAMP(1, c);
     __syncthreads();
   }
 }
@@ -202,11 +217,11 @@ __device__ __forceinline__ void fwd_issue(FwdSmem& sm, const uint32_t tmem, cons
   __syncwarp();
 }
 
-// cursor warp: issues the MMAs of chunk c+1 and runs the per-edge geometry as a three-stage software pipeline
+// cursor warp: runs the per-edge geometry as a three-stage software pipeline
 // over consecutive chunks, so that none of its dependent global loads (rowptr -> col -> pos) is waited for in
 // the iteration that issued it:   A(c+5) descriptor + neighbour index load | B(c+4) edge vector (position
 // loads) | C(c+3) distances, harmonics, cutoff -> shared memory.
-__device__ __forceinline__ void fwd_cursor(const CenterArgs& A, FwdSmem& sm, const uint32_t tmem, const uint32_t tiles) {
+__device__ __forceinline__ void fwd_cursor(const CenterArgs& A, FwdSmem& sm) {
   const int lane = threadIdx.x & 31;
   const xeq_graph_t& g = A.geo.g;
   RowCursor<FW_TC> cur_it;
@@ -224,13 +239,27 @@ __device__ __forceinline__ void fwd_cursor(const CenterArgs& A, FwdSmem& sm, con
   };
   for (int c = -5; c < 0; ++c) step(c);  // fill: geometry of chunks 0..2 in shared memory, 3 and 4 in flight
   __syncthreads();  // (P1)
+  __syncthreads();  // (P2)
+  for (int c = 0; sm.desc[c & 7].cnt >= 0; ++c) {
+    XEQ_TRACE_STAMP(0, c);
+    step(c);
+    XEQ_TRACE_STAMP(1, c);
+    __syncthreads();
+  }
+}
+
+// MMA warp: issues the MMAs of chunk c+1 at the top of iteration c (its tiles were fenced in iteration c-1, its
+// accumulator buffer was released by the consumers at the barrier that ended iteration c-1)
+__device__ __forceinline__ void fwd_mma_warp(FwdSmem& sm, const uint32_t tmem, const uint32_t tiles) {
+  __syncthreads();  // (P1)
   __syncthreads();  // (P2) tiles of chunks 0, 1 written and fenced; filter rows are in TMEM
   tc_fence_after();
   if (sm.desc[0].cnt > 0) fwd_issue(sm, tmem, tiles, 0);
   for (int c = 0; sm.desc[c & 7].cnt >= 0; ++c) {
+    XEQ_TRACE_STAMP(0, c);
     tc_fence_after();
     if (sm.desc[(c + 1) & 7].cnt > 0) fwd_issue(sm, tmem, tiles, c + 1);
-    step(c);
+    XEQ_TRACE_STAMP(1, c);
     __syncthreads();
   }
 }
@@ -238,7 +267,7 @@ __device__ __forceinline__ void fwd_cursor(const CenterArgs& A, FwdSmem& sm, con
 // radial warps: tiles of chunk c+2
 // radial warps: tiles of chunk c+2
 __device__ __forceinline__ void fwd_radial(const CenterArgs& A, FwdSmem& sm, const uint32_t tiles) {
-  const int rt = threadIdx.x - (FW_CONS + 32);
+  const int rt = threadIdx.x - (FW_CONS + 64);
   __syncthreads();  // (P1)
 #pragma unroll
   for (int i = 0; i < 2; ++i) {
@@ -249,11 +278,13 @@ __device__ __forceinline__ void fwd_radial(const CenterArgs& A, FwdSmem& sm, con
   __syncthreads();  // (P2)
   for (int c = 0;; ++c) {
     if (sm.desc[c & 7].cnt < 0) break;
+    XEQ_TRACE_STAMP(0, c);
     const int cnt = sm.desc[(c + 2) & 7].cnt;
     if (cnt > 0) {
       geo_stage_b<FW_TC, FW_RADIAL, 1>(A.geo, cnt, sm.a[(c + 2) & 3], tiles + (uint32_t)((c + 2) % FW_NSTAGE) * FW_STAGE, rt);
       proxy_fence();
     }
+    XEQ_TRACE_STAMP(1, c);
     __syncthreads();
   }
 }
@@ -269,7 +300,8 @@ __global__ void __launch_bounds__(FW_THREADS, 1) center_fwd_kernel(const CenterA
   if (t < SL_C) fwd_consumer<0, C, M1, M2>(A, sm, tmem, win_base);
   else if (t < SL_C + SL_M1) fwd_consumer<1, C, M1, M2>(A, sm, tmem, win_base);
   else if (t < FW_CONS) fwd_consumer<2, C, M1, M2>(A, sm, tmem, win_base);
-  else if (t < FW_CONS + 32) fwd_cursor(A, sm, tmem, tiles);
+  else if (t < FW_CONS + 32) fwd_cursor(A, sm);
+  else if (t < FW_CONS + 64) fwd_mma_warp(sm, tmem, tiles);
   else fwd_radial(A, sm, tiles);
   tmem_teardown(tmem);
 }
@@ -298,3 +330,9 @@ int launch_center_fwd_ws(const CenterArgs& A, bool wide, cudaStream_t st) {
 }
 
 }  // namespace xeq
+
+#ifdef XEQ_TRACE
+extern "C" int xeq_debug_fwd_trace(long long* out /* [16][2][256] host */) {
+  return (int)cudaMemcpyFromSymbol(out, xeq::g_trace, sizeof(long long) * 21 * 2 * 256);
+}
+#endif
