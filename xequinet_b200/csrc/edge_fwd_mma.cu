@@ -159,7 +159,7 @@ __device__ __forceinline__ void fwd_consumer(const CenterArgs& A, FwdSmem& sm, c
     const uint32_t dbase = lane_base + D_COL + buf * FW_DCOLS;
     auto run_chunk = [&](auto staged_c) {
       constexpr bool ST = decltype(staged_c)::value;
-#pragma unroll 1
+#pragma unroll 1  // (unroll 2 measured 25 % slower: instruction footprint)
       for (int g0 = 0; g0 < cnt; g0 += 4) {
         float ws[4], we[4], wx[4] = {0.f, 0.f, 0.f, 0.f};
         tmem_ld4(dbase + TS * TC + g0, ws);

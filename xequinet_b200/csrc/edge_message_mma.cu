@@ -20,6 +20,17 @@
 
 #include "edge_mma.cuh"
 
+#ifdef XEQ_TRACE
+// Debug timeline (scratch/trace_nbr.py): cycle stamps of every warp of CTA 0 at the per-chunk barrier.
+__device__ long long g_trace_nbr[8][2][256];
+#define XEQ_TRACE_STAMP(which, c)                                                                           \
+  do {                                                                                                      \
+    if (blockIdx.x == 0 && blockIdx.y == 0 && (threadIdx.x & 31) == 0 && (c) < 256) g_trace_nbr[threadIdx.x >> 5][which][c] = clock64(); \
+  } while (0)
+#else
+#define XEQ_TRACE_STAMP(which, c) do { } while (0)
+#endif
+
 namespace xeq {
 
 using namespace fm;
@@ -192,13 +203,13 @@ __device__ __forceinline__ void center_mma_role(const CenterArgs& A, CenterMmaSm
       for (int g0 = 0; g0 < cnt; g0 += 4) {
         float ws[4], we[4], wx[4] = {0.f, 0.f, 0.f, 0.f}, dws[4] = {0.f, 0.f, 0.f, 0.f}, dwe[4] = {0.f, 0.f, 0.f, 0.f},
                             dwx[4] = {0.f, 0.f, 0.f, 0.f};
-        tmem_ld4(dbase + TS * TC + g0, ws);
-        tmem_ld4(dbase + TE * TC + g0, we);
-        if (L == 0) tmem_ld4(dbase + TX * TC + g0, wx);
+        tmem_ld4(dbase + TS * NOUT * TC + g0, ws);
+        tmem_ld4(dbase + TE * NOUT * TC + g0, we);
+        if (L == 0) tmem_ld4(dbase + TX * NOUT * TC + g0, wx);
         if (JVP) {
-          tmem_ld4(dbase + (TILES + TS) * TC + g0, dws);
-          tmem_ld4(dbase + (TILES + TE) * TC + g0, dwe);
-          if (L == 0) tmem_ld4(dbase + (TILES + TX) * TC + g0, dwx);
+          tmem_ld4(dbase + TS * NOUT * TC + TC + g0, dws);
+          tmem_ld4(dbase + TE * NOUT * TC + TC + g0, dwe);
+          if (L == 0) tmem_ld4(dbase + TX * NOUT * TC + TC + g0, dwx);
         }
         Gathered gc[4];
 #pragma unroll
@@ -467,6 +478,7 @@ __device__ __forceinline__ void nbr_mma_role(const NeighborArgs& A, NbrMmaSmem<O
   int prev_cnt = 0;
   for (int c = 0; d0.cnt >= 0; ++c) {
     const bool has = d0.cnt > 0;
+    XEQ_TRACE_STAMP(0, c);
     flush_red((c + 1) & 1, prev_cnt);  // chunk c-1
     if (d1.cnt > 0) {  // radial terms of the next chunk -> B tiles, in the shadow of this chunk's MMAs
       geo_stage_b<TC, THREADS, NOUT>(A.geo, d1.cnt, sm.a[(c + 1) % 3], tiles + (uint32_t)((c + 1) & 1) * STAGE, threadIdx.x);
@@ -495,9 +507,9 @@ __device__ __forceinline__ void nbr_mma_role(const NeighborArgs& A, NbrMmaSmem<O
         float w[NOUT][NR][4];  // [output][role][edge of the group]
 #pragma unroll
         for (int o = 0; o < NOUT; ++o) {
-          tmem_ld4(dbase + (o * TILES + TS) * TC + g0, w[o][0]);
-          tmem_ld4(dbase + (o * TILES + TE) * TC + g0, w[o][1]);
-          if (L == 0) tmem_ld4(dbase + (o * TILES + TX) * TC + g0, w[o][NR - 1]);
+          tmem_ld4(dbase + (TS * NOUT + o) * TC + g0, w[o][0]);
+          tmem_ld4(dbase + (TE * NOUT + o) * TC + g0, w[o][1]);
+          if (L == 0) tmem_ld4(dbase + (TX * NOUT + o) * TC + g0, w[o][NR - 1]);
         }
         Gathered gc[4];
 #pragma unroll
@@ -582,6 +594,7 @@ __device__ __forceinline__ void nbr_mma_role(const NeighborArgs& A, NbrMmaSmem<O
     else run_chunk(std::false_type{});
     if (d0.rlast) emit(d0.owner);
     tc_fence_before();
+    XEQ_TRACE_STAMP(1, c);
     __syncthreads();
     prev_cnt = cnt;
     d0 = d1;
@@ -614,6 +627,7 @@ __device__ __forceinline__ void nbr_mma_producer(const NeighborArgs& A, NbrMmaSm
   __syncthreads();
   __syncthreads();  // the consumers have written the B tiles of chunk 0
   for (int c = 0; sm.desc[c & 7].cnt >= 0; ++c) {
+    XEQ_TRACE_STAMP(0, c);
     tc_fence_after();
     if (sm.desc[c & 7].cnt > 0) {
       if (elect_one()) {
@@ -623,6 +637,7 @@ __device__ __forceinline__ void nbr_mma_producer(const NeighborArgs& A, NbrMmaSm
       __syncwarp();
     }
     step(c);
+    XEQ_TRACE_STAMP(1, c);
     __syncthreads();
   }
 }
@@ -1058,3 +1073,9 @@ int launch_wgrad_mma(const NeighborArgs& A, int order, bool wide, int grid, cuda
 }
 
 }  // namespace xeq
+
+#ifdef XEQ_TRACE
+extern "C" int xeq_debug_nbr_trace(long long* out /* [8][2][256] host */) {
+  return (int)cudaMemcpyFromSymbol(out, g_trace_nbr, sizeof(long long) * 8 * 2 * 256);
+}
+#endif

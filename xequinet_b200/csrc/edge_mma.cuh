@@ -219,30 +219,31 @@ __device__ __noinline__ void geo_stage_b(const GeoArgs& A, int cnt, const GeoA<T
     for (int o = 0; o < NOUT; ++o) {
       uint32_t hi, lo;
       split_fast(val[o], hi, lo);
-      asm volatile("st.shared.b32 [%0], %1;" ::"r"(tiles + (2 * o) * b_tile_bytes<T>() + off), "r"(hi) : "memory");
-      asm volatile("st.shared.b32 [%0], %1;" ::"r"(tiles + (2 * o + 1) * b_tile_bytes<T>() + off), "r"(lo) : "memory");
+      // the outputs are stacked along the rows of ONE tile (row = o * T + edge): one MMA per (tile, k step, product)
+      // covers all of them (N = NOUT * T), instead of NOUT separate N = T MMAs that are issue-bound
+      const uint32_t off_o = off + (uint32_t)o * b_tile_bytes<T>();  // T rows = whole 8-row swizzle groups
+      asm volatile("st.shared.b32 [%0], %1;" ::"r"(tiles + off_o), "r"(hi) : "memory");
+      asm volatile("st.shared.b32 [%0], %1;" ::"r"(tiles + NOUT * b_tile_bytes<T>() + off_o), "r"(lo) : "memory");
     }
   }
 }
 
-// Issue the MMAs of one chunk: for every output o and tile t,  D[o][t] = A[t] * B[o]^T  (3 k steps x 3 products).
-// Called by ONE elected thread of a converged warp.
+// Issue the MMAs of one chunk: for every row tile t,  D[t][o * T + e] = A[t] * B^T  with the NOUT outputs stacked
+// along N (3 k steps x 3 products per tile).  Accumulator column of (tile, output o, edge e):
+// D_COL + tile * NOUT * T + o * T + e.  Called by ONE elected thread of a converged warp.
 template <int T, int NOUT>
 __device__ __forceinline__ void issue_chunk(uint32_t tmem, uint32_t tiles) {
-  const uint32_t idesc = idesc_tf32(T);
+  const uint32_t idesc = idesc_tf32(NOUT * T);
+  const uint32_t b_hi = tiles, b_lo = tiles + NOUT * b_tile_bytes<T>();
 #pragma unroll
-  for (int o = 0; o < NOUT; ++o) {
-    const uint32_t b_hi = tiles + (2 * o) * b_tile_bytes<T>(), b_lo = b_hi + b_tile_bytes<T>();
+  for (int ks = 0; ks < NBP / 8; ++ks) {
+    const uint64_t db_hi = smem_desc(b_hi + ks * 32), db_lo = smem_desc(b_lo + ks * 32);
 #pragma unroll
-    for (int ks = 0; ks < NBP / 8; ++ks) {
-      const uint64_t db_hi = smem_desc(b_hi + ks * 32), db_lo = smem_desc(b_lo + ks * 32);
-#pragma unroll
-      for (int tile = 0; tile < TILES; ++tile) {
-        const uint32_t d = tmem + D_COL + (o * TILES + tile) * T;
-        mma_ts(d, tmem + A_LO + tile * NBP + ks * 8, db_hi, idesc, ks ? 1u : 0u);
-        mma_ts(d, tmem + A_HI + tile * NBP + ks * 8, db_lo, idesc, 1u);
-        mma_ts(d, tmem + A_HI + tile * NBP + ks * 8, db_hi, idesc, 1u);
-      }
+    for (int tile = 0; tile < TILES; ++tile) {
+      const uint32_t d = tmem + D_COL + tile * NOUT * T;
+      mma_ts(d, tmem + A_LO + tile * NBP + ks * 8, db_hi, idesc, ks ? 1u : 0u);
+      mma_ts(d, tmem + A_HI + tile * NBP + ks * 8, db_lo, idesc, 1u);
+      mma_ts(d, tmem + A_HI + tile * NBP + ks * 8, db_hi, idesc, 1u);
     }
   }
 }
