@@ -27,6 +27,8 @@ XEQ_HD float xsin(float x) { return sinf(x); }
 XEQ_HD double xsin(double x) { return sin(x); }
 XEQ_HD float xcos(float x) { return cosf(x); }
 XEQ_HD double xcos(double x) { return cos(x); }
+XEQ_HD void xsincos(float x, float& s, float& c) { sincosf(x, &s, &c); }  // one argument reduction for both
+XEQ_HD void xsincos(double x, double& s, double& c) { s = sin(x); c = cos(x); }
 XEQ_HD float xsqrt(float x) { return sqrtf(x); }
 XEQ_HD double xsqrt(double x) { return sqrt(x); }
 
@@ -42,7 +44,8 @@ XEQ_HD Cutoff<T> cutoff_terms(T d, T rc) {
   const T pi = T(3.14159265358979323846);
   if (d < rc) {
     const T a = pi / rc;
-    const T sn = xsin(a * d), cs = xcos(a * d);
+    T sn, cs;
+    xsincos(a * d, sn, cs);
     c.chi = T(0.5) * (cs + T(1));
     c.dchi = -T(0.5) * a * sn;
     c.ddchi = -T(0.5) * a * a * cs;
@@ -59,12 +62,14 @@ struct Radial {
 };
 
 // One Bessel term times the cutoff envelope, with everything the kernels differentiate.
+// c0 = sqrt(2 / rc) is passed in: it is uniform, and recomputing the square root and the division per
+// (edge, k) item was a measurable part of the radial stage.
 template <typename T>
-XEQ_HD Radial<T> radial_term(T d, T f, T rc, const Cutoff<T>& c) {
-  const T c0 = xsqrt(T(2) / rc);
+XEQ_HD Radial<T> radial_term_c0(T d, T f, T c0, const Cutoff<T>& c) {
   const T den = d + T(1e-5);
   const T inv = T(1) / den;
-  const T sn = xsin(f * d), cs = xcos(f * d);
+  T sn, cs;
+  xsincos(f * d, sn, cs);
   const T phi = c0 * sn * inv;
   const T dphi = c0 * (f * cs * inv - sn * inv * inv);
   const T ddphi = c0 * (-f * f * sn * inv - T(2) * f * cs * inv * inv + T(2) * sn * inv * inv * inv);
@@ -77,6 +82,10 @@ XEQ_HD Radial<T> radial_term(T d, T f, T rc, const Cutoff<T>& c) {
   r.xi = c.chi * phif;
   r.dxi = c.dchi * phif + c.chi * dphif;
   return r;
+}
+template <typename T>
+XEQ_HD Radial<T> radial_term(T d, T f, T rc, const Cutoff<T>& c) {
+  return radial_term_c0(d, f, xsqrt(T(2) / rc), c);
 }
 
 // r -> d, u = r / max(d, 1e-12) (F.normalize inside e3nn SH)

@@ -691,6 +691,7 @@ template <int ORDER, int THREADS>
 __device__ __noinline__ void geo_stage_bt(const GeoArgs& A, int cnt, const GeoA<WgradMma<ORDER>::KE, false, ORDER == 2>& sa,
                                           uint32_t tiles, const int t /* dense index among the THREADS writers */) {
   constexpr int KE = WgradMma<ORDER>::KE, BT = WgradMma<ORDER>::BT;
+  const float c0 = sqrtf(2.f / A.rc);
   for (int idx = t; idx < NBP * KE; idx += THREADS) {
     const int k = idx / KE, ee = idx - k * KE;
     float psi = 0.f, xi = 0.f, dpsi = 0.f, dxi = 0.f;
@@ -701,7 +702,7 @@ __device__ __noinline__ void geo_stage_bt(const GeoArgs& A, int cnt, const GeoA<
       } else if (k <= NB_) {
         Cutoff<float> c;
         c.chi = sa.chi[ee][0]; c.dchi = sa.chi[ee][1]; c.ddchi = sa.chi[ee][2];
-        const Radial<float> rr = radial_term(sa.d[ee], A.freq[k - 1], A.rc, c);
+        const Radial<float> rr = radial_term_c0(sa.d[ee], A.freq[k - 1], c0, c);
         psi = rr.psi; xi = rr.xi; dpsi = rr.dpsi; dxi = rr.dxi;
       }
     }

@@ -202,6 +202,7 @@ template <int T> __device__ __forceinline__ constexpr uint32_t b_tile_bytes() { 
 template <int T, int THREADS, int NOUT, bool NEED_G, bool SECOND>
 __device__ __noinline__ void geo_stage_b(const GeoArgs& A, int cnt, const GeoA<T, NEED_G, SECOND>& sa, uint32_t tiles,
                                          const int t /* dense index of this thread among the THREADS writers */) {
+  const float c0 = sqrtf(2.f / A.rc);
   for (int idx = t; idx < T * NBP; idx += THREADS) {
     const int ee = idx / NBP, k = idx - ee * NBP;
     float val[3] = {0.f, 0.f, 0.f};
@@ -211,7 +212,7 @@ __device__ __noinline__ void geo_stage_b(const GeoArgs& A, int cnt, const GeoA<T
     } else if (k <= NB_) {
       Cutoff<float> c;
       c.chi = sa.chi[ee][0]; c.dchi = sa.chi[ee][1]; c.ddchi = sa.chi[ee][2];
-      const Radial<float> rr = radial_term(sa.d[ee], A.freq[k - 1], A.rc, c);
+      const Radial<float> rr = radial_term_c0(sa.d[ee], A.freq[k - 1], c0, c);
       val[0] = rr.psi; val[1] = rr.dpsi; val[2] = rr.ddpsi;
     }
     const uint32_t off = b_off(ee, k);
