@@ -401,26 +401,36 @@ __device__ __forceinline__ void nbr_mma_role(const NeighborArgs& A, NbrMmaSmem<O
       for (int m = 0; m < NC; ++m) A.o_v[(size_t)node * D + vbase + m * vstride] = st.acc_v[m];
     }
   };
-  auto begin_node = [&](int j) {
-    st.reset_node(); ed.reset_node(); sc.reset_node();
+  // the owner's rows (s, v and their tangents) are requested one chunk before its transposed row starts, so
+  // their latency is not paid at the row switch
+  struct RowRegs {
+    float s_st, s_ed, s_sc, sd_st, sd_ed, sd_sc, v[NC], vd[NC];
+  };
+  RowRegs nxt;
+  auto prefetch_node = [&](int j, RowRegs& o) {
     const float* sj = A.s + (size_t)j * H;
-    st.s = sj[q];
-    ed.s = sj[M + q];
-    if (L == 0) sc.s = sj[2 * M + q];
-    if (SECOND) {
-      st.sd = ed.sd = sc.sd = 0.f;
-      if (A.a_s) {
-        const float* aj = A.a_s + (size_t)j * H;
-        st.sd = aj[q];
-        ed.sd = aj[M + q];
-        if (L == 0) sc.sd = aj[2 * M + q];
-      }
+    o.s_st = sj[q];
+    o.s_ed = sj[M + q];
+    o.s_sc = (L == 0) ? sj[2 * M + q] : 0.f;
+    o.sd_st = o.sd_ed = o.sd_sc = 0.f;
+    if (SECOND && A.a_s) {
+      const float* aj = A.a_s + (size_t)j * H;
+      o.sd_st = aj[q];
+      o.sd_ed = aj[M + q];
+      if (L == 0) o.sd_sc = aj[2 * M + q];
     }
 #pragma unroll
     for (int m = 0; m < NC; ++m) {
-      st.v[m] = A.v[(size_t)j * D + vbase + m * vstride];
-      if (SECOND) st.vd[m] = A.a_v ? A.a_v[(size_t)j * D + vbase + m * vstride] : 0.f;
+      o.v[m] = A.v[(size_t)j * D + vbase + m * vstride];
+      o.vd[m] = (SECOND && A.a_v) ? A.a_v[(size_t)j * D + vbase + m * vstride] : 0.f;
     }
+  };
+  auto begin_node = [&](const RowRegs& o) {
+    st.reset_node(); ed.reset_node(); sc.reset_node();
+    st.s = o.s_st; ed.s = o.s_ed; sc.s = o.s_sc;
+    st.sd = o.sd_st; ed.sd = o.sd_ed; sc.sd = o.sd_sc;
+#pragma unroll
+    for (int m = 0; m < NC; ++m) { st.v[m] = o.v[m]; st.vd[m] = o.vd[m]; }
   };
   struct Gathered {
     float g[NC], gx;
@@ -469,6 +479,7 @@ __device__ __forceinline__ void nbr_mma_role(const NeighborArgs& A, NbrMmaSmem<O
   // pipeline prologue (the producer warp has described and measured chunks 0 and 1)
   __syncthreads();
   ChunkDesc d0 = sm.desc[0], d1 = sm.desc[1];
+  if (d0.cnt >= 0) prefetch_node(d0.owner, nxt);
   if (d0.cnt > 0) geo_stage_b<TC, THREADS, NOUT>(A.geo, d0.cnt, sm.a[0], tiles, threadIdx.x);
   proxy_fence();
   tc_fence_before();
@@ -491,7 +502,8 @@ __device__ __forceinline__ void nbr_mma_role(const NeighborArgs& A, NbrMmaSmem<O
       win_lo = d0.n0;
       if (staged) stage_window(d0.n0, d0.n1);
     }
-    if (d0.rfirst) begin_node(d0.owner);
+    if (d0.rfirst) begin_node(nxt);
+    if (d1.cnt >= 0 && d1.rfirst) prefetch_node(d1.owner, nxt);  // consumed in the next iteration
     if (t < cnt) sm.red_eid[rs][t] = sa.eid[t];
     if (has) {
       mbar_wait(bar, phase);
