@@ -185,10 +185,10 @@ def algorithmic_bytes(kind: str, cfg: orc.XPaiNNConfig, N: int, E: int, periodic
 # the committed `ncu --set full` capture profiles/r01_edge_mma_ncu_full.md (c3 shape: N = 5376, E = 106068).
 # Only valid for that shape; other workloads report traffic = null.
 NCU_TRAFFIC_C3 = {
-    "edge_fwd": 36.44e6 + 0.10e6,                                                    # center_fwd_kernel
-    "edge_bwd": 36.87e6 + 0.28e6,                                                    # nbr_mma_kernel<1>
-    "edge_bwd_wgrad": (36.87e6 + 0.28e6) + (36.79e6 + 0.08e6),                       # + wgrad_mma_kernel<1>
-    "edge_bwdbwd": (46.14e6 + 0.12e6) + (59.69e6 + 3.46e6) + (59.57e6 + 1.98e6),     # jvp + nbr<2> + wgrad<2>
+    "edge_fwd": 36.43e6 + 0.31e6,                                                    # center_fwd_kernel
+    "edge_bwd": 36.88e6 + 0.25e6,                                                    # nbr_mma_kernel<1>
+    "edge_bwd_wgrad": (36.88e6 + 0.25e6) + (36.78e6 + 0.02e6),                       # + wgrad_mma_kernel<1>
+    "edge_bwdbwd": (46.14e6 + 0.21e6) + (59.67e6 + 3.12e6) + (59.56e6 + 1.61e6),     # jvp + nbr<2> + wgrad<2>
 }
 
 
