@@ -209,7 +209,7 @@ def run_gpu(args):
     import torch.distributed as dist
 
     import xequinet_b200 as xb
-    from xequinet_b200 import _lib, ops
+    from xequinet_b200 import _lib, ops, parallel
 
     rank = int(os.environ.get("RANK", 0))
     world = int(os.environ.get("WORLD_SIZE", 1))
@@ -285,13 +285,7 @@ def run_gpu(args):
             opt.zero_grad(set_to_none=True)
             loss.backward()
             if world > 1:
-                flat = torch.cat([p.grad.reshape(-1) for p in params])
-                dist.all_reduce(flat)  # NCCL over NVLink; 3.5 MB -> latency bound, one flat bucket
-                flat /= world
-                off = 0
-                for p in params:
-                    p.grad.copy_(flat[off:off + p.numel()].view_as(p.grad))
-                    off += p.numel()
+                parallel.allreduce_gradients(params)  # NCCL over NVLink; 3.5 MB -> latency bound, one flat bucket
             opt.step()
             result = loss.detach()
             if e2e:
@@ -336,13 +330,7 @@ def run_gpu(args):
                 loss = loss_fn(out, d, forces)
                 loss.backward()
                 if world > 1:
-                    flat = torch.cat([p.grad.reshape(-1) for p in params])
-                    dist.all_reduce(flat)
-                    flat /= world
-                    off = 0
-                    for p in params:
-                        p.grad.copy_(flat[off:off + p.numel()].view_as(p.grad))
-                        off += p.numel()
+                    parallel.allreduce_gradients(params)
                 opt.step()
                 result_buf["r"] = loss.detach()
             else:
