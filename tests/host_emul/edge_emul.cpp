@@ -13,6 +13,13 @@
 using namespace xeq;
 typedef double T;
 
+// 0: the SIMT kernels' decomposition (first / second with the weight-gradient accumulators in the thread).
+// 1: the tcgen05 kernels' decomposition: filter values w, dw, ddw supplied from outside (the MMA), radial-only
+//    d/dr coefficients for rows without an angular term recombined with u / rp per edge, and the weight gradients as
+//    the outer products  pw (x) psi,  pw (x) xi  (first order) /  alpha (x) psi + (beta ddot) (x) dpsi  (second).
+static int g_decomposition = 0;
+extern "C" void emul_set_decomposition(int mode) { g_decomposition = mode; }
+
 struct Dims { int C, m0, m1, m2, B; double rc; };
 
 struct Geo {  // everything any kernel variant keeps per edge
@@ -128,6 +135,10 @@ static void nbr_node(const Dims& D, int second, int j, int h, int q, const int* 
   constexpr int NC = NeighborThread<T, L, ROLE, true, 21>::NC;
   if (ROLE == ROLE_STATE)
     for (int m = 0; m < NC; ++m) { th.v[m] = v[(size_t)j * Dd + c.vbase + m * c.vstride]; th.vd[m] = second && a_v ? a_v[(size_t)j * Dd + c.vbase + m * c.vstride] : 0; }
+  NeighborThread<T, L, ROLE, false, 21> thm;
+  thm.reset_node();
+  thm.s = th.s; thm.sd = th.sd;
+  for (int m = 0; m < NC; ++m) { thm.v[m] = ROLE == ROLE_STATE ? th.v[m] : T(0); thm.vd[m] = ROLE == ROLE_STATE ? th.vd[m] : T(0); }
   for (int sl = t_rowptr[j]; sl < t_rowptr[j + 1]; ++sl) {
     int i = t_row[sl], e = t_eid[sl];
     T r[3], rdot[3] = {0, 0, 0};
@@ -139,9 +150,33 @@ static void nbr_node(const Dims& D, int second, int j, int h, int q, const int* 
     if (ROLE == ROLE_SCALAR) gg[0] = gx[(size_t)i * D.C + (h - 2 * M)];
     else for (int m = 0; m < NC; ++m) gg[m] = gV[(size_t)i * Dd + c.vbase + m * c.vstride];
     T pr[3];
-    if (second) th.second(ne, gg, pr); else th.first(ne, gg, pr);
+    if (g_decomposition == 0) {
+      if (second) th.second(ne, gg, pr); else th.first(ne, gg, pr);
+    } else {
+      NeighborThread<T, L, ROLE, false, 21>& tm = thm;  // no in-thread weight-gradient accumulators
+      const T w = dot_nk<21>(th.Wt, g.psi), dw = dot_nk<21>(th.Wt, g.dpsi), ddw = dot_nk<21>(th.Wt, g.ddpsi);
+      constexpr bool RADIAL = !(ROLE == ROLE_EDGE && L > 0);
+      if constexpr (RADIAL) {
+        T rad[2] = {0, 0};
+        if (second) tm.template second_w<true>(ne, gg, nullptr, w, dw, ddw, rad);
+        else tm.template first_w<true>(ne, gg, nullptr, w, dw, rad);
+        for (int x = 0; x < 3; ++x) pr[x] = g.u[x] * rad[0] + (second ? g.rp[x] * rad[1] : T(0));
+      } else {
+        if (second) tm.second_w(ne, gg, pr, w, dw, ddw); else tm.first_w(ne, gg, pr, w, dw);
+      }
+      if (!second) {
+        const T pw = tm.pw_first(g.Y, gg);
+        for (int k = 0; k < NBP; ++k) { th.GW[k] += pw * g.psi[k]; th.GF[k] += pw * g.xi[k]; }
+      } else {
+        T al, be;
+        tm.ab_second(g.Y, g.Ydot, gg, al, be);
+        const T bd = be * g.ddot;
+        for (int k = 0; k < NBP; ++k) { th.GW[k] += al * g.psi[k] + bd * g.dpsi[k]; th.GF[k] += al * g.xi[k] + bd * g.dxi[k]; }
+      }
+    }
     for (int x = 0; x < 3; ++x) gr[3 * (size_t)e + x] += pr[x];
   }
+  if (g_decomposition != 0) { th.acc_s = thm.acc_s; for (int m = 0; m < NC; ++m) th.acc_v[m] = thm.acc_v[m]; }
   o_s[(size_t)j * H + h] = th.acc_s;
   if (ROLE == ROLE_STATE) for (int m = 0; m < NC; ++m) o_v[(size_t)j * Dd + c.vbase + m * c.vstride] = th.acc_v[m];
   for (int k = 0; k < NBP; ++k) { GW[h * NBP + k] += th.GW[k]; GF[h * NBP + k] += th.GF[k]; }

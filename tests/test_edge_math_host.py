@@ -56,8 +56,12 @@ def _graph(kind):
     return d, ei, co, cell, rowptr, col, t_rowptr, t_row, t_eid, offs
 
 
+@pytest.mark.parametrize("decomposition", [0, 1], ids=["simt", "tcgen05"])
 @pytest.mark.parametrize("kind", ["mol", "pbc"])
-def test_emulated_kernels_match_autograd(emul, kind):
+def test_emulated_kernels_match_autograd(emul, kind, decomposition):
+    """decomposition 0 = the per-thread math of the SIMT kernels; 1 = that of the tcgen05 kernels (filter values
+    supplied from outside, radial-only d/dr coefficients, weight gradients as outer products over the edges)."""
+    emul.emul_set_decomposition(decomposition)
     cfg = orc.XPaiNNConfig(node_dim=32, muls=(32, 32, 32), num_basis=20)
     d, ei, co, cell, rowptr, col, t_rowptr, t_row, t_eid, offs = _graph(kind)
     N, E = d["pos"].shape[0], ei.shape[1]
