@@ -406,3 +406,38 @@ def test_tcgen05_and_simt_edge_kernels_agree(staged, tmp_path):
     assert len(got) == len(ref) == 16
     for i, (a, bref) in enumerate(zip(got, ref)):
         assert _rel(a, bref) < 1e-5, f"output {i}"
+
+
+# ---------------------------------------------------------------------------------------
+# Verlet-skin neighbour-list reuse (MD loops)
+# ---------------------------------------------------------------------------------------
+@pytest.mark.parametrize("periodic", [False, True])
+def test_skin_neighbor_list_gives_exact_energies_and_forces(periodic):
+    """SkinNeighborTransform keeps a list built with cutoff + skin while atoms move less than skin / 2; edges
+    beyond the cutoff contribute exactly zero, so E and F equal those of the exact list at every step."""
+    cfg = orc.CONFIG_DEFAULT
+    torch.manual_seed(0)
+    if periodic:
+        base = orc.make_water_box(4, seed=3)  # 192 atoms, L = 12.4 A
+    else:
+        base = orc.make_molecule_batch(6, (8, 20), seed=9, with_edges=False)
+    model = xb.resolve_model("xpainn", **cfg.model_kwargs())
+    model.load_state_dict(orc.synthetic_state_dict(cfg, 1234), strict=False)
+    model = model.to(DEV).eval()
+    exact = xb.NeighborTransform(cfg.cutoff)
+    skin = xb.SkinNeighborTransform(cfg.cutoff, skin=1.0)
+    pos0 = base["pos"].to(DEV)
+    g = torch.Generator().manual_seed(1)
+    step = 0.12 * torch.nn.functional.normalize(torch.randn(pos0.shape, generator=g), dim=-1).to(DEV)
+    keys_in = [k for k in ("atomic_numbers", "batch", "ptr", "cell", "pbc") if k in base]
+    for it in range(6):  # cumulative displacement 0 .. 0.6 A: crosses skin / 2 once
+        pos = pos0 + it * step
+        outs = []
+        for tr in (exact, skin):
+            d = {k: base[k].to(DEV) for k in keys_in}
+            d["pos"] = pos.clone()
+            outs.append(model(tr(d), compute_forces=True))
+        e_ref, e_got = outs[0]["energy"].detach(), outs[1]["energy"].detach()
+        assert float((e_got - e_ref).abs().max()) <= 2e-5 * max(1.0, float(e_ref.abs().max())), it
+        assert float((outs[1]["forces"] - outs[0]["forces"]).abs().max()) < 1e-4, it
+    assert skin.n_calls == 6 and 1 < skin.n_builds < 6

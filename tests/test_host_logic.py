@@ -120,3 +120,41 @@ def test_update_block_matches_oracle_layer():
     V_ref = V + U * orc.expand_gate(a[:, :M], cfg)
     torch.testing.assert_close(out[keys.NODE_INVARIANT], x_ref, rtol=1e-5, atol=2e-5)
     torch.testing.assert_close(orc.from_cm(out[keys.NODE_EQUIVARIANT], cfg), V_ref, rtol=1e-5, atol=2e-5)
+
+
+def test_skin_neighbor_list_rebuild_policy():
+    """Verlet-skin reuse (graph.SkinNeighborTransform): the rebuild decision is pure tensor logic, exercised here
+    with a stubbed builder (K1 itself needs a GPU)."""
+    import torch
+    from xequinet_b200 import keys
+    from xequinet_b200.graph import SkinNeighborTransform
+
+    class Stub(SkinNeighborTransform):
+        def _build(self, data):
+            out = dict(data)
+            out[keys.EDGE_INDEX] = torch.zeros(2, 0, dtype=torch.long)
+            out[keys.GRAPH] = ("graph", self.n_builds)
+            return out
+
+    tr = Stub(5.0, skin=1.0)
+    torch.manual_seed(5)
+    pos = torch.randn(10, 3)
+    cell = (torch.eye(3) * 20.0).reshape(1, 3, 3)
+    d = tr({keys.POSITIONS: pos.clone(), keys.CELL: cell.clone(), keys.PBC: torch.ones(1, 3, dtype=torch.bool)})
+    assert tr.n_builds == 1 and d[keys.GRAPH] == ("graph", 0)
+    # small displacements (< skin / 2): the list is kept
+    moved = pos + 0.2 * torch.nn.functional.normalize(torch.randn(10, 3), dim=-1)
+    d = tr({keys.POSITIONS: moved, keys.CELL: cell.clone(), keys.PBC: torch.ones(1, 3, dtype=torch.bool)})
+    assert tr.n_builds == 1 and d[keys.GRAPH] == ("graph", 0) and tr.n_calls == 2
+    # one atom beyond skin / 2: rebuild, and the reference positions move with it
+    far = moved.clone()
+    far[3] = pos[3] + torch.tensor([0.6, 0.0, 0.0])  # 0.6 A from where the list was built
+    assert tr.needs_rebuild({keys.POSITIONS: far, keys.CELL: cell})
+    tr({keys.POSITIONS: far, keys.CELL: cell.clone()})
+    assert tr.n_builds == 2
+    assert not tr.needs_rebuild({keys.POSITIONS: far + 0.1, keys.CELL: cell})  # |(0.1, 0.1, 0.1)| = 0.17 < 0.5
+    # a changed cell or a different number of atoms forces a rebuild
+    assert tr.needs_rebuild({keys.POSITIONS: far, keys.CELL: cell * 1.01})
+    assert tr.needs_rebuild({keys.POSITIONS: far[:9], keys.CELL: cell})
+    with pytest.raises(ValueError):
+        SkinNeighborTransform(5.0, skin=-1.0)

@@ -335,3 +335,58 @@ class NeighborTransform:
         data[keys.EDGE_INDEX] = ei
         data[keys.GRAPH] = g
         return data
+
+
+class SkinNeighborTransform(NeighborTransform):
+    """Verlet-skin reuse of the neighbour list for MD loops (the reference rebuilds the list at
+    every step, interface/ase_calculator.py:86-88).  The list is built with `cutoff + skin` and kept while no atom has
+    moved more than `skin / 2` since the build and the cell and batch structure are unchanged.  Edges longer than the
+    model's cutoff contribute exactly zero to the message (chi(d) = 0 for d >= r_c, nn/rbf.py:47-48 -- and so do all
+    their derivatives), so energies and forces are those of the exact list; `edge_index` is then a superset of
+    the reference's edge set.  Cell offsets refer to the unwrapped positions (data/radius_graph.py:186-190), so
+    atoms may leave the cell between rebuilds.  One host synchronisation per call (the displacement test)."""
+
+    def __init__(self, cutoff: float, skin: float = 1.0) -> None:
+        super().__init__(cutoff)
+        if skin < 0:
+            raise ValueError("skin must be >= 0")
+        self.skin = float(skin)
+        self.n_calls = 0
+        self.n_builds = 0
+        self._ref = None  # (pos, cell, ptr/batch signature) at the last build
+        self._cached: Dict[str, torch.Tensor] = {}
+
+    @staticmethod
+    def _signature(data) -> tuple:
+        ptr, batch = data.get(keys.BATCH_PTR), data.get(keys.BATCH)
+        n = int(data[keys.POSITIONS].shape[0])
+        g = int(ptr.numel() - 1) if ptr is not None else (int(batch.max().item()) + 1 if (batch is not None and n) else 1)
+        return (n, g, keys.CELL in data)
+
+    def needs_rebuild(self, data: Dict[str, torch.Tensor]) -> bool:
+        """True when there is no list yet, the structure changed shape, the cell changed, or some atom has moved
+        more than skin / 2 since the list was built."""
+        if self._ref is None:
+            return True
+        pos_ref, cell_ref, sig = self._ref
+        if sig != self._signature(data) or pos_ref.device != data[keys.POSITIONS].device:
+            return True
+        if cell_ref is not None and not torch.equal(cell_ref, data[keys.CELL].detach().reshape(-1, 3, 3).to(cell_ref.dtype)):
+            return True
+        disp2 = ((data[keys.POSITIONS].detach() - pos_ref) ** 2).sum(-1)
+        return bool(disp2.max().item() > (0.5 * self.skin) ** 2) if disp2.numel() else False
+
+    def _build(self, data: Dict[str, torch.Tensor]) -> Dict[str, torch.Tensor]:
+        wide = NeighborTransform(self.cutoff + self.skin)
+        return wide(dict(data))
+
+    def __call__(self, data: Dict[str, torch.Tensor]) -> Dict[str, torch.Tensor]:
+        self.n_calls += 1
+        if self.needs_rebuild(data):
+            built = self._build(data)
+            self._cached = {k: built[k] for k in (keys.EDGE_INDEX, keys.GRAPH, keys.CELL_OFFSETS) if k in built}
+            cell = data[keys.CELL].detach().reshape(-1, 3, 3).clone() if keys.CELL in data else None
+            self._ref = (data[keys.POSITIONS].detach().clone(), cell, self._signature(data))
+            self.n_builds += 1
+        data.update(self._cached)
+        return data
