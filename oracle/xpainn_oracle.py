@@ -347,15 +347,34 @@ def xpainn_energy(
     return energy, e_atom
 
 
-def xpainn_energy_forces(sd, embed_table, data, cfg: XPaiNNConfig = CONFIG_DEFAULT, create_graph: bool = False):
-    """BaseModel.forward with compute_forces=True (nn/basic.py:143-159, 202-238)."""
+def xpainn_energy_forces(sd, embed_table, data, cfg: XPaiNNConfig = CONFIG_DEFAULT, create_graph: bool = False,
+                         compute_virial: bool = False):
+    """BaseModel.forward with compute_forces=True (nn/basic.py:143-159, 202-238); with compute_virial the strain
+    trick of nn/basic.py:93-107 (positions and cell displaced by a symmetrised per-graph strain) and
+    virial = -dE/dstrain (nn/basic.py:162-199)."""
     data = dict(data)
     pos = data["pos"].detach().clone().requires_grad_(True)
     data["pos"] = pos
+    strain = None
+    if compute_virial:
+        batch = data.get("batch")
+        if batch is None:
+            batch = torch.zeros(pos.shape[0], dtype=torch.long)
+        G = int(data["ptr"].numel() - 1) if "ptr" in data else int(batch.max().item()) + 1
+        strain = torch.zeros((G, 3, 3), dtype=pos.dtype, requires_grad=True)
+        symm = 0.5 * (strain + strain.transpose(1, 2))
+        data["pos"] = pos + torch.bmm(pos.unsqueeze(1), symm.index_select(0, batch)).squeeze(1)
+        if data.get("cell") is not None:
+            cell = data["cell"].reshape(-1, 3, 3)
+            data["cell"] = cell + torch.bmm(cell, symm)
     energy, e_atom = xpainn_energy(sd, embed_table, data, cfg)
-    (gpos,) = torch.autograd.grad([energy], [pos], grad_outputs=[torch.ones_like(energy)],
-                                  create_graph=create_graph, retain_graph=create_graph)
-    return {"energy": energy, "atomic_energies": e_atom, "forces": -gpos}
+    inputs = [pos] + ([strain] if compute_virial else [])
+    grads = torch.autograd.grad([energy], inputs, grad_outputs=[torch.ones_like(energy)],
+                                create_graph=create_graph, retain_graph=create_graph)
+    out = {"energy": energy, "atomic_energies": e_atom, "forces": -grads[0]}
+    if compute_virial:
+        out["virial"] = -grads[1]
+    return out
 
 
 # ----------------------------------------------------------------------------

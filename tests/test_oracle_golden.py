@@ -77,3 +77,25 @@ def test_radius_graph_symmetric_and_loop_free():
     fwd = set(map(tuple, ei.t().tolist()))
     assert all((b, a) in fwd for a, b in fwd)
     assert (d["batch"][ei[0]] == d["batch"][ei[1]]).all()
+
+
+@pytest.mark.parametrize("name", ["mol_small", "pbc_small", "pbc_slab", "pbc_two_graphs"])
+def test_oracle_virial_matches_reference(name):
+    """The oracle's strain trick (nn/basic.py:93-107, 162-199) against the reference's own virial
+    (tests/golden/virial.npz, oracle/make_golden_virial.py), float64."""
+    import numpy as np
+    from helpers import GOLDEN
+
+    z, cfg, data = load_golden(name)
+    ref = np.load(GOLDEN / "virial.npz")[f"{name}:virial"]
+    sd = orc.synthetic_state_dict(cfg, int(z["sd_seed"]), torch.float64)
+    d = cast_data(data, torch.float64)
+    out = orc.xpainn_energy_forces(sd, embed_table().double(), d, cfg, compute_virial=True)
+    np.testing.assert_allclose(out["virial"].detach().numpy(), ref, rtol=1e-10, atol=1e-10)
+    np.testing.assert_allclose(out["forces"].detach().numpy(), z["f64:forces"], rtol=1e-9, atol=1e-9)
+    # identity used by the B200 path: virial = -(sum_n pos_n (x) dE/dpos_n + cell^T dE/dcell), symmetrised
+    # (for non-periodic graphs the cell term vanishes: the virial follows from the forces alone)
+    if "cell" not in d:
+        G = d["ptr"].numel() - 1
+        M = torch.zeros(G, 3, 3, dtype=torch.float64).index_add(0, d["batch"], torch.einsum("na,nb->nab", d["pos"], -out["forces"].detach()))
+        np.testing.assert_allclose((-0.5 * (M + M.transpose(1, 2))).numpy(), ref, rtol=1e-9, atol=1e-9)
