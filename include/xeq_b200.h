@@ -186,6 +186,15 @@ int xeq_edge_message_bwd(const xeq_graph_t* g, const xeq_dims_t* dims, const flo
  * (a_s, a_v, a_pos) of (gs, gv, gpos) (any may be NULL = zero) this returns the gradient of
  *   Psi = <a_s, dPhi/ds> + <a_v, dPhi/dv> + <a_pos, dPhi/dpos>
  * with respect to gx, gV, s, v, pos, W_rbf, b_rbf, freq.  Output pointers may be NULL. */
+/* Per-node pieces of the CELL gradient of a periodic graph (virial / stress through the strain trick,
+ * nn/basic.py:93-107, 162-199):  rows[3a+b][n] = sum over the edges e of CSR row n of
+ * cell_offsets[e][a] * (dE/dr_e)[b], so that  dE/dcell[g][a][b] = - sum_{n in g} rows[3a+b][n]
+ * (the edge vector is pos_i - pos_j - cell_offsets @ cell, nn/basic.py:119-128).  Reads the per-edge d/dr records
+ * that the preceding xeq_edge_message_bwd call (gpos != NULL, same stream) left at the start of ITS workspace.
+ * rows: [9, n_nodes] floats.  Deterministic. */
+int xeq_edge_cell_grad_rows(const xeq_graph_t* g, const xeq_dims_t* dims, const void* bwd_workspace,
+                            float* rows, xeq_stream_t stream);
+
 size_t xeq_edge_message_bwdbwd_workspace_bytes(const xeq_graph_t* g, const xeq_dims_t* dims, int want_wgrad);
 int xeq_edge_message_bwdbwd(const xeq_graph_t* g, const xeq_dims_t* dims, const float* pos,
                             const float* s, const float* v,

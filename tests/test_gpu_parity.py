@@ -441,3 +441,50 @@ def test_skin_neighbor_list_gives_exact_energies_and_forces(periodic):
         assert float((e_got - e_ref).abs().max()) <= 2e-5 * max(1.0, float(e_ref.abs().max())), it
         assert float((outs[1]["forces"] - outs[0]["forces"]).abs().max()) < 1e-4, it
     assert skin.n_calls == 6 and 1 < skin.n_builds < 6
+
+
+# ---------------------------------------------------------------------------------------
+# virial through the strain trick (nn/basic.py:93-107, 162-199)
+# ---------------------------------------------------------------------------------------
+@pytest.mark.parametrize("name", ["mol_small", "pbc_small", "pbc_slab", "pbc_two_graphs"])
+def test_virial_matches_reference_golden(name):
+    """model(data, compute_forces=True, compute_virial=True): virial = -dE/dstrain against the reference's own
+    fp64 virial (tests/golden/virial.npz); the forces of the same pass are those of the plain force pass."""
+    from helpers import GOLDEN
+
+    z, cfg, data = load_golden(name)
+    ref = np.load(GOLDEN / "virial.npz")[f"{name}:virial"]
+    model = _model(cfg, int(z["sd_seed"]))
+    d = _dev(cast_data(data, torch.float32))
+    d.pop("pbc", None)
+    out = model(dict(d), compute_forces=True, compute_virial=True)
+    assert set(out) == {"energy", "atomic_energies", "forces", "virial"}
+    vir = out["virial"].detach().cpu().numpy()
+    scale = max(1.0, float(np.abs(ref).max()))
+    assert np.abs(vir - ref).max() <= 3e-4 * scale, (np.abs(vir - ref).max(), scale)
+    np.testing.assert_allclose(vir, np.swapaxes(vir, 1, 2), atol=1e-6 * scale)  # symmetrised strain
+    _force_gate(out["forces"].detach().cpu().numpy(), z["f64:forces"], z["f32:forces"])
+    np.testing.assert_allclose(out["energy"].detach().cpu().numpy(), z["f64:energy"], rtol=1e-5, atol=1e-6)
+    # virial alone (no forces requested)
+    out2 = model(dict(d), compute_forces=False, compute_virial=True)
+    assert "forces" not in out2
+    np.testing.assert_allclose(out2["virial"].detach().cpu().numpy(), vir, rtol=0, atol=1e-6 * scale)
+
+
+def test_virial_training_support():
+    """Non-periodic structures: the virial can sit in a training loss (double backward through K2bb).
+    Periodic structures: refused loudly (the cell gradient is first order only)."""
+    z, cfg, data = load_golden("mol_small")
+    model = _model(cfg, int(z["sd_seed"])).train()
+    d = _dev(cast_data(data, torch.float32))
+    out = model(dict(d), compute_forces=True, compute_virial=True)
+    loss = out["energy"].sum() + (out["forces"] ** 2).sum() + (out["virial"] ** 2).sum()
+    loss.backward()
+    g = model.mods["message_0"].rbf_lin.weight.grad
+    assert g is not None and bool(torch.isfinite(g).all()) and float(g.abs().max()) > 0
+    z, cfg, data = load_golden("pbc_small")
+    model = _model(cfg, int(z["sd_seed"])).train()
+    d = _dev(cast_data(data, torch.float32))
+    d.pop("pbc", None)
+    with pytest.raises(NotImplementedError):
+        model(dict(d), compute_forces=True, compute_virial=True)

@@ -57,6 +57,7 @@ _SIGNATURES = {
     "xeq_edge_message_bwdbwd": (c_int, [POINTER(XeqGraph), POINTER(XeqDims)] + [c_void_p] * 19 + [c_void_p, c_size_t, c_void_p]),
     "xeq_segment_sum": (c_int, [c_void_p, c_void_p, c_int32, c_void_p, c_void_p]),
     "xeq_colsum": (c_int, [c_void_p, c_int32, c_int32, c_int32, c_void_p, c_void_p]),
+    "xeq_edge_cell_grad_rows": (c_int, [POINTER(XeqGraph), POINTER(XeqDims), c_void_p, c_void_p, c_void_p]),
     "xeq_gemm_workspace_bytes": (c_size_t, [POINTER(XeqGemm), c_int32, c_int32]),
     "xeq_gemm_tf32x3": (c_int, [POINTER(XeqGemm), c_int32, c_int32, c_void_p, c_size_t, c_void_p]),
     "xeq_irreps_norm_workspace_bytes": (c_size_t, [c_int32] * 4),

@@ -604,6 +604,34 @@ __global__ void pos_grad_kernel(xeq_graph_t g, const float* __restrict__ gr, int
   gpos[3 * n] = a0; gpos[3 * n + 1] = a1; gpos[3 * n + 2] = a2;
 }
 
+// rows[k][n] (k = 3 a + b) = sum_{e in row n} offsets[e][a] * gr[e][b]: the per-node pieces of
+// dE/dcell[a][b] = - sum_e offsets[e][a] (dE/dr_e)[b]  (the edge vector is pos_i - pos_j - offsets @ cell,
+// nn/basic.py:119-128); the caller segment-sums the nine rows per graph.  One thread per node, fixed order.
+__global__ void cell_grad_rows_kernel(xeq_graph_t g, const float* __restrict__ gr, int n_slabs, float* __restrict__ rows) {
+  const int n = blockIdx.x * blockDim.x + threadIdx.x;
+  if (n >= g.n_nodes) return;
+  const size_t slab = 3 * (size_t)g.n_edges;
+  float acc[9];
+#pragma unroll
+  for (int k = 0; k < 9; ++k) acc[k] = 0.f;
+  for (int e = g.rowptr[n]; e < g.rowptr[n + 1]; ++e) {
+    const char4 o = reinterpret_cast<const char4*>(g.offsets)[e];
+    if (o.x == 0 && o.y == 0 && o.z == 0) continue;
+    float d[3] = {0.f, 0.f, 0.f};
+    for (int k = 0; k < n_slabs; ++k) {
+      const float* p = gr + k * slab + 3 * (size_t)e;
+      d[0] += p[0]; d[1] += p[1]; d[2] += p[2];
+    }
+    const float of[3] = {(float)o.x, (float)o.y, (float)o.z};
+#pragma unroll
+    for (int a = 0; a < 3; ++a)
+#pragma unroll
+      for (int b = 0; b < 3; ++b) acc[3 * a + b] += of[a] * d[b];
+  }
+#pragma unroll
+  for (int k = 0; k < 9; ++k) rows[(size_t)k * g.n_nodes + n] = acc[k];
+}
+
 // weight-gradient partials [nblk, H, 2*NBP] -> gW [H,B], gb [H], ftot [H, NB] (fixed order)
 __global__ void wgrad_reduce_kernel(const float* __restrict__ wpart, int nblk, int H, float* __restrict__ gW,
                                     float* __restrict__ gb, float* __restrict__ ftot) {
@@ -858,6 +886,20 @@ int xeq_edge_message_bwd(const xeq_graph_t* g, const xeq_dims_t* dims, const flo
   A.s = s; A.v = v; A.W = W_rbf; A.b = b_rbf; A.gx = gx; A.gV = gV;
   A.o_s = gs; A.o_v = gv;
   return run_neighbor(g, dims, A, 1, gpos, gW, gb, gfreq, workspace, workspace_bytes, (cudaStream_t)stream);
+}
+
+int xeq_edge_cell_grad_rows(const xeq_graph_t* g, const xeq_dims_t* dims, const void* bwd_workspace, float* rows,
+                            xeq_stream_t stream) {
+  int cfg;
+  int rc = check_dims(dims, &cfg);
+  if (rc) return rc;
+  XEQ_CHECK_ARG(g && g->rowptr && g->offsets && bwd_workspace && rows, "edge_cell_grad_rows: periodic graph, workspace and rows needed");
+  if (g->n_nodes == 0) return XEQ_OK;
+  const int slabs = use_mma() ? (cfg == 1 ? 2 : 1) : 1;  // as written by xeq_edge_message_bwd
+  cell_grad_rows_kernel<<<(g->n_nodes + 127) / 128, 128, 0, (cudaStream_t)stream>>>(*g, static_cast<const float*>(bwd_workspace),
+                                                                                  slabs, rows);
+  XEQ_LAUNCHED(1);
+  return XEQ_OK;
 }
 
 size_t xeq_edge_message_bwdbwd_workspace_bytes(const xeq_graph_t* g, const xeq_dims_t* dims, int want_wgrad) {

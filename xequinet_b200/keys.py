@@ -25,4 +25,7 @@ VIRIAL = "virial"
 GRAPH = "_xeq_graph"
 RBF_FREQ = "_xeq_rbf_freq"
 RBF_CUTOFF = "_xeq_rbf_cutoff"
+STRAIN = "strain"  # nn/basic.py:133-139
+POS_EFF = "_xeq_pos_strained"    # positions / cell with the (zero) strain of the virial computation applied:
+CELL_EFF = "_xeq_cell_strained"  # what the edge kernels differentiate (nn/basic.py:99-107)
 HALO = "_xeq_halo"  # domain.HaloPlan of a spatially sharded run (xequinet_b200/domain.py)

@@ -15,8 +15,6 @@ from ..graph import NeighborGraph, graph_from_edge_index
 
 def compute_edge_data(data: Dict[str, torch.Tensor], compute_forces: bool = True, compute_virial: bool = False):
     pos = data[keys.POSITIONS]
-    if compute_virial:
-        raise NotImplementedError("compute_virial (strain derivative, nn/basic.py:93-107) is not on the B200 path yet")
     if not pos.is_cuda:
         raise RuntimeError("xequinet_b200 models run on CUDA tensors only: there is no CPU fallback")
     if pos.dtype != torch.float32:
@@ -40,6 +38,24 @@ def compute_edge_data(data: Dict[str, torch.Tensor], compute_forces: bool = True
         data[keys.GRAPH] = graph
     if compute_forces:
         pos.requires_grad_()  # nn/basic.py:90-91
+    data.pop(keys.POS_EFF, None)
+    data.pop(keys.CELL_EFF, None)
+    strain = torch.zeros((n_graphs, 3, 3), dtype=pos.dtype, device=pos.device)
+    if compute_virial:
+        # nn/basic.py:99-107: positions and cell displaced by a symmetrised per-graph strain (evaluated at zero).
+        # The edge kernels differentiate with respect to the displaced positions and -- for periodic cells -- the
+        # displaced cell (K2b returns dE/dcell from its per-edge d/dr records); autograd carries both to `strain`.
+        if keys.HALO in data:
+            raise NotImplementedError("compute_virial is not available for spatially sharded runs")
+        strain.requires_grad_()
+        symm = 0.5 * (strain + strain.transpose(1, 2))
+        batch = data[keys.BATCH].long()
+        data[keys.POS_EFF] = pos + torch.bmm(pos.unsqueeze(1), symm.index_select(0, batch)).squeeze(1)
+        if has_cell:
+            cell = data[keys.CELL].reshape(-1, 3, 3).to(pos.dtype)
+            data[keys.CELL_EFF] = cell + torch.bmm(cell, symm)
+            graph.seg_ptr = data["_xeq_ptr32"]
+    data[keys.STRAIN] = strain
     return data
 
 
@@ -54,10 +70,32 @@ def compute_forces_only(energy: torch.Tensor, pos: torch.Tensor, training: bool 
     return -1.0 * pos_grad
 
 
+def compute_virial_and_forces(energy: torch.Tensor, pos: torch.Tensor, strain: torch.Tensor, want_forces: bool,
+                              training: bool, periodic: bool):
+    """nn/basic.py:162-199: virial = -dE/dstrain (and forces = -dE/dpos from the same backward pass)."""
+    if training and periodic:
+        raise NotImplementedError("a virial term in the training loss of a PERIODIC structure needs the second derivative "
+                                  "of the cell gradient, which the B200 kernels do not provide yet (inference and "
+                                  "non-periodic training are supported)")
+    inputs = ([pos] if want_forces else []) + [strain]
+    with ops.param_grads(False):
+        grads = torch.autograd.grad(outputs=[energy], inputs=inputs, grad_outputs=[torch.ones_like(energy)],
+                                    retain_graph=training, create_graph=training, allow_unused=True)
+    grads = [g if g is not None else torch.zeros_like(t) for g, t in zip(grads, inputs)]
+    forces = -1.0 * grads[0] if want_forces else None
+    return forces, -1.0 * grads[-1]
+
+
 def compute_properties(data, compute_forces: bool = True, compute_virial: bool = False, training: bool = True,
                        extra_properties: Optional[List[str]] = None):
     results = {}
-    if compute_forces:
+    if compute_virial:
+        forces, virial = compute_virial_and_forces(data[keys.TOTAL_ENERGY], data[keys.POSITIONS], data[keys.STRAIN],
+                                                   compute_forces, training, keys.CELL_EFF in data)
+        if compute_forces:
+            results[keys.FORCES] = forces
+        results[keys.VIRIAL] = virial
+    elif compute_forces:
         results[keys.FORCES] = compute_forces_only(data[keys.TOTAL_ENERGY], data[keys.POSITIONS], training)
     if extra_properties is not None:
         results.update({k: data[k] for k in extra_properties})

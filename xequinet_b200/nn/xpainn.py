@@ -90,8 +90,10 @@ class XPainnMessage(nn.Module):
             data[keys.NODE_INVARIANT] = x_new[: plan.n_owned]
             data[keys.NODE_EQUIVARIANT] = V_new[: plan.n_owned]
             return data
-        x_new, V_new = ops.edge_message(x, V, s, v, data[keys.POSITIONS], self.rbf_lin.weight, self.rbf_lin.bias,
-                                        data[keys.RBF_FREQ], data[keys.GRAPH], self._dims)
+        # with compute_virial the kernels differentiate the strained positions / cell (nn/basic.py:99-107)
+        x_new, V_new = ops.edge_message(x, V, s, v, data.get(keys.POS_EFF, data[keys.POSITIONS]), self.rbf_lin.weight,
+                                        self.rbf_lin.bias, data[keys.RBF_FREQ], data[keys.GRAPH], self._dims,
+                                        cell=data.get(keys.CELL_EFF))
         data[keys.NODE_INVARIANT] = x_new
         data[keys.NODE_EQUIVARIANT] = V_new
         return data

@@ -124,13 +124,15 @@ def edge_message_fwd_raw(graph: NeighborGraph, dims: Dims, pos, s, v, x_in, V_in
 
 
 def edge_message_bwd_raw(graph: NeighborGraph, dims: Dims, pos, s, v, W, b, freq, gx, gV, need_s=True, need_v=True,
-                         need_pos=True, need_w=False):
+                         need_pos=True, need_w=False, need_cell=False):
+    """K2b.  need_cell (periodic graphs; implies need_pos): additionally returns dE/dcell [G,3,3] = -sum_e offsets_e (x)
+    dE/dr_e from the per-edge d/dr records of the same launch (virial through the strain trick, nn/basic.py:93-107)."""
     lib = _lib.get()
     N, dev = graph.n_nodes, s.device
     new = lambda *shape: torch.empty(shape, dtype=torch.float32, device=dev)
     gs = new(N, dims.H) if need_s else None
     gv = new(N, dims.D) if need_v else None
-    gpos = new(N, 3) if need_pos else None
+    gpos = new(N, 3) if (need_pos or need_cell) else None
     gW = new(dims.H, dims.num_basis) if need_w else None
     gb = new(dims.H) if need_w else None
     gf = new(dims.num_basis) if need_w else None
@@ -143,7 +145,19 @@ def edge_message_bwd_raw(graph: NeighborGraph, dims: Dims, pos, s, v, W, b, freq
                                         _lib.ptr(gv), _lib.ptr(gpos), _lib.ptr(gW), _lib.ptr(gb), _lib.ptr(gf),
                                         _lib.ptr(ws), nbytes, _lib.stream()), "xeq_edge_message_bwd")
     KernelTimer.stop(ev, "edge_bwd_wgrad" if need_w else "edge_bwd", graph)
-    return gs, gv, gpos, gW, gb, gf
+    if not need_cell:
+        return gs, gv, gpos, gW, gb, gf
+    if graph.offsets is None or getattr(graph, "seg_ptr", None) is None:
+        raise RuntimeError("the cell gradient needs a periodic graph with its batch pointer (graph.seg_ptr)")
+    rows = new(9, N)
+    _lib.check(lib.xeq_edge_cell_grad_rows(graph.struct, d, _lib.ptr(ws), _lib.ptr(rows), _lib.stream()), "xeq_edge_cell_grad_rows")
+    G = graph.seg_ptr.numel() - 1
+    sums = new(9, G)
+    for k in range(9):  # nine deterministic segment sums over the nodes of each graph
+        _lib.check(lib.xeq_segment_sum(_lib.ptr(rows[k]), _lib.ptr(graph.seg_ptr), G, _lib.ptr(sums[k]), _lib.stream()),
+                   "xeq_segment_sum")
+    gcell = -sums.t().reshape(G, 3, 3)
+    return gs, gv, gpos, gW, gb, gf, gcell
 
 
 def edge_message_bwdbwd_raw(graph: NeighborGraph, dims: Dims, pos, s, v, W, b, freq, gx, gV, a_s, a_v, a_pos,
@@ -180,19 +194,21 @@ class _EdgeMessageBwd(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, gx, gV, s, v, pos, W, b, freq, graph, dims, needs):
-        need_s, need_v, need_pos, need_w = needs
+        need_s, need_v, need_pos, need_w = needs[:4]
+        need_cell = len(needs) > 4 and needs[4]
         gx, gV = _c(gx), _c(gV)
-        gs, gv, gpos, gW, gb, gf = edge_message_bwd_raw(graph, dims, pos, s, v, W, b, freq, gx, gV, need_s, need_v,
-                                                         need_pos, need_w)
+        res = edge_message_bwd_raw(graph, dims, pos, s, v, W, b, freq, gx, gV, need_s, need_v, need_pos, need_w, need_cell)
+        gs, gv, gpos, gW, gb, gf = res[:6]
+        gcell = res[6] if need_cell else None  # first order only: no derivative of the cell gradient is provided
         ctx.save_for_backward(gx, gV, s, v, pos, W, b, freq)
         ctx.graph, ctx.dims, ctx.needs = graph, dims, needs
-        outs = (gs, gv, gpos, gW, gb, gf)
+        outs = (gs, gv, gpos, gW, gb, gf, gcell)
         ctx.mark_non_differentiable(*[o for o in outs[3:] if o is not None])
         return outs
 
     @staticmethod
     @torch.autograd.function.once_differentiable
-    def backward(ctx, a_s, a_v, a_pos, a_W, a_b, a_f):
+    def backward(ctx, a_s, a_v, a_pos, a_W, a_b, a_f, a_cell=None):
         gx, gV, s, v, pos, W, b, freq = ctx.saved_tensors
         ni = ctx.needs_input_grad
         if a_s is None and a_v is None and a_pos is None:
@@ -209,7 +225,9 @@ class _EdgeMessage(torch.autograd.Function):
     """K2: (x, V, s, v, pos, W_rbf, b_rbf, freq) -> (x + sum m_s, V + sum m_e)."""
 
     @staticmethod
-    def forward(ctx, x, V, s, v, pos, W, b, freq, graph, dims):
+    def forward(ctx, x, V, s, v, pos, W, b, freq, cell, graph, dims):
+        # `cell` ([G,3,3] or None) only matters for differentiation (virial): the kernels read the lattice from the
+        # graph, which holds the same values (the strain of nn/basic.py:93-107 is zero where it is evaluated)
         x, V, s, v, pos, W, b = (_c(t) for t in (x, V, s, v, pos, W, b))
         freq = _c(freq)
         x_out, V_out = edge_message_fwd_raw(graph, dims, pos, s, v, x, V, W, b, freq)
@@ -226,18 +244,22 @@ class _EdgeMessage(torch.autograd.Function):
         if gV is None:
             gV = torch.zeros((s.shape[0], ctx.dims.D), dtype=s.dtype, device=s.device)
         need_w = (ni[5] or ni[6] or ni[7]) and _ParamGradState.wanted
-        needs = (ni[2], ni[3], ni[4], need_w)
-        gs = gv = gpos = gW = gb = gf = None
+        need_cell = bool(ni[8])
+        needs = (ni[2], ni[3], ni[4] or need_cell, need_w, need_cell)
+        gs = gv = gpos = gW = gb = gf = gcell = None
         if any(needs):
-            gs, gv, gpos, gW, gb, gf = _EdgeMessageBwd.apply(gx, gV, s, v, pos, W, b, freq, ctx.graph, ctx.dims, needs)
+            gs, gv, gpos, gW, gb, gf, gcell = _EdgeMessageBwd.apply(gx, gV, s, v, pos, W, b, freq, ctx.graph, ctx.dims, needs)
             if gf is not None:
                 gf = gf.view_as(freq)
-        return (gx if ni[0] else None, gV if ni[1] else None, gs, gv, gpos, gW, gb, gf, None, None)
+            if not ni[4]:
+                gpos = None
+        return (gx if ni[0] else None, gV if ni[1] else None, gs, gv, gpos, gW, gb, gf, gcell, None, None)
 
 
-def edge_message(x, V, s, v, pos, W_rbf, b_rbf, freq, graph: NeighborGraph, dims: Dims):
-    """Fused XPainnMessage aggregation (nn/xpainn.py:140-159); V and v in the cm layout."""
-    return _EdgeMessage.apply(x, V, s, v, pos, W_rbf, b_rbf, freq, graph, dims)
+def edge_message(x, V, s, v, pos, W_rbf, b_rbf, freq, graph: NeighborGraph, dims: Dims, cell=None):
+    """Fused XPainnMessage aggregation (nn/xpainn.py:140-159); V and v in the cm layout.  `cell` is only passed
+    when its gradient is wanted (virial of a periodic structure)."""
+    return _EdgeMessage.apply(x, V, s, v, pos, W_rbf, b_rbf, freq, cell, graph, dims)
 
 
 class _SegmentSum(torch.autograd.Function):
