@@ -17,7 +17,8 @@ Output: ONE JSON line (rank 0).  `value` = whole-job molecules/s with the inputs
 HBM; `e2e` = the same through the public API with pinned-host inputs copied in and the loss /
 energies read back every step; `roofline` = the dominant hand-written kernel of the step
 (CUDA events on the launching stream, algorithmic bytes per DESIGN.md) against the measured
-HBM peak; `cpu_baseline` = the CPU oracle (port of the reference path) on the host cores.
+HBM peak; `roofline_throughput` = the fused edge forward kernel on a working set >> L2 (8192 molecules);
+`cpu_baseline` = the CPU oracle (port of the reference path) on the host cores.
 `--impl reference` times that CPU path alone.
 """
 from __future__ import annotations
@@ -190,6 +191,44 @@ NCU_TRAFFIC_C3 = {
     "edge_bwd_wgrad": (36.88e6 + 0.25e6) + (36.78e6 + 0.02e6),                       # + wgrad_mma_kernel<1>
     "edge_bwdbwd": (46.14e6 + 0.21e6) + (59.67e6 + 3.12e6) + (59.56e6 + 1.61e6),     # jvp + nbr<2> + wgrad<2>
 }
+
+
+def edge_throughput_probe(cfg, dev, peak, n_mol=8192, reps=10):
+    """The fused edge FORWARD kernel on a batch whose working set (s, v, x, V rows: 1.4 GB at 8192 aspirin-shaped
+    molecules) is >> the 126 MB L2 -- the "roofline (throughput) mode" of SURVEY.md 8d: at the named batch sizes
+    the working set is L2-resident and HBM bandwidth is not the binding resource.  CUDA events around `reps`
+    launches of xeq_edge_message_fwd through the C ABI; algorithmic bytes as in algorithmic_bytes().  Returns a
+    roofline-shaped dict, or None when anything goes wrong (this probe must never break the bench line)."""
+    try:
+        import xequinet_b200 as xb
+        from xequinet_b200 import ops
+
+        d = orc.make_aspirin_batch(n_mol, seed=0, with_edges=False)
+        g, _, _ = xb.build_graph(d["pos"].to(dev), cfg.cutoff, ptr=d["ptr"].to(dev), batch=d["batch"].to(dev))
+        N, E = g.n_nodes, g.n_edges
+        dims = ops.Dims(cfg.node_dim, *cfg.muls, cfg.num_basis, cfg.cutoff)
+        r = lambda *shape: torch.randn(*shape, device=dev)
+        pos = d["pos"].to(dev)
+        s, v, x, V = r(N, dims.H), r(N, dims.D), r(N, dims.node_dim), r(N, dims.D)
+        W, b = 0.3 * r(dims.H, cfg.num_basis), 0.3 * r(dims.H)
+        freq = (torch.pi * torch.arange(1, cfg.num_basis + 1, device=dev) / cfg.cutoff).float()
+        for _ in range(3):
+            ops.edge_message_fwd_raw(g, dims, pos, s, v, x, V, W, b, freq)
+        torch.cuda.synchronize()
+        t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        t0.record()
+        for _ in range(reps):
+            ops.edge_message_fwd_raw(g, dims, pos, s, v, x, V, W, b, freq)
+        t1.record()
+        torch.cuda.synchronize()
+        ms = t0.elapsed_time(t1) / reps
+        achieved = algorithmic_bytes("edge_fwd", cfg, N, E, False) / (ms * 1e-3) / 1e9
+        return {"kernel": "edge_fwd", "launch": "xeq_edge_message_fwd: center_fwd_kernel", "bound": "hbm",
+                "achieved": round(achieved, 2), "peak": peak, "unit": "GB/s", "frac": round(achieved / peak, 5),
+                "n_nodes": N, "n_edges": E, "mean_launch_ms": round(ms, 4),
+                "working_set": f"{n_mol} aspirin-shaped molecules: node rows {4 * N * (dims.H + 2 * dims.D + 2 * dims.node_dim) / 1e9:.2f} GB >> L2"}
+    except Exception as exc:  # pragma: no cover
+        return {"error": str(exc)[:200]}
 
 
 def measured_hbm_peak():
@@ -473,6 +512,9 @@ def run_gpu(args):
                     "frac": round(achieved / peak, 5), "traffic": traffic, "peak_source": peak_src,
                     "n_nodes": N, "n_edges": E, "mean_launch_ms": round(mean_ms, 5)}
 
+    # the fused edge forward kernel with a working set >> L2 (SURVEY.md 8d "throughput mode"), default widths only
+    roofline_throughput = edge_throughput_probe(cfg, dev, peak) if (cfg is orc.CONFIG_DEFAULT and world == 1) else None
+
     # CPU oracle on the host cores, bounded sample
     cpu_mols = {"c1": 64, "c2": 64, "c3": 32, "c4": 8, "c5": 1}[args.workload]
     if args.no_cpu_baseline:
@@ -493,6 +535,7 @@ def run_gpu(args):
         "e2e": {"value": round(e2e_value, 2), "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h)},
         "gpu_launches": int(launches),
         "roofline": roofline,
+        "roofline_throughput": roofline_throughput,
         "kernels": kernels,
         "cpu_baseline": {"value": round(cpu_val, 3), "unit": UNIT, "cores": os.cpu_count(), "kind": "port",
                          "sample": f"CPU oracle (oracle/xpainn_oracle.py), {cpu_sample}, {round(cpu_ms, 1)} ms/step, 2 timed steps"},
