@@ -160,11 +160,13 @@ int xeq_csr_tile_bounds(const int32_t* rowptr, int32_t n_nodes, int32_t n_edges,
  * x_in / V_in may be NULL (treated as zero).  One CTA walks whole CSR rows with one thread
  * per irrep channel; the segment sum lives in registers (no atomics, deterministic).
  * ---------------------------------------------------------------------------------- */
+size_t xeq_edge_message_fwd_workspace_bytes(const xeq_graph_t* g, const xeq_dims_t* dims);
 int xeq_edge_message_fwd(const xeq_graph_t* g, const xeq_dims_t* dims, const float* pos,
                          const float* s /* [N,H] */, const float* v /* [N,D] cm */,
                          const float* x_in /* [N,C] */, const float* V_in /* [N,D] cm */,
                          const float* W_rbf /* [H,B] */, const float* b_rbf /* [H] */, const float* freq /* [B] */,
-                         float* x_out, float* V_out, xeq_stream_t stream);
+                         float* x_out, float* V_out,
+                         void* workspace, size_t workspace_bytes, xeq_stream_t stream);
 
 /* K2b  first derivatives (forces; nn/basic.py:143-159 replays the ops above in reverse).
  * Given gx = dL/dx_out [N,C], gV = dL/dV_out [N,D]:  gs [N,H], gv [N,D], gpos [N,3] and, when

@@ -50,7 +50,8 @@ _SIGNATURES = {
     "xeq_center_tile_edges": (c_int, []),
     "xeq_neighbor_tile_edges": (c_int, []),
     "xeq_csr_tile_bounds": (c_int, [c_void_p, c_int32, c_int32, c_int32, c_void_p, c_void_p]),
-    "xeq_edge_message_fwd": (c_int, [POINTER(XeqGraph), POINTER(XeqDims)] + [c_void_p] * 11),
+    "xeq_edge_message_fwd_workspace_bytes": (c_size_t, [POINTER(XeqGraph), POINTER(XeqDims)]),
+    "xeq_edge_message_fwd": (c_int, [POINTER(XeqGraph), POINTER(XeqDims)] + [c_void_p] * 10 + [c_void_p, c_size_t, c_void_p]),
     "xeq_edge_message_bwd_workspace_bytes": (c_size_t, [POINTER(XeqGraph), POINTER(XeqDims), c_int]),
     "xeq_edge_message_bwd": (c_int, [POINTER(XeqGraph), POINTER(XeqDims)] + [c_void_p] * 14 + [c_void_p, c_size_t, c_void_p]),
     "xeq_edge_message_bwdbwd_workspace_bytes": (c_size_t, [POINTER(XeqGraph), POINTER(XeqDims), c_int]),

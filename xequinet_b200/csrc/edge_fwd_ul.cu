@@ -1,0 +1,454 @@
+// K2 forward message, round-2 design: three consumer groups of 4 warps share one copy of the filter rows in
+// tensor memory (edge_ul.cuh: "unified lanes"), every group is fed by its own producer warp, and nothing in
+// the steady state is a CTA-wide barrier -- all hand-offs are mbarriers:
+//
+//   warps  0-11  consumers, group g = warp / 4 : wait acc_full[g]; per quad of 4 edge slots: 5 tcgen05.ld
+//                (filter values of the lane's five rows), 2 x 128-bit gathers of the packed neighbour row per
+//                slot (shared-memory window or L2), 10 FMAs per slot, register-resident segment sums, row
+//                write-out at the end of a CSR row; arrive acc_free[g]
+//   warps 12-14  producer of group g : walks the group's rows (dense 4-slot quads, 16 slots per chunk), runs the
+//                per-edge geometry as a software pipeline over chunks (indices | positions | arithmetic), writes
+//                chi * phi_k straight into the SWIZZLE_128B B tiles (3xTF32 hi / lo, 128-bit stores), then one
+//                elected lane issues the 45 tcgen05.mma of the chunk into the group's accumulator buffer
+//   warp  15     window loader : one elected thread streams the packed rows of the CTA's molecule tiles into
+//                the two halves of the shared-memory window with cp.async.bulk (TMA), a tile ahead
+//
+// Replaces nn/xpainn.py:66-74, 140-159 + nn/basic.py:114-131 (forward values); contract: xeq_edge_message_fwd.
+#include "edge_ul.cuh"
+
+namespace xeq {
+
+using namespace fm;
+using namespace ul;
+
+namespace {
+
+constexpr int SLOTS = 16;                    // edge slots per chunk = MMA N
+constexpr int NQ = SLOTS / 4;                // quads per chunk
+constexpr int DCOLS = TILES * SLOTS;         // accumulator columns of one group (80)
+constexpr int BSTAGE = 2 * SLOTS * 128;      // bytes of one B stage: hi + lo tile
+constexpr int NBST = 2;                      // B stages per group
+constexpr int NGEO = 3;                      // geometry records per group (ring)
+constexpr int NTHREADS = NCONS + G * 32 + 32;
+constexpr int NOSTAGE = INT_MIN;
+
+struct alignas(16) Geo {
+  float4 Yt[SLOTS][3];   // harmonics per slot and piece type
+  uint32_t goff[SLOTS];  // staged: byte offset of the gathered row inside the window; else: node index
+  Quad qd[NQ];
+  int nq;                // quads of this chunk (1..NQ), -1 = end of stream
+  int pad[3];
+};
+
+struct FwdSmem {
+  Geo geo[G][NGEO];
+  uint64_t acc_full[G], acc_free[G];
+  uint64_t win_full[2], win_free[2];
+  uint32_t slot;
+};
+
+// ------------------------------------------------------------------------------------------------------
+// pack: pk[sl][n][plane][lane] (float4) from s [N,H] and v [N,D] (cm layout)
+//   plane 0: (s_state[q0] v[q0], s_edge[q0], s_scalar[q0], s_edge[qp])     plane 1: s_state[qp] v[(qp, m)], m = 0..2
+// ------------------------------------------------------------------------------------------------------
+template <int C, int M1, int M2>
+__global__ void __launch_bounds__(256) pack_fwd_kernel(const float* __restrict__ s, const float* __restrict__ v,
+                                                      float* __restrict__ pk, int n_nodes) {
+  constexpr int M = C + M1 + M2, D = C + 3 * M1 + 5 * M2, H = C + 2 * M;
+  const int L = threadIdx.x & 127, sl = blockIdx.y;
+  const int n = blockIdx.x * 2 + (threadIdx.x >> 7);
+  if (n >= n_nodes) return;
+  const float* sn = s + (size_t)n * H;
+  const float* vn = v + (size_t)n * D;
+  const int q0 = sl * SL_C + L, qp = piece_irrep<C, M1>(L, sl);
+  int off[3], nc;
+  piece_offsets<C, M1, M2>(L, sl, off, nc);
+  const float ssp = sn[qp];
+  float4 a, b;
+  a.x = sn[q0] * vn[q0];
+  a.y = sn[M + q0];
+  a.z = sn[2 * M + q0];
+  a.w = sn[M + qp];
+  b.x = ssp * vn[off[0]];
+  b.y = ssp * vn[off[1]];
+  b.z = nc == 3 ? ssp * vn[off[2]] : 0.f;
+  b.w = 0.f;
+  float4* dst = reinterpret_cast<float4*>(pk + ((size_t)sl * n_nodes + n) * ROWF);
+  dst[L] = a;
+  dst[128 + L] = b;
+}
+
+// ------------------------------------------------------------------------------------------------------
+// consumers
+// ------------------------------------------------------------------------------------------------------
+template <int C, int M1, int M2>
+__device__ __forceinline__ void fwd_consumer(const CenterArgs& A, FwdSmem& sm, const uint32_t tmem, const uint32_t win_base,
+                                             const float* __restrict__ pk, const int grp) {
+  constexpr int D = C + 3 * M1 + 5 * M2;
+  const int L = threadIdx.x - grp * GRP, wq = L >> 5, lane = L & 31, sl = blockIdx.y;
+  const int pt = piece_type(L);
+  const int q0 = sl * SL_C + L;
+  int voff[3], nc;
+  piece_offsets<C, M1, M2>(L, sl, voff, nc);
+  const uint32_t lane_base = tmem + ((uint32_t)(32 * wq) << 16);
+  const uint32_t dbase = lane_base + D_COL + grp * DCOLS;
+  const uint32_t win_lane = win_base + 16u * (uint32_t)L;
+  const float* pk_lane = pk + (size_t)sl * A.geo.g.n_nodes * ROWF + 4 * L;
+  const uint32_t full = smem_u32(&sm.acc_full[grp]), free_ = smem_u32(&sm.acc_free[grp]);
+
+  float accx = 0.f, accV0 = 0.f, accP[3] = {0.f, 0.f, 0.f};
+  float bx = 0.f, bV0 = 0.f, bP[3] = {0.f, 0.f, 0.f};
+
+  for (int c = 0;; ++c) {
+    mbar_wait(full, (uint32_t)(c & 1));
+    tc_fence_after();
+    const Geo& ge = sm.geo[grp][c % NGEO];
+    const int nq = ge.nq;
+    if (nq < 0) break;
+#pragma unroll 1
+    for (int qd = 0; qd < nq; ++qd) {
+      const Quad q = ge.qd[qd];
+      const int fl = q.flags;
+      if (fl & F_TILE_FIRST) {
+        if (fl & F_STAGED) mbar_wait(smem_u32(&sm.win_full[(fl & F_BUF) ? 1 : 0]), (fl & F_PAR) ? 1u : 0u);
+      }
+      if (fl & F_ROW_FIRST) {  // residual row: requested now, consumed when the row ends
+        accx = accV0 = accP[0] = accP[1] = accP[2] = 0.f;
+        const size_t nd = (size_t)q.node;
+        bx = A.x_in ? A.x_in[nd * C + q0] : 0.f;
+        bV0 = A.V_in ? A.V_in[nd * D + q0] : 0.f;
+#pragma unroll
+        for (int m = 0; m < 3; ++m) bP[m] = A.V_in ? A.V_in[nd * D + voff[m]] : 0.f;
+      }
+      if (!(fl & F_NOROW)) {
+        float w[TILES][4];
+#pragma unroll
+        for (int t = 0; t < TILES; ++t) tmem_ld4(dbase + t * SLOTS + qd * 4, w[t]);
+        const uint4 go = *reinterpret_cast<const uint4*>(&ge.goff[qd * 4]);
+        const uint32_t gj[4] = {go.x, go.y, go.z, go.w};
+        float4 a[4], b[4];
+        if (fl & F_STAGED) {
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            a[j] = lds128(win_lane + gj[j]);
+            b[j] = lds128(win_lane + gj[j] + 2048u);
+          }
+        } else {
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const float* p = pk_lane + (size_t)gj[j] * ROWF;
+            a[j] = ldg128(p);
+            b[j] = ldg128(p + 512);
+          }
+        }
+        tmem_wait_ld();
+#pragma unroll
+        for (int t = 0; t < TILES; ++t) pin(w[t]);
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const float4 y = ge.Yt[qd * 4 + j][pt];
+          accx = fmaf(a[j].z, w[2][j], accx);
+          accV0 = fmaf(a[j].x, w[0][j], fmaf(a[j].y, w[1][j], accV0));
+          const float gep = a[j].w * w[4][j];
+          accP[0] = fmaf(b[j].x, w[3][j], fmaf(gep, y.x, accP[0]));
+          accP[1] = fmaf(b[j].y, w[3][j], fmaf(gep, y.y, accP[1]));
+          accP[2] = fmaf(b[j].z, w[3][j], fmaf(gep, y.z, accP[2]));
+        }
+      }
+      if (fl & F_ROW_LAST) {
+        const size_t nd = (size_t)q.node;
+        A.x_out[nd * C + q0] = bx + accx;
+        A.V_out[nd * D + q0] = bV0 + accV0;
+        A.V_out[nd * D + voff[0]] = bP[0] + accP[0];
+        A.V_out[nd * D + voff[1]] = bP[1] + accP[1];
+        if (nc == 3) A.V_out[nd * D + voff[2]] = bP[2] + accP[2];
+      }
+      if ((fl & F_TILE_LAST) && (fl & F_STAGED)) {  // this warp is done with the window of the tile
+        __syncwarp();
+        if (lane == 0) mbar_arrive(smem_u32(&sm.win_free[(fl & F_BUF) ? 1 : 0]));
+      }
+    }
+    tc_fence_before();
+    __syncwarp();
+    if (lane == 0) mbar_arrive(free_);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------------
+// producer warp of one group
+// ------------------------------------------------------------------------------------------------------
+struct SlotRegs {
+  int i, e, wb;  // center node, edge id (-1: dead slot), window base (rows) or NOSTAGE
+  int j;         // neighbor
+};
+
+template <int C, int M1, int M2>
+__device__ __forceinline__ void fwd_producer(const CenterArgs& A, FwdSmem& sm, const uint32_t tmem, const uint32_t tiles_base,
+                                             const int grp) {
+  const int lane = threadIdx.x & 31, slot = lane & 15, half = lane >> 4;
+  const xeq_graph_t& g = A.geo.g;
+  const uint32_t full = smem_u32(&sm.acc_full[grp]), free_ = smem_u32(&sm.acc_free[grp]);
+  const uint32_t my_tiles = tiles_base + (uint32_t)grp * (NBST * BSTAGE);
+
+  // frequencies of this lane's twelve radial terms (k = 12 half + kk; k = 0 is the cutoff / bias term)
+  float fr[12];
+#pragma unroll
+  for (int kk = 0; kk < 12; ++kk) {
+    const int k = 12 * half + kk;
+    fr[kk] = (k >= 1 && k <= NB_) ? A.geo.freq[k - 1] : 0.f;
+  }
+  const float c0 = sqrtf(2.f / A.geo.rc);
+
+  Walk wk;
+  wk.init(g, g.tile_ptr, g.n_tiles, grp);
+  int node = wk.valid ? wk.n0 + wk.rphase : 0;
+  int e = 0, e1 = 0;
+  bool row_open = false, row_first = false, tile_any = false;
+
+  // stage A: slot assignment of the next chunk (uniform control flow), quads -> shared memory, index loads
+  auto stage_a = [&](int c, SlotRegs& o) -> int {
+    Geo& ge = sm.geo[grp][c % NGEO];
+    o.i = 0; o.e = -1; o.wb = NOSTAGE; o.j = 0;
+    int nq = 0;
+    while (nq < NQ && wk.valid) {
+      const int stbits = wk.staged ? (F_STAGED | (wk.buf ? F_BUF : 0) | (wk.par ? F_PAR : 0)) : 0;
+      if (!row_open) {
+        if (node >= wk.n1) {
+          if (!tile_any && wk.tile_mode == 1) {  // no row of this group in the tile: keep the window accounting going
+            if (lane == 0) ge.qd[nq] = Quad{wk.n0, stbits | F_NOROW | F_TILE_FIRST | F_TILE_LAST};
+            ++nq;
+          }
+          wk.next();
+          node = wk.valid ? wk.n0 + wk.rphase : 0;
+          tile_any = false;
+          continue;
+        }
+        e = g.rowptr[node];
+        e1 = g.rowptr[node + 1];
+        row_open = true;
+        row_first = true;
+      }
+      const bool last = e + 4 >= e1;
+      int fl = stbits | (row_first ? F_ROW_FIRST : 0) | (tile_any ? 0 : F_TILE_FIRST);
+      if (last) fl |= F_ROW_LAST | ((node + wk.rstride >= wk.n1) ? F_TILE_LAST : 0);
+      if (lane == 0) ge.qd[nq] = Quad{node, fl};
+      const int idx = slot - 4 * nq;
+      if (idx >= 0 && idx < 4) {
+        o.i = node;
+        o.e = (e + idx < e1) ? e + idx : -1;
+        o.wb = wk.staged ? wk.buf * WH - wk.n0 : NOSTAGE;
+      }
+      e += 4;
+      row_first = false;
+      tile_any = true;
+      ++nq;
+      if (last) {
+        row_open = false;
+        node += wk.rstride;
+      }
+    }
+    if (nq == 0) nq = -1;  // stream exhausted
+    if (lane == 0) ge.nq = nq;
+    if (o.e >= 0) o.j = g.col[o.e];
+    return nq;
+  };
+
+  // stage B: raw position loads (and the lattice shift of periodic graphs)
+  struct PosRegs {
+    float pi[3], pj[3], sh[3];
+  };
+  auto stage_b = [&](const SlotRegs& r, PosRegs& p) {
+#pragma unroll
+    for (int x = 0; x < 3; ++x) p.pi[x] = p.pj[x] = p.sh[x] = 0.f;
+    if (r.e >= 0) {
+#pragma unroll
+      for (int x = 0; x < 3; ++x) {
+        p.pi[x] = A.geo.pos[3 * r.i + x];
+        p.pj[x] = A.geo.pos[3 * r.j + x];
+      }
+      if (g.offsets != nullptr) {  // nn/basic.py:119-128: vectors -= cell_offsets @ cell[graph(neighbor)]
+        const char4 o = reinterpret_cast<const char4*>(g.offsets)[r.e];
+        const float* cl = g.cell + 9 * (g.node_graph ? g.node_graph[r.j] : 0);
+        const float ox = (float)o.x, oy = (float)o.y, oz = (float)o.z;
+#pragma unroll
+        for (int x = 0; x < 3; ++x) p.sh[x] = ox * cl[x] + oy * cl[3 + x] + oz * cl[6 + x];
+      }
+    }
+  };
+
+  // stage C: geometry record + radial tiles of chunk c
+  auto stage_c = [&](int c, const SlotRegs& r, const PosRegs& p) {
+    Geo& ge = sm.geo[grp][c % NGEO];
+    const uint32_t t_hi = my_tiles + (uint32_t)(c & (NBST - 1)) * BSTAGE, t_lo = t_hi + SLOTS * 128;
+    float val[12];
+#pragma unroll
+    for (int kk = 0; kk < 12; ++kk) val[kk] = 0.f;
+    float4 y0 = make_float4(0.f, 0.f, 0.f, 0.f), y1 = y0, y2 = y0;
+    if (r.e >= 0) {
+      float rv[3], d, u[3], Y[8];
+#pragma unroll
+      for (int x = 0; x < 3; ++x) rv[x] = (p.pi[x] - p.pj[x]) - p.sh[x];
+      unit_vector(rv, d, u);
+      sph_harm(u, Y);
+      y0 = make_float4(Y[0], Y[1], Y[2], 0.f);
+      y1 = make_float4(Y[3], Y[4], Y[5], 0.f);
+      y2 = make_float4(Y[6], Y[7], 0.f, 0.f);
+      float chi = 0.f;
+      if (d < A.geo.rc) chi = 0.5f * (cosf(3.14159265358979323846f / A.geo.rc * d) + 1.f);
+      const float amp = chi * c0 / (d + 1e-5f);
+#pragma unroll
+      for (int kk = 0; kk < 12; ++kk) {
+        const int k = 12 * half + kk;
+        if (k == 0) val[kk] = chi;
+        else if (k <= NB_) val[kk] = amp * sinf(fr[kk] * d);
+      }
+    }
+    if (half == 0) {
+      ge.Yt[slot][0] = y0;
+      ge.Yt[slot][1] = y1;
+      ge.Yt[slot][2] = y2;
+      const int jj = r.e >= 0 ? r.j : r.i;  // dead slots gather the (always valid) row of their own center, times zero
+      ge.goff[slot] = (r.wb != NOSTAGE) ? (uint32_t)(r.wb + jj) * (uint32_t)ROWB : (uint32_t)jj;
+    }
+#pragma unroll
+    for (int i4 = 0; i4 < 3; ++i4) {
+      uint32_t hi[4], lo[4];
+#pragma unroll
+      for (int x = 0; x < 4; ++x) split_fast(val[4 * i4 + x], hi[x], lo[x]);
+      const uint32_t off = (uint32_t)(slot * 128 + (((3 * half + i4) ^ (slot & 7)) << 4));
+      sts128(t_hi + off, hi[0], hi[1], hi[2], hi[3]);
+      sts128(t_lo + off, lo[0], lo[1], lo[2], lo[3]);
+    }
+  };
+
+  auto issue = [&](int c) {
+    const uint32_t idesc = idesc_tf32(SLOTS);
+    const uint32_t b_hi = my_tiles + (uint32_t)(c & (NBST - 1)) * BSTAGE, b_lo = b_hi + SLOTS * 128;
+    const uint32_t d0 = tmem + D_COL + (uint32_t)grp * DCOLS;
+#pragma unroll
+    for (int ks = 0; ks < NBP / 8; ++ks) {
+      const uint64_t db_hi = smem_desc(b_hi + ks * 32), db_lo = smem_desc(b_lo + ks * 32);
+#pragma unroll
+      for (int tile = 0; tile < TILES; ++tile) {
+        const uint32_t d = d0 + tile * SLOTS;
+        mma_ts(d, tmem + A_LO + tile * NBP + ks * 8, db_hi, idesc, ks ? 1u : 0u);
+        mma_ts(d, tmem + A_HI + tile * NBP + ks * 8, db_lo, idesc, 1u);
+        mma_ts(d, tmem + A_HI + tile * NBP + ks * 8, db_hi, idesc, 1u);
+      }
+    }
+  };
+
+  SlotRegs ra, rb, rc;
+  PosRegs pb;
+  int nq_ring[3];
+  nq_ring[0] = stage_a(0, rc);          // chunk 0
+  stage_b(rc, pb);
+  nq_ring[1] = stage_a(1, rb);          // chunk 1
+  for (int c = 0;; ++c) {
+    const int nq = nq_ring[0];
+    if (nq > 0) stage_c(c, rc, pb);
+    proxy_fence();
+    __syncwarp();
+    if (c > 0) mbar_wait(free_, (uint32_t)((c - 1) & 1));
+    tc_fence_after();
+    if (elect_one()) {
+      if (nq > 0) issue(c);
+      umma_commit(full);
+      mbar_arrive(full);  // releases the geometry record written by the other lanes (ordered by the __syncwarp)
+    }
+    __syncwarp();
+    if (nq < 0) break;
+    // geometry pipeline: positions of chunk c+1, slot assignment + indices of chunk c+2
+    rc = rb;
+    stage_b(rc, pb);
+    nq_ring[0] = nq_ring[1];
+    nq_ring[1] = stage_a(c + 2, rb);
+    (void)ra;
+  }
+}
+
+// window loader: one elected lane streams the packed rows of the staged tiles of this CTA into the window
+template <int C>
+__device__ __forceinline__ void fwd_loader(const CenterArgs& A, FwdSmem& sm, const uint32_t win_base, const float* __restrict__ pk) {
+  const xeq_graph_t& g = A.geo.g;
+  if (g.tile_mode != 1) return;
+  if ((threadIdx.x & 31) != 0) return;
+  Walk wk;
+  wk.init(g, g.tile_ptr, g.n_tiles, 0);
+  const float* pk_sl = pk + (size_t)blockIdx.y * g.n_nodes * ROWF;
+  for (; wk.valid; wk.next()) {
+    if (!wk.staged) continue;
+    const int t = wk.staged_count - 1;  // index of this staged tile
+    const uint32_t fullb = smem_u32(&sm.win_full[wk.buf]), freeb = smem_u32(&sm.win_free[wk.buf]);
+    if (t >= 2) mbar_wait(freeb, (uint32_t)(((t >> 1) - 1) & 1));
+    const uint32_t bytes = (uint32_t)(wk.n1 - wk.n0) * ROWB;
+    mbar_expect_tx(fullb, bytes);
+    tma_bulk_g2s(win_base + (uint32_t)wk.buf * (WH * ROWB), pk_sl + (size_t)wk.n0 * ROWF, bytes, fullb);
+  }
+}
+
+template <int C, int M1, int M2>
+__global__ void __launch_bounds__(NTHREADS, 1) center_fwd_ul_kernel(const CenterArgs A, const float* __restrict__ pk) {
+  static_assert(C % SL_C == 0 && M1 == C / 2 && M2 == C / 4, "channel slices of edge_mma.cuh");
+  __shared__ FwdSmem sm;
+  const int t = threadIdx.x, warp = t >> 5;
+  if (t == 0) {
+    for (int i = 0; i < G; ++i) {
+      mbar_init(smem_u32(&sm.acc_full[i]), 2);   // tcgen05.commit + the producer's release of the geometry record
+      mbar_init(smem_u32(&sm.acc_free[i]), 4);   // one arrive per consumer warp of the group
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(smem_u32(&sm.win_full[i]), 1);
+      mbar_init(smem_u32(&sm.win_free[i]), 4 * G);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (t < 32) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&sm.slot)), "n"(TMEM_COLS) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *reinterpret_cast<volatile uint32_t*>(&sm.slot);
+  const uint32_t tiles_base = (smem_u32(xeq_dyn_smem) + 1023u) & ~1023u;
+  const uint32_t win_base = tiles_base + G * NBST * BSTAGE;
+  if (t < GRP) store_filter_rows<C, M1, M2>(A.W, A.b, t, blockIdx.y, tmem + ((uint32_t)(32 * (t >> 5)) << 16));
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  if (warp < 4 * G) fwd_consumer<C, M1, M2>(A, sm, tmem, win_base, pk, warp >> 2);
+  else if (warp < 4 * G + G) fwd_producer<C, M1, M2>(A, sm, tmem, tiles_base, warp - 4 * G);
+  else fwd_loader<C>(A, sm, win_base, pk);
+  tmem_teardown(tmem);
+}
+
+}  // namespace
+
+size_t center_fwd_ul_workspace_bytes(int n_nodes, bool wide) {
+  return 256 + (size_t)(wide ? 2 : 1) * (size_t)(n_nodes > 0 ? n_nodes : 1) * ROWB;
+}
+
+template <int C>
+static int launch_center_fwd_ul_t(const CenterArgs& A, void* ws, cudaStream_t st) {
+  constexpr int M1 = C / 2, M2 = C / 4, SLICES = C / SL_C;
+  static_assert(sizeof(FwdSmem) <= 16 * 1024, "static shared memory budget");
+  const xeq_graph_t& g = A.geo.g;
+  float* pk = reinterpret_cast<float*>((reinterpret_cast<uintptr_t>(ws) + 255) & ~(uintptr_t)255);
+  pack_fwd_kernel<C, M1, M2><<<dim3((g.n_nodes + 1) / 2, SLICES), 256, 0, st>>>(A.s, A.v, pk, g.n_nodes);
+  const size_t dyn = 1024 + (size_t)G * NBST * BSTAGE + (g.tile_mode == 1 ? (size_t)2 * WH * ROWB : 0);
+  XEQ_CUDA(cudaFuncSetAttribute(center_fwd_ul_kernel<C, M1, M2>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                (int)(1024 + (size_t)G * NBST * BSTAGE + (size_t)2 * WH * ROWB)));
+  const int work = g.tile_mode == 1 ? g.n_tiles : (g.n_tiles + G - 1) / G;
+  const int grid = max(1, min(work, num_sms() / SLICES));
+  center_fwd_ul_kernel<C, M1, M2><<<dim3(grid, SLICES), NTHREADS, dyn, st>>>(A, pk);
+  XEQ_LAUNCHED(2);
+  return XEQ_OK;
+}
+
+// `wide`: 256x0e + 128x1o + 64x2e (two channel slices per tile of edges, grid.y = 2)
+int launch_center_fwd_ul(const CenterArgs& A, bool wide, void* ws, cudaStream_t st) {
+  return wide ? launch_center_fwd_ul_t<256>(A, ws, st) : launch_center_fwd_ul_t<128>(A, ws, st);
+}
+
+}  // namespace xeq

@@ -732,7 +732,9 @@ static int launch_center(const CenterArgs& A, cudaStream_t st) {
 int launch_center_mma(const CenterArgs& A, bool jvp, bool wide, cudaStream_t st);
 int launch_wgrad_mma(const NeighborArgs& A, int order, bool wide, int grid, cudaStream_t st);
 int launch_nbr_mma(const NeighborArgs& A, int order, bool wide, cudaStream_t st);
-int launch_center_fwd_ws(const CenterArgs& A, bool wide, cudaStream_t st);  // edge_fwd_mma.cu: warp-specialised forward
+int launch_center_fwd_ws(const CenterArgs& A, bool wide, cudaStream_t st);  // edge_fwd_mma.cu: warp-specialised forward (round 1)
+int launch_center_fwd_ul(const CenterArgs& A, bool wide, void* ws, cudaStream_t st);  // edge_fwd_ul.cu: round-2 forward
+size_t center_fwd_ul_workspace_bytes(int n_nodes, bool wide);
 
 // XEQ_EDGE_SIMT=1 forces the SIMT filter contraction for the default widths too (A/B timing)
 static bool use_mma() {
@@ -740,7 +742,8 @@ static bool use_mma() {
   return !simt;
 }
 
-static int run_center(const xeq_graph_t* g, const xeq_dims_t* dims, CenterArgs& A, bool jvp, cudaStream_t st) {
+static int run_center(const xeq_graph_t* g, const xeq_dims_t* dims, CenterArgs& A, bool jvp, cudaStream_t st, void* ws = nullptr,
+                      size_t ws_bytes = 0) {
   int cfg;
   int rc = check_dims(dims, &cfg);
   if (rc) return rc;
@@ -750,8 +753,12 @@ static int run_center(const xeq_graph_t* g, const xeq_dims_t* dims, CenterArgs& 
   A.geo.g = *g;
   A.geo.rc = dims->cutoff;
   if (use_mma()) {
-    static const bool ws = [] { const char* e = getenv("XEQ_FWD_WS"); return !(e && e[0] == '0'); }();  // A/B switch
-    return (!jvp && ws) ? launch_center_fwd_ws(A, cfg == 1, st) : launch_center_mma(A, jvp, cfg == 1, st);
+    static const int fwd_kind = [] { const char* e = getenv("XEQ_FWD_KIND"); return e ? atoi(e) : 2; }();  // A/B switch (dev)
+    if (!jvp && fwd_kind == 2) {
+      XEQ_CHECK_ARG(ws && ws_bytes >= center_fwd_ul_workspace_bytes(g->n_nodes, cfg == 1), "edge_message_fwd: workspace too small");
+      return launch_center_fwd_ul(A, cfg == 1, ws, st);
+    }
+    return (!jvp && fwd_kind == 1) ? launch_center_fwd_ws(A, cfg == 1, st) : launch_center_mma(A, jvp, cfg == 1, st);
   }
   if (cfg == 0) return jvp ? launch_center<128, 64, 32, true>(A, st) : launch_center<128, 64, 32, false>(A, st);
   return jvp ? launch_center<256, 128, 64, true>(A, st) : launch_center<256, 128, 64, false>(A, st);
@@ -862,13 +869,18 @@ int xeq_csr_tile_bounds(const int32_t* rowptr, int32_t n_nodes, int32_t n_edges,
 
 int xeq_edge_message_fwd(const xeq_graph_t* g, const xeq_dims_t* dims, const float* pos, const float* s, const float* v,
                          const float* x_in, const float* V_in, const float* W_rbf, const float* b_rbf, const float* freq,
-                         float* x_out, float* V_out, xeq_stream_t stream) {
+                         float* x_out, float* V_out, void* workspace, size_t workspace_bytes, xeq_stream_t stream) {
   XEQ_CHECK_ARG(pos && s && v && W_rbf && b_rbf && freq && x_out && V_out, "edge_message_fwd: NULL argument");
   CenterArgs A{};
   A.geo.pos = pos; A.geo.freq = freq; A.geo.a_pos = nullptr;
   A.s = s; A.v = v; A.x_in = x_in; A.V_in = V_in; A.W = W_rbf; A.b = b_rbf;
   A.x_out = x_out; A.V_out = V_out;
-  return run_center(g, dims, A, false, (cudaStream_t)stream);
+  return run_center(g, dims, A, false, (cudaStream_t)stream, workspace, workspace_bytes);
+}
+
+size_t xeq_edge_message_fwd_workspace_bytes(const xeq_graph_t* g, const xeq_dims_t* dims) {
+  if (!g || !dims) return 0;
+  return center_fwd_ul_workspace_bytes(g->n_nodes, dims->node_dim > 128);
 }
 
 size_t xeq_edge_message_bwd_workspace_bytes(const xeq_graph_t* g, const xeq_dims_t* dims, int want_wgrad) {

@@ -115,10 +115,12 @@ def edge_message_fwd_raw(graph: NeighborGraph, dims: Dims, pos, s, v, x_in, V_in
     x_out = torch.empty((N, dims.node_dim), dtype=torch.float32, device=s.device)
     V_out = torch.empty((N, dims.D), dtype=torch.float32, device=s.device)
     d = dims.struct()
+    nbytes = lib.xeq_edge_message_fwd_workspace_bytes(graph.struct, d)
+    ws = _workspace(nbytes, s.device)
     ev = KernelTimer.start()
     _lib.check(lib.xeq_edge_message_fwd(graph.struct, d, _lib.ptr(pos), _lib.ptr(s), _lib.ptr(v), _lib.ptr(x_in),
                                         _lib.ptr(V_in), _lib.ptr(W), _lib.ptr(b), _lib.ptr(freq), _lib.ptr(x_out),
-                                        _lib.ptr(V_out), _lib.stream()), "xeq_edge_message_fwd")
+                                        _lib.ptr(V_out), _lib.ptr(ws), nbytes, _lib.stream()), "xeq_edge_message_fwd")
     KernelTimer.stop(ev, "edge_fwd", graph)
     return x_out, V_out
 
