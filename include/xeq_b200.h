@@ -112,7 +112,8 @@ int xeq_radius_graph_count(const float* pos, int32_t n_nodes,
 int xeq_radius_graph_fill(const float* pos, int32_t n_nodes,
                           const int32_t* graph_ptr, const int32_t* node_graph, int32_t n_graphs,
                           const float* cell, const int32_t* pbc_host, const int32_t* rep_host,
-                          float cutoff, const int32_t* rowptr, int32_t* col /* [E] out */,
+                          float cutoff, int32_t* rowptr /* in; capacity mode: clamped to edge_capacity in place */,
+                          int32_t* col /* [E] out */,
                           int8_t* offsets /* [E,4] out or NULL */,
                           int64_t* edge_index /* [2,E] out or NULL */,
                           float* cell_offsets /* [E,3] out or NULL */,
@@ -123,7 +124,9 @@ int xeq_radius_graph_fill(const float* pos, int32_t n_nodes,
  * `edge_capacity` edges once, passes n_edges = edge_capacity everywhere (xeq_graph_t.n_edges,
  * xeq_csr_transpose, xeq_csr_tile_bounds) and never reads the edge count back: every kernel takes
  * the live count from rowptr[N] on the device, tiles past it are empty.  The COO output then uses
- * row stride `edge_capacity`. */
+ * row stride `edge_capacity`.  When a structure has more than `edge_capacity` edges the surplus edges are
+ * dropped, `overflow` is raised and rowptr is clamped to the capacity, so consumers stay inside the arrays
+ * (the results are then those of the truncated list: check the flag). */
 
 /* CSR from a caller-supplied COO edge list that is already sorted by center
  * (edge_index[0] non-decreasing): rowptr from segment boundaries, col = int32(edge_index[1]),

@@ -1,4 +1,4 @@
-"""torchrun --nproc-per-node N scratch/test_domain_gpu.py : sharded E+F of a periodic water box vs the
+"""torchrun --nproc-per-node N scratch/run_domain_gpu.py : sharded E+F of a periodic water box vs the
 single-GPU result (every rank also runs the full box as the reference)."""
 import os, sys; sys.path.insert(0, ".")
 import torch, torch.distributed as dist

@@ -348,10 +348,43 @@ def test_static_graph_builder_matches_dynamic(periodic):
             dd["pos"] = d["pos"].clone()
             outs.append(model(dd, compute_forces=True))
         assert torch.equal(outs[0]["energy"], outs[1]["energy"]) and torch.equal(outs[0]["forces"], outs[1]["forces"])
-    # overflow is flagged, not silently truncated into garbage
+    # overflow: raised on the host outside graph capture ...
     small = StaticGraphBuilder(d0["pos"].shape[0], d0["ptr"], 5.0, edge_capacity=64, cell=d0.get("cell"), pbc=d0.get("pbc"))
-    small.build(d0["pos"])
+    with pytest.raises(RuntimeError, match="edge_capacity"):
+        small.build(d0["pos"])
+    # ... and memory-safe on the device when nobody looks (capture / check_overflow=False): the flag is raised, rowptr is
+    # clamped to the capacity, and the edge kernels walk the truncated list without leaving the arrays
+    g = small.build(d0["pos"], check_overflow=False)
     assert int(small.overflow.item()) == 1
+    assert int(g.rowptr.max().item()) <= 64 and int(g.rowptr[-1].item()) == 64
+    assert g.edge_index().shape[1] == 64
+    dd = {k: v for k, v in d0.items() if k not in ("pbc",)}
+    dd[keys.GRAPH] = g
+    dd["pos"] = d0["pos"].clone()
+    out = model(dd, compute_forces=True)
+    torch.cuda.synchronize()
+    assert bool(torch.isfinite(out["energy"]).all()) and bool(torch.isfinite(out["forces"]).all())
+    with pytest.raises(ValueError):
+        small.build(d0["pos"].double())
+
+
+def test_stale_graph_cache_is_not_trusted():
+    """nn/basic.py:67: `edge_index` in the dict is the source of truth.  A dict that went through the model once holds
+    the derived CSR structure; replacing positions + edge_index (reference-style MD without this package's
+    NeighborTransform) must give the energies of the NEW list, not of the cached one."""
+    cfg = orc.CONFIG_DEFAULT
+    model = _model(cfg, 1234)
+    a = orc.make_molecule_batch(3, 9, seed=1)
+    b = orc.make_molecule_batch(3, 9, seed=2)
+    d = _dev({k: a[k] for k in ("pos", "atomic_numbers", "batch", "ptr", "edge_index")})
+    e_a = model(d, compute_forces=True)["energy"].detach().clone()
+    assert keys.GRAPH in d
+    d["pos"] = b["pos"].to(DEV)
+    d["edge_index"] = b["edge_index"].to(DEV)
+    e_b = model(d, compute_forces=True)["energy"].detach().clone()
+    fresh = _dev({k: b[k] for k in ("pos", "atomic_numbers", "batch", "ptr", "edge_index")})
+    e_ref = model(fresh, compute_forces=True)["energy"].detach()
+    assert torch.equal(e_b, e_ref) and not torch.equal(e_a, e_b)
 
 
 # ---------------------------------------------------------------------------------------

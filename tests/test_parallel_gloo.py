@@ -113,3 +113,59 @@ def test_flat_gradient_allreduce_matches_single_process():
         for k, g in zip(names, ref):
             got = torch.from_numpy(results[r][k])
             assert torch.allclose(got, g, rtol=1e-9, atol=1e-11), (r, k)
+
+
+def _flat_worker(rank, world, port, q):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from xequinet_b200 import parallel
+
+        torch.manual_seed(0)
+        net = torch.nn.Sequential(torch.nn.Linear(5, 7), torch.nn.SiLU(), torch.nn.Linear(7, 3), torch.nn.Linear(3, 1)).double()
+        unused = torch.nn.Parameter(torch.ones(4, dtype=torch.float64))  # never receives a gradient
+        params = list(net.parameters()) + [unused]
+        flat = parallel.FlatGradients(params, n_buckets=3)
+        assert 2 <= len(flat.buckets) <= 3 and sum(len(b) for b in flat.buckets) == len(params)
+        out = {}
+        for step in range(2):  # two steps: zero() must reset the views and the bucket bookkeeping
+            x = torch.randn(6, 5, dtype=torch.float64, generator=torch.Generator().manual_seed(10 * step + rank))
+            flat.zero()
+            for prm in params[:1]:
+                prm.grad = None  # an optimizer's zero_grad(set_to_none=True) in between
+            flat.zero()
+            net(x).pow(2).sum().backward()
+            flat.finish()
+            assert all(p.grad.data_ptr() == flat.flat.data_ptr() + 8 * flat._range[id(p)][0] for p in params)
+            out[step] = [p.grad.detach().clone().numpy() for p in params]
+        q.put((rank, out))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_flat_gradients_bucketed_allreduce_gloo():
+    world, port = 2, 29643
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_flat_worker, args=(r, world, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    results = dict(q.get(timeout=300) for _ in range(world))
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    torch.manual_seed(0)
+    net = torch.nn.Sequential(torch.nn.Linear(5, 7), torch.nn.SiLU(), torch.nn.Linear(7, 3), torch.nn.Linear(3, 1)).double()
+    for step in range(2):
+        ref = None
+        for rank in range(world):
+            x = torch.randn(6, 5, dtype=torch.float64, generator=torch.Generator().manual_seed(10 * step + rank))
+            net.zero_grad(set_to_none=True)
+            net(x).pow(2).sum().backward()
+            g = [p.grad.clone() for p in net.parameters()]
+            ref = g if ref is None else [a + b for a, b in zip(ref, g)]
+        ref = [a / world for a in ref] + [torch.zeros(4, dtype=torch.float64)]
+        for rank in range(world):
+            for got, want in zip(results[rank][step], ref):
+                assert torch.allclose(torch.from_numpy(got), want, rtol=1e-12, atol=1e-14)

@@ -313,10 +313,8 @@ static int launch_center_fwd_t(const CenterArgs& A, cudaStream_t st) {
   constexpr int M1 = C / 2, M2 = C / 4, SLICES = C / SL_C;
   static_assert(sizeof(FwdSmem) <= 16 * 1024, "static shared memory budget");
   const size_t dyn = 1024 + (size_t)FW_NSTAGE * FW_STAGE + (size_t)FW_WIN * (SL_C * 4 + SL_M1 * 5 + SL_M2 * 7) * 4;
-  static bool attr_set = false;
-  if (!attr_set) {
+  {  // per-device attribute: set on every launch (cheap)
     XEQ_CUDA(cudaFuncSetAttribute(center_fwd_kernel<C, M1, M2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn));
-    attr_set = true;
   }
   const int grid = max(1, min(A.geo.g.n_tiles, num_sms() / SLICES));
   center_fwd_kernel<C, M1, M2><<<dim3(grid, SLICES), FW_THREADS, dyn, st>>>(A);

@@ -2,14 +2,16 @@
 // tensor memory (edge_ul.cuh: "unified lanes"), every group is fed by its own producer warp, and nothing in
 // the steady state is a CTA-wide barrier -- all hand-offs are mbarriers:
 //
-//   warps  0-11  consumers, group g = warp / 4 : wait acc_full[g]; per quad of 4 edge slots: 5 tcgen05.ld
-//                (filter values of the lane's five rows), 2 x 128-bit gathers of the packed neighbour row per
-//                slot (shared-memory window or L2), 10 FMAs per slot, register-resident segment sums, row
-//                write-out at the end of a CSR row; arrive acc_free[g]
+//   warps  0-11  consumers, group g = warp / 4 : (a) radial stage of chunk c+1 in the shadow of the MMAs of chunk c:
+//                96 threads each turn (d, chi, amp) of one slot into four chi * phi_k values and store them with
+//                128-bit stores straight into the SWIZZLE_128B B tile (3xTF32 hi / lo); (b) wait acc_full[g]; per
+//                quad of 4 edge slots: 5 tcgen05.ld (filter values of the lane's five rows), 2 x 128-bit gathers
+//                of the packed neighbour row per slot (shared-memory window or L2), 10 FMAs per slot,
+//                register-resident segment sums, row write-out at the end of a CSR row; arrive acc_free[g]
 //   warps 12-14  producer of group g : walks the group's rows (dense 4-slot quads, 16 slots per chunk), runs the
-//                per-edge geometry as a software pipeline over chunks (indices | positions | arithmetic), writes
-//                chi * phi_k straight into the SWIZZLE_128B B tiles (3xTF32 hi / lo, 128-bit stores), then one
-//                elected lane issues the 45 tcgen05.mma of the chunk into the group's accumulator buffer
+//                per-edge geometry (d, chi, harmonics, gather offsets) as a software pipeline over chunks
+//                (indices | positions | arithmetic) two chunks ahead, and one elected lane issues the 45
+//                tcgen05.mma of a chunk into the group's accumulator buffer once its tiles are written
 //   warp  15     window loader : one elected thread streams the packed rows of the CTA's molecule tiles into
 //                the two halves of the shared-memory window with cp.async.bulk (TMA), a tile ahead
 //
@@ -28,12 +30,13 @@ constexpr int NQ = SLOTS / 4;                // quads per chunk
 constexpr int DCOLS = TILES * SLOTS;         // accumulator columns of one group (80)
 constexpr int BSTAGE = 2 * SLOTS * 128;      // bytes of one B stage: hi + lo tile
 constexpr int NBST = 2;                      // B stages per group
-constexpr int NGEO = 3;                      // geometry records per group (ring)
+constexpr int NGEO = 4;                      // geometry records per group (ring; the producer runs two chunks ahead)
 constexpr int NTHREADS = NCONS + G * 32 + 32;
 constexpr int NOSTAGE = INT_MIN;
 
 struct alignas(16) Geo {
   float4 Yt[SLOTS][3];   // harmonics per slot and piece type
+  float4 rad[SLOTS];     // (d, chi * sqrt(2 / rc) / (d + 1e-5), chi, -) of the slot; zeros for dead slots
   uint32_t goff[SLOTS];  // staged: byte offset of the gathered row inside the window; else: node index
   Quad qd[NQ];
   int nq;                // quads of this chunk (1..NQ), -1 = end of stream
@@ -42,6 +45,8 @@ struct alignas(16) Geo {
 
 struct FwdSmem {
   Geo geo[G][NGEO];
+  uint64_t geo_full[G][NGEO];   // producer -> consumers: geometry record of a chunk is written
+  uint64_t tile_full[G][NBST];  // consumers -> producer: radial tiles of a chunk are written (and proxy-fenced)
   uint64_t acc_full[G], acc_free[G];
   uint64_t win_full[2], win_free[2];
   uint32_t slot;
@@ -82,8 +87,8 @@ __global__ void __launch_bounds__(256) pack_fwd_kernel(const float* __restrict__
 // consumers
 // ------------------------------------------------------------------------------------------------------
 template <int C, int M1, int M2>
-__device__ __forceinline__ void fwd_consumer(const CenterArgs& A, FwdSmem& sm, const uint32_t tmem, const uint32_t win_base,
-                                             const float* __restrict__ pk, const int grp) {
+__device__ __forceinline__ void fwd_consumer(const CenterArgs& A, FwdSmem& sm, const uint32_t tmem, const uint32_t tiles_base,
+                                             const uint32_t win_base, const float* __restrict__ pk, const int grp) {
   constexpr int D = C + 3 * M1 + 5 * M2;
   const int L = threadIdx.x - grp * GRP, wq = L >> 5, lane = L & 31, sl = blockIdx.y;
   const int pt = piece_type(L);
@@ -95,26 +100,70 @@ __device__ __forceinline__ void fwd_consumer(const CenterArgs& A, FwdSmem& sm, c
   const uint32_t win_lane = win_base + 16u * (uint32_t)L;
   const float* pk_lane = pk + (size_t)sl * A.geo.g.n_nodes * ROWF + 4 * L;
   const uint32_t full = smem_u32(&sm.acc_full[grp]), free_ = smem_u32(&sm.acc_free[grp]);
+  const uint32_t geo0 = smem_u32(&sm.geo[grp][0]), gfull0 = smem_u32(&sm.geo_full[grp][0]);
+  const uint32_t tfull0 = smem_u32(&sm.tile_full[grp][0]);
+  const uint32_t my_tiles = tiles_base + (uint32_t)grp * (NBST * BSTAGE);
+
+  // radial stage: thread L < 96 owns slot L / 6 and the four radial terms k = 4 (L % 6) .. + 3 of every chunk
+  // (k = 0: the cutoff / bias term, k = 1 .. 20: Bessel terms, k > 20: padding)
+  const int rslot = L / 6, rkc = L - 6 * rslot;
+  float fr[4];
+#pragma unroll
+  for (int x = 0; x < 4; ++x) {
+    const int k = 4 * rkc + x;
+    fr[x] = (L < 96 && k >= 1 && k <= NB_) ? A.geo.freq[k - 1] : 0.f;
+  }
+  const uint32_t rad_off = (uint32_t)offsetof(Geo, rad) + 16u * (uint32_t)rslot;
+  const uint32_t tile_off = (uint32_t)(rslot * 128 + ((rkc ^ (rslot & 7)) << 4));
+  auto radial = [&](int c) {  // tiles of chunk c (its geometry record is visible)
+    if (L < 96) {
+      const float4 rd = lds128(geo0 + (uint32_t)(c % NGEO) * (uint32_t)sizeof(Geo) + rad_off);
+      float val[4];
+#pragma unroll
+      for (int x = 0; x < 4; ++x) val[x] = rd.y * sinf(fr[x] * rd.x);  // fr = 0 -> exactly zero
+      if (rkc == 0) val[0] = rd.z;
+      uint32_t hi[4], lo[4];
+#pragma unroll
+      for (int x = 0; x < 4; ++x) split_fast(val[x], hi[x], lo[x]);
+      const uint32_t t_hi = my_tiles + (uint32_t)(c & (NBST - 1)) * BSTAGE + tile_off;
+      sts128(t_hi, hi[0], hi[1], hi[2], hi[3]);
+      sts128(t_hi + SLOTS * 128, lo[0], lo[1], lo[2], lo[3]);
+      proxy_fence();  // generic-proxy stores -> visible to the tensor core
+    }
+    __syncwarp();
+    if (lane == 0) mbar_arrive(tfull0 + 8u * (uint32_t)(c & (NBST - 1)));
+  };
+  auto geo_wait = [&](int c) { mbar_wait(gfull0 + 8u * (uint32_t)(c % NGEO), (uint32_t)((c / NGEO) & 1)); };
+  auto geo_nq = [&](int c) {
+    int v;
+    asm volatile("ld.shared.b32 %0, [%1];" : "=r"(v) : "r"(geo0 + (uint32_t)(c % NGEO) * (uint32_t)sizeof(Geo) + (uint32_t)offsetof(Geo, nq)) : "memory");
+    return v;
+  };
 
   float accx = 0.f, accV0 = 0.f, accP[3] = {0.f, 0.f, 0.f};
   float bx = 0.f, bV0 = 0.f, bP[3] = {0.f, 0.f, 0.f};
 
-  for (int c = 0;; ++c) {
+  geo_wait(0);
+  int nq = geo_nq(0);
+  if (nq > 0) radial(0);
+  for (int c = 0; nq >= 0; ++c) {
+    // radial terms of the next chunk, in the shadow of this chunk's MMAs
+    geo_wait(c + 1);
+    const int nq_next = geo_nq(c + 1);
+    if (nq_next > 0) radial(c + 1);
     mbar_wait(full, (uint32_t)(c & 1));
     tc_fence_after();
-    const Geo& ge = sm.geo[grp][c % NGEO];
-    const int nq = ge.nq;
-    if (nq < 0) break;
+    const uint32_t ge = geo0 + (uint32_t)(c % NGEO) * (uint32_t)sizeof(Geo);
 #pragma unroll 1
     for (int qd = 0; qd < nq; ++qd) {
-      const Quad q = ge.qd[qd];
-      const int fl = q.flags;
+      int node, fl;
+      asm volatile("ld.shared.v2.b32 {%0, %1}, [%2];" : "=r"(node), "=r"(fl) : "r"(ge + (uint32_t)offsetof(Geo, qd) + 8u * (uint32_t)qd) : "memory");
       if (fl & F_TILE_FIRST) {
         if (fl & F_STAGED) mbar_wait(smem_u32(&sm.win_full[(fl & F_BUF) ? 1 : 0]), (fl & F_PAR) ? 1u : 0u);
       }
       if (fl & F_ROW_FIRST) {  // residual row: requested now, consumed when the row ends
         accx = accV0 = accP[0] = accP[1] = accP[2] = 0.f;
-        const size_t nd = (size_t)q.node;
+        const size_t nd = (size_t)node;
         bx = A.x_in ? A.x_in[nd * C + q0] : 0.f;
         bV0 = A.V_in ? A.V_in[nd * D + q0] : 0.f;
 #pragma unroll
@@ -124,9 +173,10 @@ __device__ __forceinline__ void fwd_consumer(const CenterArgs& A, FwdSmem& sm, c
         float w[TILES][4];
 #pragma unroll
         for (int t = 0; t < TILES; ++t) tmem_ld4(dbase + t * SLOTS + qd * 4, w[t]);
-        const uint4 go = *reinterpret_cast<const uint4*>(&ge.goff[qd * 4]);
-        const uint32_t gj[4] = {go.x, go.y, go.z, go.w};
-        float4 a[4], b[4];
+        uint32_t gj[4];
+        asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(gj[0]), "=r"(gj[1]), "=r"(gj[2]), "=r"(gj[3])
+                     : "r"(ge + (uint32_t)offsetof(Geo, goff) + 16u * (uint32_t)qd) : "memory");
+        float4 a[4], b[4], y[4];
         if (fl & F_STAGED) {
 #pragma unroll
           for (int j = 0; j < 4; ++j) {
@@ -141,22 +191,23 @@ __device__ __forceinline__ void fwd_consumer(const CenterArgs& A, FwdSmem& sm, c
             b[j] = ldg128(p + 512);
           }
         }
+#pragma unroll
+        for (int j = 0; j < 4; ++j) y[j] = lds128(ge + (uint32_t)offsetof(Geo, Yt) + 48u * (uint32_t)(qd * 4 + j) + 16u * (uint32_t)pt);
         tmem_wait_ld();
 #pragma unroll
         for (int t = 0; t < TILES; ++t) pin(w[t]);
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
-          const float4 y = ge.Yt[qd * 4 + j][pt];
           accx = fmaf(a[j].z, w[2][j], accx);
           accV0 = fmaf(a[j].x, w[0][j], fmaf(a[j].y, w[1][j], accV0));
           const float gep = a[j].w * w[4][j];
-          accP[0] = fmaf(b[j].x, w[3][j], fmaf(gep, y.x, accP[0]));
-          accP[1] = fmaf(b[j].y, w[3][j], fmaf(gep, y.y, accP[1]));
-          accP[2] = fmaf(b[j].z, w[3][j], fmaf(gep, y.z, accP[2]));
+          accP[0] = fmaf(b[j].x, w[3][j], fmaf(gep, y[j].x, accP[0]));
+          accP[1] = fmaf(b[j].y, w[3][j], fmaf(gep, y[j].y, accP[1]));
+          accP[2] = fmaf(b[j].z, w[3][j], fmaf(gep, y[j].z, accP[2]));
         }
       }
       if (fl & F_ROW_LAST) {
-        const size_t nd = (size_t)q.node;
+        const size_t nd = (size_t)node;
         A.x_out[nd * C + q0] = bx + accx;
         A.V_out[nd * D + q0] = bV0 + accV0;
         A.V_out[nd * D + voff[0]] = bP[0] + accP[0];
@@ -171,6 +222,7 @@ __device__ __forceinline__ void fwd_consumer(const CenterArgs& A, FwdSmem& sm, c
     tc_fence_before();
     __syncwarp();
     if (lane == 0) mbar_arrive(free_);
+    nq = nq_next;
   }
 }
 
@@ -180,6 +232,8 @@ __device__ __forceinline__ void fwd_consumer(const CenterArgs& A, FwdSmem& sm, c
 struct SlotRegs {
   int i, e, wb;  // center node, edge id (-1: dead slot), window base (rows) or NOSTAGE
   int j;         // neighbor
+  int qnode, qflags;  // lane q < NQ: quad q of the chunk
+  int nq;             // quads of the chunk (1..NQ), -1 = end of stream (uniform)
 };
 
 template <int C, int M1, int M2>
@@ -188,16 +242,10 @@ __device__ __forceinline__ void fwd_producer(const CenterArgs& A, FwdSmem& sm, c
   const int lane = threadIdx.x & 31, slot = lane & 15, half = lane >> 4;
   const xeq_graph_t& g = A.geo.g;
   const uint32_t full = smem_u32(&sm.acc_full[grp]), free_ = smem_u32(&sm.acc_free[grp]);
+  const uint32_t gfull0 = smem_u32(&sm.geo_full[grp][0]), tfull0 = smem_u32(&sm.tile_full[grp][0]);
   const uint32_t my_tiles = tiles_base + (uint32_t)grp * (NBST * BSTAGE);
-
-  // frequencies of this lane's twelve radial terms (k = 12 half + kk; k = 0 is the cutoff / bias term)
-  float fr[12];
-#pragma unroll
-  for (int kk = 0; kk < 12; ++kk) {
-    const int k = 12 * half + kk;
-    fr[kk] = (k >= 1 && k <= NB_) ? A.geo.freq[k - 1] : 0.f;
-  }
   const float c0 = sqrtf(2.f / A.geo.rc);
+  const float pi_rc = 3.14159265358979323846f / A.geo.rc;
 
   Walk wk;
   wk.init(g, g.tile_ptr, g.n_tiles, grp);
@@ -205,17 +253,16 @@ __device__ __forceinline__ void fwd_producer(const CenterArgs& A, FwdSmem& sm, c
   int e = 0, e1 = 0;
   bool row_open = false, row_first = false, tile_any = false;
 
-  // stage A: slot assignment of the next chunk (uniform control flow), quads -> shared memory, index loads
-  auto stage_a = [&](int c, SlotRegs& o) -> int {
-    Geo& ge = sm.geo[grp][c % NGEO];
-    o.i = 0; o.e = -1; o.wb = NOSTAGE; o.j = 0;
+  // stage A: slot assignment of the next chunk (uniform control flow), quads kept in registers, index loads
+  auto stage_a = [&](SlotRegs& o) {
+    o.i = 0; o.e = -1; o.wb = NOSTAGE; o.j = 0; o.qnode = 0; o.qflags = 0;
     int nq = 0;
     while (nq < NQ && wk.valid) {
       const int stbits = wk.staged ? (F_STAGED | (wk.buf ? F_BUF : 0) | (wk.par ? F_PAR : 0)) : 0;
       if (!row_open) {
         if (node >= wk.n1) {
           if (!tile_any && wk.tile_mode == 1) {  // no row of this group in the tile: keep the window accounting going
-            if (lane == 0) ge.qd[nq] = Quad{wk.n0, stbits | F_NOROW | F_TILE_FIRST | F_TILE_LAST};
+            if (lane == nq) { o.qnode = wk.n0; o.qflags = stbits | F_NOROW | F_TILE_FIRST | F_TILE_LAST; }
             ++nq;
           }
           wk.next();
@@ -231,7 +278,7 @@ __device__ __forceinline__ void fwd_producer(const CenterArgs& A, FwdSmem& sm, c
       const bool last = e + 4 >= e1;
       int fl = stbits | (row_first ? F_ROW_FIRST : 0) | (tile_any ? 0 : F_TILE_FIRST);
       if (last) fl |= F_ROW_LAST | ((node + wk.rstride >= wk.n1) ? F_TILE_LAST : 0);
-      if (lane == 0) ge.qd[nq] = Quad{node, fl};
+      if (lane == nq) { o.qnode = node; o.qflags = fl; }
       const int idx = slot - 4 * nq;
       if (idx >= 0 && idx < 4) {
         o.i = node;
@@ -247,10 +294,8 @@ __device__ __forceinline__ void fwd_producer(const CenterArgs& A, FwdSmem& sm, c
         node += wk.rstride;
       }
     }
-    if (nq == 0) nq = -1;  // stream exhausted
-    if (lane == 0) ge.nq = nq;
+    o.nq = nq ? nq : -1;  // -1: stream exhausted
     if (o.e >= 0) o.j = g.col[o.e];
-    return nq;
   };
 
   // stage B: raw position loads (and the lattice shift of periodic graphs)
@@ -276,49 +321,35 @@ __device__ __forceinline__ void fwd_producer(const CenterArgs& A, FwdSmem& sm, c
     }
   };
 
-  // stage C: geometry record + radial tiles of chunk c
+  // stage C: geometry record of chunk c -> shared memory, then the release to the consumers (their radial stage)
   auto stage_c = [&](int c, const SlotRegs& r, const PosRegs& p) {
     Geo& ge = sm.geo[grp][c % NGEO];
-    const uint32_t t_hi = my_tiles + (uint32_t)(c & (NBST - 1)) * BSTAGE, t_lo = t_hi + SLOTS * 128;
-    float val[12];
+    if (r.nq > 0 && half == 0) {
+      float4 y0 = make_float4(0.f, 0.f, 0.f, 0.f), y1 = y0, y2 = y0, rad = y0;
+      if (r.e >= 0) {
+        float rv[3], d, u[3], Y[8];
 #pragma unroll
-    for (int kk = 0; kk < 12; ++kk) val[kk] = 0.f;
-    float4 y0 = make_float4(0.f, 0.f, 0.f, 0.f), y1 = y0, y2 = y0;
-    if (r.e >= 0) {
-      float rv[3], d, u[3], Y[8];
-#pragma unroll
-      for (int x = 0; x < 3; ++x) rv[x] = (p.pi[x] - p.pj[x]) - p.sh[x];
-      unit_vector(rv, d, u);
-      sph_harm(u, Y);
-      y0 = make_float4(Y[0], Y[1], Y[2], 0.f);
-      y1 = make_float4(Y[3], Y[4], Y[5], 0.f);
-      y2 = make_float4(Y[6], Y[7], 0.f, 0.f);
-      float chi = 0.f;
-      if (d < A.geo.rc) chi = 0.5f * (cosf(3.14159265358979323846f / A.geo.rc * d) + 1.f);
-      const float amp = chi * c0 / (d + 1e-5f);
-#pragma unroll
-      for (int kk = 0; kk < 12; ++kk) {
-        const int k = 12 * half + kk;
-        if (k == 0) val[kk] = chi;
-        else if (k <= NB_) val[kk] = amp * sinf(fr[kk] * d);
+        for (int x = 0; x < 3; ++x) rv[x] = (p.pi[x] - p.pj[x]) - p.sh[x];
+        unit_vector(rv, d, u);
+        sph_harm(u, Y);
+        y0 = make_float4(Y[0], Y[1], Y[2], 0.f);
+        y1 = make_float4(Y[3], Y[4], Y[5], 0.f);
+        y2 = make_float4(Y[6], Y[7], 0.f, 0.f);
+        float chi = 0.f;
+        if (d < A.geo.rc) chi = 0.5f * (cosf(pi_rc * d) + 1.f);
+        rad = make_float4(d, chi * c0 / (d + 1e-5f), chi, 0.f);
       }
-    }
-    if (half == 0) {
       ge.Yt[slot][0] = y0;
       ge.Yt[slot][1] = y1;
       ge.Yt[slot][2] = y2;
+      ge.rad[slot] = rad;
       const int jj = r.e >= 0 ? r.j : r.i;  // dead slots gather the (always valid) row of their own center, times zero
       ge.goff[slot] = (r.wb != NOSTAGE) ? (uint32_t)(r.wb + jj) * (uint32_t)ROWB : (uint32_t)jj;
+      if (lane < NQ) ge.qd[lane] = Quad{r.qnode, r.qflags};
     }
-#pragma unroll
-    for (int i4 = 0; i4 < 3; ++i4) {
-      uint32_t hi[4], lo[4];
-#pragma unroll
-      for (int x = 0; x < 4; ++x) split_fast(val[4 * i4 + x], hi[x], lo[x]);
-      const uint32_t off = (uint32_t)(slot * 128 + (((3 * half + i4) ^ (slot & 7)) << 4));
-      sts128(t_hi + off, hi[0], hi[1], hi[2], hi[3]);
-      sts128(t_lo + off, lo[0], lo[1], lo[2], lo[3]);
-    }
+    if (lane == 0) ge.nq = r.nq;
+    __syncwarp();
+    if (lane == 0) mbar_arrive(gfull0 + 8u * (uint32_t)(c % NGEO));
   };
 
   auto issue = [&](int c) {
@@ -338,32 +369,38 @@ __device__ __forceinline__ void fwd_producer(const CenterArgs& A, FwdSmem& sm, c
     }
   };
 
-  SlotRegs ra, rb, rc;
-  PosRegs pb;
-  int nq_ring[3];
-  nq_ring[0] = stage_a(0, rc);          // chunk 0
-  stage_b(rc, pb);
-  nq_ring[1] = stage_a(1, rb);          // chunk 1
-  for (int c = 0;; ++c) {
-    const int nq = nq_ring[0];
-    if (nq > 0) stage_c(c, rc, pb);
-    proxy_fence();
-    __syncwarp();
-    if (c > 0) mbar_wait(free_, (uint32_t)((c - 1) & 1));
+  // geometry pipeline: record of chunk c+2 written in iteration c, positions of chunk c+3 and indices of chunk c+4 in flight
+  SlotRegs s2, s3;
+  PosRegs p2;
+  int n0, n1;
+  stage_a(s2);
+  stage_b(s2, p2);
+  stage_a(s3);
+  stage_c(0, s2, p2);
+  n0 = s2.nq;
+  s2 = s3;
+  stage_b(s2, p2);
+  stage_a(s3);
+  stage_c(1, s2, p2);
+  n1 = s2.nq;
+  s2 = s3;
+  stage_b(s2, p2);
+  stage_a(s3);
+  for (int c = 0; n0 >= 0; ++c) {
+    mbar_wait(tfull0 + 8u * (uint32_t)(c & (NBST - 1)), (uint32_t)((c >> 1) & 1));  // radial tiles of chunk c
+    if (c > 0) mbar_wait(free_, (uint32_t)((c - 1) & 1));                             // accumulators drained
     tc_fence_after();
     if (elect_one()) {
-      if (nq > 0) issue(c);
+      issue(c);
       umma_commit(full);
-      mbar_arrive(full);  // releases the geometry record written by the other lanes (ordered by the __syncwarp)
     }
     __syncwarp();
-    if (nq < 0) break;
-    // geometry pipeline: positions of chunk c+1, slot assignment + indices of chunk c+2
-    rc = rb;
-    stage_b(rc, pb);
-    nq_ring[0] = nq_ring[1];
-    nq_ring[1] = stage_a(c + 2, rb);
-    (void)ra;
+    stage_c(c + 2, s2, p2);
+    n0 = n1;
+    n1 = s2.nq;
+    s2 = s3;
+    stage_b(s2, p2);
+    stage_a(s3);
   }
 }
 
@@ -380,7 +417,7 @@ __device__ __forceinline__ void fwd_loader(const CenterArgs& A, FwdSmem& sm, con
     if (!wk.staged) continue;
     const int t = wk.staged_count - 1;  // index of this staged tile
     const uint32_t fullb = smem_u32(&sm.win_full[wk.buf]), freeb = smem_u32(&sm.win_free[wk.buf]);
-    if (t >= 2) mbar_wait(freeb, (uint32_t)(((t >> 1) - 1) & 1));
+    if (t >= 2) mbar_wait_sleep(freeb, (uint32_t)(((t >> 1) - 1) & 1));
     const uint32_t bytes = (uint32_t)(wk.n1 - wk.n0) * ROWB;
     mbar_expect_tx(fullb, bytes);
     tma_bulk_g2s(win_base + (uint32_t)wk.buf * (WH * ROWB), pk_sl + (size_t)wk.n0 * ROWF, bytes, fullb);
@@ -394,8 +431,10 @@ __global__ void __launch_bounds__(NTHREADS, 1) center_fwd_ul_kernel(const Center
   const int t = threadIdx.x, warp = t >> 5;
   if (t == 0) {
     for (int i = 0; i < G; ++i) {
-      mbar_init(smem_u32(&sm.acc_full[i]), 2);   // tcgen05.commit + the producer's release of the geometry record
+      mbar_init(smem_u32(&sm.acc_full[i]), 1);   // tcgen05.commit
       mbar_init(smem_u32(&sm.acc_free[i]), 4);   // one arrive per consumer warp of the group
+      for (int k = 0; k < NGEO; ++k) mbar_init(smem_u32(&sm.geo_full[i][k]), 1);
+      for (int k = 0; k < NBST; ++k) mbar_init(smem_u32(&sm.tile_full[i][k]), 4);
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(smem_u32(&sm.win_full[i]), 1);
@@ -417,7 +456,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) center_fwd_ul_kernel(const Center
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
-  if (warp < 4 * G) fwd_consumer<C, M1, M2>(A, sm, tmem, win_base, pk, warp >> 2);
+  if (warp < 4 * G) fwd_consumer<C, M1, M2>(A, sm, tmem, tiles_base, win_base, pk, warp >> 2);
   else if (warp < 4 * G + G) fwd_producer<C, M1, M2>(A, sm, tmem, tiles_base, warp - 4 * G);
   else fwd_loader<C>(A, sm, win_base, pk);
   tmem_teardown(tmem);

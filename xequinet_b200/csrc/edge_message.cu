@@ -716,11 +716,9 @@ static int launch_center(const CenterArgs& A, cudaStream_t st) {
   static_assert(sizeof(CenterSmem<JVP>) <= 48 * 1024, "static shared memory limit");
   const bool window = CenterWin<C, JVP>::value > 0 && A.geo.g.tile_mode == 1;
   const size_t dyn = window ? (size_t)CenterWin<C, JVP>::value * (C * 4 + M1 * 5 + M2 * 7) * (JVP ? 2 : 1) * 4 : 0;
-  static bool attr_set = false;
-  if (dyn && !attr_set) {
+  if (dyn) {
     int rc = set_smem(center_kernel<C, M1, M2, JVP>, dyn);
     if (rc) return rc;
-    attr_set = true;
   }
   const int grid = min(n_tiles, num_sms() * ((C == 128 && (!window || !JVP)) ? 2 : 1));
   center_kernel<C, M1, M2, JVP><<<grid, C + M1 + M2, dyn, st>>>(A);
@@ -785,11 +783,9 @@ static int launch_neighbor(NeighborArgs& A, bool main, bool wgrad, int gx, cudaS
     static_assert(sizeof(NbrMainSmem<ORDER, M / 32>) <= 48 * 1024, "static shared memory limit");
     const bool window = NbrWin<C>::value > 0 && A.geo.g.tile_mode == 1;
     const size_t dyn = window ? (size_t)NbrWin<C>::value * (C * 2 + M1 * 3 + M2 * 5) * 4 : 0;
-    static bool attr_set = false;
-    if (dyn && !attr_set) {
+    if (dyn) {
       int rc = set_smem(nbr_main_kernel<C, M1, M2, ORDER>, dyn);
       if (rc) return rc;
-      attr_set = true;
     }
     const int grid = min(n_tiles, num_sms() * ((C == 128 && ORDER == 1) ? 2 : 1));
     nbr_main_kernel<C, M1, M2, ORDER><<<grid, M, dyn, st>>>(A);

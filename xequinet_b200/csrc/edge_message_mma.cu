@@ -1023,11 +1023,9 @@ static int launch_center_mma_t(const CenterArgs& A, cudaStream_t st) {
   static_assert(sizeof(CenterMmaSmem<JVP>) <= 24 * 1024, "static shared memory budget");
   const size_t dyn = 1024 + 2 * (size_t)CenterMma<JVP>::STAGE +
                      (size_t)CenterMma<JVP>::WIN * (SL_C * 4 + SL_M1 * 5 + SL_M2 * 7) * (JVP ? 2 : 1) * 4;
-  static bool attr_set = false;
-  if (!attr_set) {
+  {  // per-device attribute: set on every launch (cheap)
     int rc = set_smem(center_mma_kernel<C, M1, M2, JVP>, dyn);
     if (rc) return rc;
-    attr_set = true;
   }
   const int grid = max(1, min(A.geo.g.n_tiles, num_sms() / SLICES));
   center_mma_kernel<C, M1, M2, JVP><<<dim3(grid, SLICES), SL_M + 32, dyn, st>>>(A);
@@ -1045,11 +1043,9 @@ static int launch_wgrad_mma_t(const NeighborArgs& A, int grid, cudaStream_t st) 
   constexpr int M1 = C / 2, M2 = C / 4, SLICES = C / SL_C;
   static_assert(sizeof(WgradMmaSmem<ORDER>) <= 24 * 1024, "static shared memory budget");
   const size_t dyn = 1024 + 2 * (size_t)WgradMma<ORDER>::STAGE + 2 * (size_t)WgradMma<ORDER>::WIN * (SL_C * 2 + SL_M1 * 3 + SL_M2 * 5) * 4;
-  static bool attr_set = false;
-  if (!attr_set) {
+  {  // per-device attribute: set on every launch (cheap)
     int rc = set_smem(wgrad_mma_kernel<C, M1, M2, ORDER>, dyn);
     if (rc) return rc;
-    attr_set = true;
   }
   wgrad_mma_kernel<C, M1, M2, ORDER><<<dim3(grid, SLICES), 2 * SL_M + 32, dyn, st>>>(A);
   XEQ_LAUNCHED(1);
@@ -1061,11 +1057,9 @@ static int launch_nbr_mma_t(const NeighborArgs& A, cudaStream_t st) {
   constexpr int M1 = C / 2, M2 = C / 4, SLICES = C / SL_C;
   static_assert(sizeof(NbrMmaSmem<ORDER>) <= 40 * 1024, "static shared memory budget");
   const size_t dyn = 1024 + 2 * (size_t)NbrMma<ORDER>::STAGE + (size_t)NbrMma<ORDER>::WIN * (SL_C * 2 + SL_M1 * 3 + SL_M2 * 5) * 4;
-  static bool attr_set = false;
-  if (!attr_set) {
+  {  // per-device attribute: set on every launch (cheap)
     int rc = set_smem(nbr_mma_kernel<C, M1, M2, ORDER>, dyn);
     if (rc) return rc;
-    attr_set = true;
   }
   const int grid = max(1, min(A.geo.g.t_n_tiles, num_sms() / SLICES));
   nbr_mma_kernel<C, M1, M2, ORDER><<<dim3(grid, SLICES), SL_M + 32, dyn, st>>>(A);

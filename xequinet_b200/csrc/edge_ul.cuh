@@ -34,7 +34,7 @@ constexpr int GRP = 128;         // threads per group = accumulator lanes
 constexpr int NCONS = G * GRP;   // 384
 constexpr int ROWF = 1024;       // floats of one packed row: 2 planes x 128 lanes x 4
 constexpr int ROWB = ROWF * 4;
-constexpr int WH = 24;           // rows per window half (two halves: double-buffered tiles of <= 24 nodes)
+constexpr int WH = 23;           // rows per window half (two halves: double-buffered tiles of <= 23 nodes)
 
 // quad flags (a quad = 4 consecutive slots of one row)
 enum : int {
@@ -48,6 +48,23 @@ struct Quad {
 // ---- mbarrier / TMA helpers --------------------------------------------------------------------------
 __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
   asm volatile("mbarrier.arrive.release.cta.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+// wait of a thread that has nothing else to do for a long time (window loader): back off between polls
+__device__ __forceinline__ void mbar_wait_sleep(uint32_t bar, uint32_t parity) {
+  uint32_t ok;
+  for (;;) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t"
+        "}\n"
+        : "=r"(ok)
+        : "r"(bar), "r"(parity)
+        : "memory");
+    if (ok) break;
+    __nanosleep(256);
+  }
 }
 __device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
   asm volatile("mbarrier.arrive.expect_tx.release.cta.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");

@@ -472,10 +472,8 @@ int xeq_gemm_tf32x3(const xeq_gemm_t* problems, int32_t n_problems, int32_t spli
   }
   if (max_m == 0) return XEQ_OK;
   cudaStream_t st = (cudaStream_t)stream;
-  static bool attr_set = false;
-  if (!attr_set) {
+  {  // per-device attribute: set on every launch (cheap)
     XEQ_CUDA(cudaFuncSetAttribute(gemm_tf32x3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM));
-    attr_set = true;
   }
   dim3 grid((max_m + TILE_M - 1) / TILE_M, passes, split_k);
   gemm_tf32x3_kernel<<<grid, GEMM_THREADS, GEMM_SMEM, st>>>(args);

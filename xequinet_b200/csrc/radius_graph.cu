@@ -457,6 +457,12 @@ __global__ void coo_to_csr_kernel(const long long* __restrict__ ei, const float*
   }
 }
 
+// capacity mode, after the fill pass: rows past the capacity become empty (the overflow flag is already raised)
+__global__ void clamp_rowptr_kernel(int* __restrict__ rowptr, int n, int capacity) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) rowptr[i] = min(rowptr[i], capacity);
+}
+
 // n_edges_dev points at rowptr[n_nodes]: the edge count stays on the device (capacity mode)
 __global__ void count_cols_kernel(const int* __restrict__ col, const int* __restrict__ n_edges_dev, int capacity,
                                   int* __restrict__ cnt) {
@@ -611,7 +617,7 @@ int xeq_radius_graph_count(const float* pos, int32_t n, const int32_t* graph_ptr
 
 int xeq_radius_graph_fill(const float* pos, int32_t n, const int32_t* graph_ptr, const int32_t* node_graph, int32_t G,
                           const float* cell, const int32_t* pbc_host, const int32_t* rep_host, float cutoff,
-                          const int32_t* rowptr, int32_t* col, int8_t* offsets, int64_t* edge_index, float* cell_offsets,
+                          int32_t* rowptr, int32_t* col, int8_t* offsets, int64_t* edge_index, float* cell_offsets,
                           int32_t edge_capacity, int32_t* overflow, void* ws, size_t ws_bytes, xeq_stream_t stream) {
   cudaStream_t st = (cudaStream_t)stream;
   bool periodic;
@@ -658,6 +664,11 @@ int xeq_radius_graph_fill(const float* pos, int32_t n, const int32_t* graph_ptr,
                                                            n_edges, cap, overflow);
   }
   XEQ_LAUNCHED(periodic ? 2 : 1);
+  if (edge_capacity > 0) {
+    // capacity mode: the dropped edges must not be reachable -- every consumer walks rowptr without a bound check
+    clamp_rowptr_kernel<<<(n + 1 + 255) / 256, 256, 0, st>>>(rowptr, n + 1, edge_capacity);
+    XEQ_LAUNCHED(1);
+  }
   return XEQ_OK;
 }
 

@@ -38,6 +38,9 @@ class NeighborGraph:
         self.cell = cell  # float32 [G,3,3] or None
         self.node_graph = node_graph  # int32 [N] or None
         self._struct = None
+        # provenance: the (edge_index, cell_offsets, cell) tensors this structure was derived from, or None when
+        # it was built from positions by K1 in capacity mode; see nn/basic.py::compute_edge_data
+        self._src = None
         lib = _lib.get()
         dev = self.rowptr.device
         N, E = self.n_nodes, self.n_edges
@@ -95,7 +98,23 @@ class NeighborGraph:
         """COO [2,E] int64 in canonical order (row 0 = center, row 1 = neighbor; keys.py:16-17)."""
         counts = (self.rowptr[1:] - self.rowptr[:-1]).long()
         center = torch.repeat_interleave(torch.arange(self.n_nodes, device=self.rowptr.device), counts)
-        return torch.stack([center, self.col[: self.n_edges].long()])
+        # capacity mode: col is allocated for the capacity, the live count is rowptr[N]
+        return torch.stack([center, self.col[: center.numel()].long()])
+
+    def derived_from(self, edge_index, cell_offsets, cell) -> bool:
+        """True when this structure was derived from exactly these tensors (same objects, not modified in place
+        since), i.e. when it may stand in for them."""
+        if self._src is None:
+            return False
+        for ref, cur in zip(self._src, (edge_index, cell_offsets, cell)):
+            if (ref is None) != (cur is None):
+                return False
+            if ref is not None and (ref[0] is not cur or ref[1] != cur._version):
+                return False
+        return True
+
+    def set_source(self, edge_index, cell_offsets, cell) -> None:
+        self._src = tuple(None if t is None else (t, t._version) for t in (edge_index, cell_offsets, cell))
 
 
 def _image_repeats(cell: torch.Tensor, pbc, cutoff: float):
@@ -225,9 +244,16 @@ class StaticGraphBuilder:
                                    self.node_graph if (self.periodic and self.G > 1) else None, capacity=self.cap,
                                    mol_ptr=mol_ptr)
 
-    def build(self, pos: torch.Tensor) -> "NeighborGraph":
+    def build(self, pos: torch.Tensor, check_overflow: bool = True) -> "NeighborGraph":
+        """Launches K1 on `pos` (float32 [N,3], CUDA).  Outside CUDA-graph capture the overflow flag is read back
+        (one host sync; pass check_overflow=False to skip it) and a RuntimeError is raised when the capacity was
+        exceeded; under capture the caller checks `self.overflow` after the replay.  Either way the kernels stay
+        inside the allocated arrays (rowptr is clamped to the capacity on the device)."""
         lib = _lib.get()
         pos32 = pos.detach()
+        if pos32.dtype != torch.float32 or tuple(pos32.shape) != (self.N, 3) or not pos32.is_contiguous():
+            raise ValueError(f"StaticGraphBuilder.build: pos must be a contiguous float32 [{self.N}, 3] tensor, got "
+                             f"{pos32.dtype} {tuple(pos32.shape)}")
         st = _lib.stream()
         _lib.check(lib.xeq_radius_graph_count(_lib.ptr(pos32), self.N, _lib.ptr(self.ptr32), _lib.ptr(self.node_graph),
                                               self.G, _lib.ptr(self.cell32), self.pbc_arr, self.rep_arr, self.cutoff,
@@ -239,6 +265,10 @@ class StaticGraphBuilder:
                                              self.cap, _lib.ptr(self.overflow), _lib.ptr(self.ws), self.nbytes, st),
                    "xeq_radius_graph_fill")
         self.graph.transpose()
+        if check_overflow and not torch.cuda.is_current_stream_capturing():
+            if int(self.overflow.item()) != 0:
+                self.overflow.zero_()
+                raise RuntimeError(f"StaticGraphBuilder: more than edge_capacity = {self.cap} edges; the list was truncated")
         return self.graph
 
 
@@ -283,6 +313,7 @@ def graph_from_edge_index(edge_index: torch.Tensor, n_nodes: int, n_graphs: int 
     g = NeighborGraph(n_nodes, n_graphs, rowptr, col[:E], offsets[:E] if periodic else None, cell32, node_graph,
                       mol_ptr=mol_ptr)
     g.sorted_edge_index = ei
+    g.set_source(edge_index, cell_offsets, cell)
     return g
 
 
@@ -333,6 +364,7 @@ class NeighborTransform:
         else:
             g, ei, _ = build_graph(pos, self.cutoff, ptr=ptr, batch=batch, want_coo=True)
         data[keys.EDGE_INDEX] = ei
+        g.set_source(ei, data.get(keys.CELL_OFFSETS) if has_pbc else None, data[keys.CELL] if has_pbc else None)
         data[keys.GRAPH] = g
         return data
 

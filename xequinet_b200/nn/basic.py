@@ -27,6 +27,12 @@ def compute_edge_data(data: Dict[str, torch.Tensor], compute_forces: bool = True
     data["_xeq_ptr32"] = data[keys.BATCH_PTR].to(torch.int32).contiguous()
     has_cell = keys.CELL in data
     graph: Optional[NeighborGraph] = data.get(keys.GRAPH)
+    if graph is not None and graph.n_nodes == N and graph._src is not None:
+        # a structure derived from an edge list is only a cache of THAT list: `edge_index` / `cell_offsets` / `cell`
+        # in the dict stay the source of truth, as in the reference (nn/basic.py:67,119-128)
+        if not graph.derived_from(data.get(keys.EDGE_INDEX), data.get(keys.CELL_OFFSETS) if has_cell else None,
+                                  data[keys.CELL] if has_cell else None):
+            graph = None
     if graph is None or graph.n_nodes != N:
         graph = graph_from_edge_index(
             data[keys.EDGE_INDEX], N, n_graphs,

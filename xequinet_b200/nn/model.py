@@ -77,8 +77,9 @@ def resolve_model(model_name: str, **kwargs) -> BaseModel:
     return factory[model_name.lower()](**kwargs)
 
 
-def load_model(ckpt_file: str, device: Optional[torch.device] = None):
-    """nn/model.py:321-351 for dict-shaped data."""
+def load_model(ckpt_file: str, device: Optional[torch.device] = None, trust_pickle: bool = False):
+    """nn/model.py:321-351 for dict-shaped data.  The checkpoint holds a state_dict and a plain config dict, so it is
+    read with `weights_only=True`; `trust_pickle=True` opts into the reference's unrestricted `torch.load`."""
 
     class ModelWithTransform:
         def __init__(self, model, transform, device):
@@ -90,9 +91,15 @@ def load_model(ckpt_file: str, device: Optional[torch.device] = None):
 
     if device is None:
         device = torch.device("cuda")
-    ckpt = torch.load(ckpt_file, map_location=device, weights_only=False)
+    ckpt = torch.load(ckpt_file, map_location=device, weights_only=not trust_pickle)
     cfg = ckpt["config"]
+    # nn/model.py:340 calls set_default_units(config["default_units"]): the unit registry only drives the data
+    # pipeline's conversions, the model arithmetic is unit-free (shift / scale are baked into the read-out weights,
+    # nn/output.py:104-106).  The units the checkpoint was trained in are kept on the returned object.
+    units = dict(cfg.get("default_units") or {})
     model = resolve_model(cfg["model_name"], **cfg["model_kwargs"]).to(device)
     model.load_state_dict(ckpt["model"])
     model.eval()
-    return ModelWithTransform(model, NeighborTransform(model.cutoff_radius), device)
+    wrapped = ModelWithTransform(model, NeighborTransform(model.cutoff_radius), device)
+    wrapped.default_units = units
+    return wrapped

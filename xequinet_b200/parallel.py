@@ -8,6 +8,12 @@ take disjoint molecules and the only collective of a training step is ONE all-re
   allreduce_gradients(params, group=None, average=True)
         flat single bucket (865 141 fp32 = 3.5 MB at the defaults: latency-bound, so one launch), NCCL over
         NVLink on the GPU box, gloo in the CPU tests; replaces DDP's bucketed hooks (run/train.py:185-190)
+  FlatGradients(params, n_buckets=3, group=None, average=True)
+        the training-loop form of the same collective: ONE flat fp32 buffer owns every gradient (each p.grad is a
+        view into it, so there is no gather / scatter copy around the collective), split into contiguous buckets in
+        reverse parameter order; a bucket is all-reduced on a side stream as soon as autograd has finalised its
+        last gradient, i.e. while the backward pass of the earlier layers is still running.  Capturable: inside
+        a CUDA-graph capture the side stream is forked from / joined to the capturing stream.
 """
 from __future__ import annotations
 
@@ -65,3 +71,101 @@ def allreduce_gradients(params: Iterable[torch.nn.Parameter], group=None, averag
         else:
             p.grad.copy_(piece)
         off += n
+
+
+class FlatGradients:
+    """Flat gradient storage + bucketed, overlapped all-reduce (see the module docstring).
+
+        flat = FlatGradients(model.parameters())
+        ...
+        flat.zero()              # start of the step (one memset; autograd then accumulates into the views)
+        loss.backward()          # buckets are all-reduced as they complete (post-accumulate-grad hooks)
+        flat.finish()            # join the side stream; gradients are the averages over the ranks
+        optimizer.step()
+
+    With world size 1 (or no process group) the hooks are not installed and finish() is a no-op; zero() still
+    clears the buffer.  Gradients finalise in reverse order of use (read-out first, embedding last), so bucket 0
+    holds the LAST parameters of the list."""
+
+    def __init__(self, params: Iterable[torch.nn.Parameter], n_buckets: int = 3, group=None, average: bool = True):
+        self.params = [p for p in params if p.requires_grad]
+        if not self.params:
+            raise ValueError("FlatGradients: no trainable parameters")
+        self.group, self.average = group, average
+        self.world = dist.get_world_size(group) if dist.is_initialized() else 1
+        p0 = self.params[0]
+        total = sum(p.numel() for p in self.params)
+        self.flat = torch.zeros(total, dtype=p0.dtype, device=p0.device)
+        off = 0
+        self._range = {}
+        for p in self.params:
+            n = p.numel()
+            p.grad = self.flat[off:off + n].view_as(p)
+            self._range[id(p)] = (off, off + n)
+            off += n
+        # contiguous buckets of roughly equal size over the REVERSED parameter list
+        n_buckets = max(1, min(int(n_buckets), len(self.params)))
+        target = total / n_buckets
+        self.buckets: List[List[torch.nn.Parameter]] = [[]]
+        acc = 0
+        for p in reversed(self.params):
+            if acc >= target * len(self.buckets) and len(self.buckets) < n_buckets:
+                self.buckets.append([])
+            self.buckets[-1].append(p)
+            acc += p.numel()
+        self._bucket_of = {id(p): b for b, ps in enumerate(self.buckets) for p in ps}
+        self._slice = [(min(self._range[id(p)][0] for p in ps), max(self._range[id(p)][1] for p in ps)) for ps in self.buckets]
+        self._pending = [0] * len(self.buckets)
+        self._handles = []
+        self._side = torch.cuda.Stream(device=p0.device) if p0.is_cuda else None
+        self._launched = [False] * len(self.buckets)
+        if self.world > 1:
+            for p in self.params:
+                p.register_post_accumulate_grad_hook(self._hook)
+        self.zero()
+
+    # -- step protocol ------------------------------------------------------------------------------------
+    def zero(self) -> None:
+        self.flat.zero_()
+        for p in self.params:  # an optimizer's zero_grad(set_to_none=True) must not detach the views
+            if p.grad is None or p.grad.data_ptr() != self.flat.data_ptr() + self.flat.element_size() * self._range[id(p)][0]:
+                lo, hi = self._range[id(p)]
+                p.grad = self.flat[lo:hi].view_as(p)
+        self._pending = [len(ps) for ps in self.buckets]
+        self._launched = [False] * len(self.buckets)
+        self._handles = []
+
+    def _reduce_bucket(self, b: int) -> None:
+        lo, hi = self._slice[b]
+        piece = self.flat[lo:hi]
+        if self._side is not None:
+            self._side.wait_stream(torch.cuda.current_stream(piece.device))
+            with torch.cuda.stream(self._side):
+                if self.average and dist.get_backend(self.group) == "nccl":
+                    dist.all_reduce(piece, op=dist.ReduceOp.AVG, group=self.group)  # averaged inside the collective
+                else:
+                    dist.all_reduce(piece, group=self.group)
+                    if self.average:
+                        piece.div_(self.world)
+        else:
+            dist.all_reduce(piece, group=self.group)
+            if self.average:
+                piece.div_(self.world)
+        self._launched[b] = True
+
+    def _hook(self, p: torch.nn.Parameter) -> None:
+        b = self._bucket_of[id(p)]
+        self._pending[b] -= 1
+        if self._pending[b] == 0:
+            self._reduce_bucket(b)
+
+    def finish(self) -> None:
+        """All buckets reduced and visible to the current stream.  Parameters that received no gradient in this
+        backward pass never fire their hook: their buckets are reduced here (zeros contribute nothing)."""
+        if self.world == 1:
+            return
+        for b in range(len(self.buckets)):
+            if not self._launched[b]:
+                self._reduce_bucket(b)
+        if self._side is not None:
+            torch.cuda.current_stream(self.flat.device).wait_stream(self._side)
