@@ -32,7 +32,7 @@ def phases():
         t = time.perf_counter(); data = mod(data); mark("fwd." + name, t)
     out = {"energy": data["energy"]}
     t = time.perf_counter()
-    with ops.param_grads(False):
+    if True:
         (g,) = torch.autograd.grad([out["energy"].sum()], [pos_owned])
     mark("backward", t)
     return T, plan, graph

@@ -730,6 +730,7 @@ static int launch_center(const CenterArgs& A, cudaStream_t st) {
 int launch_center_mma(const CenterArgs& A, bool jvp, bool wide, cudaStream_t st);
 int launch_wgrad_mma(const NeighborArgs& A, int order, bool wide, int grid, cudaStream_t st);
 int launch_nbr_mma(const NeighborArgs& A, int order, bool wide, cudaStream_t st);
+int launch_nbr_bwd_ul(const NeighborArgs& A, bool wide, cudaStream_t st);  // edge_bwd_ul.cu: round-2 first-order kernel
 int launch_center_fwd_ws(const CenterArgs& A, bool wide, cudaStream_t st);  // edge_fwd_mma.cu: warp-specialised forward (round 1)
 int launch_center_fwd_ul(const CenterArgs& A, bool wide, void* ws, cudaStream_t st);  // edge_fwd_ul.cu: round-2 forward
 size_t center_fwd_ul_workspace_bytes(int n_nodes, bool wide);
@@ -827,7 +828,8 @@ static int run_neighbor(const xeq_graph_t* g, const xeq_dims_t* dims, NeighborAr
   A.gr = o_pos ? gr : nullptr;
   A.wpart = wpart;
   if (mma) {
-    if (main) rc = launch_nbr_mma(A, order, cfg == 1, st);
+    static const int bwd_kind = [] { const char* e = getenv("XEQ_BWD_KIND"); return e ? atoi(e) : 2; }();  // A/B switch (dev)
+    if (main) rc = (order == 1 && bwd_kind == 2) ? launch_nbr_bwd_ul(A, cfg == 1, st) : launch_nbr_mma(A, order, cfg == 1, st);
     if (!rc && wgrad) rc = launch_wgrad_mma(A, order, cfg == 1, gx, st);
   } else if (cfg == 0) rc = order == 1 ? launch_neighbor<128, 64, 32, 1>(A, main, wgrad, gx, st) : launch_neighbor<128, 64, 32, 2>(A, main, wgrad, gx, st);
   else rc = order == 1 ? launch_neighbor<256, 128, 64, 1>(A, main, wgrad, gx, st) : launch_neighbor<256, 128, 64, 2>(A, main, wgrad, gx, st);

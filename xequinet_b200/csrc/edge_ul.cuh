@@ -142,7 +142,7 @@ struct Walk {
   const int* __restrict__ tile_ptr;
   int n_tiles, tile, tstride, rphase, rstride, tile_mode;
   int n0, n1, staged_count;
-  bool valid, staged;
+  bool valid, staged, allow_stage = true;
   int buf, par;
 
   __device__ __forceinline__ void load() {
@@ -154,7 +154,7 @@ struct Walk {
       if (n0 < n1) break;
       tile += tstride;
     }
-    staged = tile_mode == 1 && (n1 - n0) <= WH;
+    staged = allow_stage && tile_mode == 1 && (n1 - n0) <= WH;
     if (staged) {
       buf = staged_count & 1;
       par = (staged_count >> 1) & 1;
@@ -173,6 +173,31 @@ struct Walk {
     load();
   }
 };
+
+// Sum 16 per-thread values over the 32 lanes of a warp: four halving exchanges (each keeps half of the values),
+// then one butterfly.  Lane l returns the total of v[l >> 1].  Fixed tree -> bitwise reproducible.
+__device__ __forceinline__ float warp_sum16(float (&v)[16], int lane) {
+#pragma unroll
+  for (int st = 0; st < 4; ++st) {
+    const int half = 16 >> (st + 1), off = 16 >> st;
+    const bool up = (lane & off) != 0;
+#pragma unroll
+    for (int i = 0; i < half; ++i) {
+      const float send = up ? v[i] : v[i + half];
+      const float keep = up ? v[i + half] : v[i];
+      v[i] = keep + __shfl_xor_sync(0xffffffffu, send, off);
+    }
+  }
+  return v[0] + __shfl_xor_sync(0xffffffffu, v[0], 1);
+}
+__device__ __forceinline__ void named_bar_sync(int id, int threads) {
+  asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(threads) : "memory");
+}
+__device__ __forceinline__ float lds32(uint32_t addr) {
+  float v;
+  asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(addr) : "memory");
+  return v;
+}
 
 }  // namespace ul
 }  // namespace xeq

@@ -218,10 +218,7 @@ def energy_forces_sharded(model, owned: Dict[str, torch.Tensor], rank: int, worl
     out = model(data, compute_forces=False)
     res = {keys.TOTAL_ENERGY: out[keys.TOTAL_ENERGY], keys.ATOMIC_ENERGIES: out[keys.ATOMIC_ENERGIES]}
     if compute_forces:
-        from . import ops
-
-        with ops.param_grads(False):
-            (g,) = torch.autograd.grad([out[keys.TOTAL_ENERGY].sum()], [pos_owned], retain_graph=model.training,
-                                       create_graph=model.training)
+        (g,) = torch.autograd.grad([out[keys.TOTAL_ENERGY].sum()], [pos_owned], retain_graph=model.training,
+                                   create_graph=model.training)
         res[keys.FORCES] = -g
     return res

@@ -18,6 +18,7 @@ from typing import List, Optional, Sequence
 import torch
 
 from . import _lib
+from ._state import input_wanted
 
 _TARGET_CTAS = 148
 
@@ -130,11 +131,12 @@ class _MM(torch.autograd.Function):
         A, B = ctx.saved_tensors
         ta, tb, alpha = ctx.cfg
         gA = gB = gbias = None
-        if ctx.needs_input_grad[0]:
+        # only what this graph task asks for: the force pass (d/dpos) skips every weight / bias gradient
+        if input_wanted(ctx, 0):
             gA = mm(gC, B, False, not tb, alpha=alpha) if not ta else mm(B, gC, tb, True, alpha=alpha)
-        if ctx.needs_input_grad[1]:
+        if input_wanted(ctx, 1):
             gB = mm(A, gC, not ta, False, alpha=alpha) if not tb else mm(gC, A, True, ta, alpha=alpha)
-        if ctx.needs_input_grad[2]:
+        if input_wanted(ctx, 2):
             gbias = colsum(gC)
         return gA, gB, gbias, None, None, None
 
@@ -218,11 +220,11 @@ class _IrrepsLinear(torch.autograd.Function):
         V, w = ctx.saved_tensors
         muls, transposed = ctx.cfg
         gV = gw = gb = None
-        if ctx.needs_input_grad[0]:
+        if input_wanted(ctx, 0):
             gV = _IrrepsLinear.apply(g, w, None, muls, not transposed)
-        if ctx.needs_input_grad[1]:
+        if input_wanted(ctx, 1):
             gw = _IrrepsWgrad.apply(V, g, muls) if not transposed else _IrrepsWgrad.apply(g, V, muls)
-        if ctx.needs_input_grad[2]:
+        if input_wanted(ctx, 2):
             gb = colsum(g[:, : muls[0]])
         return gV, gw, gb, None, None
 
@@ -238,8 +240,8 @@ class _IrrepsWgrad(torch.autograd.Function):
     def backward(ctx, gw):
         A, B = ctx.saved_tensors
         muls = ctx.muls
-        gA = _IrrepsLinear.apply(B, gw, None, muls, True) if ctx.needs_input_grad[0] else None
-        gB = _IrrepsLinear.apply(A, gw, None, muls, False) if ctx.needs_input_grad[1] else None
+        gA = _IrrepsLinear.apply(B, gw, None, muls, True) if input_wanted(ctx, 0) else None
+        gB = _IrrepsLinear.apply(A, gw, None, muls, False) if input_wanted(ctx, 1) else None
         return gA, gB, None
 
 

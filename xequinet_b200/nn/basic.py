@@ -68,9 +68,9 @@ def compute_edge_data(data: Dict[str, torch.Tensor], compute_forces: bool = True
 def compute_forces_only(energy: torch.Tensor, pos: torch.Tensor, training: bool = True) -> torch.Tensor:
     """nn/basic.py:143-159: the backward pass runs K2b (and records K2bb when training)."""
     grad_outputs: List[Optional[torch.Tensor]] = [torch.ones_like(energy)]
-    with ops.param_grads(False):  # only d/dpos is requested here
-        pos_grad = torch.autograd.grad(outputs=[energy], inputs=[pos], grad_outputs=grad_outputs,
-                                       retain_graph=training, create_graph=training, allow_unused=True)[0]
+    # only d/dpos is requested: the backward formulas ask the engine (xequinet_b200/_state.py) and skip weight gradients
+    pos_grad = torch.autograd.grad(outputs=[energy], inputs=[pos], grad_outputs=grad_outputs,
+                                   retain_graph=training, create_graph=training, allow_unused=True)[0]
     if pos_grad is None:
         pos_grad = torch.zeros_like(pos)
     return -1.0 * pos_grad
@@ -84,9 +84,8 @@ def compute_virial_and_forces(energy: torch.Tensor, pos: torch.Tensor, strain: t
                                   "of the cell gradient, which the B200 kernels do not provide yet (inference and "
                                   "non-periodic training are supported)")
     inputs = ([pos] if want_forces else []) + [strain]
-    with ops.param_grads(False):
-        grads = torch.autograd.grad(outputs=[energy], inputs=inputs, grad_outputs=[torch.ones_like(energy)],
-                                    retain_graph=training, create_graph=training, allow_unused=True)
+    grads = torch.autograd.grad(outputs=[energy], inputs=inputs, grad_outputs=[torch.ones_like(energy)],
+                                retain_graph=training, create_graph=training, allow_unused=True)
     grads = [g if g is not None else torch.zeros_like(t) for g, t in zip(grads, inputs)]
     forces = -1.0 * grads[0] if want_forces else None
     return forces, -1.0 * grads[-1]

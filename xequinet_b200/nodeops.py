@@ -8,7 +8,8 @@ from typing import Optional
 import torch
 
 from . import _lib
-from .ops import _ParamGradState, _c, _workspace
+from ._state import input_wanted
+from .ops import _c, _workspace
 
 
 def _norm_ws(n, muls, device):
@@ -63,9 +64,8 @@ class _IrrepsNormBwd(torch.autograd.Function):
         muls, eps = ctx.cfg
         if a is None:
             return None, None, None, None, None, None
-        need = ctx.needs_input_grad
-        dx, dg, dgam = irreps_norm_bwdbwd_raw(x, gamma, g, _c(a), muls, eps, need[0], need[2],
-                                              need[1] and _ParamGradState.wanted)
+        dx, dg, dgam = irreps_norm_bwdbwd_raw(x, gamma, g, _c(a), muls, eps, input_wanted(ctx, 0), input_wanted(ctx, 2),
+                                              input_wanted(ctx, 1))
         return dx, dgam, dg, None, None, None
 
 
@@ -81,7 +81,7 @@ class _IrrepsNorm(torch.autograd.Function):
     def backward(ctx, g):
         x, gamma = ctx.saved_tensors
         muls, eps = ctx.cfg
-        need_params = (ctx.needs_input_grad[1] or ctx.needs_input_grad[2]) and _ParamGradState.wanted
+        need_params = input_wanted(ctx, 1) or input_wanted(ctx, 2)  # not in the force pass (d/dpos only)
         gx, gg, gb = _IrrepsNormBwd.apply(x, gamma, g, muls, eps, need_params)
         return gx, gg, gb, None, None
 

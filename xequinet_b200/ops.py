@@ -52,25 +52,7 @@ def _workspace(nbytes: int, device) -> torch.Tensor:
     return torch.empty(max(int(nbytes), 256), dtype=torch.uint8, device=device)
 
 
-class _ParamGradState:
-    """`ctx.needs_input_grad` is static, so a custom backward cannot see that
-    torch.autograd.grad(E, [pos]) (the force computation, nn/basic.py:150-156) does not ask for
-    parameter gradients.  compute_forces_only() narrows it with this switch so that the
-    force pass runs the cheaper weight-gradient-free K2b instantiation."""
-
-    wanted = True
-
-
-class param_grads:
-    def __init__(self, wanted: bool):
-        self.wanted = wanted
-
-    def __enter__(self):
-        self.prev = _ParamGradState.wanted
-        _ParamGradState.wanted = self.wanted
-
-    def __exit__(self, *exc):
-        _ParamGradState.wanted = self.prev
+from ._state import input_wanted  # noqa: E402
 
 
 class KernelTimer:
@@ -245,15 +227,17 @@ class _EdgeMessage(torch.autograd.Function):
             gx = torch.zeros((s.shape[0], ctx.dims.node_dim), dtype=s.dtype, device=s.device)
         if gV is None:
             gV = torch.zeros((s.shape[0], ctx.dims.D), dtype=s.dtype, device=s.device)
-        need_w = (ni[5] or ni[6] or ni[7]) and _ParamGradState.wanted
-        need_cell = bool(ni[8])
-        needs = (ni[2], ni[3], ni[4] or need_cell, need_w, need_cell)
+        # what this graph task asks for (the force pass of nn/basic.py:150-156 wants d/dpos only: no weight gradients)
+        want = [input_wanted(ctx, i) for i in range(9)]
+        need_w = want[5] or want[6] or want[7]
+        need_cell = want[8]
+        needs = (want[2], want[3], want[4] or need_cell, need_w, need_cell)
         gs = gv = gpos = gW = gb = gf = gcell = None
         if any(needs):
             gs, gv, gpos, gW, gb, gf, gcell = _EdgeMessageBwd.apply(gx, gV, s, v, pos, W, b, freq, ctx.graph, ctx.dims, needs)
             if gf is not None:
                 gf = gf.view_as(freq)
-            if not ni[4]:
+            if not want[4]:
                 gpos = None
         return (gx if ni[0] else None, gV if ni[1] else None, gs, gv, gpos, gW, gb, gf, gcell, None, None)
 
