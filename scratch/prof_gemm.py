@@ -1,13 +1,9 @@
+"""ncu target: a few launches of the K3 GEMM on c3 shapes.  usage: python scratch/prof_gemm.py [n k]"""
 import sys; sys.path.insert(0, ".")
 import torch
 from xequinet_b200 import gemm
-dev = "cuda"
-for (m, n, k) in [(5376, 128, 128), (5376, 576, 128)]:
-    A = torch.randn(m, k, device=dev); W = torch.randn(n, k, device=dev); b = torch.randn(n, device=dev)
-    for _ in range(3):
-        gemm.mm_raw(A, W, False, True, b)
-    torch.cuda.synchronize()
-G = torch.randn(5376, 576, device=dev); X = torch.randn(5376, 128, device=dev)
-for _ in range(3):
-    gemm.mm_raw(G, X, True, False)
+M = 5376
+n, k = (int(sys.argv[1]), int(sys.argv[2])) if len(sys.argv) > 2 else (128, 128)
+A = torch.randn(M, k, device="cuda"); B = torch.randn(n, k, device="cuda")
+for _ in range(5): gemm.mm_raw(A, B, False, True)
 torch.cuda.synchronize()

@@ -22,6 +22,11 @@ void set_error(const char* fmt, ...) {
   va_end(ap);
 }
 
+bool pdl_enabled() {
+  static const bool on = [] { const char* e = getenv("XEQ_PDL"); return !(e && e[0] == '0'); }();
+  return on;
+}
+
 int num_sms() {
   static thread_local int cached_dev = -1, cached = 0;
   int dev = 0;

@@ -222,6 +222,7 @@ __device__ __forceinline__ float silu(float x) { return x / (1.f + __expf(-x)); 
 
 __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tf32x3_kernel(const __grid_constant__ GemmArgs args) {
   extern __shared__ unsigned char gemm_smem_raw[];
+  pdl_trigger();  // the next kernel of the stream may be staged now (it waits for this grid before reading memory)
   // which problem / column pass
   int pi = 0;
   while (pi + 1 < args.n_problems && (int)blockIdx.y >= args.p[pi + 1].pass_begin) ++pi;
@@ -248,17 +249,18 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tf32x3_kernel(const __gr
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   const uint32_t bias_s = bar0 + 64;  // this pass's bias values (zeros when there is none)
-  if (tid < pn) {
-    const int col = n0 + tid;
-    const float bv = (P.bias && !args.use_partials && col < P.n) ? __ldg(P.bias + col) : 0.f;
-    asm volatile("st.shared.f32 [%0], %1;" ::"r"(bias_s + 4u * tid), "f"(bv) : "memory");
-  }
   // two accumulators of pn columns each; allocations are powers of two >= 32
   uint32_t tmem_cols = 32;
   while ((int)tmem_cols < 2 * pn) tmem_cols <<= 1;
   if (warp == 0) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"(tmem_cols) : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  pdl_wait();  // everything above overlapped the tail of the previous kernel; its results are visible from here on
+  if (tid < pn) {
+    const int col = n0 + tid;
+    const float bv = (P.bias && !args.use_partials && col < P.n) ? __ldg(P.bias + col) : 0.f;
+    asm volatile("st.shared.f32 [%0], %1;" ::"r"(bias_s + 4u * tid), "f"(bv) : "memory");
   }
   asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
@@ -392,9 +394,13 @@ __global__ void gemm_reduce_kernel(const __grid_constant__ ReduceArgs args) {
   }
 }
 
-int pass_width(int n) {
+// columns per pass: at most MAX_PASS_N, and narrower when the launch would otherwise leave SMs idle (`fill` = how many
+// times more CTAs the machine can hold: M = 5376, N = 128 is 42 CTAs of 128 x 128 -- three passes of 48 columns put
+// 126 CTAs on the 148 SMs and cut the serial K loop + epilogue of every CTA)
+int pass_width(int n, int fill) {
   const int n16 = (n + 15) / 16 * 16;
-  const int np = (n16 + MAX_PASS_N - 1) / MAX_PASS_N;
+  int np = (n16 + MAX_PASS_N - 1) / MAX_PASS_N;
+  np = max(np, min(np * max(fill, 1), n16 / 16));
   return ((n16 + np - 1) / np + 15) / 16 * 16;
 }
 
@@ -454,6 +460,10 @@ int xeq_gemm_tf32x3(const xeq_gemm_t* problems, int32_t n_problems, int32_t spli
   args.partials = static_cast<float*>(workspace);
   int passes = 0, max_m = 0;
   size_t part = 0;  // in floats; slabs of consecutive problems are contiguous (needed by the grouped reduction)
+  long long base_ctas = 0;
+  for (int i = 0; i < n_problems; ++i)
+    base_ctas += (long long)((problems[i].m + TILE_M - 1) / TILE_M) * ((problems[i].n + MAX_PASS_N - 1) / MAX_PASS_N) * split_k;
+  const int fill = base_ctas > 0 ? (int)(num_sms() / base_ctas) : 1;
   for (int i = 0; i < n_problems; ++i) {
     const xeq_gemm_t& p = problems[i];
     XEQ_CHECK_ARG(!partials || p.act == 0, "gemm[%d]: activation is not available with partial sums", i);
@@ -463,7 +473,7 @@ int xeq_gemm_tf32x3(const xeq_gemm_t* problems, int32_t n_problems, int32_t spli
     q.lda = p.lda; q.ldb = p.ldb; q.ldc = p.ldc;
     q.a_trans = p.a_trans; q.b_trans = p.b_trans;
     q.alpha = p.alpha; q.act = p.act;
-    q.pass_n = pass_width(p.n);
+    q.pass_n = pass_width(p.n, fill);
     q.pass_begin = passes;
     q.part_off = part;
     passes += (p.n + q.pass_n - 1) / q.pass_n;
@@ -476,7 +486,7 @@ int xeq_gemm_tf32x3(const xeq_gemm_t* problems, int32_t n_problems, int32_t spli
     XEQ_CUDA(cudaFuncSetAttribute(gemm_tf32x3_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM));
   }
   dim3 grid((max_m + TILE_M - 1) / TILE_M, passes, split_k);
-  gemm_tf32x3_kernel<<<grid, GEMM_THREADS, GEMM_SMEM, st>>>(args);
+  XEQ_CUDA(launch_pdl(gemm_tf32x3_kernel, grid, dim3(GEMM_THREADS), (size_t)GEMM_SMEM, st, args));
   XEQ_LAUNCHED(1);
   if (partials) {
     ReduceArgs red;
