@@ -223,7 +223,7 @@ def edge_throughput_probe(cfg, dev, peak, n_mol=8192, reps=10):
         torch.cuda.synchronize()
         ms = t0.elapsed_time(t1) / reps
         achieved = algorithmic_bytes("edge_fwd", cfg, N, E, False) / (ms * 1e-3) / 1e9
-        return {"kernel": "edge_fwd", "launch": "xeq_edge_message_fwd: center_fwd_kernel", "bound": "hbm",
+        return {"kernel": "edge_fwd", "launch": "xeq_edge_message_fwd: pack_fwd_kernel + center_fwd_ul_kernel", "bound": "hbm",
                 "achieved": round(achieved, 2), "peak": peak, "unit": "GB/s", "frac": round(achieved / peak, 5),
                 "n_nodes": N, "n_edges": E, "mean_launch_ms": round(ms, 4),
                 "working_set": f"{n_mol} aspirin-shaped molecules: node rows {4 * N * (dims.H + 2 * dims.D + 2 * dims.node_dim) / 1e9:.2f} GB >> L2"}
@@ -270,6 +270,8 @@ def run_gpu(args):
         for p in params:
             p.requires_grad_(False)
     opt = torch.optim.AdamW(params, lr=5e-4, fused=True) if train else None
+    # N > 1: one flat gradient buffer (every p.grad is a view), bucketed all-reduce overlapped with the backward pass
+    flat = parallel.FlatGradients(params, n_buckets=3) if (train and world > 1) else None
     transform = xb.NeighborTransform(cfg.cutoff)
 
     # distinct synthetic batches per rank, pinned on the host
@@ -298,6 +300,7 @@ def run_gpu(args):
         for a, b in zip(resident, own_res):
             a["_owned"] = b
         energy_host = torch.zeros(1).pin_memory()
+        forces_own_host = torch.zeros(own_host[0]["pos"].shape).pin_memory()
 
     def step_sharded(batch, e2e: bool):
         o = batch["_owned"]
@@ -308,6 +311,7 @@ def run_gpu(args):
         dist.all_reduce(e_tot)  # total energy of the box (forces stay sharded)
         if e2e:
             energy_host.copy_(e_tot, non_blocking=True)
+            forces_own_host.copy_(out["forces"], non_blocking=True)  # this rank's share of the forces
         return e_tot
 
     def step(batch, e2e: bool):
@@ -321,10 +325,13 @@ def run_gpu(args):
         out = model(d, compute_forces=forces)
         if train:
             loss = loss_fn(out, d, forces)
-            opt.zero_grad(set_to_none=True)
-            loss.backward()
-            if world > 1:
-                parallel.allreduce_gradients(params)  # NCCL over NVLink; 3.5 MB -> latency bound, one flat bucket
+            if flat is not None:
+                flat.zero()
+            else:
+                opt.zero_grad(set_to_none=True)
+            loss.backward()  # N > 1: buckets are all-reduced (NCCL over NVLink) as their last gradient is written
+            if flat is not None:
+                flat.finish()
             opt.step()
             result = loss.detach()
             if e2e:
@@ -333,76 +340,49 @@ def run_gpu(args):
             result = out["energy"]
             if e2e:
                 energy_host.copy_(result.detach(), non_blocking=True)
+                if forces:
+                    forces_host.copy_(out["forces"], non_blocking=True)  # the metric is energy + forces
         return result
 
     flush_buf = torch.empty(256 * 1024 * 1024 // 4, dtype=torch.float32, device=dev)  # > 126 MB L2
 
-    # ---- CUDA-graph replay of the whole step (K1 in capacity mode + model + loss + backward + AdamW):
-    # static input buffers, one captured graph, no host synchronisation inside the step.
-    # a captured graph needs one static batch structure: workloads whose batches differ in size (c4:
-    # 30..70 atoms per molecule) are replayed eagerly
+    # ---- CUDA-graph replay of the whole step (xequinet_b200.replay.CapturedStep: K1 in capacity mode + model + loss
+    # + backward + gradient all-reduce + AdamW captured once; static input buffers, no host work inside the step;
+    # tests/test_gpu_bench_shapes.py checks replay == eager bit for bit).  A captured graph needs one static batch
+    # structure: workloads whose batches differ in size (c4: 30..70 atoms per molecule) are replayed eagerly.
     same_shape = all(d["pos"].shape == resident[0]["pos"].shape and torch.equal(d["ptr"], resident[0]["ptr"]) for d in resident)
     use_graph = (not args.eager) and same_shape and not sharded  # the halo plan has host-synchronised counts
     graph_step = None
+    forces_host = torch.zeros(host[0]["pos"].shape).pin_memory() if (forces and not train) else None
+    copied_keys = list(h2d_keys)
     if use_graph:
-        from xequinet_b200.graph import StaticGraphBuilder, build_graph
-        from xequinet_b200 import keys as K
+        from xequinet_b200.graph import build_graph
+        from xequinet_b200.replay import CapturedStep
         e_max = 0
         for d in resident:
             g_dyn, _, _ = build_graph(d["pos"], cfg.cutoff, ptr=d["ptr"], batch=d["batch"], cell=d.get("cell"), pbc=d.get("pbc"))
             e_max = max(e_max, g_dyn.n_edges)
-        cap = int(e_max * 1.15) + 1024
-        static = {k: resident[0][k].clone() for k in h2d_keys}
-        builder = StaticGraphBuilder(static["pos"].shape[0], static["ptr"], cfg.cutoff, cap, cell=static.get("cell"),
-                                     pbc=static.get("pbc"))
         if train:
             opt = torch.optim.AdamW(params, lr=5e-4, fused=True, capturable=True)
-        result_buf = {}
-
-        def body():
-            d = {k: static[k] for k in h2d_keys if k not in ("cell", "pbc")}
-            if "cell" in static:
-                d["cell"] = static["cell"]
-            d[K.GRAPH] = builder.build(static["pos"])
-            out = model(d, compute_forces=forces)
-            if train:
-                loss = loss_fn(out, d, forces)
-                loss.backward()
-                if world > 1:
-                    parallel.allreduce_gradients(params)
-                opt.step()
-                result_buf["r"] = loss.detach()
-            else:
-                result_buf["r"] = out["energy"].detach()
-
-        side = torch.cuda.Stream()
-        side.wait_stream(torch.cuda.current_stream())
-        with torch.cuda.stream(side):
-            for _ in range(3):
-                if train:
-                    opt.zero_grad(set_to_none=True)
-                static["pos"].grad = None
-                body()
-        torch.cuda.current_stream().wait_stream(side)
-        torch.cuda.synchronize()
-        cuda_graph = torch.cuda.CUDAGraph()
-        if train:
-            opt.zero_grad(set_to_none=True)
-        static["pos"].grad = None
-        with torch.cuda.graph(cuda_graph):
-            body()
-        torch.cuda.synchronize()
+        captured = CapturedStep(model, {k: resident[0][k] for k in h2d_keys}, compute_forces=forces,
+                                loss_fn=(lambda out, d: loss_fn(out, d, forces)) if train else None, optimizer=opt,
+                                flat_grads=flat, edge_capacity=int(e_max * 1.15) + 1024, input_keys=h2d_keys)
+        copied_keys = [k for k in h2d_keys if k not in ("ptr", "batch", "pbc")]  # the batch structure is static
+        if not train:  # the timed path gives the eager result, bit for bit
+            ref = {k: v.clone() for k, v in captured.eager(resident[0]).items()}
+            got = captured(resident[0])
+            assert all(torch.equal(got[k], ref[k]) for k in ref), "CUDA-graph replay differs from the eager step"
 
         def graph_step(batch, e2e: bool):
-            with torch.no_grad():
-                for k in h2d_keys:
-                    if k in ("ptr", "batch", "pbc"):
-                        continue  # batch structure is static for a captured graph
-                    static[k].copy_(batch[k], non_blocking=True)
-            cuda_graph.replay()
-            r = result_buf["r"]
+            out = captured(batch)  # H2D of the step's inputs (pinned host -> static buffers) + one graph launch
+            r = out["loss"] if train else out["energy"]
             if e2e:
-                (loss_host if train else energy_host).copy_(r.reshape(-1), non_blocking=True)
+                if train:
+                    loss_host.copy_(r.reshape(-1), non_blocking=True)
+                else:
+                    energy_host.copy_(r.reshape(-1), non_blocking=True)
+                    if forces:
+                        forces_host.copy_(out["forces"], non_blocking=True)
             return r
 
     def barrier():
@@ -444,21 +424,24 @@ def run_gpu(args):
     if use_graph:
         total_ms, _ = timed(False, args.steps, args.warmup, False, graph_step)
         e2e_ms, _ = timed(True, args.steps, max(3, args.warmup // 2), False, graph_step)
-        overflow = int(builder.overflow.item())
-        assert overflow == 0, "edge capacity of the captured graph exceeded"
+        captured.check()  # edge capacity of the captured graph never exceeded
         # kernel-level timings and the launch count come from an eager replica of the same step
         if train:
             opt = torch.optim.AdamW(params, lr=5e-4, fused=True)
-        _, launches = timed(False, min(args.steps, 5), 3, True)
-        launches = launches * args.steps // min(args.steps, 5)
         kern_steps = min(args.steps, 5)
+        _lib.start_profile()
+        eager_ms, launches = timed(False, kern_steps, 3, True)
+        calls = _lib.stop_profile()
+        kern = ops.KernelTimer.summary()
+        launches = launches * args.steps // kern_steps
     else:
+        kern_steps = args.steps
+        _lib.start_profile()
         total_ms, launches = timed(False, args.steps, args.warmup, True)
+        calls = _lib.stop_profile()
+        eager_ms = total_ms
         kern = ops.KernelTimer.summary()  # before the next timed() call clears the records
         e2e_ms, _ = timed(True, args.steps, max(3, args.warmup // 2), False)
-        kern_steps = args.steps
-    if use_graph:
-        kern = ops.KernelTimer.summary()
     if sampler:
         sampler.stop_flag.set()
         sampler.join(timeout=2)
@@ -471,10 +454,11 @@ def run_gpu(args):
     ms_per_step = total_ms / args.steps
     value = mols_per_step / (ms_per_step * 1e-3)
     e2e_value = mols_per_step / (e2e_ms / args.steps * 1e-3)
-    h2d = sum(host[0][k].numel() * host[0][k].element_size() for k in h2d_keys)
+    h2d = sum(host[0][k].numel() * host[0][k].element_size() for k in copied_keys)  # what a step really copies
+    d2h = 4 if train else energy_host.numel() * 4 + (forces_host.numel() * 4 if forces else 0)
     if sharded:
         h2d = sum(host[0]["_owned"][k].numel() * host[0]["_owned"][k].element_size() for k in ("pos", "atomic_numbers", "cell"))
-    d2h = 4 if train else energy_host.numel() * 4
+        d2h = 4 + forces_own_host.numel() * 4
 
     def hard_exit():
         # NCCL teardown with captured graphs alive can hang; all timed work is done, so leave
@@ -504,13 +488,37 @@ def run_gpu(args):
         cnt, mean_ms, N, E = kern[dom]
         achieved = algorithmic_bytes(dom, cfg, N, E, periodic) / (mean_ms * 1e-3) / 1e9
         traffic = NCU_TRAFFIC_C3.get(dom) if (args.workload == "c3" and N == 5376) else None
-        launch_of = {"edge_fwd": "xeq_edge_message_fwd: center_fwd_kernel",
-                     "edge_bwd": "xeq_edge_message_bwd: nbr_mma_kernel<1> + pos_grad",
-                     "edge_bwd_wgrad": "xeq_edge_message_bwd with weight gradients: nbr_mma_kernel<1> + wgrad_mma_kernel<1> + reductions",
+        launch_of = {"edge_fwd": "xeq_edge_message_fwd: pack_fwd_kernel + center_fwd_ul_kernel",
+                     "edge_bwd": "xeq_edge_message_bwd: nbr_bwd_ul_kernel + pos_grad",
+                     "edge_bwd_wgrad": "xeq_edge_message_bwd with weight gradients: nbr_bwd_ul_kernel + wgrad_mma_kernel<1> + reductions",
                      "edge_bwdbwd": "xeq_edge_message_bwdbwd: center_mma_kernel<jvp> + nbr_mma_kernel<2> + wgrad_mma_kernel<2> + reductions"}
         roofline = {"kernel": dom, "launch": launch_of.get(dom), "bound": "hbm", "achieved": round(achieved, 2), "peak": peak, "unit": "GB/s",
                     "frac": round(achieved / peak, 5), "traffic": traffic, "peak_source": peak_src,
                     "n_nodes": N, "n_edges": E, "mean_launch_ms": round(mean_ms, 5)}
+
+    # step shares by kernel group (C-ABI entry points bracketed by CUDA events in the eager replica of the step; what
+    # is left is torch's own elementwise / optimizer / NCCL kernels and launch gaps) and the tensor-pipe roofline of K3
+    group_of = lambda n: ("edge" if n.startswith("xeq_edge") else "gemm" if n.startswith("xeq_gemm") else
+                          "graph" if (n.startswith("xeq_radius") or n.startswith("xeq_csr")) else "node")
+    groups = {}
+    for name, (cnt, ms, fl) in calls.items():
+        c, t, f = groups.get(group_of(name), (0, 0.0, 0.0))
+        groups[group_of(name)] = (c + cnt, t + ms, f + fl)
+    eager_step_ms = eager_ms / kern_steps
+    step_shares = {k: {"calls_per_step": round(c / kern_steps, 1), "ms_per_step": round(t / kern_steps, 4),
+                       "share_of_eager_step": round(t / kern_steps / eager_step_ms, 4)} for k, (c, t, f) in sorted(groups.items())}
+    step_shares["torch_and_gaps"] = {"ms_per_step": round(eager_step_ms - sum(t for _, t, _ in groups.values()) / kern_steps, 4)}
+    step_shares["eager_step_ms"] = round(eager_step_ms, 4)
+    roofline_tensor = None
+    if "gemm" in groups and groups["gemm"][1] > 0:
+        c, t, f = groups["gemm"]
+        tf32_peak = json.loads((ROOT / "MEASURED_PEAKS.json").read_text())["bf16_tflops"] / 2 if (ROOT / "MEASURED_PEAKS.json").exists() else 1590.0 / 2
+        achieved = 3.0 * f / (t * 1e-3) / 1e12  # three TF32 products per fp32 product
+        roofline_tensor = {"kernel": "gemm_tf32x3_kernel (K3: nn.Linear / o3.Linear and their derivatives)", "bound": "tensor",
+                           "achieved": round(achieved, 2), "peak": round(tf32_peak, 1), "unit": "TFLOP/s", "frac": round(achieved / tf32_peak, 5),
+                           "peak_source": "MEASURED_PEAKS.json bf16 burst / 2 (kind::tf32 runs at half the bf16 rate)",
+                           "fp32_equivalent_TFLOP_s": round(achieved / 3.0, 2), "launches_per_step": round(c / kern_steps, 1),
+                           "mean_launch_us": round(t / c * 1e3, 2)}
 
     # the fused edge forward kernel with a working set >> L2 (SURVEY.md 8d "throughput mode"), default widths only
     roofline_throughput = edge_throughput_probe(cfg, dev, peak) if (cfg is orc.CONFIG_DEFAULT and world == 1) else None
@@ -530,13 +538,15 @@ def run_gpu(args):
                    "atoms_per_gpu": int(host[0]["pos"].shape[0]), "l2": "flushed between timed steps (256 MB write, untimed)",
                    "parallelism": (f"dp{world}" if args.workload != "c5" else
                                    (f"spatial slabs x{world} + halo exchange (NCCL all-to-all)" if sharded else "single GPU")),
-                   "execution": "whole step replayed as one CUDA graph (K1 in capacity mode)" if use_graph else
+                   "execution": "whole step replayed as one CUDA graph (xequinet_b200.replay.CapturedStep, K1 in capacity mode)" if use_graph else
                                 ("eager launches" if args.eager else "eager launches (batch shapes vary: no static graph)")},
         "e2e": {"value": round(e2e_value, 2), "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h)},
         "gpu_launches": int(launches),
         "roofline": roofline,
         "roofline_throughput": roofline_throughput,
+        "roofline_tensor": roofline_tensor,
         "kernels": kernels,
+        "step_shares": step_shares,
         "cpu_baseline": {"value": round(cpu_val, 3), "unit": UNIT, "cores": os.cpu_count(), "kind": "port",
                          "sample": f"CPU oracle (oracle/xpainn_oracle.py), {cpu_sample}, {round(cpu_ms, 1)} ms/step, 2 timed steps"},
         "clocks": sampler.summary() if sampler else None,

@@ -31,7 +31,7 @@ def test_state_dict_layout_matches_reference(cfg):
         assert tuple(sd[name].shape) == shape, name
     learnable = {n for n, _ in model.named_parameters()}
     assert learnable == {n for n, _, _ in spec}
-    assert sum(p.numel() for p in model.parameters()) == (865141 if cfg is orc.CONFIG_DEFAULT else sum(p.numel() for p in model.parameters()))
+    assert sum(p.numel() for p in model.parameters()) == (865141 if cfg is orc.CONFIG_DEFAULT else 3339861)
     # e3nn-internal buffers keep their reference names
     for k in ("mods.message_0.o3norm.scalar_index", "mods.update_0.update_U.output_mask",
               "mods.update_0.invariant.tp.weight", "mods.message_0.rsh_conv.output_mask",
@@ -39,6 +39,33 @@ def test_state_dict_layout_matches_reference(cfg):
         assert k in sd
     res = model.load_state_dict(orc.synthetic_state_dict(cfg), strict=False)
     assert not res.unexpected_keys
+
+
+@pytest.mark.parametrize("name,cfg", [("default", orc.CONFIG_DEFAULT), ("c4", orc.CONFIG_C4)])
+def test_state_dict_strict_round_trip(name, cfg):
+    """tests/golden/state_dict_keys.json = the (name, shape, dtype) list of the REAL reference model's state_dict, in
+    its own order (oracle/make_golden_state_dict.py; 137 entries incl. the e3nn-internal buffers).  A state_dict of
+    exactly that shape loads with strict=True, and what this model saves has exactly those entries."""
+    import json
+    from pathlib import Path
+
+    spec = json.loads((Path(__file__).resolve().parent / "golden" / "state_dict_keys.json").read_text())[name]
+    assert len(spec) == 137
+    g = torch.Generator().manual_seed(0)
+    ref_shaped = {}
+    for k, shape, dtype in spec:
+        dt = getattr(torch, dtype)
+        ref_shaped[k] = (torch.randn(*shape, generator=g, dtype=dt) if dt.is_floating_point
+                         else torch.arange(shape[0], dtype=dt) if shape else torch.zeros((), dtype=dt))
+    model = xb.resolve_model("xpainn", **cfg.model_kwargs())
+    res = model.load_state_dict(ref_shaped, strict=True)
+    assert not res.missing_keys and not res.unexpected_keys
+    saved = model.state_dict()
+    assert [[k, list(v.shape), str(v.dtype).replace("torch.", "")] for k, v in saved.items()] == spec
+    for k, v in saved.items():
+        assert torch.equal(v, ref_shaped[k]), k
+    twin = xb.resolve_model("xpainn", **cfg.model_kwargs())
+    twin.load_state_dict(saved, strict=True)
 
 
 def test_defaults_and_unsupported_options():

@@ -97,7 +97,61 @@ def get():
             fn = getattr(lib, name)
             fn.restype, fn.argtypes = res, args
         _lib = lib
-    return _lib
+    return _lib if _profiler is None else _profiler
+
+
+# ---------------------------------------------------------------------------------------------------------
+# per-entry-point device timing (bench.py: step shares by kernel group, tensor-pipe roofline of K3)
+# ---------------------------------------------------------------------------------------------------------
+_UNTIMED = {"xeq_version", "xeq_last_error", "xeq_num_sms", "xeq_launch_count", "xeq_center_tile_edges", "xeq_neighbor_tile_edges"}
+
+
+class _Profiled:
+    """Proxy of the loaded library that brackets every launching entry point with CUDA events on the current stream.
+    Only installed between start_profile() / stop_profile(); the product path calls the library directly."""
+
+    def __init__(self, lib):
+        self._lib = lib
+        self.records = []  # (entry point, start event, end event, flops)
+
+    def __getattr__(self, name):
+        fn = getattr(self._lib, name)
+        if name in _UNTIMED or name.endswith("_workspace_bytes"):
+            return fn
+
+        def timed(*args):
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            rc = fn(*args)
+            b.record()
+            flops = 0.0
+            if name == "xeq_gemm_tf32x3":  # (problems, n_problems, ...): 2 m n k per problem
+                flops = float(sum(2.0 * args[0][i].m * args[0][i].n * args[0][i].k for i in range(int(args[1]))))
+            self.records.append((name, a, b, flops))
+            return rc
+
+        return timed
+
+
+_profiler = None
+
+
+def start_profile():
+    global _profiler
+    _profiler = None
+    _profiler = _Profiled(get())
+
+
+def stop_profile():
+    """{entry point: (calls, total ms, total flops)}; synchronises the device."""
+    global _profiler
+    prof, _profiler = _profiler, None
+    torch.cuda.synchronize()
+    out = {}
+    for name, a, b, fl in (prof.records if prof else []):
+        c, t, f = out.get(name, (0, 0.0, 0.0))
+        out[name] = (c + 1, t + a.elapsed_time(b), f + fl)
+    return out
 
 
 def check(rc: int, what: str):

@@ -50,7 +50,9 @@ __device__ __forceinline__ void split_tf32(float x, uint32_t& hi, uint32_t& lo) 
 // tensor core ignores the 13 low mantissa bits of lo, a relative error of 2^-21 of x.
 __device__ __forceinline__ void split_fast(float x, uint32_t& hi, uint32_t& lo) {
   hi = (__float_as_uint(x) + 0x1000u) & 0xffffe000u;
-  lo = __float_as_uint(x - __uint_as_float(hi));
+  // lo = x - hi is exact (<= 13 significant bits); round it to the 11 the tensor core keeps instead of letting the
+  // hardware truncate: hi + lo then represents x to 2^-23 (round to nearest) instead of 2^-22
+  lo = (__float_as_uint(x - __uint_as_float(hi)) + 0x1000u) & 0xffffe000u;
 }
 
 // K-major SWIZZLE_128B shared-memory matrix descriptor (same encoding as node_gemm.cu)

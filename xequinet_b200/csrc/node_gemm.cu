@@ -31,7 +31,7 @@ constexpr int A_TILE_BYTES = TILE_M * 128;
 constexpr int B_TILE_BYTES = MAX_PASS_N * 128;
 constexpr int STAGE_BYTES = 2 * A_TILE_BYTES + 2 * B_TILE_BYTES;  // hi + lo of both operands
 constexpr int GEMM_SMEM = 2 * STAGE_BYTES + 1024 /* alignment slack */ + 64 /* barriers, tmem slot */ + MAX_PASS_N * 4 /* bias */;
-// TMEM: [0, pn): sum of a_hi*b_hi;  [pn, 2 pn): sum of the correction terms (pn = columns of the pass)
+// TMEM: nacc x [pn columns]: sums of a_hi*b_hi, k steps dealt round-robin;  then [pn]: sum of the correction terms
 constexpr int MAX_PROBLEMS = 20;
 
 struct Problem {
@@ -74,7 +74,9 @@ __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)_
 // bits by an integer add, lo = x - hi exactly; the tensor core ignores the 13 low mantissa bits of lo
 __device__ __forceinline__ void split_fast(float x, uint32_t& hi, uint32_t& lo) {
   hi = (__float_as_uint(x) + 0x1000u) & 0xffffe000u;
-  lo = __float_as_uint(x - __uint_as_float(hi));
+  // lo = x - hi is exact (<= 13 significant bits); round it to the 11 the tensor core keeps instead of letting the
+  // hardware truncate: hi + lo then represents x to 2^-23 (round to nearest) instead of 2^-22
+  lo = (__float_as_uint(x - __uint_as_float(hi)) + 0x1000u) & 0xffffe000u;
 }
 __device__ __forceinline__ uint32_t elect_one() {  // one lane of a converged warp
   uint32_t pred;
@@ -218,7 +220,7 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
       : "memory");
 }
 
-__device__ __forceinline__ float silu(float x) { return x / (1.f + __expf(-x)); }
+__device__ __forceinline__ float silu(float x) { return x / (1.f + expf(-x)); }
 
 __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tf32x3_kernel(const __grid_constant__ GemmArgs args) {
   extern __shared__ unsigned char gemm_smem_raw[];
@@ -249,9 +251,10 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tf32x3_kernel(const __gr
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   const uint32_t bias_s = bar0 + 64;  // this pass's bias values (zeros when there is none)
-  // two accumulators of pn columns each; allocations are powers of two >= 32
+  // nacc main accumulators + one for the correction terms, pn columns each; allocations are powers of two >= 32
+  const int nacc = max(1, min(4, 512 / pn - 1));
   uint32_t tmem_cols = 32;
-  while ((int)tmem_cols < 2 * pn) tmem_cols <<= 1;
+  while ((int)tmem_cols < (nacc + 1) * pn) tmem_cols <<= 1;
   if (warp == 0) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"(tmem_cols) : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
@@ -267,6 +270,7 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tf32x3_kernel(const __gr
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
   uint32_t tmem_base;
   asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot) : "memory");
+  const uint32_t tmem_corr = tmem_base + (uint32_t)(nacc * pn);
 
   // instruction descriptor: D = f32 (bits 4-5 = 1), A = B = tf32 (2 at bits 7-9 / 10-12), both K-major,
   // N >> 3 at bits 17-22, M >> 4 at bits 24-28
@@ -300,11 +304,15 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tf32x3_kernel(const __gr
       for (int ks = 0; ks < nks; ++ks) {
         const uint64_t da_hi = smem_desc(sa_hi + ks * 32), da_lo = smem_desc(sa_lo + ks * 32);
         const uint64_t db_hi = smem_desc(sb_hi + ks * 32), db_lo = smem_desc(sb_lo + ks * 32);
-        // the correction terms (2^-11 of the main term) get their own accumulator, so the rounding of the
-        // large running sum happens once per k step instead of three times; the epilogue adds the two
-        mma_tf32(tmem_base + pn, da_lo, db_hi, idesc, (i | ks) ? 1u : 0u);
-        mma_tf32(tmem_base + pn, da_hi, db_lo, idesc, 1u);
-        mma_tf32(tmem_base, da_hi, db_hi, idesc, (i | ks) ? 1u : 0u);
+        // the tensor core ROUNDS TOWARD ZERO when it adds a k step to the accumulator (measured: scratch/gemm_bias.py,
+        // K = 704 sums of positive terms come out 4.8e-6 low = 88 steps x 2^-24): the main products rotate over
+        // `nacc` accumulators (each sees 1 / nacc of the steps at 1 / nacc of the magnitude), the 2^-11 correction
+        // terms share one; the epilogue adds them in fp32 with round-to-nearest
+        const uint32_t acc = tmem_base + (uint32_t)((i * (KB / 8) + ks) % nacc) * (uint32_t)pn;
+        const uint32_t first = (i * (KB / 8) + ks) < nacc ? 0u : 1u;
+        mma_tf32(tmem_corr, da_lo, db_hi, idesc, (i | ks) ? 1u : 0u);
+        mma_tf32(tmem_corr, da_hi, db_lo, idesc, 1u);
+        mma_tf32(acc, da_hi, db_hi, idesc, first);
       }
       umma_commit(bar0 + 8 * s);  // implies tcgen05.fence::before_thread_sync
     }
@@ -331,11 +339,15 @@ __global__ void __launch_bounds__(GEMM_THREADS, 1) gemm_tf32x3_kernel(const __gr
     uint32_t r[16], rc[16];
     const uint32_t taddr = tmem_base + ((uint32_t)(32 * (warp & 3)) << 16) + (uint32_t)(ch * 16);
     if (nkb > 0) {
+      const int ksteps = (min(P.k, kb_end * KB) - kb_begin * KB + 7) / 8;  // k steps this CTA issued
+      const int nused = min(nacc, ksteps);                                   // accumulators that received one
       tmem_ld16(taddr, r);
-      tmem_ld16(taddr + pn, rc);
-      asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+      for (int a = 1; a <= nused; ++a) {  // a == nused: the correction accumulator
+        tmem_ld16(a < nused ? taddr + (uint32_t)(a * pn) : taddr + (uint32_t)(nacc * pn), rc);
+        asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 #pragma unroll
-      for (int j = 0; j < 16; ++j) r[j] = __float_as_uint(__uint_as_float(r[j]) + __uint_as_float(rc[j]));
+        for (int j = 0; j < 16; ++j) r[j] = __float_as_uint(__uint_as_float(r[j]) + __uint_as_float(rc[j]));
+      }
     } else {
 #pragma unroll
       for (int j = 0; j < 16; ++j) r[j] = 0u;

@@ -63,7 +63,7 @@ __device__ __forceinline__ void center_and_scale(const float* __restrict__ xr, i
     if (i < S.m0) z[k] -= mu;
     ss += z[k] * z[k];
   }
-  rho = rsqrtf(warp_sum(ss) / (float)S.M + S.eps);
+  rho = 1.f / sqrtf(warp_sum(ss) / (float)S.M + S.eps);  // IEEE sqrt + divide: the approximate rsqrt (2 ulp) scales a whole row
 }
 
 template <int NK>
