@@ -425,15 +425,18 @@ def _edge_outputs(n_mol, staged):
 
 @pytest.mark.parametrize("staged", [True, False], ids=["molecule-tiles", "edge-block-tiles"])
 def test_tcgen05_and_simt_edge_kernels_agree(staged, tmp_path):
-    """The tensor-core kernels (edge_message_mma.cu, edge_fwd_mma.cu) against the SIMT kernels (edge_message.cu,
-    run in a subprocess with XEQ_EDGE_SIMT=1): same results to fp32 round-off on every output."""
+    """The tensor-core kernels of the product library (edge_fwd_ul.cu, edge_bwd_ul.cu, edge_message_mma.cu) against an
+    independent implementation: the round-1 SIMT kernels, compiled only into the test-only libxeq_b200_simt.so and run
+    in a subprocess (XEQ_LIB + XEQ_EDGE_SIMT=1).  Same results to fp32 round-off on every output."""
     import os, subprocess, sys
     from pathlib import Path
 
     root = Path(__file__).resolve().parent.parent
     ref_file = tmp_path / "simt.pt"
     script = _SIMT_SCRIPT.format(root=str(root), tests=str(root / "tests"), n_mol=40, staged=staged, out=str(ref_file))
-    env = dict(os.environ, XEQ_EDGE_SIMT="1")
+    simt_lib = root / "xequinet_b200" / "libxeq_b200_simt.so"  # test-only build (xequinet_b200/build.py --simt)
+    assert simt_lib.exists(), "build the test-only SIMT variant: python xequinet_b200/build.py --simt"
+    env = dict(os.environ, XEQ_EDGE_SIMT="1", XEQ_LIB=str(simt_lib))
     subprocess.run([sys.executable, "-c", script], check=True, env=env, timeout=300)
     ref = torch.load(ref_file)
     got = _edge_outputs(40, staged)

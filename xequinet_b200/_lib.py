@@ -10,7 +10,10 @@ from pathlib import Path
 
 import torch
 
-LIB_PATH = Path(__file__).resolve().parent / "libxeq_b200.so"
+import os
+
+# XEQ_LIB: load another build of the same C ABI (the test-only SIMT variant, a debug build); default = the product library
+LIB_PATH = Path(os.environ.get("XEQ_LIB") or (Path(__file__).resolve().parent / "libxeq_b200.so"))
 
 
 class XeqDims(ctypes.Structure):

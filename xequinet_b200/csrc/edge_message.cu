@@ -22,6 +22,7 @@
 
 namespace xeq {
 
+#ifdef XEQ_WITH_SIMT  // SIMT filter contraction: TEST-ONLY build (libxeq_b200_simt.so, tests/test_gpu_parity.py A/B check)
 // ==========================================================================================
 // center kernel
 // ==========================================================================================
@@ -585,6 +586,8 @@ __global__ void __launch_bounds__(WTHREADS) nbr_wgrad_kernel(const NeighborArgs 
   else nbr_wgrad_role<0, ROLE_SCALAR, C, M1, M2, ORDER>(A, sm);
 }
 
+#endif  // XEQ_WITH_SIMT
+
 // gpos[n] = sum_{e in row n} gr[e] - sum_{slot in t-row n} gr[t_eid[slot]],  gr[e] = sum over the slice slabs (fixed order)
 __global__ void pos_grad_kernel(xeq_graph_t g, const float* __restrict__ gr, int n_slabs, float* __restrict__ gpos) {
   const int n = blockIdx.x * blockDim.x + threadIdx.x;
@@ -710,6 +713,7 @@ static int set_smem(Kernel k, size_t bytes) {
   return XEQ_OK;
 }
 
+#ifdef XEQ_WITH_SIMT
 template <int C, int M1, int M2, bool JVP>
 static int launch_center(const CenterArgs& A, cudaStream_t st) {
   const int n_tiles = A.geo.g.n_tiles;
@@ -727,18 +731,26 @@ static int launch_center(const CenterArgs& A, cudaStream_t st) {
 }
 
 // tensor-core variants (edge_message_mma.cu), default widths only
-int launch_center_mma(const CenterArgs& A, bool jvp, bool wide, cudaStream_t st);
-int launch_wgrad_mma(const NeighborArgs& A, int order, bool wide, int grid, cudaStream_t st);
-int launch_nbr_mma(const NeighborArgs& A, int order, bool wide, cudaStream_t st);
-int launch_nbr_bwd_ul(const NeighborArgs& A, bool wide, cudaStream_t st);  // edge_bwd_ul.cu: round-2 first-order kernel
-int launch_center_fwd_ws(const CenterArgs& A, bool wide, cudaStream_t st);  // edge_fwd_mma.cu: warp-specialised forward (round 1)
-int launch_center_fwd_ul(const CenterArgs& A, bool wide, void* ws, cudaStream_t st);  // edge_fwd_ul.cu: round-2 forward
-size_t center_fwd_ul_workspace_bytes(int n_nodes, bool wide);
+#endif
 
-// XEQ_EDGE_SIMT=1 forces the SIMT filter contraction for the default widths too (A/B timing)
+// the tcgen05 kernels of the product path
+int launch_center_fwd_ul(const CenterArgs& A, bool wide, void* ws, cudaStream_t st);  // edge_fwd_ul.cu: K2 forward
+size_t center_fwd_ul_workspace_bytes(int n_nodes, bool wide);
+int launch_nbr_bwd_ul(const NeighborArgs& A, bool wide, cudaStream_t st);             // edge_bwd_ul.cu: K2b first order
+int launch_center_jvp_mma(const CenterArgs& A, bool wide, cudaStream_t st);           // edge_message_mma.cu: K2bb JVP pass
+int launch_nbr2_mma(const NeighborArgs& A, bool wide, cudaStream_t st);               //                      K2bb reverse pass
+int launch_wgrad_mma(const NeighborArgs& A, int order, bool wide, int grid, cudaStream_t st);  //             weight gradients
+
+// The product library has ONE implementation per kernel (tcgen05).  A test-only build (-DXEQ_WITH_SIMT,
+// xequinet_b200/build.py --simt -> libxeq_b200_simt.so) also carries the round-1 SIMT filter contraction, selected for the
+// whole process with XEQ_EDGE_SIMT=1, as an independent implementation for the A/B parity test.
 static bool use_mma() {
+#ifdef XEQ_WITH_SIMT
   static const bool simt = [] { const char* e = getenv("XEQ_EDGE_SIMT"); return e && e[0] == '1'; }();
   return !simt;
+#else
+  return true;
+#endif
 }
 
 static int run_center(const xeq_graph_t* g, const xeq_dims_t* dims, CenterArgs& A, bool jvp, cudaStream_t st, void* ws = nullptr,
@@ -752,15 +764,16 @@ static int run_center(const xeq_graph_t* g, const xeq_dims_t* dims, CenterArgs& 
   A.geo.g = *g;
   A.geo.rc = dims->cutoff;
   if (use_mma()) {
-    static const int fwd_kind = [] { const char* e = getenv("XEQ_FWD_KIND"); return e ? atoi(e) : 2; }();  // A/B switch (dev)
-    if (!jvp && fwd_kind == 2) {
-      XEQ_CHECK_ARG(ws && ws_bytes >= center_fwd_ul_workspace_bytes(g->n_nodes, cfg == 1), "edge_message_fwd: workspace too small");
-      return launch_center_fwd_ul(A, cfg == 1, ws, st);
-    }
-    return (!jvp && fwd_kind == 1) ? launch_center_fwd_ws(A, cfg == 1, st) : launch_center_mma(A, jvp, cfg == 1, st);
+    if (jvp) return launch_center_jvp_mma(A, cfg == 1, st);
+    XEQ_CHECK_ARG(ws && ws_bytes >= center_fwd_ul_workspace_bytes(g->n_nodes, cfg == 1), "edge_message_fwd: workspace too small");
+    return launch_center_fwd_ul(A, cfg == 1, ws, st);
   }
+#ifdef XEQ_WITH_SIMT
   if (cfg == 0) return jvp ? launch_center<128, 64, 32, true>(A, st) : launch_center<128, 64, 32, false>(A, st);
   return jvp ? launch_center<256, 128, 64, true>(A, st) : launch_center<256, 128, 64, false>(A, st);
+#else
+  return XEQ_ERR_INVALID;
+#endif
 }
 
 static int wgrad_grid_x(const xeq_graph_t* g) { return min(g->t_n_tiles, num_sms() * 2); }
@@ -775,6 +788,7 @@ static size_t neighbor_ws_bytes(const xeq_graph_t* g, const xeq_dims_t* d, int w
   return b;
 }
 
+#ifdef XEQ_WITH_SIMT
 template <int C, int M1, int M2, int ORDER>
 static int launch_neighbor(NeighborArgs& A, bool main, bool wgrad, int gx, cudaStream_t st) {
   constexpr int M = C + M1 + M2, H = C + 2 * M;
@@ -799,6 +813,8 @@ static int launch_neighbor(NeighborArgs& A, bool main, bool wgrad, int gx, cudaS
   }
   return XEQ_OK;
 }
+
+#endif
 
 static int run_neighbor(const xeq_graph_t* g, const xeq_dims_t* dims, NeighborArgs& A, int order, float* o_pos,
                         float* o_W, float* o_b, float* o_f, void* ws, size_t ws_bytes, cudaStream_t st) {
@@ -828,11 +844,13 @@ static int run_neighbor(const xeq_graph_t* g, const xeq_dims_t* dims, NeighborAr
   A.gr = o_pos ? gr : nullptr;
   A.wpart = wpart;
   if (mma) {
-    static const int bwd_kind = [] { const char* e = getenv("XEQ_BWD_KIND"); return e ? atoi(e) : 2; }();  // A/B switch (dev)
-    if (main) rc = (order == 1 && bwd_kind == 2) ? launch_nbr_bwd_ul(A, cfg == 1, st) : launch_nbr_mma(A, order, cfg == 1, st);
+    if (main) rc = order == 1 ? launch_nbr_bwd_ul(A, cfg == 1, st) : launch_nbr2_mma(A, cfg == 1, st);
     if (!rc && wgrad) rc = launch_wgrad_mma(A, order, cfg == 1, gx, st);
-  } else if (cfg == 0) rc = order == 1 ? launch_neighbor<128, 64, 32, 1>(A, main, wgrad, gx, st) : launch_neighbor<128, 64, 32, 2>(A, main, wgrad, gx, st);
+  }
+#ifdef XEQ_WITH_SIMT
+  else if (cfg == 0) rc = order == 1 ? launch_neighbor<128, 64, 32, 1>(A, main, wgrad, gx, st) : launch_neighbor<128, 64, 32, 2>(A, main, wgrad, gx, st);
   else rc = order == 1 ? launch_neighbor<256, 128, 64, 1>(A, main, wgrad, gx, st) : launch_neighbor<256, 128, 64, 2>(A, main, wgrad, gx, st);
+#endif
   if (rc) return rc;
   if (o_pos) {
     pos_grad_kernel<<<(g->n_nodes + 127) / 128, 128, 0, st>>>(*g, gr, slices, o_pos);

@@ -1033,9 +1033,9 @@ static int launch_center_mma_t(const CenterArgs& A, cudaStream_t st) {
   return XEQ_OK;
 }
 
-int launch_center_mma(const CenterArgs& A, bool jvp, bool wide, cudaStream_t st) {
-  if (wide) return jvp ? launch_center_mma_t<256, true>(A, st) : launch_center_mma_t<256, false>(A, st);
-  return jvp ? launch_center_mma_t<128, true>(A, st) : launch_center_mma_t<128, false>(A, st);
+// JVP pass of the double backward (the forward values come from edge_fwd_ul.cu)
+int launch_center_jvp_mma(const CenterArgs& A, bool wide, cudaStream_t st) {
+  return wide ? launch_center_mma_t<256, true>(A, st) : launch_center_mma_t<128, true>(A, st);
 }
 
 template <int C, int ORDER>
@@ -1068,9 +1068,9 @@ static int launch_nbr_mma_t(const NeighborArgs& A, cudaStream_t st) {
 }
 
 // A.gr holds one [E, 3] slab of per-edge d/dr partials per channel slice (pos_grad_kernel sums them)
-int launch_nbr_mma(const NeighborArgs& A, int order, bool wide, cudaStream_t st) {
-  if (wide) return order == 1 ? launch_nbr_mma_t<256, 1>(A, st) : launch_nbr_mma_t<256, 2>(A, st);
-  return order == 1 ? launch_nbr_mma_t<128, 1>(A, st) : launch_nbr_mma_t<128, 2>(A, st);
+// second-order (reverse half of the double backward); the first-order pass is edge_bwd_ul.cu
+int launch_nbr2_mma(const NeighborArgs& A, bool wide, cudaStream_t st) {
+  return wide ? launch_nbr_mma_t<256, 2>(A, st) : launch_nbr_mma_t<128, 2>(A, st);
 }
 
 // grid = number of per-CTA partial slabs written to A.wpart ([grid, H, 48]; the slices write disjoint rows)
