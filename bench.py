@@ -351,11 +351,24 @@ def run_gpu(args):
     # tests/test_gpu_bench_shapes.py checks replay == eager bit for bit).  A captured graph needs one static batch
     # structure: workloads whose batches differ in size (c4: 30..70 atoms per molecule) are replayed eagerly.
     same_shape = all(d["pos"].shape == resident[0]["pos"].shape and torch.equal(d["ptr"], resident[0]["ptr"]) for d in resident)
-    use_graph = (not args.eager) and same_shape and not sharded  # the halo plan has host-synchronised counts
+    use_graph = (not args.eager) and same_shape
     graph_step = None
     forces_host = torch.zeros(host[0]["pos"].shape).pin_memory() if (forces and not train) else None
     copied_keys = list(h2d_keys)
-    if use_graph:
+    if use_graph and sharded:
+        # one CUDA graph per rank (domain.ShardedStep): skin-padded halo plan built once, K1 in capacity mode, the
+        # per-layer NCCL all-to-alls are graph nodes; a step copies the rank's positions in and E / F out
+        captured = domain.ShardedStep(model, own_res[0], rank, world, skin=0.5)
+        copied_keys = ["pos"]
+
+        def graph_step(batch, e2e: bool):
+            out = captured(batch["_owned"]["pos"])
+            if e2e:
+                energy_host.copy_(out["energy"], non_blocking=True)
+                forces_own_host.copy_(out["forces"], non_blocking=True)
+            return out["energy"]
+
+    elif use_graph:
         from xequinet_b200.graph import build_graph
         from xequinet_b200.replay import CapturedStep
         e_max = 0
@@ -457,7 +470,7 @@ def run_gpu(args):
     h2d = sum(host[0][k].numel() * host[0][k].element_size() for k in copied_keys)  # what a step really copies
     d2h = 4 if train else energy_host.numel() * 4 + (forces_host.numel() * 4 if forces else 0)
     if sharded:
-        h2d = sum(host[0]["_owned"][k].numel() * host[0]["_owned"][k].element_size() for k in ("pos", "atomic_numbers", "cell"))
+        h2d = sum(host[0]["_owned"][k].numel() * host[0]["_owned"][k].element_size() for k in (copied_keys if use_graph else ("pos", "atomic_numbers", "cell")))
         d2h = 4 + forces_own_host.numel() * 4
 
     def hard_exit():
@@ -537,8 +550,9 @@ def run_gpu(args):
         "config": {"workload": f"{args.workload}: {w['desc']}", "molecules_per_gpu": n_mol,
                    "atoms_per_gpu": int(host[0]["pos"].shape[0]), "l2": "flushed between timed steps (256 MB write, untimed)",
                    "parallelism": (f"dp{world}" if args.workload != "c5" else
-                                   (f"spatial slabs x{world} + halo exchange (NCCL all-to-all)" if sharded else "single GPU")),
-                   "execution": "whole step replayed as one CUDA graph (xequinet_b200.replay.CapturedStep, K1 in capacity mode)" if use_graph else
+                                   (f"spatial slabs x{world} + per-layer halo exchange (NCCL all-to-all), one CUDA graph per rank" if sharded else "single GPU")),
+                   "execution": ("whole step replayed as one CUDA graph per rank (xequinet_b200.domain.ShardedStep)" if sharded else
+                                 "whole step replayed as one CUDA graph (xequinet_b200.replay.CapturedStep, K1 in capacity mode)") if use_graph else
                                 ("eager launches" if args.eager else "eager launches (batch shapes vary: no static graph)")},
         "e2e": {"value": round(e2e_value, 2), "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h)},
         "gpu_launches": int(launches),

@@ -142,13 +142,15 @@ int xeq_csr_transpose(const int32_t* rowptr, const int32_t* col, int32_t n_nodes
                       int32_t* t_rowptr, int32_t* t_row, int32_t* t_eid,
                       void* workspace, size_t workspace_bytes, xeq_stream_t stream);
 
-/* Work partition of the edge kernels: tile k = the nodes whose CSR row starts inside edges
- * [k*T, (k+1)*T); tile_ptr[k] = first such node, k = 0 .. n_edges/T + 1 (last entry = n_nodes).
- * Node-aligned tiles let one CTA own whole rows, so segment sums need no atomics. */
+/* Work partition of the edge kernels: rows are weighed as (edges + 4) slots -- a row switch costs about a quad of
+ * slots, and rows without edges (ghost atoms of a sharded run) must not pile up in one tile; tile k = the nodes whose
+ * weighted prefix falls inside [k*T, (k+1)*T); tile_ptr[k] = first such node, k = 0 .. xeq_csr_tile_count(...)
+ * (last entry = n_nodes).  Node-aligned tiles let one CTA own whole rows, so segment sums need no atomics. */
+int xeq_csr_tile_count(int32_t n_nodes, int32_t n_edges, int32_t tile_edges);
 int xeq_center_tile_edges(void);
 int xeq_neighbor_tile_edges(void);
 int xeq_csr_tile_bounds(const int32_t* rowptr, int32_t n_nodes, int32_t n_edges, int32_t tile_edges,
-                        int32_t* tile_ptr /* [n_edges/tile_edges + 2] out */, xeq_stream_t stream);
+                        int32_t* tile_ptr /* [xeq_csr_tile_count(...) + 1] out */, xeq_stream_t stream);
 
 /* ------------------------------------------------------------------------------------
  * K2  fused edge message.  Replaces, per XPainnMessage.forward (nn/xpainn.py:140-159):

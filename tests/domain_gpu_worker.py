@@ -70,8 +70,28 @@ if rank == 0:
     rms_single = float((F_ref.double() - F64).pow(2).mean().sqrt())
     print(f"rms |F - F64| single-GPU {rms_single:.2e}", flush=True)
     assert abs(float(E - E_ref)) <= 1e-5 * abs(float(E_ref)), "sharded energy differs"
-    assert float(e_shard) <= max(1e-4, 4 * float(e32.max())), "sharded forces differ beyond the fp32 noise floor of the reference arithmetic"
+    # the tail of the force error is chaotic in fp32 (tests/helpers.py::force_gate): the yardsticks are the reference
+    # arithmetic in fp32 and the unsharded run of the same kernels; the bulk is judged by the rms error
+    assert float(e_shard) <= max(1e-4, 4 * max(float(e32.max()), float(e_single))), "sharded forces differ beyond the fp32 noise floor"
+    assert float((rms_sh / F64.numel()).sqrt()) <= 1.5 * rms_single + 1e-6, "sharded forces: rms error above the unsharded run's"
     print("SHARDED OK", flush=True)
+# the same step as ONE CUDA graph per rank (domain.ShardedStep: skin-padded halo plan, K1 in capacity mode, NCCL
+# all-to-alls as graph nodes): energies and forces of the eager sharded path, then a displaced structure inside the skin
+sstep = domain.ShardedStep(model, owned, rank, world, skin=0.5)
+o2 = sstep()
+dE = abs(float(o2["energy"].double().sum() - E)); dF = (o2["forces"] - out["forces"]).abs().max(); dist.all_reduce(dF, op=dist.ReduceOp.MAX)
+gen = torch.Generator(device="cpu").manual_seed(100 + rank)
+moved = dict(owned); moved["pos"] = owned["pos"] + 0.1 * torch.nn.functional.normalize(torch.randn(owned["pos"].shape, generator=gen), dim=-1).to(dev)
+assert not sstep.needs_replan(moved["pos"])
+o3 = {k: v.clone() for k, v in sstep(moved["pos"]).items()}
+ref3 = domain.energy_forces_sharded(model, moved, rank, world)
+E3 = ref3["energy"].detach().double().sum(); dist.all_reduce(E3)
+dE3 = abs(float(o3["energy"].double().sum() - E3)); dF3 = (o3["forces"] - ref3["forces"]).abs().max(); dist.all_reduce(dF3, op=dist.ReduceOp.MAX)
+sstep.check()
+if rank == 0:
+    print(f"ShardedStep (CUDA graph) vs eager sharded: |dE| {dE:.2e} max|dF| {float(dF):.2e}; displaced: |dE| {dE3:.2e} max|dF| {float(dF3):.2e}", flush=True)
+    assert dE <= 1e-5 * abs(float(E)) and float(dF) <= 1e-4 and dE3 <= 1e-5 * abs(float(E3)) and float(dF3) <= 1e-4
+    print("SHARDED GRAPH OK", flush=True)
 # timing
 def tm(f, n=5):
     f(); torch.cuda.synchronize(); dist.barrier(); a = torch.cuda.Event(enable_timing=True); b = torch.cuda.Event(enable_timing=True); a.record()
@@ -82,5 +102,6 @@ def full():
     dd = xb.NeighborTransform(cfg.cutoff)({k: box[k] for k in ["pos", "atomic_numbers", "batch", "ptr", "cell", "pbc"]})
     return model(dd, compute_forces=True)
 t_full = tm(full)
-if rank == 0: print(f"ms/step sharded {t_sh:.2f}  single-GPU full box {t_full:.2f}", flush=True)
+t_graph = tm(lambda: sstep(), n=20)
+if rank == 0: print(f"ms/step sharded eager {t_sh:.2f}  sharded CUDA graph {t_graph:.2f}  single-GPU full box (eager) {t_full:.2f}", flush=True)
 torch.cuda.synchronize(); sys.stdout.flush(); os._exit(0)

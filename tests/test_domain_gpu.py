@@ -16,4 +16,4 @@ def test_sharded_energy_forces_two_gpus():
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
            "--master-port", "29577", str(ROOT / "tests" / "domain_gpu_worker.py"), "6"]
     r = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
-    assert "SHARDED OK" in r.stdout, r.stdout[-3000:] + r.stderr[-3000:]
+    assert "SHARDED OK" in r.stdout and "SHARDED GRAPH OK" in r.stdout, r.stdout[-3000:] + r.stderr[-3000:]

@@ -52,6 +52,7 @@ _SIGNATURES = {
                                   c_size_t, c_void_p]),
     "xeq_center_tile_edges": (c_int, []),
     "xeq_neighbor_tile_edges": (c_int, []),
+    "xeq_csr_tile_count": (c_int, [c_int32, c_int32, c_int32]),
     "xeq_csr_tile_bounds": (c_int, [c_void_p, c_int32, c_int32, c_int32, c_void_p, c_void_p]),
     "xeq_edge_message_fwd_workspace_bytes": (c_size_t, [POINTER(XeqGraph), POINTER(XeqDims)]),
     "xeq_edge_message_fwd": (c_int, [POINTER(XeqGraph), POINTER(XeqDims)] + [c_void_p] * 10 + [c_void_p, c_size_t, c_void_p]),
@@ -106,7 +107,7 @@ def get():
 # ---------------------------------------------------------------------------------------------------------
 # per-entry-point device timing (bench.py: step shares by kernel group, tensor-pipe roofline of K3)
 # ---------------------------------------------------------------------------------------------------------
-_UNTIMED = {"xeq_version", "xeq_last_error", "xeq_num_sms", "xeq_launch_count", "xeq_center_tile_edges", "xeq_neighbor_tile_edges"}
+_UNTIMED = {"xeq_csr_tile_count", "xeq_version", "xeq_last_error", "xeq_num_sms", "xeq_launch_count", "xeq_center_tile_edges", "xeq_neighbor_tile_edges"}
 
 
 class _Profiled:

@@ -663,16 +663,20 @@ __global__ void freq_grad_kernel(const float* __restrict__ W, const float* __res
 }
 
 // tile_ptr[k] = first node whose row starts at or after edge k * tile_edges  (k = 0 .. n_tiles)
+constexpr int TILE_ROW_COST = 4;
 __global__ void tile_bounds_kernel(const int* __restrict__ rowptr, int n_nodes, int n_tiles, int tile_edges,
                                    int* __restrict__ tile_ptr) {
   const int k = blockIdx.x * blockDim.x + threadIdx.x;
   if (k > n_tiles) return;
   if (k == n_tiles) { tile_ptr[k] = n_nodes; return; }
+  // work of the rows before node n = rowptr[n] edge slots + TILE_ROW_COST slots per row (row switch: owner loads,
+  // write-out, a partly empty quad): rows WITHOUT edges count too -- the ghost atoms of a spatially sharded run sit at
+  // the end of the node range with empty rows, and a tile that collects hundreds of them stalls one CTA
   const long long x = (long long)k * tile_edges;
   int lo = 0, hi = n_nodes;
   while (lo < hi) {
     const int mid = (lo + hi) >> 1;
-    if (rowptr[mid] < x) lo = mid + 1; else hi = mid;
+    if ((long long)rowptr[mid] + (long long)TILE_ROW_COST * mid < x) lo = mid + 1; else hi = mid;
   }
   tile_ptr[k] = lo;
 }
@@ -873,10 +877,14 @@ extern "C" {
 int xeq_center_tile_edges(void) { return CT; }
 int xeq_neighbor_tile_edges(void) { return NT; }
 
+int xeq_csr_tile_count(int32_t n_nodes, int32_t n_edges, int32_t tile_edges) {
+  return (int)(((long long)n_edges + (long long)TILE_ROW_COST * n_nodes) / tile_edges) + 1;
+}
+
 int xeq_csr_tile_bounds(const int32_t* rowptr, int32_t n_nodes, int32_t n_edges, int32_t tile_edges, int32_t* tile_ptr,
                         xeq_stream_t stream) {
   XEQ_CHECK_ARG(rowptr && tile_ptr && n_nodes >= 0 && n_edges >= 0 && tile_edges > 0, "csr_tile_bounds: bad arguments");
-  const int n_tiles = n_edges / tile_edges + 1;
+  const int n_tiles = xeq_csr_tile_count(n_nodes, n_edges, tile_edges);
   tile_bounds_kernel<<<(n_tiles + 1 + 255) / 256, 256, 0, (cudaStream_t)stream>>>(rowptr, n_nodes, n_tiles, tile_edges,
                                                                                  tile_ptr);
   XEQ_LAUNCHED(1);

@@ -57,9 +57,11 @@ class NeighborGraph:
             self.n_tiles = self.t_n_tiles = int(mol_ptr.numel()) - 1
             self.tile_mode = 1
         else:
-            self.tile_ptr = torch.empty(E // tc + 2, dtype=torch.int32, device=dev)
-            self.t_tile_ptr = torch.empty(E // tn + 2, dtype=torch.int32, device=dev)
-            self.n_tiles, self.t_n_tiles, self.tile_mode = E // tc + 1, E // tn + 1, 0
+            self.n_tiles = lib.xeq_csr_tile_count(self.n_centers, E, tc)
+            self.t_n_tiles = lib.xeq_csr_tile_count(N, E, tn)
+            self.tile_mode = 0
+            self.tile_ptr = torch.empty(lib.xeq_csr_tile_count(N, E, tc) + 1, dtype=torch.int32, device=dev)
+            self.t_tile_ptr = torch.empty(self.t_n_tiles + 1, dtype=torch.int32, device=dev)
         self.transpose()
 
     def transpose(self):
@@ -211,7 +213,8 @@ class StaticGraphBuilder:
     sync) and always returns the same NeighborGraph, whose live edge count stays on the device.
     `overflow` (device int32) is raised when a structure has more than `edge_capacity` edges."""
 
-    def __init__(self, n_nodes: int, ptr: torch.Tensor, cutoff: float, edge_capacity: int, cell=None, pbc=None):
+    def __init__(self, n_nodes: int, ptr: torch.Tensor, cutoff: float, edge_capacity: int, cell=None, pbc=None,
+                 n_centers: Optional[int] = None):
         lib = _lib.get()
         dev = ptr.device
         self.cutoff = float(cutoff)
@@ -242,7 +245,7 @@ class StaticGraphBuilder:
         mol_ptr = self.ptr32 if (0 < max_nodes <= NeighborGraph.MOLECULE_TILE_MAX_NODES) else None
         self.graph = NeighborGraph(self.N, self.G, self.rowptr, self.col, self.offsets, self.cell32,
                                    self.node_graph if (self.periodic and self.G > 1) else None, capacity=self.cap,
-                                   mol_ptr=mol_ptr)
+                                   mol_ptr=mol_ptr, n_centers=n_centers)
 
     def build(self, pos: torch.Tensor, check_overflow: bool = True) -> "NeighborGraph":
         """Launches K1 on `pos` (float32 [N,3], CUDA).  Outside CUDA-graph capture the overflow flag is read back
