@@ -72,7 +72,8 @@ typedef struct {
   int32_t tile_mode;        /* 0: edge-block tiles (xeq_csr_tile_bounds).  1: molecule tiles -- tile_ptr = t_tile_ptr = the batch  */
                             /*    `ptr` array, every neighbor of a tile's nodes lies inside the tile: the kernels then stage the   */
                             /*    tile's rows in shared memory once instead of gathering them per edge                             */
-  int32_t _pad2;
+  int32_t max_tile_nodes;   /* tile_mode 1: upper bound of the nodes per tile known to the caller (0 = unknown).  When every tile   */
+                            /* fits the shared-memory window the forward kernel packs rows in-kernel and skips its packing pass    */
 } xeq_graph_t;
 
 int xeq_version(void);

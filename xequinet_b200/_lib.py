@@ -26,7 +26,7 @@ class XeqGraph(ctypes.Structure):
                 ("rowptr", c_void_p), ("col", c_void_p), ("t_rowptr", c_void_p), ("t_row", c_void_p),
                 ("t_eid", c_void_p), ("offsets", c_void_p), ("cell", c_void_p), ("node_graph", c_void_p),
                 ("tile_ptr", c_void_p), ("t_tile_ptr", c_void_p),
-                ("n_tiles", c_int32), ("t_n_tiles", c_int32), ("tile_mode", c_int32), ("_pad2", c_int32)]
+                ("n_tiles", c_int32), ("t_n_tiles", c_int32), ("tile_mode", c_int32), ("max_tile_nodes", c_int32)]
 
 
 class XeqGemm(ctypes.Structure):

@@ -424,6 +424,59 @@ __device__ __forceinline__ void fwd_loader(const CenterArgs& A, FwdSmem& sm, con
   }
 }
 
+// window packer (all tiles of the launch fit the window: xeq_graph_t.max_tile_nodes <= WH): warp 15 reads the RAW s / v
+// rows of the CTA's next tile (coalesced 128-byte loads), forms the per-lane packed entries and writes them straight
+// into the free window half -- the packing pass and its HBM round trip (write + re-read of 4 KB per node) disappear.
+template <int C, int M1, int M2>
+__device__ __forceinline__ void fwd_packer(const CenterArgs& A, FwdSmem& sm, const uint32_t win_base) {
+  constexpr int M = C + M1 + M2, D = C + 3 * M1 + 5 * M2, H = C + 2 * M;
+  const xeq_graph_t& g = A.geo.g;
+  const int lane = threadIdx.x & 31, sl = blockIdx.y;
+  int q0[4], qp[4], off[4][3], nc[4];
+#pragma unroll
+  for (int it = 0; it < 4; ++it) {
+    const int L = lane + 32 * it;
+    q0[it] = sl * SL_C + L;
+    qp[it] = piece_irrep<C, M1>(L, sl);
+    piece_offsets<C, M1, M2>(L, sl, off[it], nc[it]);
+  }
+  Walk wk;
+  wk.init(g, g.tile_ptr, g.n_tiles, 0);
+  for (; wk.valid; wk.next()) {
+    if (!wk.staged) continue;
+    const int t = wk.staged_count - 1;
+    const uint32_t fullb = smem_u32(&sm.win_full[wk.buf]), freeb = smem_u32(&sm.win_free[wk.buf]);
+    if (t >= 2) mbar_wait_sleep(freeb, (uint32_t)(((t >> 1) - 1) & 1));
+    const uint32_t half = win_base + (uint32_t)wk.buf * (WH * ROWB) + 16u * (uint32_t)lane;
+#pragma unroll 2
+    for (int n = wk.n0; n < wk.n1; ++n) {
+      const float* sn = A.s + (size_t)n * H;
+      const float* vn = A.v + (size_t)n * D;
+      const uint32_t row = half + (uint32_t)(n - wk.n0) * ROWB;
+      float4 a[4], b[4];
+#pragma unroll
+      for (int it = 0; it < 4; ++it) {
+        const float ssp = sn[qp[it]];
+        a[it].x = sn[q0[it]] * vn[q0[it]];
+        a[it].y = sn[M + q0[it]];
+        a[it].z = sn[2 * M + q0[it]];
+        a[it].w = sn[M + qp[it]];
+        b[it].x = ssp * vn[off[it][0]];
+        b[it].y = ssp * vn[off[it][1]];
+        b[it].z = nc[it] == 3 ? ssp * vn[off[it][2]] : 0.f;
+        b[it].w = 0.f;
+      }
+#pragma unroll
+      for (int it = 0; it < 4; ++it) {
+        sts128(row + 512u * it, __float_as_uint(a[it].x), __float_as_uint(a[it].y), __float_as_uint(a[it].z), __float_as_uint(a[it].w));
+        sts128(row + 2048u + 512u * it, __float_as_uint(b[it].x), __float_as_uint(b[it].y), __float_as_uint(b[it].z), __float_as_uint(b[it].w));
+      }
+    }
+    __syncwarp();
+    if (lane == 0) mbar_arrive(fullb);  // release: the rows of this tile are in the window
+  }
+}
+
 template <int C, int M1, int M2>
 __global__ void __launch_bounds__(NTHREADS, 1) center_fwd_ul_kernel(const CenterArgs A, const float* __restrict__ pk) {
   static_assert(C % SL_C == 0 && M1 == C / 2 && M2 == C / 4, "channel slices of edge_mma.cuh");
@@ -458,7 +511,8 @@ __global__ void __launch_bounds__(NTHREADS, 1) center_fwd_ul_kernel(const Center
   tc_fence_after();
   if (warp < 4 * G) fwd_consumer<C, M1, M2>(A, sm, tmem, tiles_base, win_base, pk, warp >> 2);
   else if (warp < 4 * G + G) fwd_producer<C, M1, M2>(A, sm, tmem, tiles_base, warp - 4 * G);
-  else fwd_loader<C>(A, sm, win_base, pk);
+  else if (pk != nullptr) fwd_loader<C>(A, sm, win_base, pk);   // packed rows from the packing pass, TMA bulk copies
+  else fwd_packer<C, M1, M2>(A, sm, win_base);                // every tile fits the window: packed in-kernel
   tmem_teardown(tmem);
 }
 
@@ -473,15 +527,18 @@ static int launch_center_fwd_ul_t(const CenterArgs& A, void* ws, cudaStream_t st
   constexpr int M1 = C / 2, M2 = C / 4, SLICES = C / SL_C;
   static_assert(sizeof(FwdSmem) <= 16 * 1024, "static shared memory budget");
   const xeq_graph_t& g = A.geo.g;
-  float* pk = reinterpret_cast<float*>((reinterpret_cast<uintptr_t>(ws) + 255) & ~(uintptr_t)255);
-  pack_fwd_kernel<C, M1, M2><<<dim3((g.n_nodes + 1) / 2, SLICES), 256, 0, st>>>(A.s, A.v, pk, g.n_nodes);
+  // when the caller vouches that every molecule tile fits the window, warp 15 packs the rows in-kernel and the packing
+  // pass (and the consumers' global-memory path) is not needed
+  const bool inline_pack = g.tile_mode == 1 && g.max_tile_nodes > 0 && g.max_tile_nodes <= WH;
+  float* pk = inline_pack ? nullptr : reinterpret_cast<float*>((reinterpret_cast<uintptr_t>(ws) + 255) & ~(uintptr_t)255);
+  if (!inline_pack) pack_fwd_kernel<C, M1, M2><<<dim3((g.n_nodes + 1) / 2, SLICES), 256, 0, st>>>(A.s, A.v, pk, g.n_nodes);
   const size_t dyn = 1024 + (size_t)G * NBST * BSTAGE + (g.tile_mode == 1 ? (size_t)2 * WH * ROWB : 0);
   XEQ_CUDA(cudaFuncSetAttribute(center_fwd_ul_kernel<C, M1, M2>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                 (int)(1024 + (size_t)G * NBST * BSTAGE + (size_t)2 * WH * ROWB)));
   const int work = g.tile_mode == 1 ? g.n_tiles : (g.n_tiles + G - 1) / G;
   const int grid = max(1, min(work, num_sms() / SLICES));
   center_fwd_ul_kernel<C, M1, M2><<<dim3(grid, SLICES), NTHREADS, dyn, st>>>(A, pk);
-  XEQ_LAUNCHED(2);
+  XEQ_LAUNCHED(inline_pack ? 1 : 2);
   return XEQ_OK;
 }
 

@@ -23,7 +23,7 @@ class NeighborGraph:
 
     def __init__(self, n_nodes: int, n_graphs: int, rowptr, col, offsets=None, cell=None, node_graph=None,
                  capacity: Optional[int] = None, mol_ptr: Optional[torch.Tensor] = None,
-                 n_centers: Optional[int] = None):
+                 n_centers: Optional[int] = None, max_tile_nodes: int = 0):
         self.n_nodes = int(n_nodes)
         # nodes that can be centers (rows of the CSR that are walked); the rest (ghost atoms of a spatially
         # sharded run, xequinet_b200/domain.py) only ever appear as neighbours
@@ -52,6 +52,7 @@ class NeighborGraph:
         # work tiles: one per molecule when the caller vouches that every graph is small (mol_ptr = the
         # batch `ptr` array, int32), else node-aligned blocks of tc / tn edges
         self.mol_ptr = mol_ptr
+        self.max_tile_nodes = int(max_tile_nodes) if mol_ptr is not None else 0  # host-known bound of the molecule sizes
         if mol_ptr is not None:
             self.tile_ptr = self.t_tile_ptr = mol_ptr
             self.n_tiles = self.t_n_tiles = int(mol_ptr.numel()) - 1
@@ -93,6 +94,7 @@ class NeighborGraph:
             g.node_graph = self.node_graph.data_ptr() if self.node_graph is not None else None
             g.tile_ptr, g.t_tile_ptr = self.tile_ptr.data_ptr(), self.t_tile_ptr.data_ptr()
             g.n_tiles, g.t_n_tiles, g.tile_mode = self.n_tiles, self.t_n_tiles, self.tile_mode
+            g.max_tile_nodes = self.max_tile_nodes
             self._struct = g
         return self._struct
 
@@ -203,7 +205,7 @@ def build_graph(pos: torch.Tensor, cutoff: float, ptr: Optional[torch.Tensor] = 
                                          st),
                "xeq_radius_graph_fill")
     g = NeighborGraph(N, G, rowptr, col[:E] if E else col[:0], offsets[:E] if (periodic and E) else (offsets[:0] if periodic else None),
-                      cell32, node_graph if (periodic and G > 1) else None, mol_ptr=mol_ptr)
+                      cell32, node_graph if (periodic and G > 1) else None, mol_ptr=mol_ptr, max_tile_nodes=int(max_nodes))
     return g, ei, co
 
 
@@ -245,7 +247,7 @@ class StaticGraphBuilder:
         mol_ptr = self.ptr32 if (0 < max_nodes <= NeighborGraph.MOLECULE_TILE_MAX_NODES) else None
         self.graph = NeighborGraph(self.N, self.G, self.rowptr, self.col, self.offsets, self.cell32,
                                    self.node_graph if (self.periodic and self.G > 1) else None, capacity=self.cap,
-                                   mol_ptr=mol_ptr, n_centers=n_centers)
+                                   mol_ptr=mol_ptr, n_centers=n_centers, max_tile_nodes=max_nodes)
 
     def build(self, pos: torch.Tensor, check_overflow: bool = True) -> "NeighborGraph":
         """Launches K1 on `pos` (float32 [N,3], CUDA).  Outside CUDA-graph capture the overflow flag is read back
@@ -308,13 +310,14 @@ def graph_from_edge_index(edge_index: torch.Tensor, n_nodes: int, n_graphs: int 
         if batch is None:
             raise ValueError("batch is required for multi-graph periodic input")
         node_graph = batch.to(device=dev, dtype=torch.int32).contiguous()
-    mol_ptr = None
+    mol_ptr, max_nodes = None, 0
     if ptr is not None and n_nodes > 0:
         ptr32 = ptr.to(device=dev, dtype=torch.int32).contiguous()
-        if int((ptr32[1:] - ptr32[:-1]).max().item()) <= NeighborGraph.MOLECULE_TILE_MAX_NODES:
+        max_nodes = int((ptr32[1:] - ptr32[:-1]).max().item())
+        if max_nodes <= NeighborGraph.MOLECULE_TILE_MAX_NODES:
             mol_ptr = ptr32
     g = NeighborGraph(n_nodes, n_graphs, rowptr, col[:E], offsets[:E] if periodic else None, cell32, node_graph,
-                      mol_ptr=mol_ptr)
+                      mol_ptr=mol_ptr, max_tile_nodes=max_nodes)
     g.sorted_edge_index = ei
     g.set_source(edge_index, cell_offsets, cell)
     return g

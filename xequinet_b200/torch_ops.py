@@ -41,7 +41,7 @@ class _GraphView:
     def __init__(self, tensors: Sequence[Optional[Tensor]], meta: Sequence[int]):
         (self.rowptr, self.col, self.t_rowptr, self.t_row, self.t_eid, self.tile_ptr, self.t_tile_ptr,
          self.offsets, self.cell, self.node_graph, self.seg_ptr) = tensors
-        self.n_nodes, self.n_edges, self.n_graphs, self.n_tiles, self.t_n_tiles, self.tile_mode = (int(m) for m in meta)
+        self.n_nodes, self.n_edges, self.n_graphs, self.n_tiles, self.t_n_tiles, self.tile_mode, self.max_tile_nodes = (int(m) for m in meta)
         self.n_centers = self.n_nodes
         self._struct = None
 
@@ -51,7 +51,7 @@ class _GraphView:
 def pack_graph(g: NeighborGraph) -> Tuple[List[Optional[Tensor]], List[int]]:
     tensors = [g.rowptr, g.col, g.t_rowptr, g.t_row, g.t_eid, g.tile_ptr, g.t_tile_ptr, g.offsets, g.cell, g.node_graph,
                getattr(g, "seg_ptr", None)]
-    return tensors, [g.n_nodes, g.n_edges, g.n_graphs, g.n_tiles, g.t_n_tiles, g.tile_mode]
+    return tensors, [g.n_nodes, g.n_edges, g.n_graphs, g.n_tiles, g.t_n_tiles, g.tile_mode, g.max_tile_nodes]
 
 
 def _dims(d: Sequence[int], cutoff: float) -> _ops.Dims:
