@@ -120,7 +120,7 @@ __device__ __forceinline__ void fwd_consumer(const CenterArgs& A, FwdSmem& sm, c
       const float4 rd = lds128(geo0 + (uint32_t)(c % NGEO) * (uint32_t)sizeof(Geo) + rad_off);
       float val[4];
 #pragma unroll
-      for (int x = 0; x < 4; ++x) val[x] = rd.y * sinf(fr[x] * rd.x);  // fr = 0 -> exactly zero
+      for (int x = 0; x < 4; ++x) val[x] = rd.y * sin_reduced(fr[x] * rd.x);  // fr = 0 -> exactly zero
       if (rkc == 0) val[0] = rd.z;
       uint32_t hi[4], lo[4];
 #pragma unroll
