@@ -191,14 +191,15 @@ int xeq_edge_message_bwd(const xeq_graph_t* g, const xeq_dims_t* dims, const flo
 /* K2bb  double backward (force training: utils/trainer.py:295-302 calls loss.backward()
  * through forces obtained with create_graph=True, nn/basic.py:150-156).
  * With Phi = <gx, dx> + <gV, dV> the outputs of K2b are dPhi/d(s, v, pos).  Given cotangents
- * (a_s, a_v, a_pos) of (gs, gv, gpos) (any may be NULL = zero) this returns the gradient of
- *   Psi = <a_s, dPhi/ds> + <a_v, dPhi/dv> + <a_pos, dPhi/dpos>
+ * (a_s, a_v, a_pos, a_cell) of (gs, gv, gpos, gcell) (any may be NULL = zero) this returns the gradient of
+ *   Psi = <a_s, dPhi/ds> + <a_v, dPhi/dv> + <a_pos, dPhi/dpos> + <a_cell, dPhi/dcell>
  * with respect to gx, gV, s, v, pos, W_rbf, b_rbf, freq.  Output pointers may be NULL. */
 /* Per-node pieces of the CELL gradient of a periodic graph (virial / stress through the strain trick,
  * nn/basic.py:93-107, 162-199):  rows[3a+b][n] = sum over the edges e of CSR row n of
  * cell_offsets[e][a] * (dE/dr_e)[b], so that  dE/dcell[g][a][b] = - sum_{n in g} rows[3a+b][n]
  * (the edge vector is pos_i - pos_j - cell_offsets @ cell, nn/basic.py:119-128).  Reads the per-edge d/dr records
- * that the preceding xeq_edge_message_bwd call (gpos != NULL, same stream) left at the start of ITS workspace.
+ * that the preceding xeq_edge_message_bwd / xeq_edge_message_bwdbwd call (gpos / o_pos != NULL, same stream) left at
+ * the start of ITS workspace.
  * rows: [9, n_nodes] floats.  Deterministic. */
 int xeq_edge_cell_grad_rows(const xeq_graph_t* g, const xeq_dims_t* dims, const void* bwd_workspace,
                             float* rows, xeq_stream_t stream);
@@ -209,6 +210,10 @@ int xeq_edge_message_bwdbwd(const xeq_graph_t* g, const xeq_dims_t* dims, const 
                             const float* W_rbf, const float* b_rbf, const float* freq,
                             const float* gx, const float* gV,
                             const float* a_s, const float* a_v, const float* a_pos,
+                            const float* a_cell /* [G,3,3] cotangent of the cell gradient (periodic virial in a training
+                                                   loss): the edge tangent becomes a_pos_i - a_pos_j - offsets @ a_cell;
+                                                   NULL = zero.  The second-order cell gradient follows from the per-edge
+                                                   records of THIS call with xeq_edge_cell_grad_rows */,
                             float* o_gx, float* o_gV, float* o_s, float* o_v, float* o_pos,
                             float* o_W, float* o_b, float* o_freq,
                             void* workspace, size_t workspace_bytes, xeq_stream_t stream);

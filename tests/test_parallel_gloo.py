@@ -132,12 +132,10 @@ def _flat_worker(rank, world, port, q):
         for step in range(2):  # two steps: zero() must reset the views and the bucket bookkeeping
             x = torch.randn(6, 5, dtype=torch.float64, generator=torch.Generator().manual_seed(10 * step + rank))
             flat.zero()
-            for prm in params[:1]:
-                prm.grad = None  # an optimizer's zero_grad(set_to_none=True) in between
-            flat.zero()
+            assert all(p.grad is None for p in params)
             net(x).pow(2).sum().backward()
             flat.finish()
-            assert all(p.grad.data_ptr() == flat.flat.data_ptr() + 8 * flat._range[id(p)][0] for p in params)
+            assert all(p.grad.data_ptr() == flat.flat.data_ptr() + 8 * flat._range[id(p)][0] for p in params)  # views of the flat buffer
             out[step] = [p.grad.detach().clone().numpy() for p in params]
         q.put((rank, out))
     finally:

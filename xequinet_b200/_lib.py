@@ -59,7 +59,7 @@ _SIGNATURES = {
     "xeq_edge_message_bwd_workspace_bytes": (c_size_t, [POINTER(XeqGraph), POINTER(XeqDims), c_int]),
     "xeq_edge_message_bwd": (c_int, [POINTER(XeqGraph), POINTER(XeqDims)] + [c_void_p] * 14 + [c_void_p, c_size_t, c_void_p]),
     "xeq_edge_message_bwdbwd_workspace_bytes": (c_size_t, [POINTER(XeqGraph), POINTER(XeqDims), c_int]),
-    "xeq_edge_message_bwdbwd": (c_int, [POINTER(XeqGraph), POINTER(XeqDims)] + [c_void_p] * 19 + [c_void_p, c_size_t, c_void_p]),
+    "xeq_edge_message_bwdbwd": (c_int, [POINTER(XeqGraph), POINTER(XeqDims)] + [c_void_p] * 20 + [c_void_p, c_size_t, c_void_p]),
     "xeq_segment_sum": (c_int, [c_void_p, c_void_p, c_int32, c_void_p, c_void_p]),
     "xeq_colsum": (c_int, [c_void_p, c_int32, c_int32, c_int32, c_void_p, c_void_p]),
     "xeq_edge_cell_grad_rows": (c_int, [POINTER(XeqGraph), POINTER(XeqDims), c_void_p, c_void_p, c_void_p]),

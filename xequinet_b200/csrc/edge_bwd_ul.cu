@@ -537,6 +537,7 @@ template <int C, int M1, int M2>
 __global__ void __launch_bounds__(NTHREADS, 1) nbr_bwd_ul_kernel(const NeighborArgs A) {
   static_assert(C % SL_C == 0 && M1 == C / 2 && M2 == C / 4, "channel slices of edge_mma.cuh");
   __shared__ BwdSmem sm;
+  pdl_trigger();
   const int t = threadIdx.x, warp = t >> 5;
   if (t == 0) {
     for (int i = 0; i < G; ++i) {
@@ -561,6 +562,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) nbr_bwd_ul_kernel(const NeighborA
   const uint32_t tmem = *reinterpret_cast<volatile uint32_t*>(&sm.slot);
   const uint32_t tiles_base = (smem_u32(xeq_dyn_smem) + 1023u) & ~1023u;
   const uint32_t win_base = tiles_base + G * NBST * BSTAGE;
+  pdl_wait();
   if (t < GRP) store_filter_rows<C, M1, M2>(A.W, A.b, t, blockIdx.y, tmem + ((uint32_t)(32 * (t >> 5)) << 16));
   tc_fence_before();
   __syncthreads();
@@ -583,7 +585,7 @@ static int launch_nbr_bwd_ul_t(const NeighborArgs& A, cudaStream_t st) {
   XEQ_CUDA(cudaFuncSetAttribute(nbr_bwd_ul_kernel<C, M1, M2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn_max));
   const int work = g.tile_mode == 1 ? g.t_n_tiles : (g.t_n_tiles + G - 1) / G;
   const int grid = max(1, min(work, num_sms() / SLICES));
-  nbr_bwd_ul_kernel<C, M1, M2><<<dim3(grid, SLICES), NTHREADS, dyn, st>>>(A);
+  XEQ_CUDA(launch_pdl(nbr_bwd_ul_kernel<C, M1, M2>, dim3(grid, SLICES), dim3(NTHREADS), dyn, st, A));
   XEQ_LAUNCHED(1);
   return XEQ_OK;
 }

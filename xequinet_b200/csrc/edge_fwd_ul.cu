@@ -481,6 +481,7 @@ template <int C, int M1, int M2>
 __global__ void __launch_bounds__(NTHREADS, 1) center_fwd_ul_kernel(const CenterArgs A, const float* __restrict__ pk) {
   static_assert(C % SL_C == 0 && M1 == C / 2 && M2 == C / 4, "channel slices of edge_mma.cuh");
   __shared__ FwdSmem sm;
+  pdl_trigger();  // the next kernel of the stream may be staged; it waits for this grid before it reads memory
   const int t = threadIdx.x, warp = t >> 5;
   if (t == 0) {
     for (int i = 0; i < G; ++i) {
@@ -505,6 +506,7 @@ __global__ void __launch_bounds__(NTHREADS, 1) center_fwd_ul_kernel(const Center
   const uint32_t tmem = *reinterpret_cast<volatile uint32_t*>(&sm.slot);
   const uint32_t tiles_base = (smem_u32(xeq_dyn_smem) + 1023u) & ~1023u;
   const uint32_t win_base = tiles_base + G * NBST * BSTAGE;
+  pdl_wait();  // barrier setup and the TMEM allocation overlapped the previous kernel's tail; its results are visible now
   if (t < GRP) store_filter_rows<C, M1, M2>(A.W, A.b, t, blockIdx.y, tmem + ((uint32_t)(32 * (t >> 5)) << 16));
   tc_fence_before();
   __syncthreads();
@@ -537,7 +539,7 @@ static int launch_center_fwd_ul_t(const CenterArgs& A, void* ws, cudaStream_t st
                                 (int)(1024 + (size_t)G * NBST * BSTAGE + (size_t)2 * WH * ROWB)));
   const int work = g.tile_mode == 1 ? g.n_tiles : (g.n_tiles + G - 1) / G;
   const int grid = max(1, min(work, num_sms() / SLICES));
-  center_fwd_ul_kernel<C, M1, M2><<<dim3(grid, SLICES), NTHREADS, dyn, st>>>(A, pk);
+  XEQ_CUDA(launch_pdl(center_fwd_ul_kernel<C, M1, M2>, dim3(grid, SLICES), dim3(NTHREADS), dyn, st, A, (const float*)pk));
   XEQ_LAUNCHED(inline_pack ? 1 : 2);
   return XEQ_OK;
 }

@@ -227,6 +227,7 @@ struct GeoArgs {
   xeq_graph_t g;
   const float* pos;
   const float* a_pos;  // tangent of pos (second order) or NULL
+  const float* a_cell; // tangent of the lattice [G,3,3] (second order, periodic virial in a training loss) or NULL
   const float* freq;
   float rc;
 };
@@ -297,6 +298,13 @@ __device__ __noinline__ void geo_stage_a1(const GeoArgs& A, const ChunkDesc d, G
 #pragma unroll
     for (int x = 0; x < 3; ++x) rdot[x] = A.a_pos[3 * i + x] - A.a_pos[3 * j + x];
   }
+  if (SECOND && A.a_cell && g.offsets != nullptr) {  // r = p_i - p_j - o @ cell  =>  rdot -= o @ a_cell
+    const char4 o = reinterpret_cast<const char4*>(g.offsets)[e];
+    const float* c = A.a_cell + 9 * (g.node_graph ? g.node_graph[j] : 0);
+    const float ox = (float)o.x, oy = (float)o.y, oz = (float)o.z;
+#pragma unroll
+    for (int x = 0; x < 3; ++x) rdot[x] -= ox * c[x] + oy * c[3 + x] + oz * c[6 + x];
+  }
   geo_record<T, NEED_G, SECOND>(A, sa, t, TRANSPOSED ? i : j, owner, e, r, rdot);
 }
 
@@ -307,14 +315,14 @@ template <int T, bool TRANSPOSED, bool NEED_G, bool SECOND>
 struct GeoPipe {
   ChunkDesc dB, dC;
   int iB, jB, eB, iC, jC, eC;
-  float pi[3], pj[3], sh[3], ai[3], aj[3];
+  float pi[3], pj[3], sh[3], ai[3], aj[3], ash[3];
 
   __device__ __forceinline__ void init() {
     dB.cnt = dC.cnt = -1;
     dB.owner = dC.owner = 0;
     iB = jB = eB = iC = jC = eC = 0;
 #pragma unroll
-    for (int x = 0; x < 3; ++x) pi[x] = pj[x] = sh[x] = ai[x] = aj[x] = 0.f;
+    for (int x = 0; x < 3; ++x) pi[x] = pj[x] = sh[x] = ai[x] = aj[x] = ash[x] = 0.f;
   }
   __device__ __forceinline__ void stage_a(const GeoArgs& A, const ChunkDesc& d, const int lane) {
     dB = d;
@@ -344,6 +352,11 @@ struct GeoPipe {
         const float ox = (float)o.x, oy = (float)o.y, oz = (float)o.z;
 #pragma unroll
         for (int x = 0; x < 3; ++x) sh[x] = ox * cl[x] + oy * cl[3 + x] + oz * cl[6 + x];
+        if (SECOND && A.a_cell) {  // tangent of the lattice shift
+          const float* ac = A.a_cell + 9 * (g.node_graph ? g.node_graph[jB] : 0);
+#pragma unroll
+          for (int x = 0; x < 3; ++x) ash[x] = ox * ac[x] + oy * ac[3 + x] + oz * ac[6 + x];
+        }
       }
     }
   }
@@ -353,7 +366,7 @@ struct GeoPipe {
 #pragma unroll
       for (int x = 0; x < 3; ++x) {
         r[x] = (pi[x] - pj[x]) - sh[x];
-        rdot[x] = SECOND ? ai[x] - aj[x] : 0.f;
+        rdot[x] = SECOND ? (ai[x] - aj[x]) - ash[x] : 0.f;
       }
       geo_record<T, NEED_G, SECOND>(A, sa, lane, TRANSPOSED ? iC : jC, dC.owner, eC, r, rdot);
     }

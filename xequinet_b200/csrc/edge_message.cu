@@ -590,6 +590,8 @@ __global__ void __launch_bounds__(WTHREADS) nbr_wgrad_kernel(const NeighborArgs 
 
 // gpos[n] = sum_{e in row n} gr[e] - sum_{slot in t-row n} gr[t_eid[slot]],  gr[e] = sum over the slice slabs (fixed order)
 __global__ void pos_grad_kernel(xeq_graph_t g, const float* __restrict__ gr, int n_slabs, float* __restrict__ gpos) {
+  pdl_trigger();
+  pdl_wait();
   const int n = blockIdx.x * blockDim.x + threadIdx.x;
   if (n >= g.n_nodes) return;
   const size_t slab = 3 * (size_t)g.n_edges;
@@ -638,6 +640,8 @@ __global__ void cell_grad_rows_kernel(xeq_graph_t g, const float* __restrict__ g
 // weight-gradient partials [nblk, H, 2*NBP] -> gW [H,B], gb [H], ftot [H, NB] (fixed order)
 __global__ void wgrad_reduce_kernel(const float* __restrict__ wpart, int nblk, int H, float* __restrict__ gW,
                                     float* __restrict__ gb, float* __restrict__ ftot) {
+  pdl_trigger();
+  pdl_wait();
   const int h = blockIdx.x, k = threadIdx.x;  // k < 2*NBP
   float acc = 0.f;
   for (int bk = 0; bk < nblk; ++bk) acc += wpart[((size_t)bk * H + h) * (2 * NBP) + k];
@@ -649,6 +653,8 @@ __global__ void wgrad_reduce_kernel(const float* __restrict__ wpart, int nblk, i
 // gfreq[k] = sum_h W[h,k] * ftot[h,k]
 __global__ void freq_grad_kernel(const float* __restrict__ W, const float* __restrict__ ftot, int H,
                                  float* __restrict__ gfreq) {
+  pdl_trigger();
+  pdl_wait();
   __shared__ float red[256];
   const int k = blockIdx.x;
   float acc = 0.f;
@@ -857,12 +863,12 @@ static int run_neighbor(const xeq_graph_t* g, const xeq_dims_t* dims, NeighborAr
 #endif
   if (rc) return rc;
   if (o_pos) {
-    pos_grad_kernel<<<(g->n_nodes + 127) / 128, 128, 0, st>>>(*g, gr, slices, o_pos);
+    XEQ_CUDA(launch_pdl(pos_grad_kernel, dim3((g->n_nodes + 127) / 128), dim3(128), (size_t)0, st, *g, (const float*)gr, slices, o_pos));
     XEQ_LAUNCHED(1);
   }
   if (wgrad) {
-    wgrad_reduce_kernel<<<H, 2 * NBP, 0, st>>>(wpart, gx, H, o_W, o_b, ftot);
-    freq_grad_kernel<<<NB_, 256, 0, st>>>(A.W, ftot, H, o_f);
+    XEQ_CUDA(launch_pdl(wgrad_reduce_kernel, dim3(H), dim3(2 * NBP), (size_t)0, st, (const float*)wpart, gx, H, o_W, o_b, ftot));
+    XEQ_CUDA(launch_pdl(freq_grad_kernel, dim3(NB_), dim3(256), (size_t)0, st, A.W, (const float*)ftot, H, o_f));
     XEQ_LAUNCHED(2);
   }
   return XEQ_OK;
@@ -945,7 +951,7 @@ size_t xeq_edge_message_bwdbwd_workspace_bytes(const xeq_graph_t* g, const xeq_d
 
 int xeq_edge_message_bwdbwd(const xeq_graph_t* g, const xeq_dims_t* dims, const float* pos, const float* s, const float* v,
                             const float* W_rbf, const float* b_rbf, const float* freq, const float* gx, const float* gV,
-                            const float* a_s, const float* a_v, const float* a_pos, float* o_gx, float* o_gV, float* o_s,
+                            const float* a_s, const float* a_v, const float* a_pos, const float* a_cell, float* o_gx, float* o_gV, float* o_s,
                             float* o_v, float* o_pos, float* o_W, float* o_b, float* o_freq, void* workspace,
                             size_t workspace_bytes, xeq_stream_t stream) {
   XEQ_CHECK_ARG(pos && s && v && W_rbf && b_rbf && freq && gx && gV, "edge_message_bwdbwd: NULL argument");
@@ -953,7 +959,7 @@ int xeq_edge_message_bwdbwd(const xeq_graph_t* g, const xeq_dims_t* dims, const 
   if (o_gx || o_gV) {  // d/d(gx, gV): tangent of the forward message along (a_s, a_v, a_pos)
     XEQ_CHECK_ARG(o_gx && o_gV, "edge_message_bwdbwd: o_gx and o_gV must be given together");
     CenterArgs C{};
-    C.geo.pos = pos; C.geo.freq = freq; C.geo.a_pos = a_pos;
+    C.geo.pos = pos; C.geo.freq = freq; C.geo.a_pos = a_pos; C.geo.a_cell = a_cell;
     C.s = s; C.v = v; C.W = W_rbf; C.b = b_rbf;
     C.a_s = a_s; C.a_v = a_v; C.x_out = o_gx; C.V_out = o_gV;
     int rc = run_center(g, dims, C, true, st);
@@ -961,7 +967,7 @@ int xeq_edge_message_bwdbwd(const xeq_graph_t* g, const xeq_dims_t* dims, const 
   }
   if (o_s || o_v || o_pos || o_W) {
     NeighborArgs A{};
-    A.geo.pos = pos; A.geo.freq = freq; A.geo.a_pos = a_pos;
+    A.geo.pos = pos; A.geo.freq = freq; A.geo.a_pos = a_pos; A.geo.a_cell = a_cell;
     A.s = s; A.v = v; A.W = W_rbf; A.b = b_rbf; A.gx = gx; A.gV = gV;
     A.a_s = a_s; A.a_v = a_v; A.o_s = o_s; A.o_v = o_v;
     return run_neighbor(g, dims, A, 2, o_pos, o_W, o_b, o_freq, workspace, workspace_bytes, st);

@@ -295,7 +295,9 @@ template <int C, int M1, int M2, bool JVP>
 __global__ void __launch_bounds__(SL_M + 32, 1) center_mma_kernel(const CenterArgs A) {
   static_assert(C % SL_C == 0 && M1 == C / 2 && M2 == C / 4, "channel slices of edge_mma.cuh");
   __shared__ CenterMmaSmem<JVP> sm;
+  pdl_trigger();
   const uint32_t tmem = tmem_setup(&sm.slot, &sm.bar, 1);
+  pdl_wait();  // setup overlapped the previous kernel's tail
   const uint32_t tiles = (smem_u32(xeq_dyn_smem) + 1023u) & ~1023u;
   const uint32_t win_base = tiles + 2u * CenterMma<JVP>::STAGE;
   const int t = threadIdx.x;
@@ -659,7 +661,9 @@ __global__ void __launch_bounds__(SL_M + 32, 1) nbr_mma_kernel(const NeighborArg
   static_assert(C % SL_C == 0 && M1 == C / 2 && M2 == C / 4, "channel slices of edge_mma.cuh");
   static_assert(SL_M / 32 == NbrMma<ORDER>::NW, "consumer warps");
   __shared__ NbrMmaSmem<ORDER> sm;
+  pdl_trigger();
   const uint32_t tmem = tmem_setup(&sm.slot, &sm.bar, 1);
+  pdl_wait();  // setup overlapped the previous kernel's tail
   const uint32_t tiles = (smem_u32(xeq_dyn_smem) + 1023u) & ~1023u;
   const uint32_t win_base = tiles + 2u * NbrMma<ORDER>::STAGE;
   const int t = threadIdx.x;
@@ -997,7 +1001,9 @@ template <int C, int M1, int M2, int ORDER>
 __global__ void __launch_bounds__(2 * SL_M + 32, 1) wgrad_mma_kernel(const NeighborArgs A) {
   static_assert(C % SL_C == 0 && M1 == C / 2 && M2 == C / 4, "channel slices of edge_mma.cuh");
   __shared__ WgradMmaSmem<ORDER> sm;
+  pdl_trigger();
   const uint32_t tmem = tmem_setup(&sm.slot, &sm.bar, 1);
+  pdl_wait();  // setup overlapped the previous kernel's tail
   const uint32_t tiles = (smem_u32(xeq_dyn_smem) + 1023u) & ~1023u;
   const uint32_t win_base = tiles + 2u * WgradMma<ORDER>::STAGE;
   const int t = threadIdx.x;
@@ -1028,7 +1034,7 @@ static int launch_center_mma_t(const CenterArgs& A, cudaStream_t st) {
     if (rc) return rc;
   }
   const int grid = max(1, min(A.geo.g.n_tiles, num_sms() / SLICES));
-  center_mma_kernel<C, M1, M2, JVP><<<dim3(grid, SLICES), SL_M + 32, dyn, st>>>(A);
+  XEQ_CUDA(launch_pdl(center_mma_kernel<C, M1, M2, JVP>, dim3(grid, SLICES), dim3(SL_M + 32), dyn, st, A));
   XEQ_LAUNCHED(1);
   return XEQ_OK;
 }
@@ -1047,7 +1053,7 @@ static int launch_wgrad_mma_t(const NeighborArgs& A, int grid, cudaStream_t st) 
     int rc = set_smem(wgrad_mma_kernel<C, M1, M2, ORDER>, dyn);
     if (rc) return rc;
   }
-  wgrad_mma_kernel<C, M1, M2, ORDER><<<dim3(grid, SLICES), 2 * SL_M + 32, dyn, st>>>(A);
+  XEQ_CUDA(launch_pdl(wgrad_mma_kernel<C, M1, M2, ORDER>, dim3(grid, SLICES), dim3(2 * SL_M + 32), dyn, st, A));
   XEQ_LAUNCHED(1);
   return XEQ_OK;
 }
@@ -1062,7 +1068,7 @@ static int launch_nbr_mma_t(const NeighborArgs& A, cudaStream_t st) {
     if (rc) return rc;
   }
   const int grid = max(1, min(A.geo.g.t_n_tiles, num_sms() / SLICES));
-  nbr_mma_kernel<C, M1, M2, ORDER><<<dim3(grid, SLICES), SL_M + 32, dyn, st>>>(A);
+  XEQ_CUDA(launch_pdl(nbr_mma_kernel<C, M1, M2, ORDER>, dim3(grid, SLICES), dim3(SL_M + 32), dyn, st, A));
   XEQ_LAUNCHED(1);
   return XEQ_OK;
 }

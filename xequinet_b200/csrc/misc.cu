@@ -43,6 +43,8 @@ int num_sms() {
 // one warp per segment, lanes stride over the segment, fixed-order butterfly => deterministic
 __global__ void segment_sum_kernel(const float* __restrict__ src, const int* __restrict__ ptr, int n_seg,
                                    float* __restrict__ out) {
+  pdl_trigger();
+  pdl_wait();
   const int seg = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int lane = threadIdx.x & 31;
   if (seg >= n_seg) return;
@@ -100,6 +102,8 @@ __global__ void __cluster_dims__(1, COLSUM_CLUSTER, 1) __launch_bounds__(COLSUM_
 
 __global__ void layout_convert_kernel(const float* __restrict__ src, float* __restrict__ dst, int n, int m0, int m1,
                                       int m2, int direction) {
+  pdl_trigger();
+  pdl_wait();
   const int D = m0 + 3 * m1 + 5 * m2;
   const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= (size_t)n * D) return;
@@ -128,7 +132,7 @@ int xeq_segment_sum(const float* src, const int32_t* seg_ptr, int32_t n_segments
   if (n_segments == 0) return XEQ_OK;
   XEQ_CHECK_ARG(src, "segment_sum: src is NULL");
   const int blocks = (int)(((size_t)n_segments * 32 + 255) / 256);
-  segment_sum_kernel<<<blocks, 256, 0, (cudaStream_t)stream>>>(src, seg_ptr, n_segments, out);
+  XEQ_CUDA(launch_pdl(segment_sum_kernel, dim3(blocks), dim3(256), (size_t)(0), (cudaStream_t)stream, src, seg_ptr, n_segments, out));
   XEQ_LAUNCHED(1);
   return XEQ_OK;
 }
@@ -148,8 +152,8 @@ int xeq_layout_convert(const float* src, float* dst, int32_t n_nodes, const xeq_
   XEQ_CHECK_ARG(direction == 0 || direction == 1, "layout_convert: direction must be 0 or 1");
   const size_t total = (size_t)n_nodes * (dims->mul0 + 3 * dims->mul1 + 5 * dims->mul2);
   if (total == 0) return XEQ_OK;
-  layout_convert_kernel<<<(unsigned)((total + 255) / 256), 256, 0, (cudaStream_t)stream>>>(src, dst, n_nodes, dims->mul0,
-                                                                                         dims->mul1, dims->mul2, direction);
+  XEQ_CUDA(launch_pdl(layout_convert_kernel, dim3((unsigned)((total + 255) / 256)), dim3(256), (size_t)(0), (cudaStream_t)stream, src, dst, n_nodes, dims->mul0,
+                                                                                         dims->mul1, dims->mul2, direction));
   XEQ_LAUNCHED(1);
   return XEQ_OK;
 }

@@ -82,6 +82,8 @@ template <int NK>
 __global__ void __launch_bounds__(NORM_WARPS * 32) norm_fwd_kernel(const float* __restrict__ x, const float* __restrict__ gamma,
                                                                     const float* __restrict__ beta, int n, NormShape S,
                                                                     float* __restrict__ y) {
+  pdl_trigger();
+  pdl_wait();
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   float gam[NK], bet[NK];
 #pragma unroll
@@ -121,6 +123,8 @@ template <int NK>
 __global__ void __launch_bounds__(NORM_WARPS * 32) norm_bwd_kernel(const float* __restrict__ x, const float* __restrict__ gamma,
                                                                     const float* __restrict__ g, int n, NormShape S,
                                                                     float* __restrict__ gx, float* __restrict__ partials) {
+  pdl_trigger();
+  pdl_wait();
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   float gam[NK], acc[2][NK];
 #pragma unroll
@@ -162,6 +166,8 @@ __global__ void __launch_bounds__(NORM_WARPS * 32) norm_bwdbwd_kernel(const floa
                                                                        const float* __restrict__ g, const float* __restrict__ a,
                                                                        int n, NormShape S, float* __restrict__ dx,
                                                                        float* __restrict__ dg, float* __restrict__ partials) {
+  pdl_trigger();
+  pdl_wait();
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   float gam[NK], acc[1][NK];
 #pragma unroll
@@ -215,6 +221,8 @@ __global__ void __launch_bounds__(NORM_WARPS * 32) norm_bwdbwd_kernel(const floa
 __global__ void __launch_bounds__(256) norm_param_reduce_kernel(const float* __restrict__ partials, int n_part, int n_acc,
                                                                 NormShape S, float* __restrict__ out_gamma,
                                                                 float* __restrict__ out_beta) {
+  pdl_trigger();
+  pdl_wait();
   __shared__ float red[2][8][33];
   const int c = threadIdx.x & 31, rl = threadIdx.x >> 5;
   const int q = blockIdx.x * 32 + c;
@@ -273,13 +281,13 @@ int norm_grid(int n) { return max(1, min((n + NORM_WARPS - 1) / NORM_WARPS, num_
 
 #define NORM_DISPATCH(NKV, KERNEL, ...)                                      \
   switch (NKV) {                                                            \
-    case 1: KERNEL<1><<<grid, NORM_WARPS * 32, 0, st>>>(__VA_ARGS__); break;  \
-    case 2: KERNEL<2><<<grid, NORM_WARPS * 32, 0, st>>>(__VA_ARGS__); break;  \
-    case 4: KERNEL<4><<<grid, NORM_WARPS * 32, 0, st>>>(__VA_ARGS__); break;  \
-    case 8: KERNEL<8><<<grid, NORM_WARPS * 32, 0, st>>>(__VA_ARGS__); break;  \
-    case 9: KERNEL<9><<<grid, NORM_WARPS * 32, 0, st>>>(__VA_ARGS__); break;  \
-    case 15: KERNEL<15><<<grid, NORM_WARPS * 32, 0, st>>>(__VA_ARGS__); break; \
-    default: KERNEL<30><<<grid, NORM_WARPS * 32, 0, st>>>(__VA_ARGS__); break; \
+    case 1: XEQ_CUDA(launch_pdl(KERNEL<1>, dim3(grid), dim3(NORM_WARPS * 32), (size_t)(0), st, __VA_ARGS__)); break;  \
+    case 2: XEQ_CUDA(launch_pdl(KERNEL<2>, dim3(grid), dim3(NORM_WARPS * 32), (size_t)(0), st, __VA_ARGS__)); break;  \
+    case 4: XEQ_CUDA(launch_pdl(KERNEL<4>, dim3(grid), dim3(NORM_WARPS * 32), (size_t)(0), st, __VA_ARGS__)); break;  \
+    case 8: XEQ_CUDA(launch_pdl(KERNEL<8>, dim3(grid), dim3(NORM_WARPS * 32), (size_t)(0), st, __VA_ARGS__)); break;  \
+    case 9: XEQ_CUDA(launch_pdl(KERNEL<9>, dim3(grid), dim3(NORM_WARPS * 32), (size_t)(0), st, __VA_ARGS__)); break;  \
+    case 15: XEQ_CUDA(launch_pdl(KERNEL<15>, dim3(grid), dim3(NORM_WARPS * 32), (size_t)(0), st, __VA_ARGS__)); break; \
+    default: XEQ_CUDA(launch_pdl(KERNEL<30>, dim3(grid), dim3(NORM_WARPS * 32), (size_t)(0), st, __VA_ARGS__)); break; \
   }
 
 }  // namespace
@@ -327,7 +335,7 @@ int xeq_irreps_norm_bwd(const float* x, const float* gamma, const float* g, int3
     XEQ_LAUNCHED(1);
   }
   if (params) {
-    norm_param_reduce_kernel<<<S.M / 32, 256, 0, st>>>(partials, n_rows > 0 ? grid : 0, 2, S, ggamma, gbeta);
+    XEQ_CUDA(launch_pdl(norm_param_reduce_kernel, dim3(S.M / 32), dim3(256), (size_t)(0), st, partials, n_rows > 0 ? grid : 0, 2, S, ggamma, gbeta));
     XEQ_LAUNCHED(1);
   }
   return XEQ_OK;
@@ -351,7 +359,7 @@ int xeq_irreps_norm_bwdbwd(const float* x, const float* gamma, const float* g, c
     XEQ_LAUNCHED(1);
   }
   if (dgamma) {
-    norm_param_reduce_kernel<<<S.M / 32, 256, 0, st>>>(partials, n_rows > 0 ? grid : 0, 1, S, dgamma, nullptr);
+    XEQ_CUDA(launch_pdl(norm_param_reduce_kernel, dim3(S.M / 32), dim3(256), (size_t)(0), st, partials, n_rows > 0 ? grid : 0, 1, S, dgamma, nullptr));
     XEQ_LAUNCHED(1);
   }
   return XEQ_OK;

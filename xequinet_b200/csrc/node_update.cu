@@ -36,6 +36,8 @@ constexpr float INV_EPS = 1e-5f;  // Invariant(eps=1e-5): sqrt(s + eps^2) - eps
 // ---------------------------------------------------------------- (1) invariant + dot
 __global__ void invdot_fwd_kernel(const float* __restrict__ U, const float* __restrict__ W, int n, IrrepShape S,
                                   float* __restrict__ nrm, int ld_nrm, float* __restrict__ t0) {
+  pdl_trigger();
+  pdl_wait();
   const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= (size_t)n * S.M) return;
   const int node = (int)(idx / S.M), q = (int)(idx % S.M);
@@ -55,6 +57,8 @@ __global__ void invdot_fwd_kernel(const float* __restrict__ U, const float* __re
 __global__ void invdot_bwd_kernel(const float* __restrict__ U, const float* __restrict__ W, const float* __restrict__ gn,
                                   int ld_gn, const float* __restrict__ gt, int n, IrrepShape S, float* __restrict__ gU,
                                   float* __restrict__ gW) {
+  pdl_trigger();
+  pdl_wait();
   const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= (size_t)n * S.M) return;
   const int node = (int)(idx / S.M), q = (int)(idx % S.M);
@@ -79,6 +83,8 @@ __global__ void invdot_bwdbwd_kernel(const float* __restrict__ U, const float* _
                                      int ld_gn, const float* __restrict__ gt, const float* __restrict__ aU,
                                      const float* __restrict__ aW, int n, IrrepShape S, float* __restrict__ d_gn,
                                      float* __restrict__ d_gt, float* __restrict__ dU, float* __restrict__ dW) {
+  pdl_trigger();
+  pdl_wait();
   const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= (size_t)n * S.M) return;
   const int node = (int)(idx / S.M), q = (int)(idx % S.M);
@@ -110,6 +116,8 @@ __global__ void invdot_bwdbwd_kernel(const float* __restrict__ U, const float* _
 __global__ void gate_fwd_kernel(const float* __restrict__ a, const float* __restrict__ U, const float* __restrict__ t,
                                 const float* __restrict__ x, const float* __restrict__ V, int n, IrrepShape S,
                                 float* __restrict__ x_out, float* __restrict__ V_out) {
+  pdl_trigger();
+  pdl_wait();
   const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= (size_t)n * S.M) return;
   const int node = (int)(idx / S.M), q = (int)(idx % S.M);
@@ -129,6 +137,8 @@ __global__ void gate_fwd_kernel(const float* __restrict__ a, const float* __rest
 __global__ void gate_bwd_kernel(const float* __restrict__ a, const float* __restrict__ U, const float* __restrict__ t,
                                 const float* __restrict__ gx, const float* __restrict__ gV, int n, IrrepShape S,
                                 float* __restrict__ ga, float* __restrict__ gU, float* __restrict__ gt) {
+  pdl_trigger();
+  pdl_wait();
   const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= (size_t)n * S.M) return;
   const int node = (int)(idx / S.M), q = (int)(idx % S.M);
@@ -160,6 +170,8 @@ __global__ void gate_bwdbwd_kernel(const float* __restrict__ a, const float* __r
                                    const float* __restrict__ c_U, const float* __restrict__ c_t, int n, IrrepShape S,
                                    float* __restrict__ d_gx, float* __restrict__ d_gV, float* __restrict__ d_a,
                                    float* __restrict__ d_U, float* __restrict__ d_t) {
+  pdl_trigger();
+  pdl_wait();
   const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= (size_t)n * S.M) return;
   const int node = (int)(idx / S.M), q = (int)(idx % S.M);
@@ -194,10 +206,14 @@ __global__ void gate_bwdbwd_kernel(const float* __restrict__ a, const float* __r
 __device__ __forceinline__ float sigmoidf_(float u) { return 1.f / (1.f + expf(-u)); }  // accurate exp: __expf loses 2 + |1.17 u| ulp
 
 __global__ void silu_fwd_kernel(const float* __restrict__ u, size_t n, float* __restrict__ y) {
+  pdl_trigger();
+  pdl_wait();
   const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n) y[i] = u[i] * sigmoidf_(u[i]);
 }
 __global__ void silu_bwd_kernel(const float* __restrict__ u, const float* __restrict__ g, size_t n, float* __restrict__ gu) {
+  pdl_trigger();
+  pdl_wait();
   const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   const float x = u[i], s = sigmoidf_(x);
@@ -206,6 +222,8 @@ __global__ void silu_bwd_kernel(const float* __restrict__ u, const float* __rest
 // cotangent c of gu -> d/dg = c s'(u),  d/du = c g s''(u),  s'' = sig (1 - sig) (2 + u (1 - 2 sig))
 __global__ void silu_bwdbwd_kernel(const float* __restrict__ u, const float* __restrict__ g, const float* __restrict__ c, size_t n,
                                    float* __restrict__ dg, float* __restrict__ du) {
+  pdl_trigger();
+  pdl_wait();
   const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   const float x = u[i], s = sigmoidf_(x), cv = c[i];
@@ -237,7 +255,7 @@ int xeq_invariant_dot_fwd(const float* U, const float* W, int32_t n, int32_t mul
   if (rc) return rc;
   XEQ_CHECK_ARG(n >= 0 && (n == 0 || (U && W && nrm && t0)) && ld_nrm >= S.M, "invariant_dot_fwd: bad arguments");
   if (n == 0) return XEQ_OK;
-  invdot_fwd_kernel<<<blocks_for((size_t)n * S.M), 256, 0, (cudaStream_t)stream>>>(U, W, n, S, nrm, ld_nrm, t0);
+  XEQ_CUDA(launch_pdl(invdot_fwd_kernel, dim3(blocks_for((size_t)n * S.M)), dim3(256), (size_t)(0), (cudaStream_t)stream, U, W, n, S, nrm, ld_nrm, t0));
   XEQ_LAUNCHED(1);
   return XEQ_OK;
 }
@@ -249,7 +267,7 @@ int xeq_invariant_dot_bwd(const float* U, const float* W, const float* gn, int32
   if (rc) return rc;
   XEQ_CHECK_ARG(n >= 0 && (n == 0 || (U && W && gU && gW)), "invariant_dot_bwd: bad arguments");
   if (n == 0) return XEQ_OK;
-  invdot_bwd_kernel<<<blocks_for((size_t)n * S.M), 256, 0, (cudaStream_t)stream>>>(U, W, gn, ld_gn, gt, n, S, gU, gW);
+  XEQ_CUDA(launch_pdl(invdot_bwd_kernel, dim3(blocks_for((size_t)n * S.M)), dim3(256), (size_t)(0), (cudaStream_t)stream, U, W, gn, ld_gn, gt, n, S, gU, gW));
   XEQ_LAUNCHED(1);
   return XEQ_OK;
 }
@@ -262,8 +280,8 @@ int xeq_invariant_dot_bwdbwd(const float* U, const float* W, const float* gn, in
   if (rc) return rc;
   XEQ_CHECK_ARG(n >= 0 && (n == 0 || (U && W)), "invariant_dot_bwdbwd: bad arguments");
   if (n == 0) return XEQ_OK;
-  invdot_bwdbwd_kernel<<<blocks_for((size_t)n * S.M), 256, 0, (cudaStream_t)stream>>>(U, W, gn, ld_gn, gt, aU, aW, n, S, d_gn,
-                                                                                     d_gt, dU, dW);
+  XEQ_CUDA(launch_pdl(invdot_bwdbwd_kernel, dim3(blocks_for((size_t)n * S.M)), dim3(256), (size_t)(0), (cudaStream_t)stream, U, W, gn, ld_gn, gt, aU, aW, n, S, d_gn,
+                                                                                     d_gt, dU, dW));
   XEQ_LAUNCHED(1);
   return XEQ_OK;
 }
@@ -275,7 +293,7 @@ int xeq_gate_residual_fwd(const float* a, const float* U, const float* t, const 
   if (rc) return rc;
   XEQ_CHECK_ARG(n >= 0 && (n == 0 || (a && U && t && x && V && x_out && V_out)), "gate_residual_fwd: bad arguments");
   if (n == 0) return XEQ_OK;
-  gate_fwd_kernel<<<blocks_for((size_t)n * S.M), 256, 0, (cudaStream_t)stream>>>(a, U, t, x, V, n, S, x_out, V_out);
+  XEQ_CUDA(launch_pdl(gate_fwd_kernel, dim3(blocks_for((size_t)n * S.M)), dim3(256), (size_t)(0), (cudaStream_t)stream, a, U, t, x, V, n, S, x_out, V_out));
   XEQ_LAUNCHED(1);
   return XEQ_OK;
 }
@@ -287,7 +305,7 @@ int xeq_gate_residual_bwd(const float* a, const float* U, const float* t, const 
   if (rc) return rc;
   XEQ_CHECK_ARG(n >= 0 && (n == 0 || (a && U && t && ga && gU && gt)), "gate_residual_bwd: bad arguments");
   if (n == 0) return XEQ_OK;
-  gate_bwd_kernel<<<blocks_for((size_t)n * S.M), 256, 0, (cudaStream_t)stream>>>(a, U, t, gx, gV, n, S, ga, gU, gt);
+  XEQ_CUDA(launch_pdl(gate_bwd_kernel, dim3(blocks_for((size_t)n * S.M)), dim3(256), (size_t)(0), (cudaStream_t)stream, a, U, t, gx, gV, n, S, ga, gU, gt));
   XEQ_LAUNCHED(1);
   return XEQ_OK;
 }
@@ -301,8 +319,8 @@ int xeq_gate_residual_bwdbwd(const float* a, const float* U, const float* t, con
   if (rc) return rc;
   XEQ_CHECK_ARG(n >= 0 && (n == 0 || (a && U && t && d_gx && d_gV && d_a && d_U && d_t)), "gate_residual_bwdbwd: bad arguments");
   if (n == 0) return XEQ_OK;
-  gate_bwdbwd_kernel<<<blocks_for((size_t)n * S.M), 256, 0, (cudaStream_t)stream>>>(a, U, t, gx, gV, c_a, c_U, c_t, n, S, d_gx,
-                                                                                   d_gV, d_a, d_U, d_t);
+  XEQ_CUDA(launch_pdl(gate_bwdbwd_kernel, dim3(blocks_for((size_t)n * S.M)), dim3(256), (size_t)(0), (cudaStream_t)stream, a, U, t, gx, gV, c_a, c_U, c_t, n, S, d_gx,
+                                                                                   d_gV, d_a, d_U, d_t));
   XEQ_LAUNCHED(1);
   return XEQ_OK;
 }
@@ -310,21 +328,21 @@ int xeq_gate_residual_bwdbwd(const float* a, const float* U, const float* t, con
 int xeq_silu_fwd(const float* u, size_t n, float* y, xeq_stream_t stream) {
   XEQ_CHECK_ARG(n == 0 || (u && y), "silu_fwd: bad arguments");
   if (n == 0) return XEQ_OK;
-  silu_fwd_kernel<<<blocks_for(n), 256, 0, (cudaStream_t)stream>>>(u, n, y);
+  XEQ_CUDA(launch_pdl(silu_fwd_kernel, dim3(blocks_for(n)), dim3(256), (size_t)(0), (cudaStream_t)stream, u, n, y));
   XEQ_LAUNCHED(1);
   return XEQ_OK;
 }
 int xeq_silu_bwd(const float* u, const float* g, size_t n, float* gu, xeq_stream_t stream) {
   XEQ_CHECK_ARG(n == 0 || (u && g && gu), "silu_bwd: bad arguments");
   if (n == 0) return XEQ_OK;
-  silu_bwd_kernel<<<blocks_for(n), 256, 0, (cudaStream_t)stream>>>(u, g, n, gu);
+  XEQ_CUDA(launch_pdl(silu_bwd_kernel, dim3(blocks_for(n)), dim3(256), (size_t)(0), (cudaStream_t)stream, u, g, n, gu));
   XEQ_LAUNCHED(1);
   return XEQ_OK;
 }
 int xeq_silu_bwdbwd(const float* u, const float* g, const float* c, size_t n, float* dg, float* du, xeq_stream_t stream) {
   XEQ_CHECK_ARG(n == 0 || (u && g && c), "silu_bwdbwd: bad arguments");
   if (n == 0) return XEQ_OK;
-  silu_bwdbwd_kernel<<<blocks_for(n), 256, 0, (cudaStream_t)stream>>>(u, g, c, n, dg, du);
+  XEQ_CUDA(launch_pdl(silu_bwdbwd_kernel, dim3(blocks_for(n)), dim3(256), (size_t)(0), (cudaStream_t)stream, u, g, c, n, dg, du));
   XEQ_LAUNCHED(1);
   return XEQ_OK;
 }

@@ -79,10 +79,6 @@ def compute_forces_only(energy: torch.Tensor, pos: torch.Tensor, training: bool 
 def compute_virial_and_forces(energy: torch.Tensor, pos: torch.Tensor, strain: torch.Tensor, want_forces: bool,
                               training: bool, periodic: bool):
     """nn/basic.py:162-199: virial = -dE/dstrain (and forces = -dE/dpos from the same backward pass)."""
-    if training and periodic:
-        raise NotImplementedError("a virial term in the training loss of a PERIODIC structure needs the second derivative "
-                                  "of the cell gradient, which the B200 kernels do not provide yet (inference and "
-                                  "non-periodic training are supported)")
     inputs = ([pos] if want_forces else []) + [strain]
     grads = torch.autograd.grad(outputs=[energy], inputs=inputs, grad_outputs=[torch.ones_like(energy)],
                                 retain_graph=training, create_graph=training, allow_unused=True)

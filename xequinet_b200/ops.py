@@ -131,22 +131,31 @@ def edge_message_bwd_raw(graph: NeighborGraph, dims: Dims, pos, s, v, W, b, freq
     KernelTimer.stop(ev, "edge_bwd_wgrad" if need_w else "edge_bwd", graph)
     if not need_cell:
         return gs, gv, gpos, gW, gb, gf
+    return gs, gv, gpos, gW, gb, gf, _cell_grad_from_records(graph, d, ws)
+
+
+def _cell_grad_from_records(graph: NeighborGraph, d, ws) -> torch.Tensor:
+    """dE/dcell [G,3,3] = -sum_e offsets_e (x) dE/dr_e from the per-edge d/dr records a backward launch left in `ws`."""
+    lib = _lib.get()
     if graph.offsets is None or getattr(graph, "seg_ptr", None) is None:
         raise RuntimeError("the cell gradient needs a periodic graph with its batch pointer (graph.seg_ptr)")
-    rows = new(9, N)
+    N, dev = graph.n_nodes, ws.device
+    rows = torch.empty((9, N), dtype=torch.float32, device=dev)
     _lib.check(lib.xeq_edge_cell_grad_rows(graph.struct, d, _lib.ptr(ws), _lib.ptr(rows), _lib.stream()), "xeq_edge_cell_grad_rows")
     G = graph.seg_ptr.numel() - 1
-    sums = new(9, G)
+    sums = torch.empty((9, G), dtype=torch.float32, device=dev)
     for k in range(9):  # nine deterministic segment sums over the nodes of each graph
         _lib.check(lib.xeq_segment_sum(_lib.ptr(rows[k]), _lib.ptr(graph.seg_ptr), G, _lib.ptr(sums[k]), _lib.stream()),
                    "xeq_segment_sum")
-    gcell = -sums.t().reshape(G, 3, 3)
-    return gs, gv, gpos, gW, gb, gf, gcell
+    return -sums.t().reshape(G, 3, 3)
 
 
 def edge_message_bwdbwd_raw(graph: NeighborGraph, dims: Dims, pos, s, v, W, b, freq, gx, gV, a_s, a_v, a_pos,
-                            need_g=True, need_s=True, need_v=True, need_pos=True, need_w=True):
+                            need_g=True, need_s=True, need_v=True, need_pos=True, need_w=True, a_cell=None, need_cell=False):
+    """K2bb.  a_cell [G,3,3]: cotangent of the first-order cell gradient (periodic virial in a training loss); with
+    need_cell the second-order cell gradient is appended to the result (it implies need_pos)."""
     lib = _lib.get()
+    need_pos = need_pos or need_cell
     N, dev = graph.n_nodes, s.device
     new = lambda *shape: torch.empty(shape, dtype=torch.float32, device=dev)
     o_gx = new(N, dims.node_dim) if need_g else None
@@ -163,10 +172,12 @@ def edge_message_bwdbwd_raw(graph: NeighborGraph, dims: Dims, pos, s, v, W, b, f
     ev = KernelTimer.start()
     _lib.check(lib.xeq_edge_message_bwdbwd(graph.struct, d, _lib.ptr(pos), _lib.ptr(s), _lib.ptr(v), _lib.ptr(W),
                                            _lib.ptr(b), _lib.ptr(freq), _lib.ptr(gx), _lib.ptr(gV), _lib.ptr(a_s),
-                                           _lib.ptr(a_v), _lib.ptr(a_pos), _lib.ptr(o_gx), _lib.ptr(o_gV), _lib.ptr(o_s),
+                                           _lib.ptr(a_v), _lib.ptr(a_pos), _lib.ptr(a_cell), _lib.ptr(o_gx), _lib.ptr(o_gV), _lib.ptr(o_s),
                                            _lib.ptr(o_v), _lib.ptr(o_pos), _lib.ptr(o_W), _lib.ptr(o_b), _lib.ptr(o_f),
                                            _lib.ptr(ws), nbytes, _lib.stream()), "xeq_edge_message_bwdbwd")
     KernelTimer.stop(ev, "edge_bwdbwd", graph)
+    if need_cell:
+        return o_gx, o_gV, o_s, o_v, o_pos, o_W, o_b, o_f, _cell_grad_from_records(graph, d, ws)
     return o_gx, o_gV, o_s, o_v, o_pos, o_W, o_b, o_f
 
 
@@ -174,20 +185,20 @@ def edge_message_bwdbwd_raw(graph: NeighborGraph, dims: Dims, pos, s, v, W, b, f
 # autograd
 # ------------------------------------------------------------------------------------------
 class _EdgeMessageBwd(torch.autograd.Function):
-    """K2b as a differentiable function of (gx, gV, s, v, pos, W, b, freq); its backward is K2bb."""
+    """K2b as a differentiable function of (gx, gV, s, v, pos, W, b, freq, cell); its backward is K2bb."""
 
     @staticmethod
-    def forward(ctx, gx, gV, s, v, pos, W, b, freq, graph, dims, needs):
+    def forward(ctx, gx, gV, s, v, pos, W, b, freq, cell, graph, dims, needs):
         need_s, need_v, need_pos, need_w = needs[:4]
         need_cell = len(needs) > 4 and needs[4]
         gx, gV = _c(gx), _c(gV)
         res = edge_message_bwd_raw(graph, dims, pos, s, v, W, b, freq, gx, gV, need_s, need_v, need_pos, need_w, need_cell)
         gs, gv, gpos, gW, gb, gf = res[:6]
-        gcell = res[6] if need_cell else None  # first order only: no derivative of the cell gradient is provided
+        gcell = res[6] if need_cell else None
         ctx.save_for_backward(gx, gV, s, v, pos, W, b, freq)
         ctx.graph, ctx.dims, ctx.needs = graph, dims, needs
         outs = (gs, gv, gpos, gW, gb, gf, gcell)
-        ctx.mark_non_differentiable(*[o for o in outs[3:] if o is not None])
+        ctx.mark_non_differentiable(*[o for o in outs[3:6] if o is not None])
         return outs
 
     @staticmethod
@@ -195,14 +206,18 @@ class _EdgeMessageBwd(torch.autograd.Function):
     def backward(ctx, a_s, a_v, a_pos, a_W, a_b, a_f, a_cell=None):
         gx, gV, s, v, pos, W, b, freq = ctx.saved_tensors
         ni = ctx.needs_input_grad
-        if a_s is None and a_v is None and a_pos is None:
-            return (None,) * 11
+        if a_s is None and a_v is None and a_pos is None and a_cell is None:
+            return (None,) * 12
         need_g = ni[0] or ni[1]
         need_w = ni[5] or ni[6] or ni[7]
+        need_cell = bool(ni[8])
         o = edge_message_bwdbwd_raw(ctx.graph, ctx.dims, pos, s, v, W, b, freq, gx, gV, _c(a_s), _c(a_v), _c(a_pos),
-                                    need_g=need_g, need_s=ni[2], need_v=ni[3], need_pos=ni[4], need_w=need_w)
-        o_gx, o_gV, o_s, o_v, o_pos, o_W, o_b, o_f = o
-        return o_gx, o_gV, o_s, o_v, o_pos, o_W, o_b, (o_f.view_as(freq) if o_f is not None else None), None, None, None
+                                    need_g=need_g, need_s=ni[2], need_v=ni[3], need_pos=ni[4], need_w=need_w,
+                                    a_cell=_c(a_cell), need_cell=need_cell)
+        o_gx, o_gV, o_s, o_v, o_pos, o_W, o_b, o_f = o[:8]
+        o_cell = o[8] if need_cell else None
+        return (o_gx, o_gV, o_s, o_v, (o_pos if ni[4] else None), o_W, o_b, (o_f.view_as(freq) if o_f is not None else None),
+                o_cell, None, None, None)
 
 
 class _EdgeMessage(torch.autograd.Function):
@@ -215,13 +230,13 @@ class _EdgeMessage(torch.autograd.Function):
         x, V, s, v, pos, W, b = (_c(t) for t in (x, V, s, v, pos, W, b))
         freq = _c(freq)
         x_out, V_out = edge_message_fwd_raw(graph, dims, pos, s, v, x, V, W, b, freq)
-        ctx.save_for_backward(s, v, pos, W, b, freq)
+        ctx.save_for_backward(s, v, pos, W, b, freq, cell)  # cell: only to route its gradient (None otherwise)
         ctx.graph, ctx.dims = graph, dims
         return x_out, V_out
 
     @staticmethod
     def backward(ctx, gx, gV):
-        s, v, pos, W, b, freq = ctx.saved_tensors
+        s, v, pos, W, b, freq, cell = ctx.saved_tensors
         ni = ctx.needs_input_grad
         if gx is None:
             gx = torch.zeros((s.shape[0], ctx.dims.node_dim), dtype=s.dtype, device=s.device)
@@ -234,7 +249,7 @@ class _EdgeMessage(torch.autograd.Function):
         needs = (want[2], want[3], want[4] or need_cell, need_w, need_cell)
         gs = gv = gpos = gW = gb = gf = gcell = None
         if any(needs):
-            gs, gv, gpos, gW, gb, gf, gcell = _EdgeMessageBwd.apply(gx, gV, s, v, pos, W, b, freq, ctx.graph, ctx.dims, needs)
+            gs, gv, gpos, gW, gb, gf, gcell = _EdgeMessageBwd.apply(gx, gV, s, v, pos, W, b, freq, cell, ctx.graph, ctx.dims, needs)
             if gf is not None:
                 gf = gf.view_as(freq)
             if not want[4]:

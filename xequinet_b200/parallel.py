@@ -78,14 +78,17 @@ class FlatGradients:
 
         flat = FlatGradients(model.parameters())
         ...
-        flat.zero()              # start of the step (one memset; autograd then accumulates into the views)
-        loss.backward()          # buckets are all-reduced as they complete (post-accumulate-grad hooks)
-        flat.finish()            # join the side stream; gradients are the averages over the ranks
+        flat.zero()              # start of the step: p.grad = None, autograd ASSIGNS fresh gradients (no accumulate kernels)
+        loss.backward()          # a bucket is gathered (one multi-tensor copy) and all-reduced as soon as it is complete
+        flat.finish()            # join the side stream; every p.grad is now a view of the averaged flat buffer
         optimizer.step()
 
-    With world size 1 (or no process group) the hooks are not installed and finish() is a no-op; zero() still
-    clears the buffer.  Gradients finalise in reverse order of use (read-out first, embedding last), so bucket 0
-    holds the LAST parameters of the list."""
+    Per bucket the step costs one `_foreach_copy_` launch and one all-reduce (three buckets: six launches per step,
+    against ~75 gather + ~75 scatter copies of a cat / split formulation, or ~75 accumulate kernels when autograd is
+    made to add into preallocated views).  With world size 1 (or no process group) nothing is hooked: finish() is a
+    no-op.  Gradients finalise in reverse order of use (read-out first, embedding last), so bucket 0 holds the LAST
+    parameters of the list.  Capturable: under CUDA-graph capture the side stream is forked from / joined to the
+    capturing stream and the gradient tensors autograd produced during capture keep their addresses on replay."""
 
     def __init__(self, params: Iterable[torch.nn.Parameter], n_buckets: int = 3, group=None, average: bool = True):
         self.params = [p for p in params if p.requires_grad]
@@ -98,10 +101,11 @@ class FlatGradients:
         self.flat = torch.zeros(total, dtype=p0.dtype, device=p0.device)
         off = 0
         self._range = {}
+        self._view = {}
         for p in self.params:
             n = p.numel()
-            p.grad = self.flat[off:off + n].view_as(p)
             self._range[id(p)] = (off, off + n)
+            self._view[id(p)] = self.flat[off:off + n].view_as(p)
             off += n
         # contiguous buckets of roughly equal size over the REVERSED parameter list
         n_buckets = max(1, min(int(n_buckets), len(self.params)))
@@ -116,7 +120,6 @@ class FlatGradients:
         self._bucket_of = {id(p): b for b, ps in enumerate(self.buckets) for p in ps}
         self._slice = [(min(self._range[id(p)][0] for p in ps), max(self._range[id(p)][1] for p in ps)) for ps in self.buckets]
         self._pending = [0] * len(self.buckets)
-        self._handles = []
         self._side = torch.cuda.Stream(device=p0.device) if p0.is_cuda else None
         self._launched = [False] * len(self.buckets)
         if self.world > 1:
@@ -126,16 +129,21 @@ class FlatGradients:
 
     # -- step protocol ------------------------------------------------------------------------------------
     def zero(self) -> None:
-        self.flat.zero_()
-        for p in self.params:  # an optimizer's zero_grad(set_to_none=True) must not detach the views
-            if p.grad is None or p.grad.data_ptr() != self.flat.data_ptr() + self.flat.element_size() * self._range[id(p)][0]:
-                lo, hi = self._range[id(p)]
-                p.grad = self.flat[lo:hi].view_as(p)
+        for p in self.params:
+            p.grad = None
         self._pending = [len(ps) for ps in self.buckets]
         self._launched = [False] * len(self.buckets)
-        self._handles = []
 
     def _reduce_bucket(self, b: int) -> None:
+        ps = [p for p in self.buckets[b] if p.grad is not None]
+        missing = [p for p in self.buckets[b] if p.grad is None]
+        if ps:
+            torch._foreach_copy_([self._view[id(p)] for p in ps], [p.grad for p in ps])  # one multi-tensor launch
+            for p in ps:
+                p.grad = self._view[id(p)]
+        for p in missing:  # no gradient on this rank: contributes zeros, receives the other ranks' share
+            self._view[id(p)].zero_()
+            p.grad = self._view[id(p)]
         lo, hi = self._slice[b]
         piece = self.flat[lo:hi]
         if self._side is not None:
@@ -161,7 +169,7 @@ class FlatGradients:
 
     def finish(self) -> None:
         """All buckets reduced and visible to the current stream.  Parameters that received no gradient in this
-        backward pass never fire their hook: their buckets are reduced here (zeros contribute nothing)."""
+        backward pass never fire their hook: their buckets are reduced here."""
         if self.world == 1:
             return
         for b in range(len(self.buckets)):

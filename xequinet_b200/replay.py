@@ -67,8 +67,6 @@ class CapturedStep:
         out = self.model(d, compute_forces=self.forces)
         if self.train:
             loss = self.loss_fn(out, d)
-            if self.flat is not None:
-                self.flat.zero()
             loss.backward()
             if self.flat is not None:
                 self.flat.finish()
@@ -79,8 +77,11 @@ class CapturedStep:
         return res
 
     def _reset_grads(self) -> None:
-        if self.train and self.flat is None:
-            self.opt.zero_grad(set_to_none=True)
+        if self.train:
+            if self.flat is not None:
+                self.flat.zero()
+            else:
+                self.opt.zero_grad(set_to_none=True)
         self.static[keys.POSITIONS].grad = None
 
     def _capture(self, warmup: int) -> None:
