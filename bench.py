@@ -182,15 +182,18 @@ def algorithmic_bytes(kind: str, cfg: orc.XPaiNNConfig, N: int, E: int, periodic
     raise KeyError(kind)
 
 
-# DRAM bytes per launch (dram__bytes_read.sum + dram__bytes_write.sum) of the kernels behind each timed op, from
-# the committed `ncu --set full` capture profiles/r01_edge_mma_ncu_full.md (c3 shape: N = 5376, E = 106068).
-# Only valid for that shape; other workloads report traffic = null.
+# DRAM bytes per launch (dram__bytes_read.sum + dram__bytes_write.sum) of the kernels behind each timed op, from the
+# committed `ncu --set full` captures (c3 shape: N = 5376, E = 106068): profiles/r02_edge_ncu_full.md for the round-2
+# kernels, profiles/r01_edge_mma_ncu_full.md for nbr_mma_kernel<2> (unchanged).  Only valid for that shape; other
+# workloads report traffic = null.
 NCU_TRAFFIC_C3 = {
-    "edge_fwd": 36.43e6 + 0.31e6,                                                    # center_fwd_kernel
-    "edge_bwd": 36.88e6 + 0.25e6,                                                    # nbr_mma_kernel<1>
-    "edge_bwd_wgrad": (36.88e6 + 0.25e6) + (36.78e6 + 0.02e6),                       # + wgrad_mma_kernel<1>
-    "edge_bwdbwd": (46.14e6 + 0.21e6) + (59.67e6 + 3.12e6) + (59.56e6 + 1.61e6),     # jvp + nbr<2> + wgrad<2>
+    "edge_fwd": 35.73e6 + 0.01e6,                                                    # center_fwd_ul_kernel (rows packed in-kernel)
+    "edge_bwd": 36.85e6 + 0.16e6,                                                    # nbr_bwd_ul_kernel
+    "edge_bwd_wgrad": (36.85e6 + 0.16e6) + (36.78e6 + 0.08e6),                       # + wgrad_mma_kernel<1>
+    "edge_bwdbwd": (46.14e6 + 0.05e6) + (59.67e6 + 3.12e6) + (59.57e6 + 1.37e6),     # jvp + nbr<2> + wgrad<2>
 }
+# the same for the throughput probe (8192 molecules): center_fwd_ul_kernel, profiles/r02_edge_ncu_full.md (r02b capture)
+NCU_TRAFFIC_PROBE_FWD = 1.1395e9 + 0.3939e9
 
 
 def edge_throughput_probe(cfg, dev, peak, n_mol=8192, reps=10):
@@ -223,8 +226,9 @@ def edge_throughput_probe(cfg, dev, peak, n_mol=8192, reps=10):
         torch.cuda.synchronize()
         ms = t0.elapsed_time(t1) / reps
         achieved = algorithmic_bytes("edge_fwd", cfg, N, E, False) / (ms * 1e-3) / 1e9
-        return {"kernel": "edge_fwd", "launch": "xeq_edge_message_fwd: pack_fwd_kernel + center_fwd_ul_kernel", "bound": "hbm",
+        return {"kernel": "edge_fwd", "launch": "xeq_edge_message_fwd: center_fwd_ul_kernel (window rows packed in-kernel)", "bound": "hbm",
                 "achieved": round(achieved, 2), "peak": peak, "unit": "GB/s", "frac": round(achieved / peak, 5),
+                "traffic": NCU_TRAFFIC_PROBE_FWD if n_mol == 8192 else None,
                 "n_nodes": N, "n_edges": E, "mean_launch_ms": round(ms, 4),
                 "working_set": f"{n_mol} aspirin-shaped molecules: node rows {4 * N * (dims.H + 2 * dims.D + 2 * dims.node_dim) / 1e9:.2f} GB >> L2"}
     except Exception as exc:  # pragma: no cover
@@ -501,7 +505,7 @@ def run_gpu(args):
         cnt, mean_ms, N, E = kern[dom]
         achieved = algorithmic_bytes(dom, cfg, N, E, periodic) / (mean_ms * 1e-3) / 1e9
         traffic = NCU_TRAFFIC_C3.get(dom) if (args.workload == "c3" and N == 5376) else None
-        launch_of = {"edge_fwd": "xeq_edge_message_fwd: pack_fwd_kernel + center_fwd_ul_kernel",
+        launch_of = {"edge_fwd": "xeq_edge_message_fwd: center_fwd_ul_kernel (+ pack_fwd_kernel when tiles exceed the window)",
                      "edge_bwd": "xeq_edge_message_bwd: nbr_bwd_ul_kernel + pos_grad",
                      "edge_bwd_wgrad": "xeq_edge_message_bwd with weight gradients: nbr_bwd_ul_kernel + wgrad_mma_kernel<1> + reductions",
                      "edge_bwdbwd": "xeq_edge_message_bwdbwd: center_mma_kernel<jvp> + nbr_mma_kernel<2> + wgrad_mma_kernel<2> + reductions"}

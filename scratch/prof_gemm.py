@@ -1,9 +1,18 @@
-"""ncu target: a few launches of the K3 GEMM on c3 shapes.  usage: python scratch/prof_gemm.py [n k]"""
+"""ncu target: the K3 GEMM on the c3 shapes (M = 5376): forward Linear shapes, the grouped o3.Linear, a split-K weight gradient."""
 import sys; sys.path.insert(0, ".")
 import torch
 from xequinet_b200 import gemm
 M = 5376
-n, k = (int(sys.argv[1]), int(sys.argv[2])) if len(sys.argv) > 2 else (128, 128)
-A = torch.randn(M, k, device="cuda"); B = torch.randn(n, k, device="cuda")
-for _ in range(5): gemm.mm_raw(A, B, False, True)
+dev = "cuda"
+shapes = [(128, 128), (576, 128), (128, 352), (480, 128), (128, 224)]
+ops = []
+for n, k in shapes:
+    A = torch.randn(M, k, device=dev); B = torch.randn(n, k, device=dev)
+    ops.append(lambda A=A, B=B: gemm.mm_raw(A, B, False, True))
+V = torch.randn(M, 480, device=dev); w = torch.randn(128 * 128 + 64 * 64 + 32 * 32, device=dev)
+ops.append(lambda: gemm.irreps_linear_raw(V, w, None, (128, 64, 32), False))
+G = torch.randn(M, 576, device=dev); X = torch.randn(M, 128, device=dev)
+ops.append(lambda: gemm.mm_raw(X, G, True, False))
+for _ in range(3):
+    for f in ops: f()
 torch.cuda.synchronize()
