@@ -748,7 +748,7 @@ int launch_center_fwd_ul(const CenterArgs& A, bool wide, void* ws, cudaStream_t 
 size_t center_fwd_ul_workspace_bytes(int n_nodes, bool wide);
 int launch_nbr_bwd_ul(const NeighborArgs& A, bool wide, cudaStream_t st);             // edge_bwd_ul.cu: K2b first order
 int launch_center_jvp_mma(const CenterArgs& A, bool wide, cudaStream_t st);           // edge_message_mma.cu: K2bb JVP pass
-int launch_nbr2_mma(const NeighborArgs& A, bool wide, cudaStream_t st);               //                      K2bb reverse pass
+int launch_nbr2_ul(const NeighborArgs& A, bool wide, cudaStream_t st);                // edge_bwd2_ul.cu: K2bb reverse pass (main + w'' passes)
 int launch_wgrad_mma(const NeighborArgs& A, int order, bool wide, int grid, cudaStream_t st);  //             weight gradients
 
 // The product library has ONE implementation per kernel (tcgen05).  A test-only build (-DXEQ_WITH_SIMT,
@@ -854,7 +854,7 @@ static int run_neighbor(const xeq_graph_t* g, const xeq_dims_t* dims, NeighborAr
   A.gr = o_pos ? gr : nullptr;
   A.wpart = wpart;
   if (mma) {
-    if (main) rc = order == 1 ? launch_nbr_bwd_ul(A, cfg == 1, st) : launch_nbr2_mma(A, cfg == 1, st);
+    if (main) rc = order == 1 ? launch_nbr_bwd_ul(A, cfg == 1, st) : launch_nbr2_ul(A, cfg == 1, st);
     if (!rc && wgrad) rc = launch_wgrad_mma(A, order, cfg == 1, gx, st);
   }
 #ifdef XEQ_WITH_SIMT

@@ -1,3 +1,7 @@
+// Round-1 mapping (one thread per irrep channel, one consumer group per CTA) of the kernels that have not moved to the
+// unified-lane design yet: the JVP pass of K2bb (center_mma_kernel<JVP>) and the weight-gradient kernels.  The forward,
+// first-order and second-order neighbor passes live in edge_fwd_ul.cu / edge_bwd_ul.cu / edge_bwd2_ul.cu.
+//
 // K2 / K2b / K2bb with the filter contraction on the tensor cores (tcgen05, operands in TMEM).
 //
 // Same three kernel families, thread <-> channel mapping, CSR walk, shared-memory row window and
@@ -305,372 +309,6 @@ __global__ void __launch_bounds__(SL_M + 32, 1) center_mma_kernel(const CenterAr
   else if (t < SL_C + SL_M1) center_mma_role<1, C, M1, M2, JVP>(A, sm, tmem, tiles, win_base);
   else if (t < SL_M) center_mma_role<2, C, M1, M2, JVP>(A, sm, tmem, tiles, win_base);
   else center_mma_producer<C, M1, M2, JVP>(A, sm, tmem, tiles);
-  tmem_teardown(tmem);
-}
-
-// ==========================================================================================
-// neighbor kernel (K2b forces, reverse half of K2bb)
-// ==========================================================================================
-template <int ORDER> struct NbrMma {
-  static constexpr int TC = 16;                 // slots per chunk = MMA N
-  static constexpr int NOUT = ORDER + 1;        // filter outputs: w, dw (, ddw)
-  static constexpr int STAGE = NOUT * 2 * TC * 128;
-  static constexpr int WIN = 24;                // rows of the shared-memory window (gV | gx rows)
-  static constexpr int NW = 7;                  // consumer warps
-};
-
-template <int ORDER>
-struct NbrMmaSmem {
-  GeoA<NbrMma<ORDER>::TC, true, ORDER == 2> a[3];
-  ChunkDesc desc[8];
-  float red[2][NbrMma<ORDER>::TC][NbrMma<ORDER>::NW][3];
-  int red_eid[2][NbrMma<ORDER>::TC];
-  uint64_t bar;
-  uint32_t slot;
-};
-
-// Sum NV (4, 8 or 16) per-thread values over the 32 lanes of a warp: halving exchanges (offsets 16, 8, ..: each
-// keeps half of the values) until one value per lane is left, then plain butterflies over the remaining
-// offsets.  NV = 16: 16 shuffles instead of 80.  Lane l returns the total of v[l / (32 / NV)].  Fixed tree ->
-// bitwise reproducible.
-template <int NV>
-__device__ __forceinline__ float warp_sum(float (&v)[NV], int lane) {
-  static_assert(NV == 4 || NV == 8 || NV == 16, "NV");
-  constexpr int STEPS = (NV == 16) ? 4 : (NV == 8 ? 3 : 2);
-#pragma unroll
-  for (int st = 0; st < STEPS; ++st) {
-    const int half = NV >> (st + 1), off = 16 >> st;
-    const bool up = (lane & off) != 0;
-#pragma unroll
-    for (int i = 0; i < half; ++i) {
-      const float send = up ? v[i] : v[i + half];
-      const float keep = up ? v[i + half] : v[i];
-      v[i] = keep + __shfl_xor_sync(0xffffffffu, send, off);
-    }
-  }
-  float r = v[0];
-#pragma unroll
-  for (int off = 16 >> STEPS; off >= 1; off >>= 1) r += __shfl_xor_sync(0xffffffffu, r, off);
-  return r;
-}
-
-template <int L, int C, int M1, int M2, int ORDER>
-__device__ __forceinline__ void nbr_mma_role(const NeighborArgs& A, NbrMmaSmem<ORDER>& sm, const uint32_t tmem,
-                                             const uint32_t tiles, const uint32_t win_base) {
-  constexpr int M = C + M1 + M2, D = C + 3 * M1 + 5 * M2, H = C + 2 * M, NC = 2 * L + 1;
-  constexpr int THREADS = SL_M, NW = NbrMma<ORDER>::NW;
-  constexpr bool SECOND = ORDER == 2;
-  constexpr int TC = NbrMma<ORDER>::TC, NOUT = NbrMma<ORDER>::NOUT, STAGE = NbrMma<ORDER>::STAGE;
-  constexpr int TS = (L == 0) ? 0 : 3, TE = (L == 0) ? 1 : 4, TX = 2;
-  const int t = threadIdx.x, lane = t & 31, warp = t >> 5;
-  const int q = slice_channel<L, C, M1>(t, blockIdx.y);  // irrep channel of this thread
-  const int vbase = (L == 0) ? q : (L == 1 ? C + (q - C) : C + 3 * M1 + (q - C - M1));
-  constexpr int vstride = (L == 0) ? 0 : (L == 1 ? M1 : M2);
-  const xeq_graph_t& g = A.geo.g;
-  const uint32_t lane_base = tmem + ((uint32_t)(32 * (warp & 3)) << 16);
-  const uint32_t bar = smem_u32(&sm.bar);
-
-  {  // filter rows -> TMEM (once per CTA)
-    float row[NBP];
-    load_wrow(A.W, A.b, q, row);
-    store_a_row(lane_base, TS, row);
-    load_wrow(A.W, A.b, M + q, row);
-    store_a_row(lane_base, TE, row);
-    if (L == 0) {
-      load_wrow(A.W, A.b, 2 * M + q, row);
-      store_a_row(lane_base, TX, row);
-    }
-    tmem_wait_st();
-  }
-
-  NeighborThread<float, L, ROLE_STATE, false, NK_> st;
-  NeighborThread<float, L, ROLE_EDGE, false, NK_> ed;
-  NeighborThread<float, 0, ROLE_SCALAR, false, NK_> sc;
-  st.s = st.sd = ed.s = ed.sd = sc.s = sc.sd = 0.f;
-#pragma unroll
-  for (int m = 0; m < NC; ++m) st.v[m] = st.vd[m] = 0.f;
-  st.reset_node(); ed.reset_node(); sc.reset_node();
-
-  auto emit = [&](int node) {
-    if (A.o_s) {
-      float* os = A.o_s + (size_t)node * H;
-      os[q] = st.acc_s;
-      os[M + q] = ed.acc_s;
-      if (L == 0) os[2 * M + q] = sc.acc_s;
-    }
-    if (A.o_v) {
-#pragma unroll
-      for (int m = 0; m < NC; ++m) A.o_v[(size_t)node * D + vbase + m * vstride] = st.acc_v[m];
-    }
-  };
-  // the owner's rows (s, v and their tangents) are requested one chunk before its transposed row starts, so
-  // their latency is not paid at the row switch
-  struct RowRegs {
-    float s_st, s_ed, s_sc, sd_st, sd_ed, sd_sc, v[NC], vd[NC];
-  };
-  RowRegs nxt;
-  auto prefetch_node = [&](int j, RowRegs& o) {
-    const float* sj = A.s + (size_t)j * H;
-    o.s_st = sj[q];
-    o.s_ed = sj[M + q];
-    o.s_sc = (L == 0) ? sj[2 * M + q] : 0.f;
-    o.sd_st = o.sd_ed = o.sd_sc = 0.f;
-    if (SECOND && A.a_s) {
-      const float* aj = A.a_s + (size_t)j * H;
-      o.sd_st = aj[q];
-      o.sd_ed = aj[M + q];
-      if (L == 0) o.sd_sc = aj[2 * M + q];
-    }
-#pragma unroll
-    for (int m = 0; m < NC; ++m) {
-      o.v[m] = A.v[(size_t)j * D + vbase + m * vstride];
-      o.vd[m] = (SECOND && A.a_v) ? A.a_v[(size_t)j * D + vbase + m * vstride] : 0.f;
-    }
-  };
-  auto begin_node = [&](const RowRegs& o) {
-    st.reset_node(); ed.reset_node(); sc.reset_node();
-    st.s = o.s_st; ed.s = o.s_ed; sc.s = o.s_sc;
-    st.sd = o.sd_st; ed.sd = o.sd_ed; sc.sd = o.sd_sc;
-#pragma unroll
-    for (int m = 0; m < NC; ++m) { st.v[m] = o.v[m]; st.vd[m] = o.vd[m]; }
-  };
-  struct Gathered {
-    float g[NC], gx;
-  };
-  auto gather = [&](int i, Gathered& o) {
-#pragma unroll
-    for (int m = 0; m < NC; ++m) o.g[m] = A.gV[(size_t)i * D + vbase + m * vstride];
-    o.gx = (L == 0) ? A.gx[(size_t)i * C + q] : 0.f;
-  };
-  constexpr int WMAX = NbrMma<ORDER>::WIN;
-  constexpr int ROWF = SL_C * 2 + SL_M1 * 3 + SL_M2 * 5;
-  constexpr int NTHR = (L == 0) ? SL_C : (L == 1 ? SL_M1 : SL_M2);
-  constexpr int ROLE_OFF = (L == 0) ? 0 : (L == 1 ? SL_C * 2 : SL_C * 2 + SL_M1 * 3);
-  const int tt = (L == 0) ? t : (L == 1 ? t - SL_C : t - SL_C - SL_M1);
-  const uint32_t win0 = win_base + 4u * (ROLE_OFF + tt);
-  bool staged = false;
-  int win_lo = 0;
-  auto stage_window = [&](int n0, int n1) {
-#pragma unroll 4
-    for (int i = n0; i < n1; ++i) {
-      const uint32_t a = win0 + 4u * (uint32_t)((i - n0) * ROWF);
-      Gathered gc;
-      gather(i, gc);
-#pragma unroll
-      for (int m = 0; m < NC; ++m) sts_f32(a + 4u * (uint32_t)(NTHR * m), gc.g[m]);
-      if (L == 0) sts_f32(a + 4u * (uint32_t)(NTHR * NC), gc.gx);
-    }
-  };
-  auto gather_window = [&](int i, Gathered& o) {
-    const uint32_t a = win0 + 4u * (uint32_t)((i - win_lo) * ROWF);
-#pragma unroll
-    for (int m = 0; m < NC; ++m) o.g[m] = lds_f32(a + 4u * (uint32_t)(NTHR * m));
-    o.gx = (L == 0) ? lds_f32(a + 4u * (uint32_t)(NTHR * NC)) : 0.f;
-  };
-  // per-edge d/dr of a finished chunk: fixed-order sum over the warps, one thread per edge
-  auto flush_red = [&](int rs, int n) {
-    if (t < n && A.gr) {
-      float a0 = 0.f, a1 = 0.f, a2 = 0.f;
-#pragma unroll
-      for (int w = 0; w < NW; ++w) { a0 += sm.red[rs][t][w][0]; a1 += sm.red[rs][t][w][1]; a2 += sm.red[rs][t][w][2]; }
-      float* dst = A.gr + ((size_t)blockIdx.y * g.n_edges + sm.red_eid[rs][t]) * 3;
-      dst[0] = a0; dst[1] = a1; dst[2] = a2;
-    }
-  };
-
-  // pipeline prologue (the producer warp has described and measured chunks 0 and 1)
-  __syncthreads();
-  ChunkDesc d0 = sm.desc[0], d1 = sm.desc[1];
-  if (d0.cnt >= 0) prefetch_node(d0.owner, nxt);
-  if (d0.cnt > 0) geo_stage_b<TC, THREADS, NOUT>(A.geo, d0.cnt, sm.a[0], tiles, threadIdx.x);
-  proxy_fence();
-  tc_fence_before();
-  __syncthreads();
-
-  uint32_t phase = 0;
-  int prev_cnt = 0;
-  for (int c = 0; d0.cnt >= 0; ++c) {
-    const bool has = d0.cnt > 0;
-    XEQ_TRACE_STAMP(0, c);
-    flush_red((c + 1) & 1, prev_cnt);  // chunk c-1
-    if (d1.cnt > 0) {  // radial terms of the next chunk -> B tiles, in the shadow of this chunk's MMAs
-      geo_stage_b<TC, THREADS, NOUT>(A.geo, d1.cnt, sm.a[(c + 1) % 3], tiles + (uint32_t)((c + 1) & 1) * STAGE, threadIdx.x);
-      proxy_fence();
-    }
-    const GeoA<TC, true, SECOND>& sa = sm.a[c % 3];
-    const int cnt = d0.cnt, rs = c & 1;
-    if (d0.first) {
-      staged = WMAX > 0 && g.tile_mode == 1 && (d0.n1 - d0.n0) <= WMAX;
-      win_lo = d0.n0;
-      if (staged) stage_window(d0.n0, d0.n1);
-    }
-    if (d0.rfirst) begin_node(nxt);
-    if (d1.cnt >= 0 && d1.rfirst) prefetch_node(d1.owner, nxt);  // consumed in the next iteration
-    if (t < cnt) sm.red_eid[rs][t] = sa.eid[t];
-    if (has) {
-      mbar_wait(bar, phase);
-      phase ^= 1u;
-      tc_fence_after();
-    }
-    const uint32_t dbase = lane_base + D_COL;
-    auto run_chunk = [&](auto staged_c) {
-      constexpr bool ST = decltype(staged_c)::value;
-      constexpr int NR = (L == 0) ? 3 : 2;  // filter rows of this thread: state, edge (, scalar)
-#pragma unroll 1
-      for (int g0 = 0; g0 < cnt; g0 += 4) {
-        float w[NOUT][NR][4];  // [output][role][edge of the group]
-#pragma unroll
-        for (int o = 0; o < NOUT; ++o) {
-          tmem_ld4(dbase + (TS * NOUT + o) * TC + g0, w[o][0]);
-          tmem_ld4(dbase + (TE * NOUT + o) * TC + g0, w[o][1]);
-          if (L == 0) tmem_ld4(dbase + (TX * NOUT + o) * TC + g0, w[o][NR - 1]);
-        }
-        Gathered gc[4];
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          if (ST) gather_window(sa.gat[g0 + j], gc[j]);
-          else gather(sa.gat[g0 + j], gc[j]);
-        }
-        tmem_wait_ld();
-#pragma unroll
-        for (int o = 0; o < NOUT; ++o)
-#pragma unroll
-          for (int r = 0; r < NR; ++r) pin(w[o][r]);
-        // l = 0 rows have no angular term: only the coefficients of u (and rp) cross the warp
-        constexpr int NV = (L == 0) ? (SECOND ? 8 : 4) : 16;
-        float vals[NV];
-#pragma unroll
-        for (int i = 0; i < NV; ++i) vals[i] = 0.f;
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          const int e = g0 + j;
-          NbrEdge<float> ne;
-          ne.psi = nullptr; ne.dpsi = nullptr; ne.ddpsi = nullptr; ne.xi = nullptr; ne.dxi = nullptr;
-          // geometry rows -> registers with 128-bit loads (only the entries this irrep type uses)
-          float Yr[8], Gr[24], Hr[24], Ydr[8], ur[3], rpr[3];
-          load_rows8<L, 1>(sa.Y[e], Yr);
-          load_rows8<L, 3>(sa.G[e], Gr);
-          load_vec3(sa.u[e], ur);
-          if (SECOND) {
-            load_rows8<L, 3>(sa.Hm[e], Hr);
-            load_rows8<L, 1>(sa.Ydot[e], Ydr);
-            load_vec3(sa.rp[e], rpr);
-          }
-          ne.Y = Yr; ne.G = Gr;
-          ne.Hm = SECOND ? Hr : nullptr;
-          ne.Ydot = SECOND ? Ydr : nullptr;
-          ne.u = ur;
-          ne.rp = SECOND ? rpr : nullptr;
-          ne.ddot = SECOND ? sa.ddot[e] : 0.f;
-          if constexpr (L == 0) {
-            float ra[2] = {0.f, 0.f}, rb[2] = {0.f, 0.f}, rc[2] = {0.f, 0.f};
-            if constexpr (!SECOND) {
-              st.template first_w<true>(ne, gc[j].g, nullptr, w[0][0][j], w[1][0][j], ra);
-              ed.template first_w<true>(ne, gc[j].g, nullptr, w[0][1][j], w[1][1][j], rb);
-              sc.template first_w<true>(ne, &gc[j].gx, nullptr, w[0][NR - 1][j], w[1][NR - 1][j], rc);
-              vals[j] = (ra[0] + rb[0]) + rc[0];
-            } else {
-              st.template second_w<true>(ne, gc[j].g, nullptr, w[0][0][j], w[1][0][j], w[NOUT - 1][0][j], ra);
-              ed.template second_w<true>(ne, gc[j].g, nullptr, w[0][1][j], w[1][1][j], w[NOUT - 1][1][j], rb);
-              sc.template second_w<true>(ne, &gc[j].gx, nullptr, w[0][NR - 1][j], w[1][NR - 1][j], w[NOUT - 1][NR - 1][j], rc);
-              vals[(2 * j) % NV] = (ra[0] + rb[0]) + rc[0];
-              vals[(2 * j + 1) % NV] = (ra[1] + rb[1]) + rc[1];
-            }
-          } else {
-            float pr[3], pe[3];
-            if (!SECOND) {
-              st.first_w(ne, gc[j].g, pr, w[0][0][j], w[1][0][j]);
-              ed.first_w(ne, gc[j].g, pe, w[0][1][j], w[1][1][j]);
-            } else {
-              st.second_w(ne, gc[j].g, pr, w[0][0][j], w[1][0][j], w[NOUT - 1][0][j]);
-              ed.second_w(ne, gc[j].g, pe, w[0][1][j], w[1][1][j], w[NOUT - 1][1][j]);
-            }
-#pragma unroll
-            for (int x = 0; x < 3; ++x) vals[(3 * j + x) % NV] = pr[x] + pe[x];
-          }
-        }
-        const float tot = warp_sum<NV>(vals, lane);
-        if (L == 0) {
-          const float tot1 = SECOND ? __shfl_down_sync(0xffffffffu, tot, 4) : 0.f;  // coefficient of rp
-          const int j = lane >> 3;
-          if ((lane & 7) == 0 && g0 + j < cnt) {
-#pragma unroll
-            for (int x = 0; x < 3; ++x)
-              sm.red[rs][g0 + j][warp][x] = sa.u[g0 + j][x] * tot + (SECOND ? sa.rp[g0 + j][x] * tot1 : 0.f);
-          }
-        } else {
-          const int idx = lane >> 1;  // component idx % 3 of edge g0 + idx / 3
-          if ((lane & 1) == 0 && idx < 12 && g0 + idx / 3 < cnt) sm.red[rs][g0 + idx / 3][warp][idx % 3] = tot;
-        }
-      }
-    };
-    if (staged) run_chunk(std::true_type{});
-    else run_chunk(std::false_type{});
-    if (d0.rlast) emit(d0.owner);
-    tc_fence_before();
-    XEQ_TRACE_STAMP(1, c);
-    __syncthreads();
-    prev_cnt = cnt;
-    d0 = d1;
-    d1 = sm.desc[(c + 2) & 7];
-    if (d0.cnt < 0) flush_red(c & 1, prev_cnt);  // last chunk
-  }
-}
-
-template <int C, int M1, int M2, int ORDER>
-__device__ __forceinline__ void nbr_mma_producer(const NeighborArgs& A, NbrMmaSmem<ORDER>& sm, const uint32_t tmem,
-                                                 const uint32_t tiles) {
-  constexpr int TC = NbrMma<ORDER>::TC, NOUT = NbrMma<ORDER>::NOUT, STAGE = NbrMma<ORDER>::STAGE;
-  constexpr bool SECOND = ORDER == 2;
-  const int lane = threadIdx.x & 31;
-  const xeq_graph_t& g = A.geo.g;
-  const uint32_t bar = smem_u32(&sm.bar);
-  RowCursor<TC> cur_it;
-  cur_it.init(g.t_rowptr, g.t_tile_ptr, g.t_n_tiles);
-  GeoPipe<TC, true, true, SECOND> gp;
-  gp.init();
-  auto step = [&](int c) {  // geometry pipeline of iteration c: C(c+2) -> shared memory, B(c+3), A(c+4)
-    if (c + 2 >= 0) gp.stage_c(A.geo, sm.a[(c + 2) % 3], lane);
-    if (c + 3 >= 0) gp.stage_b(A.geo, lane);
-    const ChunkDesc d = cur_it.next();
-    if (lane == 0) sm.desc[(c + 4) & 7] = d;
-    gp.stage_a(A.geo, d, lane);
-    __syncwarp();
-  };
-  for (int c = -4; c < 0; ++c) step(c);
-  __syncthreads();
-  __syncthreads();  // the consumers have written the B tiles of chunk 0
-  for (int c = 0; sm.desc[c & 7].cnt >= 0; ++c) {
-    XEQ_TRACE_STAMP(0, c);
-    tc_fence_after();
-    if (sm.desc[c & 7].cnt > 0) {
-      if (elect_one()) {
-        issue_chunk<TC, NOUT>(tmem, tiles + (uint32_t)(c & 1) * STAGE);
-        umma_commit(bar);
-      }
-      __syncwarp();
-    }
-    step(c);
-    XEQ_TRACE_STAMP(1, c);
-    __syncthreads();
-  }
-}
-
-template <int C, int M1, int M2, int ORDER>
-__global__ void __launch_bounds__(SL_M + 32, 1) nbr_mma_kernel(const NeighborArgs A) {
-  static_assert(C % SL_C == 0 && M1 == C / 2 && M2 == C / 4, "channel slices of edge_mma.cuh");
-  static_assert(SL_M / 32 == NbrMma<ORDER>::NW, "consumer warps");
-  __shared__ NbrMmaSmem<ORDER> sm;
-  pdl_trigger();
-  const uint32_t tmem = tmem_setup(&sm.slot, &sm.bar, 1);
-  pdl_wait();  // setup overlapped the previous kernel's tail
-  const uint32_t tiles = (smem_u32(xeq_dyn_smem) + 1023u) & ~1023u;
-  const uint32_t win_base = tiles + 2u * NbrMma<ORDER>::STAGE;
-  const int t = threadIdx.x;
-  if (t < SL_C) nbr_mma_role<0, C, M1, M2, ORDER>(A, sm, tmem, tiles, win_base);
-  else if (t < SL_C + SL_M1) nbr_mma_role<1, C, M1, M2, ORDER>(A, sm, tmem, tiles, win_base);
-  else if (t < SL_M) nbr_mma_role<2, C, M1, M2, ORDER>(A, sm, tmem, tiles, win_base);
-  else nbr_mma_producer<C, M1, M2, ORDER>(A, sm, tmem, tiles);
   tmem_teardown(tmem);
 }
 
@@ -1056,27 +694,6 @@ static int launch_wgrad_mma_t(const NeighborArgs& A, int grid, cudaStream_t st) 
   XEQ_CUDA(launch_pdl(wgrad_mma_kernel<C, M1, M2, ORDER>, dim3(grid, SLICES), dim3(2 * SL_M + 32), dyn, st, A));
   XEQ_LAUNCHED(1);
   return XEQ_OK;
-}
-
-template <int C, int ORDER>
-static int launch_nbr_mma_t(const NeighborArgs& A, cudaStream_t st) {
-  constexpr int M1 = C / 2, M2 = C / 4, SLICES = C / SL_C;
-  static_assert(sizeof(NbrMmaSmem<ORDER>) <= 40 * 1024, "static shared memory budget");
-  const size_t dyn = 1024 + 2 * (size_t)NbrMma<ORDER>::STAGE + (size_t)NbrMma<ORDER>::WIN * (SL_C * 2 + SL_M1 * 3 + SL_M2 * 5) * 4;
-  {  // per-device attribute: set on every launch (cheap)
-    int rc = set_smem(nbr_mma_kernel<C, M1, M2, ORDER>, dyn);
-    if (rc) return rc;
-  }
-  const int grid = max(1, min(A.geo.g.t_n_tiles, num_sms() / SLICES));
-  XEQ_CUDA(launch_pdl(nbr_mma_kernel<C, M1, M2, ORDER>, dim3(grid, SLICES), dim3(SL_M + 32), dyn, st, A));
-  XEQ_LAUNCHED(1);
-  return XEQ_OK;
-}
-
-// A.gr holds one [E, 3] slab of per-edge d/dr partials per channel slice (pos_grad_kernel sums them)
-// second-order (reverse half of the double backward); the first-order pass is edge_bwd_ul.cu
-int launch_nbr2_mma(const NeighborArgs& A, bool wide, cudaStream_t st) {
-  return wide ? launch_nbr_mma_t<256, 2>(A, st) : launch_nbr_mma_t<128, 2>(A, st);
 }
 
 // grid = number of per-CTA partial slabs written to A.wpart ([grid, H, 48]; the slices write disjoint rows)
