@@ -6,7 +6,7 @@ for row in csv.DictReader(lines):
     if row.get('Metric Name')!='gpu__time_duration.sum': continue
     full=row['Kernel Name']; v=float(row['Metric Value'].replace(',',''))
     v = v/1000 if row['Metric Unit']=='ns' else v
-    name=re.sub(r'\(.*','',full); name=re.sub(r'<.*','',name)[-60:]
+    name=full.replace('(anonymous namespace)::','').replace('<unnamed>::',''); name=re.sub(r'\(.*','',name); name=re.sub(r'^void ','',name); m=re.match(r'([\w:]+)(<[\d, ]+>)?',name); name=(m.group(0) if m else name)[:60]
     agg[name][0]+=1; agg[name][1]+=v; n+=1
     if 'gemm_tf32x3' in full: gem[row['Grid Size']][0]+=1; gem[row['Grid Size']][1]+=v
 tot=sum(v[1] for v in agg.values())

@@ -19,7 +19,6 @@ gx, gV, a_s, a_v, a_p = r(N, dims.node_dim), r(N, dims.D), r(N, dims.H), r(N, di
 print('N', N, 'E', g.n_edges)
 for _ in range(reps):
     ops.edge_message_fwd_raw(g, dims, pos, s, v, x, V, W, b, freq)
-    ops.edge_message_bwd_raw(g, dims, pos, s, v, W, b, freq, gx, gV, need_w=False)
     ops.edge_message_bwd_raw(g, dims, pos, s, v, W, b, freq, gx, gV, need_w=True)
     ops.edge_message_bwdbwd_raw(g, dims, pos, s, v, W, b, freq, gx, gV, a_s, a_v, a_p)
 torch.cuda.synchronize()
