@@ -749,7 +749,7 @@ size_t center_fwd_ul_workspace_bytes(int n_nodes, bool wide);
 int launch_nbr_bwd_ul(const NeighborArgs& A, bool wide, cudaStream_t st);             // edge_bwd_ul.cu: K2b first order
 int launch_center_jvp_mma(const CenterArgs& A, bool wide, cudaStream_t st);           // edge_message_mma.cu: K2bb JVP pass
 int launch_nbr2_ul(const NeighborArgs& A, bool wide, cudaStream_t st);                // edge_bwd2_ul.cu: K2bb reverse pass (main + w'' passes)
-int launch_wgrad_mma(const NeighborArgs& A, int order, bool wide, int grid, cudaStream_t st);  //             weight gradients
+int launch_wgrad_ul(const NeighborArgs& A, int order, bool wide, int grid, cudaStream_t st);   // edge_wgrad_ul.cu: weight gradients
 
 // The product library has ONE implementation per kernel (tcgen05).  A test-only build (-DXEQ_WITH_SIMT,
 // xequinet_b200/build.py --simt -> libxeq_b200_simt.so) also carries the round-1 SIMT filter contraction, selected for the
@@ -855,7 +855,7 @@ static int run_neighbor(const xeq_graph_t* g, const xeq_dims_t* dims, NeighborAr
   A.wpart = wpart;
   if (mma) {
     if (main) rc = order == 1 ? launch_nbr_bwd_ul(A, cfg == 1, st) : launch_nbr2_ul(A, cfg == 1, st);
-    if (!rc && wgrad) rc = launch_wgrad_mma(A, order, cfg == 1, gx, st);
+    if (!rc && wgrad) rc = launch_wgrad_ul(A, order, cfg == 1, gx, st);
   }
 #ifdef XEQ_WITH_SIMT
   else if (cfg == 0) rc = order == 1 ? launch_neighbor<128, 64, 32, 1>(A, main, wgrad, gx, st) : launch_neighbor<128, 64, 32, 2>(A, main, wgrad, gx, st);
