@@ -34,17 +34,30 @@ constexpr int NGEO = 4;                      // geometry records per group (ring
 constexpr int NTHREADS = NCONS + G * 32 + 32;
 constexpr int NOSTAGE = INT_MIN;
 
+// MODE 0: forward message.  The JVP half of the double backward (tangent of the message along (a_s, a_v, a_pos, a_cell))
+// is two more instances of the same kernel, because the message is linear in the gathered rows and in the filter:
+//   MODE 1 (tangent rows): the packed rows carry (sdot v + s vdot, sdot) instead of (s v, s), plus the term
+//          w_edge s_edge Ydot of the rotating harmonics (Ydot = (dY/dr)^T rdot, s_edge rides in the spare packed entry);
+//   MODE 2 (tangent filter): the rows are the forward's, the radial tiles carry ddot psi'_k(d) instead of psi_k(d), so
+//          the MMA yields wdot = ddot w'(d); it adds onto the output of the MODE 1 launch (x_in = x_out).
+enum : int { MODE_FWD = 0, MODE_TAN = 1, MODE_DW = 2 };
+
+template <int MODE>
 struct alignas(16) Geo {
-  float4 Yt[SLOTS][3];   // harmonics per slot and piece type
-  float4 rad[SLOTS];     // (d, chi * sqrt(2 / rc) / (d + 1e-5), chi, -) of the slot; zeros for dead slots
+  // harmonics per slot: MODE 0 / 2: one float4 per piece type; MODE 1: (Y0 Y1 Y2 Y6) (Y3 Y4 Y5 Y7) and the same of Ydot
+  float4 Yt[SLOTS][MODE == MODE_TAN ? 4 : 3];
+  // MODE 0 / 1: (d, chi * sqrt(2 / rc) / (d + 1e-5), chi, -); MODE 2: (d, ddot c0 dchi / (d + 1e-5), ddot c0 chi / (d + 1e-5),
+  // 1 / (d + 1e-5)); zeros for dead slots
+  float4 rad[SLOTS];
   uint32_t goff[SLOTS];  // staged: byte offset of the gathered row inside the window; else: node index
   Quad qd[NQ];
   int nq;                // quads of this chunk (1..NQ), -1 = end of stream
   int pad[3];
 };
 
+template <int MODE>
 struct FwdSmem {
-  Geo geo[G][NGEO];
+  Geo<MODE> geo[G][NGEO];
   uint64_t geo_full[G][NGEO];   // producer -> consumers: geometry record of a chunk is written
   uint64_t tile_full[G][NBST];  // consumers -> producer: radial tiles of a chunk are written (and proxy-fenced)
   uint64_t acc_full[G], acc_free[G];
@@ -56,28 +69,46 @@ struct FwdSmem {
 // pack: pk[sl][n][plane][lane] (float4) from s [N,H] and v [N,D] (cm layout)
 //   plane 0: (s_state[q0] v[q0], s_edge[q0], s_scalar[q0], s_edge[qp])     plane 1: s_state[qp] v[(qp, m)], m = 0..2
 // ------------------------------------------------------------------------------------------------------
-template <int C, int M1, int M2>
-__global__ void __launch_bounds__(256) pack_fwd_kernel(const float* __restrict__ s, const float* __restrict__ v,
-                                                      float* __restrict__ pk, int n_nodes) {
+// packed entry of lane (q0, qp, off) of node row (sn, vn); MODE 1: the tangent entries from (asn, avn) (either may be NULL)
+template <int M, int MODE>
+__device__ __forceinline__ void pack_entry(const float* __restrict__ sn, const float* __restrict__ vn, const float* __restrict__ asn,
+                                           const float* __restrict__ avn, int q0, int qp, const int (&off)[3], int nc, float4& a, float4& b) {
+  const float ssp = sn[qp];
+  if (MODE != MODE_TAN) {
+    a.x = sn[q0] * vn[q0];
+    a.y = sn[M + q0];
+    a.z = sn[2 * M + q0];
+    a.w = sn[M + qp];
+    b.x = ssp * vn[off[0]];
+    b.y = ssp * vn[off[1]];
+    b.z = nc == 3 ? ssp * vn[off[2]] : 0.f;
+    b.w = 0.f;
+  } else {
+    const float sd0 = asn ? asn[q0] : 0.f, sdp = asn ? asn[qp] : 0.f;
+    a.x = fmaf(sd0, vn[q0], avn ? sn[q0] * avn[q0] : 0.f);
+    a.y = asn ? asn[M + q0] : 0.f;
+    a.z = asn ? asn[2 * M + q0] : 0.f;
+    a.w = asn ? asn[M + qp] : 0.f;
+    b.x = fmaf(sdp, vn[off[0]], avn ? ssp * avn[off[0]] : 0.f);
+    b.y = fmaf(sdp, vn[off[1]], avn ? ssp * avn[off[1]] : 0.f);
+    b.z = nc == 3 ? fmaf(sdp, vn[off[2]], avn ? ssp * avn[off[2]] : 0.f) : 0.f;
+    b.w = sn[M + qp];  // s_edge of the piece: multiplies w_edge Ydot
+  }
+}
+
+template <int C, int M1, int M2, int MODE>
+__global__ void __launch_bounds__(256) pack_fwd_kernel(const float* __restrict__ s, const float* __restrict__ v, const float* __restrict__ a_s,
+                                                      const float* __restrict__ a_v, float* __restrict__ pk, int n_nodes) {
   constexpr int M = C + M1 + M2, D = C + 3 * M1 + 5 * M2, H = C + 2 * M;
   const int L = threadIdx.x & 127, sl = blockIdx.y;
   const int n = blockIdx.x * 2 + (threadIdx.x >> 7);
   if (n >= n_nodes) return;
-  const float* sn = s + (size_t)n * H;
-  const float* vn = v + (size_t)n * D;
   const int q0 = sl * SL_C + L, qp = piece_irrep<C, M1>(L, sl);
   int off[3], nc;
   piece_offsets<C, M1, M2>(L, sl, off, nc);
-  const float ssp = sn[qp];
   float4 a, b;
-  a.x = sn[q0] * vn[q0];
-  a.y = sn[M + q0];
-  a.z = sn[2 * M + q0];
-  a.w = sn[M + qp];
-  b.x = ssp * vn[off[0]];
-  b.y = ssp * vn[off[1]];
-  b.z = nc == 3 ? ssp * vn[off[2]] : 0.f;
-  b.w = 0.f;
+  pack_entry<M, MODE>(s + (size_t)n * H, v + (size_t)n * D, a_s ? a_s + (size_t)n * H : nullptr, a_v ? a_v + (size_t)n * D : nullptr,
+                      q0, qp, off, nc, a, b);
   float4* dst = reinterpret_cast<float4*>(pk + ((size_t)sl * n_nodes + n) * ROWF);
   dst[L] = a;
   dst[128 + L] = b;
@@ -86,10 +117,11 @@ __global__ void __launch_bounds__(256) pack_fwd_kernel(const float* __restrict__
 // ------------------------------------------------------------------------------------------------------
 // consumers
 // ------------------------------------------------------------------------------------------------------
-template <int C, int M1, int M2>
-__device__ __forceinline__ void fwd_consumer(const CenterArgs& A, FwdSmem& sm, const uint32_t tmem, const uint32_t tiles_base,
+template <int C, int M1, int M2, int MODE>
+__device__ __forceinline__ void fwd_consumer(const CenterArgs& A, FwdSmem<MODE>& sm, const uint32_t tmem, const uint32_t tiles_base,
                                              const uint32_t win_base, const float* __restrict__ pk, const int grp) {
   constexpr int D = C + 3 * M1 + 5 * M2;
+  using GeoT = Geo<MODE>;
   const int L = threadIdx.x - grp * GRP, wq = L >> 5, lane = L & 31, sl = blockIdx.y;
   const int pt = piece_type(L);
   const int q0 = sl * SL_C + L;
@@ -113,15 +145,26 @@ __device__ __forceinline__ void fwd_consumer(const CenterArgs& A, FwdSmem& sm, c
     const int k = 4 * rkc + x;
     fr[x] = (L < 96 && k >= 1 && k <= NB_) ? A.geo.freq[k - 1] : 0.f;
   }
-  const uint32_t rad_off = (uint32_t)offsetof(Geo, rad) + 16u * (uint32_t)rslot;
+  const float inv_c0 = sqrtf(0.5f * A.geo.rc);
+  const uint32_t rad_off = (uint32_t)offsetof(GeoT, rad) + 16u * (uint32_t)rslot;
   const uint32_t tile_off = (uint32_t)(rslot * 128 + ((rkc ^ (rslot & 7)) << 4));
   auto radial = [&](int c) {  // tiles of chunk c (its geometry record is visible)
     if (L < 96) {
-      const float4 rd = lds128(geo0 + (uint32_t)(c % NGEO) * (uint32_t)sizeof(Geo) + rad_off);
+      const float4 rd = lds128(geo0 + (uint32_t)(c % NGEO) * (uint32_t)sizeof(GeoT) + rad_off);
       float val[4];
+      if (MODE != MODE_DW) {
 #pragma unroll
-      for (int x = 0; x < 4; ++x) val[x] = rd.y * sin_reduced(fr[x] * rd.x);  // fr = 0 -> exactly zero
-      if (rkc == 0) val[0] = rd.z;
+        for (int x = 0; x < 4; ++x) val[x] = rd.y * sin_reduced(fr[x] * rd.x);  // fr = 0 -> exactly zero
+        if (rkc == 0) val[0] = rd.z;
+      } else {  // ddot psi'_k = ddot (dchi phi_k + chi phi'_k): rd = (d, P = ddot c0 dchi inv, Q = ddot c0 chi inv, inv)
+#pragma unroll
+        for (int x = 0; x < 4; ++x) {
+          float sn, cs;
+          sincos_reduced(fr[x] * rd.x, sn, cs);
+          val[x] = fmaf(rd.y, sn, rd.z * fmaf(fr[x], cs, -sn * rd.w));  // fr = 0 -> exactly zero
+        }
+        if (rkc == 0) val[0] = rd.y * inv_c0 * (rd.x + 1e-5f);  // k = 0: ddot dchi
+      }
       uint32_t hi[4], lo[4];
 #pragma unroll
       for (int x = 0; x < 4; ++x) split_fast(val[x], hi[x], lo[x]);
@@ -136,7 +179,7 @@ __device__ __forceinline__ void fwd_consumer(const CenterArgs& A, FwdSmem& sm, c
   auto geo_wait = [&](int c) { mbar_wait(gfull0 + 8u * (uint32_t)(c % NGEO), (uint32_t)((c / NGEO) & 1)); };
   auto geo_nq = [&](int c) {
     int v;
-    asm volatile("ld.shared.b32 %0, [%1];" : "=r"(v) : "r"(geo0 + (uint32_t)(c % NGEO) * (uint32_t)sizeof(Geo) + (uint32_t)offsetof(Geo, nq)) : "memory");
+    asm volatile("ld.shared.b32 %0, [%1];" : "=r"(v) : "r"(geo0 + (uint32_t)(c % NGEO) * (uint32_t)sizeof(GeoT) + (uint32_t)offsetof(GeoT, nq)) : "memory");
     return v;
   };
 
@@ -153,11 +196,11 @@ __device__ __forceinline__ void fwd_consumer(const CenterArgs& A, FwdSmem& sm, c
     if (nq_next > 0) radial(c + 1);
     mbar_wait(full, (uint32_t)(c & 1));
     tc_fence_after();
-    const uint32_t ge = geo0 + (uint32_t)(c % NGEO) * (uint32_t)sizeof(Geo);
+    const uint32_t ge = geo0 + (uint32_t)(c % NGEO) * (uint32_t)sizeof(GeoT);
 #pragma unroll 1
     for (int qd = 0; qd < nq; ++qd) {
       int node, fl;
-      asm volatile("ld.shared.v2.b32 {%0, %1}, [%2];" : "=r"(node), "=r"(fl) : "r"(ge + (uint32_t)offsetof(Geo, qd) + 8u * (uint32_t)qd) : "memory");
+      asm volatile("ld.shared.v2.b32 {%0, %1}, [%2];" : "=r"(node), "=r"(fl) : "r"(ge + (uint32_t)offsetof(GeoT, qd) + 8u * (uint32_t)qd) : "memory");
       if (fl & F_TILE_FIRST) {
         if (fl & F_STAGED) mbar_wait(smem_u32(&sm.win_full[(fl & F_BUF) ? 1 : 0]), (fl & F_PAR) ? 1u : 0u);
       }
@@ -175,8 +218,8 @@ __device__ __forceinline__ void fwd_consumer(const CenterArgs& A, FwdSmem& sm, c
         for (int t = 0; t < TILES; ++t) tmem_ld4(dbase + t * SLOTS + qd * 4, w[t]);
         uint32_t gj[4];
         asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(gj[0]), "=r"(gj[1]), "=r"(gj[2]), "=r"(gj[3])
-                     : "r"(ge + (uint32_t)offsetof(Geo, goff) + 16u * (uint32_t)qd) : "memory");
-        float4 a[4], b[4], y[4];
+                     : "r"(ge + (uint32_t)offsetof(GeoT, goff) + 16u * (uint32_t)qd) : "memory");
+        float4 a[4], b[4], y[4], yd[4];
         if (fl & F_STAGED) {
 #pragma unroll
           for (int j = 0; j < 4; ++j) {
@@ -191,8 +234,22 @@ __device__ __forceinline__ void fwd_consumer(const CenterArgs& A, FwdSmem& sm, c
             b[j] = ldg128(p + 512);
           }
         }
+        if (MODE != MODE_TAN) {
 #pragma unroll
-        for (int j = 0; j < 4; ++j) y[j] = lds128(ge + (uint32_t)offsetof(Geo, Yt) + 48u * (uint32_t)(qd * 4 + j) + 16u * (uint32_t)pt);
+          for (int j = 0; j < 4; ++j) y[j] = lds128(ge + (uint32_t)offsetof(GeoT, Yt) + 48u * (uint32_t)(qd * 4 + j) + 16u * (uint32_t)pt);
+        } else {  // warp-uniform: pieces 0 / 1 take one float4 of Y and one of Ydot, piece 2 the .w entries of all four
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const uint32_t yb = ge + (uint32_t)offsetof(GeoT, Yt) + 64u * (uint32_t)(qd * 4 + j);
+            if (pt < 2) {
+              y[j] = lds128(yb + 16u * (uint32_t)pt);
+              yd[j] = lds128(yb + 32u + 16u * (uint32_t)pt);
+            } else {
+              y[j] = make_float4(lds32(yb + 12u), lds32(yb + 28u), 0.f, 0.f);
+              yd[j] = make_float4(lds32(yb + 44u), lds32(yb + 60u), 0.f, 0.f);
+            }
+          }
+        }
         tmem_wait_ld();
 #pragma unroll
         for (int t = 0; t < TILES; ++t) pin(w[t]);
@@ -204,6 +261,12 @@ __device__ __forceinline__ void fwd_consumer(const CenterArgs& A, FwdSmem& sm, c
           accP[0] = fmaf(b[j].x, w[3][j], fmaf(gep, y[j].x, accP[0]));
           accP[1] = fmaf(b[j].y, w[3][j], fmaf(gep, y[j].y, accP[1]));
           accP[2] = fmaf(b[j].z, w[3][j], fmaf(gep, y[j].z, accP[2]));
+          if (MODE == MODE_TAN) {  // w_edge s_edge Ydot
+            const float ged = b[j].w * w[4][j];
+            accP[0] = fmaf(ged, yd[j].x, accP[0]);
+            accP[1] = fmaf(ged, yd[j].y, accP[1]);
+            accP[2] = fmaf(ged, yd[j].z, accP[2]);
+          }
         }
       }
       if (fl & F_ROW_LAST) {
@@ -236,8 +299,8 @@ struct SlotRegs {
   int nq;             // quads of the chunk (1..NQ), -1 = end of stream (uniform)
 };
 
-template <int C, int M1, int M2>
-__device__ __forceinline__ void fwd_producer(const CenterArgs& A, FwdSmem& sm, const uint32_t tmem, const uint32_t tiles_base,
+template <int C, int M1, int M2, int MODE>
+__device__ __forceinline__ void fwd_producer(const CenterArgs& A, FwdSmem<MODE>& sm, const uint32_t tmem, const uint32_t tiles_base,
                                              const int grp) {
   const int lane = threadIdx.x & 31, slot = lane & 15, half = lane >> 4;
   const xeq_graph_t& g = A.geo.g;
@@ -301,47 +364,82 @@ __device__ __forceinline__ void fwd_producer(const CenterArgs& A, FwdSmem& sm, c
   // stage B: raw position loads (and the lattice shift of periodic graphs)
   struct PosRegs {
     float pi[3], pj[3], sh[3];
+    float rd[3];  // MODE 1 / 2: tangent of the edge vector, a_pos[i] - a_pos[j] - offsets @ a_cell
   };
   auto stage_b = [&](const SlotRegs& r, PosRegs& p) {
 #pragma unroll
-    for (int x = 0; x < 3; ++x) p.pi[x] = p.pj[x] = p.sh[x] = 0.f;
+    for (int x = 0; x < 3; ++x) p.pi[x] = p.pj[x] = p.sh[x] = p.rd[x] = 0.f;
     if (r.e >= 0) {
 #pragma unroll
       for (int x = 0; x < 3; ++x) {
         p.pi[x] = A.geo.pos[3 * r.i + x];
         p.pj[x] = A.geo.pos[3 * r.j + x];
+        if (MODE != MODE_FWD && A.geo.a_pos) p.rd[x] = A.geo.a_pos[3 * r.i + x] - A.geo.a_pos[3 * r.j + x];
       }
       if (g.offsets != nullptr) {  // nn/basic.py:119-128: vectors -= cell_offsets @ cell[graph(neighbor)]
         const char4 o = reinterpret_cast<const char4*>(g.offsets)[r.e];
-        const float* cl = g.cell + 9 * (g.node_graph ? g.node_graph[r.j] : 0);
+        const int gi = g.node_graph ? g.node_graph[r.j] : 0;
+        const float* cl = g.cell + 9 * gi;
         const float ox = (float)o.x, oy = (float)o.y, oz = (float)o.z;
 #pragma unroll
         for (int x = 0; x < 3; ++x) p.sh[x] = ox * cl[x] + oy * cl[3 + x] + oz * cl[6 + x];
+        if (MODE != MODE_FWD && A.geo.a_cell) {
+          const float* ac = A.geo.a_cell + 9 * gi;
+#pragma unroll
+          for (int x = 0; x < 3; ++x) p.rd[x] -= ox * ac[x] + oy * ac[3 + x] + oz * ac[6 + x];
+        }
       }
     }
   };
 
   // stage C: geometry record of chunk c -> shared memory, then the release to the consumers (their radial stage)
   auto stage_c = [&](int c, const SlotRegs& r, const PosRegs& p) {
-    Geo& ge = sm.geo[grp][c % NGEO];
+    Geo<MODE>& ge = sm.geo[grp][c % NGEO];
     if (r.nq > 0 && half == 0) {
-      float4 y0 = make_float4(0.f, 0.f, 0.f, 0.f), y1 = y0, y2 = y0, rad = y0;
+      float4 y0 = make_float4(0.f, 0.f, 0.f, 0.f), y1 = y0, y2 = y0, y3 = y0, rad = y0;
       if (r.e >= 0) {
         float rv[3], d, u[3], Y[8];
 #pragma unroll
         for (int x = 0; x < 3; ++x) rv[x] = (p.pi[x] - p.pj[x]) - p.sh[x];
         unit_vector(rv, d, u);
-        sph_harm(u, Y);
-        y0 = make_float4(Y[0], Y[1], Y[2], 0.f);
-        y1 = make_float4(Y[3], Y[4], Y[5], 0.f);
-        y2 = make_float4(Y[6], Y[7], 0.f, 0.f);
-        float chi = 0.f;
-        if (d < A.geo.rc) chi = 0.5f * (cosf(pi_rc * d) + 1.f);
-        rad = make_float4(d, chi * c0 / (d + 1e-5f), chi, 0.f);
+        float chi = 0.f, dchi = 0.f;
+        if (d < A.geo.rc) {
+          if (MODE != MODE_DW) {
+            chi = 0.5f * (cosf(pi_rc * d) + 1.f);
+          } else {
+            float sn, cs;
+            sincosf(pi_rc * d, &sn, &cs);
+            chi = 0.5f * (cs + 1.f);
+            dchi = -0.5f * pi_rc * sn;
+          }
+        }
+        const float inv = 1.f / (d + 1e-5f);
+        if (MODE == MODE_TAN) {  // Ydot = (dY/dr)^T rdot
+          float Gm[3][8], Yd[8];
+          angular_first(u, d, Y, Gm);
+#pragma unroll
+          for (int m = 0; m < 8; ++m) Yd[m] = Gm[0][m] * p.rd[0] + Gm[1][m] * p.rd[1] + Gm[2][m] * p.rd[2];
+          y0 = make_float4(Y[0], Y[1], Y[2], Y[6]);
+          y1 = make_float4(Y[3], Y[4], Y[5], Y[7]);
+          y2 = make_float4(Yd[0], Yd[1], Yd[2], Yd[6]);
+          y3 = make_float4(Yd[3], Yd[4], Yd[5], Yd[7]);
+        } else {
+          sph_harm(u, Y);
+          y0 = make_float4(Y[0], Y[1], Y[2], 0.f);
+          y1 = make_float4(Y[3], Y[4], Y[5], 0.f);
+          y2 = make_float4(Y[6], Y[7], 0.f, 0.f);
+        }
+        if (MODE != MODE_DW) {
+          rad = make_float4(d, chi * c0 / (d + 1e-5f), chi, 0.f);
+        } else {
+          const float ddot = u[0] * p.rd[0] + u[1] * p.rd[1] + u[2] * p.rd[2];
+          rad = make_float4(d, ddot * c0 * dchi * inv, ddot * c0 * chi * inv, inv);
+        }
       }
       ge.Yt[slot][0] = y0;
       ge.Yt[slot][1] = y1;
       ge.Yt[slot][2] = y2;
+      if (MODE == MODE_TAN) ge.Yt[slot][3] = y3;
       ge.rad[slot] = rad;
       const int jj = r.e >= 0 ? r.j : r.i;  // dead slots gather the (always valid) row of their own center, times zero
       ge.goff[slot] = (r.wb != NOSTAGE) ? (uint32_t)(r.wb + jj) * (uint32_t)ROWB : (uint32_t)jj;
@@ -405,8 +503,8 @@ __device__ __forceinline__ void fwd_producer(const CenterArgs& A, FwdSmem& sm, c
 }
 
 // window loader: one elected lane streams the packed rows of the staged tiles of this CTA into the window
-template <int C>
-__device__ __forceinline__ void fwd_loader(const CenterArgs& A, FwdSmem& sm, const uint32_t win_base, const float* __restrict__ pk) {
+template <int C, int MODE>
+__device__ __forceinline__ void fwd_loader(const CenterArgs& A, FwdSmem<MODE>& sm, const uint32_t win_base, const float* __restrict__ pk) {
   const xeq_graph_t& g = A.geo.g;
   if (g.tile_mode != 1) return;
   if ((threadIdx.x & 31) != 0) return;
@@ -427,8 +525,8 @@ __device__ __forceinline__ void fwd_loader(const CenterArgs& A, FwdSmem& sm, con
 // window packer (all tiles of the launch fit the window: xeq_graph_t.max_tile_nodes <= WH): warp 15 reads the RAW s / v
 // rows of the CTA's next tile (coalesced 128-byte loads), forms the per-lane packed entries and writes them straight
 // into the free window half -- the packing pass and its HBM round trip (write + re-read of 4 KB per node) disappear.
-template <int C, int M1, int M2>
-__device__ __forceinline__ void fwd_packer(const CenterArgs& A, FwdSmem& sm, const uint32_t win_base) {
+template <int C, int M1, int M2, int MODE>
+__device__ __forceinline__ void fwd_packer(const CenterArgs& A, FwdSmem<MODE>& sm, const uint32_t win_base) {
   constexpr int M = C + M1 + M2, D = C + 3 * M1 + 5 * M2, H = C + 2 * M;
   const xeq_graph_t& g = A.geo.g;
   const int lane = threadIdx.x & 31, sl = blockIdx.y;
@@ -452,20 +550,12 @@ __device__ __forceinline__ void fwd_packer(const CenterArgs& A, FwdSmem& sm, con
     for (int n = wk.n0; n < wk.n1; ++n) {
       const float* sn = A.s + (size_t)n * H;
       const float* vn = A.v + (size_t)n * D;
+      const float* asn = (MODE == MODE_TAN && A.a_s) ? A.a_s + (size_t)n * H : nullptr;
+      const float* avn = (MODE == MODE_TAN && A.a_v) ? A.a_v + (size_t)n * D : nullptr;
       const uint32_t row = half + (uint32_t)(n - wk.n0) * ROWB;
       float4 a[4], b[4];
 #pragma unroll
-      for (int it = 0; it < 4; ++it) {
-        const float ssp = sn[qp[it]];
-        a[it].x = sn[q0[it]] * vn[q0[it]];
-        a[it].y = sn[M + q0[it]];
-        a[it].z = sn[2 * M + q0[it]];
-        a[it].w = sn[M + qp[it]];
-        b[it].x = ssp * vn[off[it][0]];
-        b[it].y = ssp * vn[off[it][1]];
-        b[it].z = nc[it] == 3 ? ssp * vn[off[it][2]] : 0.f;
-        b[it].w = 0.f;
-      }
+      for (int it = 0; it < 4; ++it) pack_entry<M, MODE>(sn, vn, asn, avn, q0[it], qp[it], off[it], nc[it], a[it], b[it]);
 #pragma unroll
       for (int it = 0; it < 4; ++it) {
         sts128(row + 512u * it, __float_as_uint(a[it].x), __float_as_uint(a[it].y), __float_as_uint(a[it].z), __float_as_uint(a[it].w));
@@ -477,10 +567,10 @@ __device__ __forceinline__ void fwd_packer(const CenterArgs& A, FwdSmem& sm, con
   }
 }
 
-template <int C, int M1, int M2>
+template <int C, int M1, int M2, int MODE>
 __global__ void __launch_bounds__(NTHREADS, 1) center_fwd_ul_kernel(const CenterArgs A, const float* __restrict__ pk) {
   static_assert(C % SL_C == 0 && M1 == C / 2 && M2 == C / 4, "channel slices of edge_mma.cuh");
-  __shared__ FwdSmem sm;
+  __shared__ FwdSmem<MODE> sm;
   pdl_trigger();  // the next kernel of the stream may be staged; it waits for this grid before it reads memory
   const int t = threadIdx.x, warp = t >> 5;
   if (t == 0) {
@@ -511,10 +601,10 @@ __global__ void __launch_bounds__(NTHREADS, 1) center_fwd_ul_kernel(const Center
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
-  if (warp < 4 * G) fwd_consumer<C, M1, M2>(A, sm, tmem, tiles_base, win_base, pk, warp >> 2);
-  else if (warp < 4 * G + G) fwd_producer<C, M1, M2>(A, sm, tmem, tiles_base, warp - 4 * G);
-  else if (pk != nullptr) fwd_loader<C>(A, sm, win_base, pk);   // packed rows from the packing pass, TMA bulk copies
-  else fwd_packer<C, M1, M2>(A, sm, win_base);                // every tile fits the window: packed in-kernel
+  if (warp < 4 * G) fwd_consumer<C, M1, M2, MODE>(A, sm, tmem, tiles_base, win_base, pk, warp >> 2);
+  else if (warp < 4 * G + G) fwd_producer<C, M1, M2, MODE>(A, sm, tmem, tiles_base, warp - 4 * G);
+  else if (pk != nullptr) fwd_loader<C, MODE>(A, sm, win_base, pk);   // packed rows from the packing pass, TMA bulk copies
+  else fwd_packer<C, M1, M2, MODE>(A, sm, win_base);                // every tile fits the window: packed in-kernel
   tmem_teardown(tmem);
 }
 
@@ -524,29 +614,43 @@ size_t center_fwd_ul_workspace_bytes(int n_nodes, bool wide) {
   return 256 + (size_t)(wide ? 2 : 1) * (size_t)(n_nodes > 0 ? n_nodes : 1) * ROWB;
 }
 
-template <int C>
-static int launch_center_fwd_ul_t(const CenterArgs& A, void* ws, cudaStream_t st) {
+template <int C, int MODE>
+static int launch_center_ul_t(const CenterArgs& A, void* ws, cudaStream_t st) {
   constexpr int M1 = C / 2, M2 = C / 4, SLICES = C / SL_C;
-  static_assert(sizeof(FwdSmem) <= 16 * 1024, "static shared memory budget");
+  static_assert(sizeof(FwdSmem<MODE>) <= (MODE == MODE_TAN ? 17 : 16) * 1024, "static shared memory budget");
   const xeq_graph_t& g = A.geo.g;
   // when the caller vouches that every molecule tile fits the window, warp 15 packs the rows in-kernel and the packing
   // pass (and the consumers' global-memory path) is not needed
   const bool inline_pack = g.tile_mode == 1 && g.max_tile_nodes > 0 && g.max_tile_nodes <= WH;
   float* pk = inline_pack ? nullptr : reinterpret_cast<float*>((reinterpret_cast<uintptr_t>(ws) + 255) & ~(uintptr_t)255);
-  if (!inline_pack) pack_fwd_kernel<C, M1, M2><<<dim3((g.n_nodes + 1) / 2, SLICES), 256, 0, st>>>(A.s, A.v, pk, g.n_nodes);
+  if (!inline_pack)
+    pack_fwd_kernel<C, M1, M2, MODE><<<dim3((g.n_nodes + 1) / 2, SLICES), 256, 0, st>>>(A.s, A.v, A.a_s, A.a_v, pk, g.n_nodes);
   const size_t dyn = 1024 + (size_t)G * NBST * BSTAGE + (g.tile_mode == 1 ? (size_t)2 * WH * ROWB : 0);
-  XEQ_CUDA(cudaFuncSetAttribute(center_fwd_ul_kernel<C, M1, M2>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+  XEQ_CUDA(cudaFuncSetAttribute(center_fwd_ul_kernel<C, M1, M2, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                 (int)(1024 + (size_t)G * NBST * BSTAGE + (size_t)2 * WH * ROWB)));
   const int work = g.tile_mode == 1 ? g.n_tiles : (g.n_tiles + G - 1) / G;
   const int grid = max(1, min(work, num_sms() / SLICES));
-  XEQ_CUDA(launch_pdl(center_fwd_ul_kernel<C, M1, M2>, dim3(grid, SLICES), dim3(NTHREADS), dyn, st, A, (const float*)pk));
+  XEQ_CUDA(launch_pdl(center_fwd_ul_kernel<C, M1, M2, MODE>, dim3(grid, SLICES), dim3(NTHREADS), dyn, st, A, (const float*)pk));
   XEQ_LAUNCHED(inline_pack ? 1 : 2);
   return XEQ_OK;
 }
 
 // `wide`: 256x0e + 128x1o + 64x2e (two channel slices per tile of edges, grid.y = 2)
 int launch_center_fwd_ul(const CenterArgs& A, bool wide, void* ws, cudaStream_t st) {
-  return wide ? launch_center_fwd_ul_t<256>(A, ws, st) : launch_center_fwd_ul_t<128>(A, ws, st);
+  return wide ? launch_center_ul_t<256, MODE_FWD>(A, ws, st) : launch_center_ul_t<128, MODE_FWD>(A, ws, st);
+}
+
+// JVP half of the double backward: (x_out, V_out) = tangent of the message along (a_s, a_v, a_pos, a_cell).  Two
+// launches of the forward kernel family (header of this file); the second one only when the geometry has a tangent.
+int launch_center_jvp_ul(const CenterArgs& A, bool wide, void* ws, cudaStream_t st) {
+  CenterArgs T = A;
+  T.x_in = nullptr;
+  T.V_in = nullptr;
+  int rc = wide ? launch_center_ul_t<256, MODE_TAN>(T, ws, st) : launch_center_ul_t<128, MODE_TAN>(T, ws, st);
+  if (rc || (!A.geo.a_pos && !A.geo.a_cell)) return rc;
+  T.x_in = A.x_out;  // accumulate in place: a lane reads its residual entries at the start of a row and writes them at its end
+  T.V_in = A.V_out;
+  return wide ? launch_center_ul_t<256, MODE_DW>(T, ws, st) : launch_center_ul_t<128, MODE_DW>(T, ws, st);
 }
 
 }  // namespace xeq

@@ -747,7 +747,7 @@ static int launch_center(const CenterArgs& A, cudaStream_t st) {
 int launch_center_fwd_ul(const CenterArgs& A, bool wide, void* ws, cudaStream_t st);  // edge_fwd_ul.cu: K2 forward
 size_t center_fwd_ul_workspace_bytes(int n_nodes, bool wide);
 int launch_nbr_bwd_ul(const NeighborArgs& A, bool wide, cudaStream_t st);             // edge_bwd_ul.cu: K2b first order
-int launch_center_jvp_mma(const CenterArgs& A, bool wide, cudaStream_t st);           // edge_message_mma.cu: K2bb JVP pass
+int launch_center_jvp_ul(const CenterArgs& A, bool wide, void* ws, cudaStream_t st);  // edge_fwd_ul.cu: K2bb JVP pass (tangent rows + tangent filter)
 int launch_nbr2_ul(const NeighborArgs& A, bool wide, cudaStream_t st);                // edge_bwd2_ul.cu: K2bb reverse pass (main + w'' passes)
 int launch_wgrad_ul(const NeighborArgs& A, int order, bool wide, int grid, cudaStream_t st);   // edge_wgrad_ul.cu: weight gradients
 
@@ -774,9 +774,8 @@ static int run_center(const xeq_graph_t* g, const xeq_dims_t* dims, CenterArgs& 
   A.geo.g = *g;
   A.geo.rc = dims->cutoff;
   if (use_mma()) {
-    if (jvp) return launch_center_jvp_mma(A, cfg == 1, st);
-    XEQ_CHECK_ARG(ws && ws_bytes >= center_fwd_ul_workspace_bytes(g->n_nodes, cfg == 1), "edge_message_fwd: workspace too small");
-    return launch_center_fwd_ul(A, cfg == 1, ws, st);
+    XEQ_CHECK_ARG(ws && ws_bytes >= center_fwd_ul_workspace_bytes(g->n_nodes, cfg == 1), "edge_message: workspace too small");
+    return jvp ? launch_center_jvp_ul(A, cfg == 1, ws, st) : launch_center_fwd_ul(A, cfg == 1, ws, st);
   }
 #ifdef XEQ_WITH_SIMT
   if (cfg == 0) return jvp ? launch_center<128, 64, 32, true>(A, st) : launch_center<128, 64, 32, false>(A, st);
@@ -946,7 +945,9 @@ int xeq_edge_cell_grad_rows(const xeq_graph_t* g, const xeq_dims_t* dims, const 
 
 size_t xeq_edge_message_bwdbwd_workspace_bytes(const xeq_graph_t* g, const xeq_dims_t* dims, int want_wgrad) {
   if (!g || !dims) return 0;
-  return neighbor_ws_bytes(g, dims, want_wgrad);
+  // the JVP pass (packed rows) runs first; the reverse pass reuses the region
+  const size_t a = neighbor_ws_bytes(g, dims, want_wgrad), b = center_fwd_ul_workspace_bytes(g->n_nodes, dims->node_dim > 128);
+  return a > b ? a : b;
 }
 
 int xeq_edge_message_bwdbwd(const xeq_graph_t* g, const xeq_dims_t* dims, const float* pos, const float* s, const float* v,
@@ -962,7 +963,7 @@ int xeq_edge_message_bwdbwd(const xeq_graph_t* g, const xeq_dims_t* dims, const 
     C.geo.pos = pos; C.geo.freq = freq; C.geo.a_pos = a_pos; C.geo.a_cell = a_cell;
     C.s = s; C.v = v; C.W = W_rbf; C.b = b_rbf;
     C.a_s = a_s; C.a_v = a_v; C.x_out = o_gx; C.V_out = o_gV;
-    int rc = run_center(g, dims, C, true, st);
+    int rc = run_center(g, dims, C, true, st, workspace, workspace_bytes);
     if (rc) return rc;
   }
   if (o_s || o_v || o_pos || o_W) {

@@ -97,6 +97,14 @@ __device__ __forceinline__ float sin_reduced(float x) {
   return __sinf(r);
 }
 
+__device__ __forceinline__ void sincos_reduced(float x, float& sn, float& cs) {  // same reduction, both SFU functions
+  const float n = rintf(x * 0.15915494309189535f);
+  float r = fmaf(n, -6.2831854820251465f, x);
+  r = fmaf(n, 1.7484555e-7f, r);
+  sn = __sinf(r);
+  cs = __cosf(r);
+}
+
 // ---- lane -> channel maps ----------------------------------------------------------------------------
 // irrep index (0..M) of the piece of lane L in slice sl
 template <int C, int M1>
