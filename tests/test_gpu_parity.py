@@ -438,7 +438,7 @@ def _edge_outputs(n_mol, staged):
 
 @pytest.mark.parametrize("staged", [True, False], ids=["molecule-tiles", "edge-block-tiles"])
 def test_tcgen05_and_simt_edge_kernels_agree(staged, tmp_path):
-    """The tensor-core kernels of the product library (edge_fwd_ul.cu, edge_bwd_ul.cu, edge_message_mma.cu) against an
+    """The tensor-core kernels of the product library (edge_fwd_ul.cu, edge_bwd_ul.cu, edge_bwd2_ul.cu, edge_wgrad_ul.cu) against an
     independent implementation: the round-1 SIMT kernels, compiled only into the test-only libxeq_b200_simt.so and run
     in a subprocess (XEQ_LIB + XEQ_EDGE_SIMT=1).  Same results to fp32 round-off on every output."""
     import os, subprocess, sys

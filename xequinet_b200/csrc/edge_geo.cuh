@@ -1,5 +1,5 @@
-// Shared device pieces of the fused edge kernels (edge_message.cu: SIMT filter contraction;
-// edge_message_mma.cu: filter contraction on tcgen05): chunk stream over node-aligned tiles,
+// Shared device pieces of the fused edge kernels (edge_message.cu: test-only SIMT filter contraction;
+// edge_*_ul.cu: filter contraction on tcgen05): chunk stream over node-aligned tiles,
 // per-edge geometry records in shared memory and the stages that fill them, kernel arguments.
 #pragma once
 #include "common.cuh"

@@ -740,7 +740,6 @@ static int launch_center(const CenterArgs& A, cudaStream_t st) {
   return XEQ_OK;
 }
 
-// tensor-core variants (edge_message_mma.cu), default widths only
 #endif
 
 // the tcgen05 kernels of the product path

@@ -1,21 +1,16 @@
-// tcgen05 building blocks of the fused edge kernels (edge_message_mma.cu).
+// tcgen05 building blocks of the fused edge kernels (edge_ul.cuh and the edge_*_ul.cu kernels build on these).
 //
 // The filter contraction  w[h, e] = sum_k [b | W_rbf][h, k] * psi_k(d_e)  (nn/xpainn.py:140, K = 21 -> 24)
 // runs on the tensor cores as D[h, e] = A[h, k] B[e, k]^T with
-//   A = the filter rows, resident in TENSOR MEMORY for the whole kernel: every thread writes the
-//       rows of its own channels once with tcgen05.st (3xTF32 split: hi and lo copies), so the rows
-//       leave the register file (63 registers per thread in the SIMT kernels) and need no shared
-//       memory;
-//   B = the per-edge radial terms of one chunk, produced by the geometry stage directly in the
-//       canonical K-major SWIZZLE_128B shared-memory layout (hi and lo tiles);
-//   D = fp32 accumulators in TMEM with lane = filter row: warp w reads lanes 32 (w % 4) .. +31 with
-//       tcgen05.ld, i.e. exactly the rows of the channels its threads own -- the thread <-> channel
-//       mapping of the SIMT kernels is unchanged.
-// Row -> (tile, lane): the 128 l = 0 channels use tiles 0 (state gate), 1 (edge gate), 2 (scalar
-// message) at lane q; the 96 l > 0 channels use tiles 3 (state gate) and 4 (edge gate) at lane q - 128.
+//   A = the filter rows, resident in TENSOR MEMORY for the whole kernel (tcgen05.st once per CTA, 3xTF32 split: hi and
+//       lo copies), so the rows leave the register file and need no shared memory;
+//   B = the per-edge radial terms of one chunk, written directly in the canonical K-major SWIZZLE_128B shared-memory
+//       layout (hi and lo tiles);
+//   D = fp32 accumulators in TMEM with lane = filter row: warp w reads lanes 32 (w % 4) .. +31 with tcgen05.ld.
+// Row -> (tile, lane): edge_ul.cuh ("unified lanes").
 // Products are evaluated as a_lo*b_hi + a_hi*b_lo + a_hi*b_hi (fp32-level accuracy, see node_gemm.cu).
 // Measured on B200 (profiles/r01_ts_mma_probe.log): 45 MMAs (one filter output of a 32-edge chunk)
-// = 837 cycles, 26 cycles per edge; TMEM reads of the 7 warps ~10 cycles per edge.
+// = 837 cycles, 26 cycles per edge.
 #pragma once
 #include "edge_geo.cuh"
 
@@ -27,11 +22,6 @@ namespace fm {
 // its own channels in TMEM -- the geometry of an edge is recomputed per slice, the feature traffic is not.
 constexpr int SL_C = 128, SL_M1 = 64, SL_M2 = 32, SL_M = SL_C + SL_M1 + SL_M2;
 constexpr int TILES = 5;
-// irrep channel of consumer thread t (< 224) of slice sl
-template <int L, int C, int M1>
-__device__ __forceinline__ int slice_channel(int t, int sl) {
-  return (L == 0) ? sl * SL_C + t : (L == 1 ? C + sl * SL_M1 + (t - SL_C) : C + M1 + sl * SL_M2 + (t - SL_C - SL_M1));
-}
 constexpr int A_HI = 0;                  // TMEM columns [0, 120): hi parts, tile-major, 24 per tile
 constexpr int A_LO = TILES * NBP;        // [120, 240): lo parts
 constexpr int D_COL = 2 * TILES * NBP;   // [240, ...): accumulators, (output, tile)-major, T columns each
@@ -168,86 +158,6 @@ __device__ __forceinline__ void store_a_row(uint32_t lane_base, int tile, const 
     for (int j = 0; j < 8; ++j) split_tf32(row[c8 * 8 + j], hi[j], lo[j]);
     tmem_st8(lane_base + A_HI + tile * NBP + c8 * 8, hi);
     tmem_st8(lane_base + A_LO + tile * NBP + c8 * 8, lo);
-  }
-}
-
-// Per-edge geometry rows of GeoA, fetched with 128-bit shared-memory loads into registers: only the entries the
-// thread's irrep type uses (l = 1: m = 0..2, l = 2: m = 3..7 of each 8-wide row), a third of the scalar loads.
-// dst keeps the row's own indexing so that edge_thread.cuh can address it unchanged.
-template <int L, int ROWS>
-__device__ __forceinline__ void load_rows8(const float* __restrict__ src, float* dst) {
-  if constexpr (L > 0) {
-#pragma unroll
-    for (int x = 0; x < ROWS; ++x) {
-      if (L == 1) {
-        const float4 v = *reinterpret_cast<const float4*>(src + x * 8);
-        dst[x * 8] = v.x; dst[x * 8 + 1] = v.y; dst[x * 8 + 2] = v.z;
-      } else {
-        const float4 v = *reinterpret_cast<const float4*>(src + x * 8 + 4);
-        dst[x * 8 + 3] = src[x * 8 + 3];
-        dst[x * 8 + 4] = v.x; dst[x * 8 + 5] = v.y; dst[x * 8 + 6] = v.z; dst[x * 8 + 7] = v.w;
-      }
-    }
-  }
-}
-__device__ __forceinline__ void load_vec3(const float* __restrict__ src /* [4], 16-byte aligned */, float* dst) {
-  const float4 v = *reinterpret_cast<const float4*>(src);
-  dst[0] = v.x; dst[1] = v.y; dst[2] = v.z;
-}
-
-// Shared-memory B tiles of one chunk: [output o][hi, lo][T rows x 128 bytes].
-template <int T> __device__ __forceinline__ constexpr uint32_t b_tile_bytes() { return T * 128; }
-
-// Geometry stage B: radial terms of a chunk, split and written straight into the B tiles
-// (output 0 = psi, 1 = dpsi, 2 = ddpsi).  One thread per (edge, k); rows >= cnt are zero-filled, so the filter
-// values of the slots past the end of a row piece are exact zeros.
-template <int T, int THREADS, int NOUT, bool NEED_G, bool SECOND>
-__device__ __noinline__ void geo_stage_b(const GeoArgs& A, int cnt, const GeoA<T, NEED_G, SECOND>& sa, uint32_t tiles,
-                                         const int t /* dense index of this thread among the THREADS writers */) {
-  const float c0 = sqrtf(2.f / A.rc);
-  for (int idx = t; idx < T * NBP; idx += THREADS) {
-    const int ee = idx / NBP, k = idx - ee * NBP;
-    float val[3] = {0.f, 0.f, 0.f};
-    if (ee >= cnt) {
-    } else if (k == 0) {
-      val[0] = sa.chi[ee][0]; val[1] = sa.chi[ee][1]; val[2] = sa.chi[ee][2];
-    } else if (k <= NB_) {
-      Cutoff<float> c;
-      c.chi = sa.chi[ee][0]; c.dchi = sa.chi[ee][1]; c.ddchi = sa.chi[ee][2];
-      const Radial<float> rr = radial_term_c0(sa.d[ee], A.freq[k - 1], c0, c);
-      val[0] = rr.psi; val[1] = rr.dpsi; val[2] = rr.ddpsi;
-    }
-    const uint32_t off = b_off(ee, k);
-#pragma unroll
-    for (int o = 0; o < NOUT; ++o) {
-      uint32_t hi, lo;
-      split_fast(val[o], hi, lo);
-      // the outputs are stacked along the rows of ONE tile (row = o * T + edge): one MMA per (tile, k step, product)
-      // covers all of them (N = NOUT * T), instead of NOUT separate N = T MMAs that are issue-bound
-      const uint32_t off_o = off + (uint32_t)o * b_tile_bytes<T>();  // T rows = whole 8-row swizzle groups
-      asm volatile("st.shared.b32 [%0], %1;" ::"r"(tiles + off_o), "r"(hi) : "memory");
-      asm volatile("st.shared.b32 [%0], %1;" ::"r"(tiles + NOUT * b_tile_bytes<T>() + off_o), "r"(lo) : "memory");
-    }
-  }
-}
-
-// Issue the MMAs of one chunk: for every row tile t,  D[t][o * T + e] = A[t] * B^T  with the NOUT outputs stacked
-// along N (3 k steps x 3 products per tile).  Accumulator column of (tile, output o, edge e):
-// D_COL + tile * NOUT * T + o * T + e.  Called by ONE elected thread of a converged warp.
-template <int T, int NOUT>
-__device__ __forceinline__ void issue_chunk(uint32_t tmem, uint32_t tiles) {
-  const uint32_t idesc = idesc_tf32(NOUT * T);
-  const uint32_t b_hi = tiles, b_lo = tiles + NOUT * b_tile_bytes<T>();
-#pragma unroll
-  for (int ks = 0; ks < NBP / 8; ++ks) {
-    const uint64_t db_hi = smem_desc(b_hi + ks * 32), db_lo = smem_desc(b_lo + ks * 32);
-#pragma unroll
-    for (int tile = 0; tile < TILES; ++tile) {
-      const uint32_t d = tmem + D_COL + tile * NOUT * T;
-      mma_ts(d, tmem + A_LO + tile * NBP + ks * 8, db_hi, idesc, ks ? 1u : 0u);
-      mma_ts(d, tmem + A_HI + tile * NBP + ks * 8, db_lo, idesc, 1u);
-      mma_ts(d, tmem + A_HI + tile * NBP + ks * 8, db_hi, idesc, 1u);
-    }
   }
 }
 
