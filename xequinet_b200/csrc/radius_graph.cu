@@ -470,12 +470,15 @@ __global__ void count_cols_kernel(const int* __restrict__ col, const int* __rest
   if (e < min(*n_edges_dev, capacity)) atomicAdd(&cnt[col[e]], 1);
 }
 
+// one warp per row i: lanes stride over the row's edges (coalesced reads of col); slot order inside a transposed row is
+// whatever the atomics give -- the rows are sorted right after
 __global__ void fill_transposed_kernel(const int* __restrict__ rowptr, const int* __restrict__ col, int n_nodes,
                                        int capacity, const int* __restrict__ t_rowptr, int* __restrict__ cursor,
                                        int* __restrict__ t_row, int* __restrict__ t_eid) {
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  const int i = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
   if (i >= n_nodes) return;
-  for (int e = rowptr[i]; e < min(rowptr[i + 1], capacity); ++e) {
+  const int e1 = min(rowptr[i + 1], capacity);
+  for (int e = rowptr[i] + lane; e < e1; e += 32) {
     const int j = col[e];
     const int slot = t_rowptr[j] + atomicAdd(&cursor[j], 1);
     t_row[slot] = i;
@@ -483,22 +486,44 @@ __global__ void fill_transposed_kernel(const int* __restrict__ rowptr, const int
   }
 }
 
-// slots of one transposed row sorted by edge id (== by center): deterministic order
-__global__ void sort_transposed_rows_kernel(const int* __restrict__ t_rowptr, int n_nodes, int* __restrict__ t_row,
-                                            int* __restrict__ t_eid) {
-  const int j = blockIdx.x * blockDim.x + threadIdx.x;
+// slots of one transposed row sorted by edge id (== by center): deterministic order.  One warp per row: the row is
+// staged in shared memory and every entry finds its rank by counting the smaller keys (edge ids are unique); rows
+// longer than the staging buffer fall back to an insertion sort by one lane.
+constexpr int SORT_CAP = 256;
+__global__ void __launch_bounds__(128) sort_transposed_rows_kernel(const int* __restrict__ t_rowptr, int n_nodes, int* __restrict__ t_row,
+                                                                   int* __restrict__ t_eid) {
+  __shared__ int keys[4][SORT_CAP], vals[4][SORT_CAP];
+  const int w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int j = blockIdx.x * 4 + w;
   if (j >= n_nodes) return;
-  const int b = t_rowptr[j], e = t_rowptr[j + 1];
-  for (int a = b + 1; a < e; ++a) {
-    const int ke = t_eid[a], kr = t_row[a];
-    int k = a - 1;
-    while (k >= b && t_eid[k] > ke) {
-      t_eid[k + 1] = t_eid[k];
-      t_row[k + 1] = t_row[k];
-      --k;
+  const int b = t_rowptr[j], n = t_rowptr[j + 1] - b;
+  if (n <= 1) return;
+  if (n <= SORT_CAP) {
+    for (int k = lane; k < n; k += 32) {
+      keys[w][k] = t_eid[b + k];
+      vals[w][k] = t_row[b + k];
     }
-    t_eid[k + 1] = ke;
-    t_row[k + 1] = kr;
+    __syncwarp();
+    for (int k = lane; k < n; k += 32) {
+      const int my = keys[w][k];
+      int rank = 0;
+      for (int m = 0; m < n; ++m) rank += keys[w][m] < my ? 1 : 0;
+      t_eid[b + rank] = my;
+      t_row[b + rank] = vals[w][k];
+    }
+  } else if (lane == 0) {
+    const int e = b + n;
+    for (int a = b + 1; a < e; ++a) {
+      const int ke = t_eid[a], kr = t_row[a];
+      int k = a - 1;
+      while (k >= b && t_eid[k] > ke) {
+        t_eid[k + 1] = t_eid[k];
+        t_row[k + 1] = t_row[k];
+        --k;
+      }
+      t_eid[k + 1] = ke;
+      t_row[k + 1] = kr;
+    }
   }
 }
 
@@ -710,9 +735,9 @@ int xeq_csr_transpose(const int32_t* rowptr, const int32_t* col, int32_t n_nodes
   if (rc) return rc;
   if (n_edges > 0 && n_nodes > 0) {
     XEQ_CUDA(cudaMemsetAsync(cnt, 0, sizeof(int) * (size_t)(n_nodes + 1), st));
-    fill_transposed_kernel<<<(n_nodes + 127) / 128, 128, 0, st>>>(rowptr, col, n_nodes, n_edges, t_rowptr, cnt, t_row,
+    fill_transposed_kernel<<<(n_nodes + 3) / 4, 128, 0, st>>>(rowptr, col, n_nodes, n_edges, t_rowptr, cnt, t_row,
                                                                   t_eid);
-    sort_transposed_rows_kernel<<<(n_nodes + 127) / 128, 128, 0, st>>>(t_rowptr, n_nodes, t_row, t_eid);
+    sort_transposed_rows_kernel<<<(n_nodes + 3) / 4, 128, 0, st>>>(t_rowptr, n_nodes, t_row, t_eid);
     XEQ_LAUNCHED(2);
   }
   XEQ_LAUNCH_CHECK();
