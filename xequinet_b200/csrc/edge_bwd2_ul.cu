@@ -127,7 +127,7 @@ __device__ __forceinline__ void bwd2_consumer(const NeighborArgs& A, Smem<MODE>&
 #pragma unroll
         for (int x = 0; x < 2; ++x) {
           float sn, cs;
-          sincosf(fr[x] * d, &sn, &cs);
+          sincos_reduced(fr[x] * d, sn, cs);
           const float phi = c0 * sn * inv;
           const float dphi = c0 * (fr[x] * cs * inv - sn * inv * inv);
           psi[x] = chi * phi;
@@ -149,7 +149,7 @@ __device__ __forceinline__ void bwd2_consumer(const NeighborArgs& A, Smem<MODE>&
         for (int x = 0; x < 4; ++x) {
           const float f = fr[x];
           float sn, cs;
-          sincosf(f * d, &sn, &cs);
+          sincos_reduced(f * d, sn, cs);
           const float phi = c0 * sn * inv;
           const float dphi = c0 * (f * cs * inv - sn * inv * inv);
           const float ddphi = c0 * (-f * f * sn * inv - 2.f * f * cs * inv * inv + 2.f * sn * inv * inv * inv);

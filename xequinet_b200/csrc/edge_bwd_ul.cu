@@ -113,7 +113,7 @@ __device__ __forceinline__ void bwd_consumer(const NeighborArgs& A, BwdSmem& sm,
 #pragma unroll
       for (int x = 0; x < 2; ++x) {
         float sn, cs;
-        sincosf(fr[x] * d, &sn, &cs);
+        sincos_reduced(fr[x] * d, sn, cs);
         const float phi = c0 * sn * inv;
         const float dphi = c0 * (fr[x] * cs * inv - sn * inv * inv);
         psi[x] = chi * phi;                    // fr = 0 (k = 0 or padding) -> exactly zero

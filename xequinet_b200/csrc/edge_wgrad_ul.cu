@@ -129,7 +129,7 @@ __device__ __forceinline__ void wg_consumer(const NeighborArgs& A, Smem<ORDER>& 
         const int k = rk + x;
         const float f = fr[x];
         float sn, cs;
-        sincosf(f * d, &sn, &cs);
+        sincos_reduced(f * d, sn, cs);
         const float phi = c0 * sn * inv, phif = c0 * d * cs * inv;  // phi_k, d phi_k / d f_k
         float psi = chi * phi, xi = chi * phif;                    // f = 0 (k = 0, padding): psi = 0, xi = chi c0 d inv
         if (k == 0) psi = chi;
