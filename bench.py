@@ -183,17 +183,18 @@ def algorithmic_bytes(kind: str, cfg: orc.XPaiNNConfig, N: int, E: int, periodic
 
 
 # DRAM bytes per launch (dram__bytes_read.sum + dram__bytes_write.sum) of the kernels behind each timed op, from the
-# committed `ncu --set full` captures (c3 shape: N = 5376, E = 106068): profiles/r02_edge_ncu_full.md for the round-2
-# kernels, profiles/r01_edge_mma_ncu_full.md for nbr_mma_kernel<2> (unchanged).  Only valid for that shape; other
-# workloads report traffic = null.
+# committed `ncu --set full` capture of the final round-2 kernels at the c3 shape (N = 5376, E = 106068):
+# profiles/r02_edge_ncu_full.md.  Only valid for that shape; other workloads report traffic = null.  (Writes mostly
+# stay in the 126 MB L2 at this size.)
 NCU_TRAFFIC_C3 = {
-    "edge_fwd": 35.73e6 + 0.01e6,                                                    # center_fwd_ul_kernel (rows packed in-kernel)
-    "edge_bwd": 36.85e6 + 0.16e6,                                                    # nbr_bwd_ul_kernel
-    "edge_bwd_wgrad": (36.85e6 + 0.16e6) + (36.78e6 + 0.08e6),                       # + wgrad_mma_kernel<1>
-    "edge_bwdbwd": (46.14e6 + 0.05e6) + (59.67e6 + 3.12e6) + (59.57e6 + 1.37e6),     # jvp + nbr<2> + wgrad<2>
+    "edge_fwd": 36.41e6 + 0.03e6,                                                    # center_fwd_ul_kernel<.., 0> (rows packed in-kernel)
+    "edge_bwd": 36.84e6 + 0.32e6,                                                    # nbr_bwd_ul_kernel
+    "edge_bwd_wgrad": (36.84e6 + 0.32e6) + (36.77e6 + 0.03e6),                       # + wgrad_ul_kernel<1>
+    # JVP = center_fwd_ul<.., 1> + <.., 2>; reverse pass = nbr_bwd2_ul<2> + <3>; wgrad_ul_kernel<2>
+    "edge_bwdbwd": (40.64e6 + 0.02e6) + (36.48e6 + 0.0) + (59.65e6 + 2.32e6) + (38.19e6 + 0.04e6) + (59.54e6 + 1.17e6),
 }
-# the same for the throughput probe (8192 molecules): center_fwd_ul_kernel, profiles/r02_edge_ncu_full.md (r02b capture)
-NCU_TRAFFIC_PROBE_FWD = 1.1395e9 + 0.3939e9
+# the same for the throughput probe (8192 molecules): center_fwd_ul_kernel, profiles/r02_edge_ncu_full.md (final capture)
+NCU_TRAFFIC_PROBE_FWD = 1.162e9 + 0.396e9
 
 
 def edge_throughput_probe(cfg, dev, peak, n_mol=8192, reps=10):
@@ -516,7 +517,7 @@ def run_gpu(args):
         launch_of = {"edge_fwd": "xeq_edge_message_fwd: center_fwd_ul_kernel (+ pack_fwd_kernel when tiles exceed the window)",
                      "edge_bwd": "xeq_edge_message_bwd: nbr_bwd_ul_kernel + pos_grad",
                      "edge_bwd_wgrad": "xeq_edge_message_bwd with weight gradients: nbr_bwd_ul_kernel + wgrad_ul_kernel<1> + reductions",
-                     "edge_bwdbwd": "xeq_edge_message_bwdbwd: center_mma_kernel<jvp> + nbr_bwd2_ul_kernel<2>, <3> + wgrad_ul_kernel<2> + reductions"}
+                     "edge_bwdbwd": "xeq_edge_message_bwdbwd: JVP = center_fwd_ul_kernel<.., 1> + <.., 2>; reverse = nbr_bwd2_ul_kernel<.., 2> + <.., 3>; wgrad_ul_kernel<2> + reductions"}
         roofline = {"kernel": dom, "launch": launch_of.get(dom), "bound": "hbm", "achieved": round(achieved, 2), "peak": peak, "unit": "GB/s",
                     "frac": round(achieved / peak, 5), "traffic": traffic, "peak_source": peak_src,
                     "n_nodes": N, "n_edges": E, "mean_launch_ms": round(mean_ms, 5)}
