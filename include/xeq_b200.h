@@ -281,6 +281,8 @@ int xeq_gemm_tf32x3(const xeq_gemm_t* problems_host, int32_t n_problems, int32_t
  *     z = x with the mul0 scalars centred;  rho = rsqrt(sum z^2 / (mul0+mul1+mul2) + eps)
  *     y_i = gamma[irrep(i)] z_i rho + (i < mul0 ? beta[i] : 0)
  * bwd:    g = dL/dy  ->  gx [N,D]; ggamma [M], gbeta [mul0] (either NULL = skipped)
+ * bwd: gx = d<g,y>/dx (+ gx_add: the gradient reaching x through its other consumer, e.g. the residual -- summed
+ *      here instead of by a separate elementwise kernel)
  * bwdbwd: cotangent a of gx -> dx = d<a,gx>/dx, dg = d<a,gx>/dg, dgamma [M]  (outputs may be NULL)
  * One warp per row; parameter gradients via per-CTA partial rows in the workspace and a fixed-order
  * reduction (deterministic).  Row widths D in {32,64,128,256,288,480,960}; mul* multiples of 32.
@@ -288,8 +290,8 @@ int xeq_gemm_tf32x3(const xeq_gemm_t* problems_host, int32_t n_problems, int32_t
 size_t xeq_irreps_norm_workspace_bytes(int32_t n_rows, int32_t mul0, int32_t mul1, int32_t mul2);
 int xeq_irreps_norm_fwd(const float* x, const float* gamma, const float* beta, int32_t n_rows,
                         int32_t mul0, int32_t mul1, int32_t mul2, float eps, float* y, xeq_stream_t stream);
-int xeq_irreps_norm_bwd(const float* x, const float* gamma, const float* g, int32_t n_rows,
-                        int32_t mul0, int32_t mul1, int32_t mul2, float eps,
+int xeq_irreps_norm_bwd(const float* x, const float* gamma, const float* g, const float* gx_add /* NULL or [N,D] */,
+                        int32_t n_rows, int32_t mul0, int32_t mul1, int32_t mul2, float eps,
                         float* gx, float* ggamma, float* gbeta,
                         void* workspace, size_t workspace_bytes, xeq_stream_t stream);
 int xeq_irreps_norm_bwdbwd(const float* x, const float* gamma, const float* g, const float* a, int32_t n_rows,

@@ -67,7 +67,7 @@ _SIGNATURES = {
     "xeq_gemm_tf32x3": (c_int, [POINTER(XeqGemm), c_int32, c_int32, c_void_p, c_size_t, c_void_p]),
     "xeq_irreps_norm_workspace_bytes": (c_size_t, [c_int32] * 4),
     "xeq_irreps_norm_fwd": (c_int, [c_void_p] * 3 + [c_int32] * 4 + [c_float, c_void_p, c_void_p]),
-    "xeq_irreps_norm_bwd": (c_int, [c_void_p] * 3 + [c_int32] * 4 + [c_float] + [c_void_p] * 3 + [c_void_p, c_size_t, c_void_p]),
+    "xeq_irreps_norm_bwd": (c_int, [c_void_p] * 4 + [c_int32] * 4 + [c_float] + [c_void_p] * 3 + [c_void_p, c_size_t, c_void_p]),
     "xeq_irreps_norm_bwdbwd": (c_int, [c_void_p] * 4 + [c_int32] * 4 + [c_float] + [c_void_p] * 3 + [c_void_p, c_size_t, c_void_p]),
     "xeq_invariant_dot_fwd": (c_int, [c_void_p] * 2 + [c_int32] * 4 + [c_void_p, c_int32, c_void_p, c_void_p]),
     "xeq_invariant_dot_bwd": (c_int, [c_void_p] * 3 + [c_int32, c_void_p] + [c_int32] * 4 + [c_void_p] * 3),

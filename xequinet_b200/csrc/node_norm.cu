@@ -121,8 +121,9 @@ __device__ __forceinline__ void flush_partials(float (&acc)[NACC][NK], int lane,
 
 template <int NK>
 __global__ void __launch_bounds__(NORM_WARPS * 32) norm_bwd_kernel(const float* __restrict__ x, const float* __restrict__ gamma,
-                                                                    const float* __restrict__ g, int n, NormShape S,
-                                                                    float* __restrict__ gx, float* __restrict__ partials) {
+                                                                    const float* __restrict__ g, const float* __restrict__ gx_add,
+                                                                    int n, NormShape S, float* __restrict__ gx,
+                                                                    float* __restrict__ partials) {
   pdl_trigger();
   pdl_wait();
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -153,9 +154,10 @@ __global__ void __launch_bounds__(NORM_WARPS * 32) norm_bwd_kernel(const float* 
       acc[1][k] += gr[k];               // d/dbeta
     }
     project<NK>(gz, lane, S);
-    if (gx) {
+    if (gx) {  // gx_add: the gradient that reaches x through its other consumer (the residual), summed here
 #pragma unroll
-      for (int k = 0; k < NK; ++k) gx[(size_t)row * S.D + lane + 32 * k] = gz[k];
+      for (int k = 0; k < NK; ++k)
+        gx[(size_t)row * S.D + lane + 32 * k] = gz[k] + (gx_add ? gx_add[(size_t)row * S.D + lane + 32 * k] : 0.f);
     }
   }
   if (partials) flush_partials<NK, 2>(acc, lane, warp, S.D, partials + (size_t)blockIdx.x * 2 * S.D);
@@ -316,8 +318,8 @@ int xeq_irreps_norm_fwd(const float* x, const float* gamma, const float* beta, i
   return XEQ_OK;
 }
 
-int xeq_irreps_norm_bwd(const float* x, const float* gamma, const float* g, int32_t n_rows, int32_t mul0, int32_t mul1,
-                        int32_t mul2, float eps, float* gx, float* ggamma, float* gbeta, void* workspace,
+int xeq_irreps_norm_bwd(const float* x, const float* gamma, const float* g, const float* gx_add, int32_t n_rows, int32_t mul0,
+                        int32_t mul1, int32_t mul2, float eps, float* gx, float* ggamma, float* gbeta, void* workspace,
                         size_t workspace_bytes, xeq_stream_t stream) {
   NormShape S;
   int rc = make_shape(mul0, mul1, mul2, eps, &S);
@@ -331,7 +333,7 @@ int xeq_irreps_norm_bwd(const float* x, const float* gamma, const float* g, int3
                   "irreps_norm_bwd: workspace too small");
   float* partials = params ? static_cast<float*>(workspace) : nullptr;
   if (n_rows > 0) {
-    NORM_DISPATCH(S.D / 32, norm_bwd_kernel, x, gamma, g, n_rows, S, gx, partials);
+    NORM_DISPATCH(S.D / 32, norm_bwd_kernel, x, gamma, g, gx_add, n_rows, S, gx, partials);
     XEQ_LAUNCHED(1);
   }
   if (params) {

@@ -36,6 +36,10 @@ class LayerNorm(nn.LayerNorm):
     def forward(self, x: torch.Tensor) -> torch.Tensor:
         return nodeops.layer_norm(x, self.weight, self.bias, self.eps)
 
+    def with_passthrough(self, x: torch.Tensor):
+        """(norm(x), x) -- nodeops._IrrepsNorm: feed the residual from the second output."""
+        return nodeops.layer_norm_pass(x, self.weight, self.bias, self.eps)
+
 
 def resolve_activation(activation: str) -> nn.Module:
     """xequinet/nn/basic.py:241-262; only SiLU is on the XPaiNN path (basic.py:255-256)."""
@@ -157,6 +161,10 @@ class EquivariantLayerNorm(nn.Module):
     def forward(self, V: torch.Tensor) -> torch.Tensor:
         assert V.shape[-1] == self.dim, "Input tensor must have the same last dimension as the irreps"
         return nodeops.irreps_norm(V, self.affine_weight, self.affine_bias, self.muls, self.eps)
+
+    def with_passthrough(self, V: torch.Tensor):
+        """(norm(V), V) -- nodeops._IrrepsNorm: feed the residual from the second output."""
+        return nodeops.irreps_norm_pass(V, self.affine_weight, self.affine_bias, self.muls, self.eps)
 
 
 class O3Linear(nn.Module):

@@ -48,6 +48,13 @@ class XEmbedding(nn.Module):
         return data
 
 
+def _norm_pass(norm: nn.Module, t: torch.Tensor):
+    """(norm(t), t) with t routed through the norm's pass-through output when the norm is one of ours."""
+    if hasattr(norm, "with_passthrough"):
+        return norm.with_passthrough(t)
+    return norm(t), t
+
+
 class XPainnMessage(nn.Module):
     def __init__(self, node_dim: int = 128, node_irreps: Iterable = "128x0e + 64x1o + 32x2e", num_basis: int = 20,
                  activation: str = "silu", layer_norm: bool = True) -> None:
@@ -73,8 +80,11 @@ class XPainnMessage(nn.Module):
         cutoff = float(data[keys.RBF_CUTOFF])
         if self._dims is None or self._dims.cutoff != cutoff:
             self._dims = ops.Dims(self.node_dim, *self.muls, self.num_basis, cutoff)
-        s = self.scalar_mlp(self.norm(x))
-        v = self.o3norm(V)
+        # x and V feed both their norm and the residual inside the edge kernel: take the residual from the norm's
+        # pass-through output, so that the two gradient contributions are summed inside the norm's backward kernel
+        xn, x = _norm_pass(self.norm, x)
+        v, V = _norm_pass(self.o3norm, V)
+        s = self.scalar_mlp(xn)
         plan = data.get(keys.HALO)
         if plan is not None:
             # spatially sharded run (xequinet_b200/domain.py): the rows of boundary atoms travel to the ranks
@@ -124,8 +134,8 @@ class XPainnUpdate(nn.Module):
     def forward(self, data: Dict[str, torch.Tensor]) -> Dict[str, torch.Tensor]:
         x, V = data[keys.NODE_INVARIANT], data[keys.NODE_EQUIVARIANT]
         M, C = self.node_num_irreps, self.node_dim
-        xn = self.norm(x)
-        vn = self.o3norm(V)
+        xn, x = _norm_pass(self.norm, x)
+        vn, V = _norm_pass(self.o3norm, V)
         U = self.update_U(vn)
         W = self.update_V(vn)
         n, t0 = nodeops.invariant_dot(U, W, self.muls)  # Invariant(W), EquivariantDot(U, W): one kernel

@@ -24,12 +24,12 @@ def irreps_norm_fwd_raw(x, gamma, beta, muls, eps):
     return y
 
 
-def irreps_norm_bwd_raw(x, gamma, g, muls, eps, need_x=True, need_params=True):
+def irreps_norm_bwd_raw(x, gamma, g, muls, eps, need_x=True, need_params=True, gx_add=None):
     gx = torch.empty_like(x) if need_x else None
     gg = torch.empty(sum(muls), dtype=torch.float32, device=x.device) if need_params else None
     gb = torch.empty(muls[0], dtype=torch.float32, device=x.device) if need_params else None
     ws, nbytes = _norm_ws(x.shape[0], muls, x.device) if need_params else (None, 0)
-    _lib.check(_lib.get().xeq_irreps_norm_bwd(_lib.ptr(x), _lib.ptr(gamma), _lib.ptr(g), x.shape[0], *muls, eps, _lib.ptr(gx),
+    _lib.check(_lib.get().xeq_irreps_norm_bwd(_lib.ptr(x), _lib.ptr(gamma), _lib.ptr(g), _lib.ptr(gx_add), x.shape[0], *muls, eps, _lib.ptr(gx),
                                               _lib.ptr(gg), _lib.ptr(gb), _lib.ptr(ws), nbytes, _lib.stream()),
                "xeq_irreps_norm_bwd")
     return gx, gg, gb
@@ -47,13 +47,15 @@ def irreps_norm_bwdbwd_raw(x, gamma, g, a, muls, eps, need_x=True, need_g=True, 
 
 
 class _IrrepsNormBwd(torch.autograd.Function):
+    """gx = d<g, norm(x)>/dx + g_pass (the gradient that reaches x through its pass-through output, summed in-kernel)."""
+
     @staticmethod
-    def forward(ctx, x, gamma, g, muls, eps, need_params):
+    def forward(ctx, x, gamma, g, g_pass, muls, eps, need_params):
         g = _c(g)
         ctx.save_for_backward(x, gamma, g)
-        ctx.cfg = (muls, eps)
+        ctx.cfg = (muls, eps, g_pass is not None)
         ctx.set_materialize_grads(False)
-        gx, gg, gb = irreps_norm_bwd_raw(x, gamma, g, muls, eps, True, need_params)
+        gx, gg, gb = irreps_norm_bwd_raw(x, gamma, g, muls, eps, True, need_params, _c(g_pass) if g_pass is not None else None)
         return gx, gg, gb
 
     @staticmethod
@@ -61,39 +63,56 @@ class _IrrepsNormBwd(torch.autograd.Function):
         if a_gamma is not None or a_beta is not None:
             raise NotImplementedError("second derivatives through the norm's parameter gradients are not on the XPaiNN path")
         x, gamma, g = ctx.saved_tensors
-        muls, eps = ctx.cfg
+        muls, eps, has_pass = ctx.cfg
         if a is None:
-            return None, None, None, None, None, None
+            return None, None, None, None, None, None, None
         dx, dg, dgam = irreps_norm_bwdbwd_raw(x, gamma, g, _c(a), muls, eps, input_wanted(ctx, 0), input_wanted(ctx, 2),
                                               input_wanted(ctx, 1))
-        return dx, dgam, dg, None, None, None
+        return dx, dgam, dg, (a if has_pass else None), None, None, None
 
 
 class _IrrepsNorm(torch.autograd.Function):
+    """passthrough: additionally returns x itself.  A caller that feeds BOTH the norm and a residual from x uses the
+    returned alias for the residual: x then has one consumer in the autograd graph, and the two gradient contributions
+    are summed inside the norm's backward kernel instead of by a separate elementwise add per tensor and pass."""
+
     @staticmethod
-    def forward(ctx, x, gamma, beta, muls, eps):
+    def forward(ctx, x, gamma, beta, muls, eps, passthrough):
         x, gamma, beta = _c(x), _c(gamma), _c(beta)
         ctx.save_for_backward(x, gamma)
         ctx.cfg = (muls, eps)
-        return irreps_norm_fwd_raw(x, gamma, beta, muls, eps)
+        ctx.set_materialize_grads(False)
+        y = irreps_norm_fwd_raw(x, gamma, beta, muls, eps)
+        return (y, x.view_as(x)) if passthrough else y
 
     @staticmethod
-    def backward(ctx, g):
+    def backward(ctx, g, g_pass=None):
         x, gamma = ctx.saved_tensors
         muls, eps = ctx.cfg
+        if g is None:
+            return g_pass, None, None, None, None, None
         need_params = input_wanted(ctx, 1) or input_wanted(ctx, 2)  # not in the force pass (d/dpos only)
-        gx, gg, gb = _IrrepsNormBwd.apply(x, gamma, g, muls, eps, need_params)
-        return gx, gg, gb, None, None
+        gx, gg, gb = _IrrepsNormBwd.apply(x, gamma, g, g_pass, muls, eps, need_params)
+        return gx, gg, gb, None, None, None
 
 
 def irreps_norm(x: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, muls, eps: float = 1e-5) -> torch.Tensor:
     """EquivariantLayerNorm on the cm layout (nn/o3layer.py:145-171)."""
-    return _IrrepsNorm.apply(x, gamma, beta, tuple(int(m) for m in muls), float(eps))
+    return _IrrepsNorm.apply(x, gamma, beta, tuple(int(m) for m in muls), float(eps), False)
 
 
 def layer_norm(x: torch.Tensor, weight: torch.Tensor, bias: torch.Tensor, eps: float = 1e-5) -> torch.Tensor:
     """nn.LayerNorm(C) = the irreps norm of "Cx0e"."""
-    return _IrrepsNorm.apply(x, weight, bias, (int(x.shape[1]), 0, 0), float(eps))
+    return _IrrepsNorm.apply(x, weight, bias, (int(x.shape[1]), 0, 0), float(eps), False)
+
+
+def irreps_norm_pass(x: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, muls, eps: float = 1e-5):
+    """(norm(x), x): use the second output wherever x itself is consumed next to its norm (residuals)."""
+    return _IrrepsNorm.apply(x, gamma, beta, tuple(int(m) for m in muls), float(eps), True)
+
+
+def layer_norm_pass(x: torch.Tensor, weight: torch.Tensor, bias: torch.Tensor, eps: float = 1e-5):
+    return _IrrepsNorm.apply(x, weight, bias, (int(x.shape[1]), 0, 0), float(eps), True)
 
 
 # ------------------------------------------------------------------------------------------
