@@ -314,8 +314,9 @@ int xeq_irreps_norm_bwdbwd(const float* x, const float* gamma, const float* g, c
  * ---------------------------------------------------------------------------------- */
 int xeq_invariant_dot_fwd(const float* U, const float* W, int32_t n, int32_t mul0, int32_t mul1, int32_t mul2,
                           float* nrm, int32_t ld_nrm, float* t0, xeq_stream_t stream);
-int xeq_invariant_dot_bwd(const float* U, const float* W, const float* gn, int32_t ld_gn, const float* gt, int32_t n,
-                          int32_t mul0, int32_t mul1, int32_t mul2, float* gU, float* gW, xeq_stream_t stream);
+int xeq_invariant_dot_bwd(const float* U, const float* W, const float* gn, int32_t ld_gn, const float* gt,
+                          const float* gU_add /* NULL or [N,D]: summed onto gU (gradient through U's other consumer) */,
+                          int32_t n, int32_t mul0, int32_t mul1, int32_t mul2, float* gU, float* gW, xeq_stream_t stream);
 int xeq_invariant_dot_bwdbwd(const float* U, const float* W, const float* gn, int32_t ld_gn, const float* gt,
                              const float* aU, const float* aW, int32_t n, int32_t mul0, int32_t mul1, int32_t mul2,
                              float* d_gn, float* d_gt, float* dU, float* dW, xeq_stream_t stream);

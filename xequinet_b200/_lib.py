@@ -70,7 +70,7 @@ _SIGNATURES = {
     "xeq_irreps_norm_bwd": (c_int, [c_void_p] * 4 + [c_int32] * 4 + [c_float] + [c_void_p] * 3 + [c_void_p, c_size_t, c_void_p]),
     "xeq_irreps_norm_bwdbwd": (c_int, [c_void_p] * 4 + [c_int32] * 4 + [c_float] + [c_void_p] * 3 + [c_void_p, c_size_t, c_void_p]),
     "xeq_invariant_dot_fwd": (c_int, [c_void_p] * 2 + [c_int32] * 4 + [c_void_p, c_int32, c_void_p, c_void_p]),
-    "xeq_invariant_dot_bwd": (c_int, [c_void_p] * 3 + [c_int32, c_void_p] + [c_int32] * 4 + [c_void_p] * 3),
+    "xeq_invariant_dot_bwd": (c_int, [c_void_p] * 3 + [c_int32, c_void_p, c_void_p] + [c_int32] * 4 + [c_void_p] * 3),
     "xeq_invariant_dot_bwdbwd": (c_int, [c_void_p] * 3 + [c_int32] + [c_void_p] * 3 + [c_int32] * 4 + [c_void_p] * 5),
     "xeq_gate_residual_fwd": (c_int, [c_void_p] * 5 + [c_int32] * 4 + [c_void_p] * 3),
     "xeq_gate_residual_bwd": (c_int, [c_void_p] * 5 + [c_int32] * 4 + [c_void_p] * 4),

@@ -55,8 +55,8 @@ __global__ void invdot_fwd_kernel(const float* __restrict__ U, const float* __re
 }
 
 __global__ void invdot_bwd_kernel(const float* __restrict__ U, const float* __restrict__ W, const float* __restrict__ gn,
-                                  int ld_gn, const float* __restrict__ gt, int n, IrrepShape S, float* __restrict__ gU,
-                                  float* __restrict__ gW) {
+                                  int ld_gn, const float* __restrict__ gt, const float* __restrict__ gU_add, int n, IrrepShape S,
+                                  float* __restrict__ gU, float* __restrict__ gW) {
   pdl_trigger();
   pdl_wait();
   const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -73,7 +73,7 @@ __global__ void invdot_bwd_kernel(const float* __restrict__ U, const float* __re
   const float k = gnv / sqrtf(s + INV_EPS * INV_EPS);
   for (int m = 0; m < 2 * I.l + 1; ++m) {
     const float wv = W[off + m * I.mul], uv = U[off + m * I.mul];
-    gU[off + m * I.mul] = gtv * wv;
+    gU[off + m * I.mul] = gtv * wv + (gU_add ? gU_add[off + m * I.mul] : 0.f);  // + the gradient through U's other consumer
     gW[off + m * I.mul] = gtv * uv + k * wv;
   }
 }
@@ -260,14 +260,14 @@ int xeq_invariant_dot_fwd(const float* U, const float* W, int32_t n, int32_t mul
   return XEQ_OK;
 }
 
-int xeq_invariant_dot_bwd(const float* U, const float* W, const float* gn, int32_t ld_gn, const float* gt, int32_t n,
-                          int32_t mul0, int32_t mul1, int32_t mul2, float* gU, float* gW, xeq_stream_t stream) {
+int xeq_invariant_dot_bwd(const float* U, const float* W, const float* gn, int32_t ld_gn, const float* gt, const float* gU_add,
+                          int32_t n, int32_t mul0, int32_t mul1, int32_t mul2, float* gU, float* gW, xeq_stream_t stream) {
   IrrepShape S;
   int rc = make_irreps(mul0, mul1, mul2, &S);
   if (rc) return rc;
   XEQ_CHECK_ARG(n >= 0 && (n == 0 || (U && W && gU && gW)), "invariant_dot_bwd: bad arguments");
   if (n == 0) return XEQ_OK;
-  XEQ_CUDA(launch_pdl(invdot_bwd_kernel, dim3(blocks_for((size_t)n * S.M)), dim3(256), (size_t)(0), (cudaStream_t)stream, U, W, gn, ld_gn, gt, n, S, gU, gW));
+  XEQ_CUDA(launch_pdl(invdot_bwd_kernel, dim3(blocks_for((size_t)n * S.M)), dim3(256), (size_t)(0), (cudaStream_t)stream, U, W, gn, ld_gn, gt, gU_add, n, S, gU, gW));
   XEQ_LAUNCHED(1);
   return XEQ_OK;
 }

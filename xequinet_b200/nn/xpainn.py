@@ -138,7 +138,7 @@ class XPainnUpdate(nn.Module):
         vn, V = _norm_pass(self.o3norm, V)
         U = self.update_U(vn)
         W = self.update_V(vn)
-        n, t0 = nodeops.invariant_dot(U, W, self.muls)  # Invariant(W), EquivariantDot(U, W): one kernel
+        n, t0, U = nodeops.invariant_dot_pass(U, W, self.muls)  # Invariant(W), EquivariantDot(U, W): one kernel; U passes through
         a = self.update_mlp(torch.cat([xn, n], dim=-1))  # [a_vv | a_sv | a_ss]
         t = self.dot_lin(t0)
         # x + a_sv * t + a_ss ,  V + expand(a_vv) * U : one kernel

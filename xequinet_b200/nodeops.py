@@ -124,14 +124,16 @@ def _e(*shape, like):
 
 class _InvDotBwd(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, U, W, gn, gt, muls):
+    def forward(ctx, U, W, gn, gt, gU_pass, muls):
         gn, gt = _c(gn), _c(gt)
         ctx.save_for_backward(U, W, gn, gt)
         ctx.muls = muls
+        ctx.has_pass = gU_pass is not None
         ctx.set_materialize_grads(False)
         gU, gW = torch.empty_like(U), torch.empty_like(W)
         M = sum(muls)
-        _lib.check(_lib.get().xeq_invariant_dot_bwd(_lib.ptr(U), _lib.ptr(W), _lib.ptr(gn), M, _lib.ptr(gt), U.shape[0], *muls,
+        _lib.check(_lib.get().xeq_invariant_dot_bwd(_lib.ptr(U), _lib.ptr(W), _lib.ptr(gn), M, _lib.ptr(gt),
+                                                    _lib.ptr(_c(gU_pass) if gU_pass is not None else None), U.shape[0], *muls,
                                                     _lib.ptr(gU), _lib.ptr(gW), _lib.stream()), "xeq_invariant_dot_bwd")
         return gU, gW
 
@@ -140,19 +142,22 @@ class _InvDotBwd(torch.autograd.Function):
         U, W, gn, gt = ctx.saved_tensors
         muls = ctx.muls
         if aU is None and aW is None:
-            return None, None, None, None, None
+            return None, None, None, None, None, None
         N, M = U.shape[0], sum(muls)
         d_gn, d_gt = _e(N, M, like=U), _e(N, M, like=U)
         dU, dW = torch.empty_like(U), torch.empty_like(W)
         _lib.check(_lib.get().xeq_invariant_dot_bwdbwd(_lib.ptr(U), _lib.ptr(W), _lib.ptr(gn), M, _lib.ptr(gt), _lib.ptr(_c(aU)),
                                                        _lib.ptr(_c(aW)), N, *muls, _lib.ptr(d_gn), _lib.ptr(d_gt), _lib.ptr(dU),
                                                        _lib.ptr(dW), _lib.stream()), "xeq_invariant_dot_bwdbwd")
-        return dU, dW, (d_gn if gn is not None else None), (d_gt if gt is not None else None), None
+        return dU, dW, (d_gn if gn is not None else None), (d_gt if gt is not None else None), (aU if ctx.has_pass else None), None
 
 
 class _InvDot(torch.autograd.Function):
+    """passthrough: additionally returns U itself (see _IrrepsNorm): the gate takes U from there, and the two gradient
+    contributions to U are summed inside the backward kernel."""
+
     @staticmethod
-    def forward(ctx, U, W, muls):
+    def forward(ctx, U, W, muls, passthrough=False):
         U, W = _c(U), _c(W)
         ctx.save_for_backward(U, W)
         ctx.muls = muls
@@ -161,20 +166,25 @@ class _InvDot(torch.autograd.Function):
         nrm, t0 = _e(N, M, like=U), _e(N, M, like=U)
         _lib.check(_lib.get().xeq_invariant_dot_fwd(_lib.ptr(U), _lib.ptr(W), N, *muls, _lib.ptr(nrm), M, _lib.ptr(t0),
                                                     _lib.stream()), "xeq_invariant_dot_fwd")
-        return nrm, t0
+        return (nrm, t0, U.view_as(U)) if passthrough else (nrm, t0)
 
     @staticmethod
-    def backward(ctx, gn, gt):
+    def backward(ctx, gn, gt, gU_pass=None):
         U, W = ctx.saved_tensors
         if gn is None and gt is None:
-            return None, None, None
-        gU, gW = _InvDotBwd.apply(U, W, gn, gt, ctx.muls)
-        return gU, gW, None
+            return gU_pass, None, None, None
+        gU, gW = _InvDotBwd.apply(U, W, gn, gt, gU_pass, ctx.muls)
+        return gU, gW, None, None
 
 
 def invariant_dot(U: torch.Tensor, W: torch.Tensor, muls):
     """(Invariant(W), EquivariantDot(U, W)) -> ([N, M], [N, M])."""
-    return _InvDot.apply(U, W, tuple(int(m) for m in muls))
+    return _InvDot.apply(U, W, tuple(int(m) for m in muls), False)
+
+
+def invariant_dot_pass(U: torch.Tensor, W: torch.Tensor, muls):
+    """(Invariant(W), EquivariantDot(U, W), U): feed U's other consumer (the gate) from the third output."""
+    return _InvDot.apply(U, W, tuple(int(m) for m in muls), True)
 
 
 # ------------------------------------------------------------------------------------------
