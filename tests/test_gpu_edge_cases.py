@@ -71,3 +71,61 @@ def test_model_on_a_single_atom_and_a_dimer():
         assert out["energy"].shape == (1,) and out["forces"].shape == (len(pos), 3)
         assert bool(torch.isfinite(out["energy"]).all()) and bool(torch.isfinite(out["forces"]).all())
         assert float(out["forces"].sum(0).abs().max()) < 1e-5  # no net force
+
+
+def _second_order(g, cfg, pos, seed=0, a_pos=True, a_sv=True):
+    dims = ops.Dims(cfg.node_dim, *cfg.muls, cfg.num_basis, cfg.cutoff)
+    gen = torch.Generator().manual_seed(seed)
+    r = lambda *s: torch.randn(*s, generator=gen).to(DEV)
+    N = g.n_nodes
+    s, v, gx, gV, a_s, a_v, a_p = r(N, dims.H), r(N, dims.D), r(N, dims.node_dim), r(N, dims.D), r(N, dims.H), r(N, dims.D), r(N, 3)
+    W, b = 0.3 * r(dims.H, 20), 0.3 * r(dims.H)
+    freq = (torch.pi * torch.arange(1, 21) / 5.0).float().to(DEV)
+    out = ops.edge_message_bwdbwd_raw(g, dims, pos, s, v, W, b, freq, gx, gV, a_s if a_sv else None, a_v if a_sv else None,
+                                      a_p if a_pos else None)
+    w1 = ops.edge_message_bwd_raw(g, dims, pos, s, v, W, b, freq, gx, gV, need_w=True)[3:]
+    torch.cuda.synchronize()
+    return list(out) + list(w1), dict(s=s, v=v, gx=gx, gV=gV, a_s=a_s, a_v=a_v, a_p=a_p, W=W, b=b, freq=freq, dims=dims)
+
+
+@pytest.mark.parametrize("sizes", [(5, 40), (22, 25)])
+@pytest.mark.parametrize("cfg", [orc.CONFIG_DEFAULT, orc.CONFIG_C4], ids=["c128", "c256"])
+def test_second_order_tiles_equal_blocks_and_repeat_bitwise(sizes, cfg):
+    """K2bb (JVP = two forward instances, reverse pass = two launches) and the weight-gradient kernels (one MMA-issuing warp
+    serving three groups in a fixed order): molecule tiles == edge-block tiles for everything computed per row, and every
+    output -- the weight gradients included, whose summation order depends on the tile walk -- repeats bit for bit."""
+    d = orc.make_molecule_batch(16, sizes, seed=sizes[0], with_edges=False)
+    pos, batch, ptr = d["pos"].to(DEV), d["batch"].to(DEV), d["ptr"].to(DEV)
+    g_mol, _, _ = build_graph(pos, cfg.cutoff, ptr=ptr, batch=batch)
+    g_blk = graph_from_edge_index(g_mol.edge_index(), g_mol.n_nodes, g_mol.n_graphs, batch=batch)
+    a, _ = _second_order(g_mol, cfg, pos)
+    a2, _ = _second_order(g_mol, cfg, pos)
+    b, _ = _second_order(g_blk, cfg, pos)
+    assert all(torch.equal(x, y) for x, y in zip(a, a2)), "second-order outputs are not reproducible"
+    names = ["o_gx", "o_gV", "o_s", "o_v", "o_pos"]
+    for k, name in enumerate(names):
+        if name == "o_pos":  # per-edge records summed per node: same order in both tilings
+            assert torch.allclose(a[k], b[k], rtol=0, atol=2e-5 * float(b[k].abs().max())), name
+        else:
+            assert torch.equal(a[k], b[k]), f"{name}: molecule tiles != edge-block tiles"
+    for k in range(5, len(a)):  # weight gradients: different partial-sum order across tilings, fp32 noise only
+        scale = float(b[k].abs().max()) + 1e-30
+        assert float((a[k] - b[k]).abs().max()) <= 1e-4 * scale  # (frequency gradients: sums with cancellation)
+
+
+def test_second_order_with_missing_tangents():
+    """NULL a_pos (no geometry tangent: the tangent-filter launch is skipped) and NULL a_s / a_v (zero row tangents) give
+    what explicit zero tensors give."""
+    cfg = orc.CONFIG_DEFAULT
+    d = orc.make_molecule_batch(6, (3, 30), seed=2, with_edges=False)
+    pos, batch, ptr = d["pos"].to(DEV), d["batch"].to(DEV), d["ptr"].to(DEV)
+    g, _, _ = build_graph(pos, cfg.cutoff, ptr=ptr, batch=batch)
+    for a_pos, a_sv in ((False, True), (True, False)):
+        got, t = _second_order(g, cfg, pos, seed=3, a_pos=a_pos, a_sv=a_sv)
+        z = torch.zeros_like
+        ref = ops.edge_message_bwdbwd_raw(g, t["dims"], pos, t["s"], t["v"], t["W"], t["b"], t["freq"], t["gx"], t["gV"],
+                                          t["a_s"] if a_sv else z(t["a_s"]), t["a_v"] if a_sv else z(t["a_v"]),
+                                          t["a_p"] if a_pos else z(t["a_p"]))
+        for x, y in zip(got[:8], ref):
+            assert torch.isfinite(x).all()
+            assert torch.allclose(x, y, rtol=0, atol=1e-6 * (float(y.abs().max()) + 1e-30))
