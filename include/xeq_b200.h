@@ -290,11 +290,12 @@ int xeq_gemm_tf32x3(const xeq_gemm_t* problems_host, int32_t n_problems, int32_t
 size_t xeq_irreps_norm_workspace_bytes(int32_t n_rows, int32_t mul0, int32_t mul1, int32_t mul2);
 int xeq_irreps_norm_fwd(const float* x, const float* gamma, const float* beta, int32_t n_rows,
                         int32_t mul0, int32_t mul1, int32_t mul2, float eps, float* y, xeq_stream_t stream);
-int xeq_irreps_norm_bwd(const float* x, const float* gamma, const float* g, const float* gx_add /* NULL or [N,D] */,
+int xeq_irreps_norm_bwd(const float* x, const float* gamma, const float* g, int32_t ld_g /* row stride of g, 0 = D */,
+                        const float* gx_add /* NULL or [N,D] */,
                         int32_t n_rows, int32_t mul0, int32_t mul1, int32_t mul2, float eps,
                         float* gx, float* ggamma, float* gbeta,
                         void* workspace, size_t workspace_bytes, xeq_stream_t stream);
-int xeq_irreps_norm_bwdbwd(const float* x, const float* gamma, const float* g, const float* a, int32_t n_rows,
+int xeq_irreps_norm_bwdbwd(const float* x, const float* gamma, const float* g, int32_t ld_g, const float* a, int32_t n_rows,
                            int32_t mul0, int32_t mul1, int32_t mul2, float eps,
                            float* dx, float* dg, float* dgamma,
                            void* workspace, size_t workspace_bytes, xeq_stream_t stream);

@@ -67,8 +67,8 @@ _SIGNATURES = {
     "xeq_gemm_tf32x3": (c_int, [POINTER(XeqGemm), c_int32, c_int32, c_void_p, c_size_t, c_void_p]),
     "xeq_irreps_norm_workspace_bytes": (c_size_t, [c_int32] * 4),
     "xeq_irreps_norm_fwd": (c_int, [c_void_p] * 3 + [c_int32] * 4 + [c_float, c_void_p, c_void_p]),
-    "xeq_irreps_norm_bwd": (c_int, [c_void_p] * 4 + [c_int32] * 4 + [c_float] + [c_void_p] * 3 + [c_void_p, c_size_t, c_void_p]),
-    "xeq_irreps_norm_bwdbwd": (c_int, [c_void_p] * 4 + [c_int32] * 4 + [c_float] + [c_void_p] * 3 + [c_void_p, c_size_t, c_void_p]),
+    "xeq_irreps_norm_bwd": (c_int, [c_void_p] * 3 + [c_int32, c_void_p] + [c_int32] * 4 + [c_float] + [c_void_p] * 3 + [c_void_p, c_size_t, c_void_p]),
+    "xeq_irreps_norm_bwdbwd": (c_int, [c_void_p] * 3 + [c_int32, c_void_p] + [c_int32] * 4 + [c_float] + [c_void_p] * 3 + [c_void_p, c_size_t, c_void_p]),
     "xeq_invariant_dot_fwd": (c_int, [c_void_p] * 2 + [c_int32] * 4 + [c_void_p, c_int32, c_void_p, c_void_p]),
     "xeq_invariant_dot_bwd": (c_int, [c_void_p] * 3 + [c_int32, c_void_p, c_void_p] + [c_int32] * 4 + [c_void_p] * 3),
     "xeq_invariant_dot_bwdbwd": (c_int, [c_void_p] * 3 + [c_int32] + [c_void_p] * 3 + [c_int32] * 4 + [c_void_p] * 5),
@@ -172,6 +172,17 @@ def ptr(t):
         raise RuntimeError("xequinet_b200 ops need CUDA tensors: there is no CPU fallback")
     if not t.is_contiguous():
         raise RuntimeError("xequinet_b200 ops need contiguous tensors")
+    return t.data_ptr()
+
+
+def ptr_rows(t):
+    """Device pointer of a 2-D CUDA tensor with dense rows (unit inner stride; the row stride travels as an `ld` argument)."""
+    if t is None:
+        return None
+    if not t.is_cuda:
+        raise RuntimeError("xequinet_b200 ops need CUDA tensors: there is no CPU fallback")
+    if t.dim() != 2 or t.stride(1) != 1 or t.stride(0) < t.shape[1]:
+        raise RuntimeError("xequinet_b200 ops need row-dense 2-D tensors here")
     return t.data_ptr()
 
 

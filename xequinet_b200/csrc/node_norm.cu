@@ -121,8 +121,9 @@ __device__ __forceinline__ void flush_partials(float (&acc)[NACC][NK], int lane,
 
 template <int NK>
 __global__ void __launch_bounds__(NORM_WARPS * 32) norm_bwd_kernel(const float* __restrict__ x, const float* __restrict__ gamma,
-                                                                    const float* __restrict__ g, const float* __restrict__ gx_add,
-                                                                    int n, NormShape S, float* __restrict__ gx,
+                                                                    const float* __restrict__ g, int ld_g,
+                                                                    const float* __restrict__ gx_add, int n, NormShape S,
+                                                                    float* __restrict__ gx,
                                                                     float* __restrict__ partials) {
   pdl_trigger();
   pdl_wait();
@@ -140,7 +141,7 @@ __global__ void __launch_bounds__(NORM_WARPS * 32) norm_bwd_kernel(const float* 
     float A = 0.f;
 #pragma unroll
     for (int k = 0; k < NK; ++k) {
-      gr[k] = g[(size_t)row * S.D + lane + 32 * k];
+      gr[k] = g[(size_t)row * ld_g + lane + 32 * k];
       h[k] = gam[k] * gr[k];
       A += h[k] * z[k];
     }
@@ -165,8 +166,9 @@ __global__ void __launch_bounds__(NORM_WARPS * 32) norm_bwd_kernel(const float* 
 
 template <int NK>
 __global__ void __launch_bounds__(NORM_WARPS * 32) norm_bwdbwd_kernel(const float* __restrict__ x, const float* __restrict__ gamma,
-                                                                       const float* __restrict__ g, const float* __restrict__ a,
-                                                                       int n, NormShape S, float* __restrict__ dx,
+                                                                       const float* __restrict__ g, int ld_g,
+                                                                       const float* __restrict__ a, int n, NormShape S,
+                                                                       float* __restrict__ dx,
                                                                        float* __restrict__ dg, float* __restrict__ partials) {
   pdl_trigger();
   pdl_wait();
@@ -183,7 +185,7 @@ __global__ void __launch_bounds__(NORM_WARPS * 32) norm_bwdbwd_kernel(const floa
     center_and_scale<NK>(x + (size_t)row * S.D, lane, S, z, rho);
 #pragma unroll
     for (int k = 0; k < NK; ++k) {
-      gr[k] = g[(size_t)row * S.D + lane + 32 * k];
+      gr[k] = g[(size_t)row * ld_g + lane + 32 * k];
       h[k] = gam[k] * gr[k];
       c[k] = a[(size_t)row * S.D + lane + 32 * k];
     }
@@ -318,7 +320,7 @@ int xeq_irreps_norm_fwd(const float* x, const float* gamma, const float* beta, i
   return XEQ_OK;
 }
 
-int xeq_irreps_norm_bwd(const float* x, const float* gamma, const float* g, const float* gx_add, int32_t n_rows, int32_t mul0,
+int xeq_irreps_norm_bwd(const float* x, const float* gamma, const float* g, int32_t ld_g, const float* gx_add, int32_t n_rows, int32_t mul0,
                         int32_t mul1, int32_t mul2, float eps, float* gx, float* ggamma, float* gbeta, void* workspace,
                         size_t workspace_bytes, xeq_stream_t stream) {
   NormShape S;
@@ -333,7 +335,7 @@ int xeq_irreps_norm_bwd(const float* x, const float* gamma, const float* g, cons
                   "irreps_norm_bwd: workspace too small");
   float* partials = params ? static_cast<float*>(workspace) : nullptr;
   if (n_rows > 0) {
-    NORM_DISPATCH(S.D / 32, norm_bwd_kernel, x, gamma, g, gx_add, n_rows, S, gx, partials);
+    NORM_DISPATCH(S.D / 32, norm_bwd_kernel, x, gamma, g, ld_g > 0 ? ld_g : S.D, gx_add, n_rows, S, gx, partials);
     XEQ_LAUNCHED(1);
   }
   if (params) {
@@ -343,7 +345,7 @@ int xeq_irreps_norm_bwd(const float* x, const float* gamma, const float* g, cons
   return XEQ_OK;
 }
 
-int xeq_irreps_norm_bwdbwd(const float* x, const float* gamma, const float* g, const float* a, int32_t n_rows, int32_t mul0,
+int xeq_irreps_norm_bwdbwd(const float* x, const float* gamma, const float* g, int32_t ld_g, const float* a, int32_t n_rows, int32_t mul0,
                            int32_t mul1, int32_t mul2, float eps, float* dx, float* dg, float* dgamma, void* workspace,
                            size_t workspace_bytes, xeq_stream_t stream) {
   NormShape S;
@@ -357,7 +359,7 @@ int xeq_irreps_norm_bwdbwd(const float* x, const float* gamma, const float* g, c
                   "irreps_norm_bwdbwd: workspace too small");
   float* partials = dgamma ? static_cast<float*>(workspace) : nullptr;
   if (n_rows > 0) {
-    NORM_DISPATCH(S.D / 32, norm_bwdbwd_kernel, x, gamma, g, a, n_rows, S, dx, dg, partials);
+    NORM_DISPATCH(S.D / 32, norm_bwdbwd_kernel, x, gamma, g, ld_g > 0 ? ld_g : S.D, a, n_rows, S, dx, dg, partials);
     XEQ_LAUNCHED(1);
   }
   if (dgamma) {

@@ -12,6 +12,19 @@ from ._state import input_wanted
 from .ops import _c, _workspace
 
 
+def _rows(t):
+    """(tensor, row stride) of a 2-D fp32 tensor whose rows are dense: column slices of a wider tensor (the halves of a
+    torch.cat gradient) are passed to the kernels as they are instead of through a .contiguous() copy."""
+    if t is None:
+        return None, 0
+    if t.dtype != torch.float32:
+        raise RuntimeError(f"xequinet_b200 kernels compute in fp32, got {t.dtype}")
+    if t.dim() == 2 and t.stride(1) == 1 and t.stride(0) >= t.shape[1]:
+        return t, t.stride(0)
+    t = t.contiguous()
+    return t, t.shape[-1]
+
+
 def _norm_ws(n, muls, device):
     nbytes = _lib.get().xeq_irreps_norm_workspace_bytes(n, *muls)
     return _workspace(nbytes, device), nbytes
@@ -29,7 +42,8 @@ def irreps_norm_bwd_raw(x, gamma, g, muls, eps, need_x=True, need_params=True, g
     gg = torch.empty(sum(muls), dtype=torch.float32, device=x.device) if need_params else None
     gb = torch.empty(muls[0], dtype=torch.float32, device=x.device) if need_params else None
     ws, nbytes = _norm_ws(x.shape[0], muls, x.device) if need_params else (None, 0)
-    _lib.check(_lib.get().xeq_irreps_norm_bwd(_lib.ptr(x), _lib.ptr(gamma), _lib.ptr(g), _lib.ptr(gx_add), x.shape[0], *muls, eps, _lib.ptr(gx),
+    g, ld_g = _rows(g)
+    _lib.check(_lib.get().xeq_irreps_norm_bwd(_lib.ptr(x), _lib.ptr(gamma), _lib.ptr_rows(g), ld_g, _lib.ptr(gx_add), x.shape[0], *muls, eps, _lib.ptr(gx),
                                               _lib.ptr(gg), _lib.ptr(gb), _lib.ptr(ws), nbytes, _lib.stream()),
                "xeq_irreps_norm_bwd")
     return gx, gg, gb
@@ -40,7 +54,8 @@ def irreps_norm_bwdbwd_raw(x, gamma, g, a, muls, eps, need_x=True, need_g=True, 
     dg = torch.empty_like(x) if need_g else None
     dgam = torch.empty(sum(muls), dtype=torch.float32, device=x.device) if need_gamma else None
     ws, nbytes = _norm_ws(x.shape[0], muls, x.device) if need_gamma else (None, 0)
-    _lib.check(_lib.get().xeq_irreps_norm_bwdbwd(_lib.ptr(x), _lib.ptr(gamma), _lib.ptr(g), _lib.ptr(a), x.shape[0], *muls, eps,
+    g, ld_g = _rows(g)
+    _lib.check(_lib.get().xeq_irreps_norm_bwdbwd(_lib.ptr(x), _lib.ptr(gamma), _lib.ptr_rows(g), ld_g, _lib.ptr(a), x.shape[0], *muls, eps,
                                                  _lib.ptr(dx), _lib.ptr(dg), _lib.ptr(dgam), _lib.ptr(ws), nbytes,
                                                  _lib.stream()), "xeq_irreps_norm_bwdbwd")
     return dx, dg, dgam
@@ -51,7 +66,7 @@ class _IrrepsNormBwd(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, x, gamma, g, g_pass, muls, eps, need_params):
-        g = _c(g)
+        g = _rows(g)[0]
         ctx.save_for_backward(x, gamma, g)
         ctx.cfg = (muls, eps, g_pass is not None)
         ctx.set_materialize_grads(False)
@@ -125,14 +140,14 @@ def _e(*shape, like):
 class _InvDotBwd(torch.autograd.Function):
     @staticmethod
     def forward(ctx, U, W, gn, gt, gU_pass, muls):
-        gn, gt = _c(gn), _c(gt)
+        (gn, ld_gn), gt = _rows(gn), _c(gt)  # gn: usually a column slice of the update MLP's input gradient
         ctx.save_for_backward(U, W, gn, gt)
         ctx.muls = muls
         ctx.has_pass = gU_pass is not None
         ctx.set_materialize_grads(False)
         gU, gW = torch.empty_like(U), torch.empty_like(W)
         M = sum(muls)
-        _lib.check(_lib.get().xeq_invariant_dot_bwd(_lib.ptr(U), _lib.ptr(W), _lib.ptr(gn), M, _lib.ptr(gt),
+        _lib.check(_lib.get().xeq_invariant_dot_bwd(_lib.ptr(U), _lib.ptr(W), _lib.ptr_rows(gn), ld_gn or M, _lib.ptr(gt),
                                                     _lib.ptr(_c(gU_pass) if gU_pass is not None else None), U.shape[0], *muls,
                                                     _lib.ptr(gU), _lib.ptr(gW), _lib.stream()), "xeq_invariant_dot_bwd")
         return gU, gW
@@ -146,7 +161,7 @@ class _InvDotBwd(torch.autograd.Function):
         N, M = U.shape[0], sum(muls)
         d_gn, d_gt = _e(N, M, like=U), _e(N, M, like=U)
         dU, dW = torch.empty_like(U), torch.empty_like(W)
-        _lib.check(_lib.get().xeq_invariant_dot_bwdbwd(_lib.ptr(U), _lib.ptr(W), _lib.ptr(gn), M, _lib.ptr(gt), _lib.ptr(_c(aU)),
+        _lib.check(_lib.get().xeq_invariant_dot_bwdbwd(_lib.ptr(U), _lib.ptr(W), _lib.ptr_rows(gn), (gn.stride(0) if gn is not None else M), _lib.ptr(gt), _lib.ptr(_c(aU)),
                                                        _lib.ptr(_c(aW)), N, *muls, _lib.ptr(d_gn), _lib.ptr(d_gt), _lib.ptr(dU),
                                                        _lib.ptr(dW), _lib.stream()), "xeq_invariant_dot_bwdbwd")
         return dU, dW, (d_gn if gn is not None else None), (d_gt if gt is not None else None), (aU if ctx.has_pass else None), None
