@@ -139,7 +139,7 @@ class XPainnUpdate(nn.Module):
         U = self.update_U(vn)
         W = self.update_V(vn)
         n, t0, U = nodeops.invariant_dot_pass(U, W, self.muls)  # Invariant(W), EquivariantDot(U, W): one kernel; U passes through
-        a = self.update_mlp(torch.cat([xn, n], dim=-1))  # [a_vv | a_sv | a_ss]
+        a = self.update_mlp(nodeops.cat2(xn, n))  # [a_vv | a_sv | a_ss]
         t = self.dot_lin(t0)
         # x + a_sv * t + a_ss ,  V + expand(a_vv) * U : one kernel
         data[keys.NODE_INVARIANT], data[keys.NODE_EQUIVARIANT] = nodeops.gate_residual(a, U, t, x, V, self.muls)

@@ -260,6 +260,48 @@ def gate_residual(a, U, t, x, V, muls):
 
 
 # ------------------------------------------------------------------------------------------
+# cat([a, b], -1) whose derivatives stay one kernel per order
+# ------------------------------------------------------------------------------------------
+class _Split2(torch.autograd.Function):
+    """(g[:, :n1], g[:, n1:]) as views; the backward of the pair is ONE cat (torch's own slice backward is a zero fill
+    plus a copy per slice plus an add)."""
+
+    @staticmethod
+    def forward(ctx, g, n1):
+        ctx.n = (n1, g.shape[1] - n1)
+        ctx.set_materialize_grads(False)
+        return g[:, :n1], g[:, n1:]
+
+    @staticmethod
+    def backward(ctx, a1, a2):
+        if a1 is None and a2 is None:
+            return None, None
+        ref = a1 if a1 is not None else a2
+        if a1 is None:
+            a1 = ref.new_zeros((ref.shape[0], ctx.n[0]))
+        if a2 is None:
+            a2 = ref.new_zeros((ref.shape[0], ctx.n[1]))
+        return _Cat2.apply(a1, a2), None
+
+
+class _Cat2(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, a, b):
+        ctx.n1 = a.shape[1]
+        return torch.cat([a, b], dim=1)
+
+    @staticmethod
+    def backward(ctx, g):
+        g1, g2 = _Split2.apply(g, ctx.n1)
+        return g1, g2
+
+
+def cat2(a: torch.Tensor, b: torch.Tensor) -> torch.Tensor:
+    """torch.cat([a, b], dim=1) of two 2-D tensors."""
+    return _Cat2.apply(a, b)
+
+
+# ------------------------------------------------------------------------------------------
 # SiLU
 # ------------------------------------------------------------------------------------------
 class _SiluBwd(torch.autograd.Function):
