@@ -220,14 +220,15 @@ __global__ void __launch_bounds__(NORM_WARPS * 32) norm_bwdbwd_kernel(const floa
 }
 
 // partial rows [n_part][n_acc * D] -> out_gamma[M] (components folded into irreps), out_beta[m0].
-// One CTA per 32 consecutive irreps of one l (multiplicities are multiples of 32): 32 columns x 8 row
+// One CTA per 32 consecutive irreps of one l (multiplicities are multiples of 32): 32 columns x 32 row
 // lanes, every load is a coalesced 128-byte row segment, rows are summed in a fixed order.
-__global__ void __launch_bounds__(256) norm_param_reduce_kernel(const float* __restrict__ partials, int n_part, int n_acc,
-                                                                NormShape S, float* __restrict__ out_gamma,
-                                                                float* __restrict__ out_beta) {
+constexpr int PR_ROWS = 32;
+__global__ void __launch_bounds__(32 * PR_ROWS) norm_param_reduce_kernel(const float* __restrict__ partials, int n_part, int n_acc,
+                                                                         NormShape S, float* __restrict__ out_gamma,
+                                                                         float* __restrict__ out_beta) {
   pdl_trigger();
   pdl_wait();
-  __shared__ float red[2][8][33];
+  __shared__ float red[2][PR_ROWS][33];
   const int c = threadIdx.x & 31, rl = threadIdx.x >> 5;
   const int q = blockIdx.x * 32 + c;
   int l, u, base, mul;
@@ -240,18 +241,18 @@ __global__ void __launch_bounds__(256) norm_param_reduce_kernel(const float* __r
     const float* col = partials + base + m * mul + u;
     float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
     int p = rl;
-    for (; p + 24 < n_part; p += 32) {
+    for (; p + 3 * PR_ROWS < n_part; p += 4 * PR_ROWS) {
       s0 += col[(size_t)p * stride];
-      s1 += col[(size_t)(p + 8) * stride];
-      s2 += col[(size_t)(p + 16) * stride];
-      s3 += col[(size_t)(p + 24) * stride];
+      s1 += col[(size_t)(p + PR_ROWS) * stride];
+      s2 += col[(size_t)(p + 2 * PR_ROWS) * stride];
+      s3 += col[(size_t)(p + 3 * PR_ROWS) * stride];
     }
-    for (; p < n_part; p += 8) s0 += col[(size_t)p * stride];
+    for (; p < n_part; p += PR_ROWS) s0 += col[(size_t)p * stride];
     sg += (s0 + s1) + (s2 + s3);
   }
   if (n_acc > 1 && l == 0) {
     const float* col = partials + S.D + u;
-    for (int p = rl; p < n_part; p += 8) sb += col[(size_t)p * stride];
+    for (int p = rl; p < n_part; p += PR_ROWS) sb += col[(size_t)p * stride];
   }
   red[0][rl][c] = sg;
   red[1][rl][c] = sb;
@@ -259,7 +260,7 @@ __global__ void __launch_bounds__(256) norm_param_reduce_kernel(const float* __r
   if (rl == 0) {
     float tg = 0.f, tb = 0.f;
 #pragma unroll
-    for (int r = 0; r < 8; ++r) {
+    for (int r = 0; r < PR_ROWS; ++r) {
       tg += red[0][r][c];
       tb += red[1][r][c];
     }
@@ -339,7 +340,7 @@ int xeq_irreps_norm_bwd(const float* x, const float* gamma, const float* g, int3
     XEQ_LAUNCHED(1);
   }
   if (params) {
-    XEQ_CUDA(launch_pdl(norm_param_reduce_kernel, dim3(S.M / 32), dim3(256), (size_t)(0), st, partials, n_rows > 0 ? grid : 0, 2, S, ggamma, gbeta));
+    XEQ_CUDA(launch_pdl(norm_param_reduce_kernel, dim3(S.M / 32), dim3(32 * PR_ROWS), (size_t)(0), st, partials, n_rows > 0 ? grid : 0, 2, S, ggamma, gbeta));
     XEQ_LAUNCHED(1);
   }
   return XEQ_OK;
@@ -363,7 +364,7 @@ int xeq_irreps_norm_bwdbwd(const float* x, const float* gamma, const float* g, i
     XEQ_LAUNCHED(1);
   }
   if (dgamma) {
-    XEQ_CUDA(launch_pdl(norm_param_reduce_kernel, dim3(S.M / 32), dim3(256), (size_t)(0), st, partials, n_rows > 0 ? grid : 0, 1, S, dgamma, nullptr));
+    XEQ_CUDA(launch_pdl(norm_param_reduce_kernel, dim3(S.M / 32), dim3(32 * PR_ROWS), (size_t)(0), st, partials, n_rows > 0 ? grid : 0, 1, S, dgamma, nullptr));
     XEQ_LAUNCHED(1);
   }
   return XEQ_OK;
