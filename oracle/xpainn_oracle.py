@@ -130,13 +130,13 @@ def state_dict_spec(cfg: XPaiNNConfig) -> List[Tuple[str, Tuple[int, ...], str]]
     return spec
 
 
-def synthetic_state_dict(cfg: XPaiNNConfig, seed: int = 1234, dtype=torch.float32) -> Dict[str, torch.Tensor]:
+def synthetic_state_dict(cfg: XPaiNNConfig, seed: int = 1234, dtype=torch.float32, spec=None) -> Dict[str, torch.Tensor]:
     """Default-init-like values plus an N(0, 0.1^2) perturbation of every parameter,
     so zero biases / unit gains cannot hide bugs.  Generated in fp64
     from a CPU generator, then cast, so every box and dtype sees the same numbers."""
     g = torch.Generator().manual_seed(seed)
     sd: Dict[str, torch.Tensor] = {}
-    for name, shape, kind in state_dict_spec(cfg):
+    for name, shape, kind in (spec if spec is not None else state_dict_spec(cfg)):
         if kind == "lin":  # nn.Linear default: U(-1/sqrt(fan_in), 1/sqrt(fan_in))
             bound = 1.0 / math.sqrt(shape[1])
             t = (torch.rand(shape, generator=g, dtype=torch.float64) * 2 - 1) * bound
@@ -281,13 +281,14 @@ def o3_linear(Vn: torch.Tensor, weight: torch.Tensor, bias: torch.Tensor, cfg: X
 # ----------------------------------------------------------------------------
 # the model (nn/model.py:26-46, nn/xpainn.py, nn/output.py:114-128)
 # ----------------------------------------------------------------------------
-def xpainn_energy(
+def xpainn_features(
     sd: Dict[str, torch.Tensor],
     embed_table: torch.Tensor,
     data: Dict[str, torch.Tensor],
     cfg: XPaiNNConfig = CONFIG_DEFAULT,
-) -> Tuple[torch.Tensor, torch.Tensor]:
-    """BaseModel.forward up to the energy head.  Returns (energy [G], atomic_energies [N])."""
+):
+    """BaseModel.forward up to (not including) the read-out heads: embedding, optional charge / spin conditioning,
+    message / update blocks.  Returns (x [N,C], V [N,D] in the e3nn layout, batch [N], G)."""
     pos = data["pos"]
     Z = data["atomic_numbers"].long()
     ei = data["edge_index"]
@@ -310,6 +311,11 @@ def xpainn_energy(
         [Y[:, 0:1].repeat(1, m0), Y[:, 1:4].repeat(1, m1), Y[:, 4:9].repeat(1, m2)], dim=1
     )  # [E,D], layout [u][m]
     V = pos.new_zeros(pos.shape[0], cfg.D)
+    # nn/model.py:85-96: conditioning modules sit between the embedding and message_0
+    if "mods.charge_embedding.linear_q.weight" in sd and "charge" in data:
+        x = charge_embedding(sd, "mods.charge_embedding.", x, data["charge"], batch, G)
+    if "mods.spin_embedding.linear_q.weight" in sd and "spin" in data:
+        x = spin_embedding(sd, "mods.spin_embedding.", x, data["spin"], batch, G)
 
     for i in range(cfg.action_blocks):
         # XPainnMessage.forward, nn/xpainn.py:128-161
@@ -339,12 +345,182 @@ def xpainn_energy(
         x = x + a_sv * t + a_ss
         V = V + dV
 
+    return x, V, batch, G
+
+
+def xpainn_energy(
+    sd: Dict[str, torch.Tensor],
+    embed_table: torch.Tensor,
+    data: Dict[str, torch.Tensor],
+    cfg: XPaiNNConfig = CONFIG_DEFAULT,
+) -> Tuple[torch.Tensor, torch.Tensor]:
+    """BaseModel.forward up to the energy head.  Returns (energy [G], atomic_energies [N])."""
+    x, V, batch, G = xpainn_features(sd, embed_table, data, cfg)
     # EnergyOut.forward, nn/output.py:114-128
     p = "mods.output_energy."
     e_atom = F.linear(F.silu(F.linear(x, sd[p + "out_mlp.0.weight"], sd[p + "out_mlp.0.bias"])),
                       sd[p + "out_mlp.2.weight"], sd[p + "out_mlp.2.bias"]).reshape(-1)
     energy = torch.zeros(G, dtype=e_atom.dtype).index_add(0, batch, e_atom)
     return energy, e_atom
+
+
+# ----------------------------------------------------------------------------
+# optional conditioning and read-out heads (nn/electronic.py, nn/output.py) -- SURVEY.md 8f rank 4
+# ----------------------------------------------------------------------------
+def _mlp(sd, p, x):
+    return F.linear(F.silu(F.linear(x, sd[p + "0.weight"], sd[p + "0.bias"])), sd[p + "2.weight"], sd[p + "2.bias"])
+
+
+def _scatter(src, batch, G):
+    return src.new_zeros((G,) + tuple(src.shape[1:])).index_add(0, batch, src)
+
+
+def _conditioning(sd, p, x, feat, batch, G):
+    """Common arithmetic of ChargeEmbedding / SpinEmbedding (nn/electronic.py:36-51, 76-90)."""
+    norm = torch.maximum(feat, torch.ones_like(feat))
+    query = F.linear(x, sd[p + "linear_q.weight"], sd[p + "linear_q.bias"])
+    key = F.linear(feat / norm, sd[p + "linear_k.weight"]).index_select(0, batch)
+    value = F.linear(feat, sd[p + "linear_v.weight"]).index_select(0, batch)
+    dot = (query * key).sum(-1, keepdim=True)
+    attn = F.softplus(dot / math.sqrt(x.shape[1]))
+    attn_sum = _scatter(attn, batch, G).index_select(0, batch)
+    h = attn * value / attn_sum
+    # ResidualLayer (nn/basic.py:11-31): two bias-free Linear + SiLU, output scaled by 1/sqrt(2)
+    r = F.silu(F.linear(F.silu(F.linear(h, sd[p + "residual.mlp.0.weight"])), sd[p + "residual.mlp.2.weight"]))
+    return x + (h + r) / math.sqrt(2)
+
+
+def charge_embedding(sd, p, x, charge, batch, G):
+    """nn/electronic.py:31-51: positive and negative charge are separate features."""
+    c = charge.to(x.dtype).reshape(-1)
+    return _conditioning(sd, p, x, F.relu(torch.stack([c, -c], dim=-1)), batch, G)
+
+
+def spin_embedding(sd, p, x, spin, batch, G):
+    """nn/electronic.py:71-90 with `spin` as a [G, 1] column."""
+    return _conditioning(sd, p, x, spin.to(x.dtype).reshape(-1, 1), batch, G)
+
+
+def o3_linear_map(V, weight, bias, muls_in, muls_out):
+    """e3nn o3.Linear between different multiplicities (nn/output.py:218-222, 282-286), e3nn layout:
+    one path per l present on both sides, out[w,m] = sum_u W_l[u,w] in[u,m] / sqrt(mul_in_l); bias on 0e."""
+    outs, woff, ioff = [], 0, 0
+    for l in range(3):
+        mi, mo, d = muls_in[l], muls_out[l], 2 * l + 1
+        if mo:
+            if mi:
+                W = weight[woff : woff + mi * mo].view(mi, mo)
+                woff += mi * mo
+                y = torch.einsum("uw,zui->zwi", W, V[:, ioff : ioff + mi * d].view(-1, mi, d)) / math.sqrt(mi)
+            else:
+                y = V.new_zeros(V.shape[0], mo, d)
+            if l == 0 and bias is not None and bias.numel():
+                y = y + bias.view(1, mo, 1)
+            outs.append(y.reshape(-1, mo * d))
+        ioff += mi * d
+    return torch.cat(outs, dim=1)
+
+
+def gate(V, muls, eps: float = 1e-5):
+    """Gate(irreps, "silu") (nn/o3layer.py:47-75): x * sigmoid(Invariant(x)) per irrep, e3nn layout."""
+    outs, off = [], 0
+    for l, mul in enumerate(muls):
+        d = 2 * l + 1
+        if mul:
+            blk = V[:, off : off + mul * d].view(-1, mul, d)
+            inv = torch.sqrt((blk * blk).sum(-1) + eps**2) - eps
+            outs.append((blk * torch.sigmoid(inv).unsqueeze(-1)).reshape(-1, mul * d))
+        off += mul * d
+    return torch.cat(outs, dim=1)
+
+
+def xpainn_heads(sd, embed_table, data, cfg: XPaiNNConfig, modes, atom_mass: Optional[torch.Tensor] = None,
+                 hidden_dipole=(0, 32, 0), hidden_polar=(64, 0, 16)) -> Dict[str, torch.Tensor]:
+    """Every head of `modes` on the features of xpainn_features (nn/output.py; defaults of each constructor)."""
+    x, V, batch, G = xpainn_features(sd, embed_table, data, cfg)
+    out: Dict[str, torch.Tensor] = {}
+    n_atoms = _scatter(torch.ones_like(x[:, 0]), batch, G)
+    for mode in modes:
+        p = f"mods.output_{mode}."
+        if mode == "energy":  # nn/output.py:114-128
+            e_atom = _mlp(sd, p + "out_mlp.", x).reshape(-1)
+            out["atomic_energies"], out["energy"] = e_atom, _scatter(e_atom, batch, G)
+        elif mode == "scalar":  # nn/output.py:65-76
+            out["scalar_output"] = _scatter(_mlp(sd, p + "out_mlp.", x).reshape(-1), batch, G)
+        elif mode in ("charges", "atomic_charges"):  # nn/output.py:160-180
+            q = _mlp(sd, p + "out_mlp.", x).reshape(-1)
+            total = data["charge"].to(q.dtype).reshape(-1) if "charge" in data else torch.zeros(G, dtype=q.dtype)
+            out["atomic_charges"] = q + ((total - _scatter(q, batch, G)) / n_atoms).index_select(0, batch)
+        elif mode == "dipole":  # nn/output.py:226-243
+            h = gate(o3_linear_map(V, sd[p + "equi_out_mlp.0.weight"], None, cfg.muls, hidden_dipole), hidden_dipole)
+            e = o3_linear_map(h, sd[p + "equi_out_mlp.2.weight"], None, hidden_dipole, (0, 1, 0))[:, [2, 0, 1]]
+            out["dipole"] = _scatter(e * _mlp(sd, p + "scalar_out_mlp.", x), batch, G)
+        elif mode == "polar":  # nn/output.py:291-327
+            h = gate(o3_linear_map(V, sd[p + "equi_out_mlp.0.weight"], sd[p + "equi_out_mlp.0.bias"], cfg.muls,
+                                   hidden_polar), hidden_polar)
+            e = o3_linear_map(h, sd[p + "equi_out_mlp.2.weight"], sd[p + "equi_out_mlp.2.bias"], hidden_polar, (1, 0, 1))
+            sc = _mlp(sd, p + "scalar_out_mlp.", x)
+            pol = _scatter(torch.cat([e[:, :1] * sc[:, :1], e[:, 1:] * sc[:, 1:2]], dim=1), batch, G)
+            z, d = pol[:, 0], pol[:, 1:6]
+            dn = torch.linalg.norm(d, dim=-1)
+            r3 = 1 / math.sqrt(3)
+            a = torch.zeros(G, 3, 3, dtype=pol.dtype)
+            a[:, 0, 0] = r3 * (dn - d[:, 2]) + d[:, 4] + z
+            a[:, 1, 1] = r3 * (dn - d[:, 2]) - d[:, 4] + z
+            a[:, 2, 2] = r3 * (dn + 2 * d[:, 2]) + z
+            a[:, 0, 1] = a[:, 1, 0] = d[:, 0]
+            a[:, 1, 2] = a[:, 2, 1] = d[:, 1]
+            a[:, 0, 2] = a[:, 2, 0] = d[:, 3]
+            out["polarizability"] = a
+        elif mode == "spatial":  # nn/output.py:356-373
+            m = atom_mass.to(x.dtype)[data["atomic_numbers"].long()].unsqueeze(-1)
+            cen = _scatter(m * data["pos"], batch, G) / _scatter(m, batch, G)
+            rel = data["pos"] - cen.index_select(0, batch)
+            out["spatial_extent"] = _scatter(_mlp(sd, p + "scalar_out_mlp.", x) * (rel * rel).sum(1, keepdim=True), batch, G)
+        else:
+            raise NotImplementedError(mode)
+    return out
+
+
+def heads_state_dict_spec(cfg: XPaiNNConfig, charge_embed: bool, spin_embed: bool, modes,
+                          hidden_dipole=(0, 32, 0), hidden_polar=(64, 0, 16)):
+    """state_dict_spec plus the entries of the conditioning modules and heads (names observed on the reference)."""
+    C, hd = cfg.node_dim, cfg.hidden_dim
+    spec = [e for e in state_dict_spec(cfg) if not e[0].startswith("mods.output_energy.")]
+    for on, name, nf in ((charge_embed, "charge", 2), (spin_embed, "spin", 1)):
+        if on:
+            p = f"mods.{name}_embedding."
+            spec += [(p + "linear_q.weight", (C, C), "lin"), (p + "linear_q.bias", (C,), "bias"),
+                     (p + "linear_k.weight", (C, nf), "lin"), (p + "linear_v.weight", (C, nf), "lin"),
+                     (p + "residual.mlp.0.weight", (C, C), "lin"), (p + "residual.mlp.2.weight", (C, C), "lin")]
+
+    def mlp(p, n_out):
+        return [(p + "0.weight", (hd, C), "lin"), (p + "0.bias", (hd,), "bias"),
+                (p + "2.weight", (n_out, hd), "lin"), (p + "2.bias", (n_out,), "bias")]
+
+    def nw(mi, mo):
+        return sum(a * b for a, b in zip(mi, mo))
+
+    for mode in modes:
+        p = f"mods.output_{mode}."
+        if mode in ("energy", "scalar", "charges", "atomic_charges"):
+            spec += mlp(p + "out_mlp.", 1)
+        elif mode == "dipole":
+            spec += mlp(p + "scalar_out_mlp.", 1)
+            spec += [(p + "equi_out_mlp.0.weight", (nw(cfg.muls, hidden_dipole),), "o3"),
+                     (p + "equi_out_mlp.2.weight", (nw(hidden_dipole, (0, 1, 0)),), "o3")]
+        elif mode == "polar":
+            spec += mlp(p + "scalar_out_mlp.", 2)
+            spec += [(p + "equi_out_mlp.0.weight", (nw(cfg.muls, hidden_polar),), "o3"),
+                     (p + "equi_out_mlp.0.bias", (hidden_polar[0],), "bias"),
+                     (p + "equi_out_mlp.2.weight", (nw(hidden_polar, (1, 0, 1)),), "o3"),
+                     (p + "equi_out_mlp.2.bias", (1,), "bias")]
+        elif mode == "spatial":
+            spec += mlp(p + "scalar_out_mlp.", 1)
+        else:
+            raise NotImplementedError(mode)
+    return spec
+
 
 
 def xpainn_energy_forces(sd, embed_table, data, cfg: XPaiNNConfig = CONFIG_DEFAULT, create_graph: bool = False,

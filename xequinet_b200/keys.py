@@ -29,3 +29,22 @@ STRAIN = "strain"  # nn/basic.py:133-139
 POS_EFF = "_xeq_pos_strained"    # positions / cell with the (zero) strain of the virial computation applied:
 CELL_EFF = "_xeq_cell_strained"  # what the edge kernels differentiate (nn/basic.py:99-107)
 HALO = "_xeq_halo"  # domain.HaloPlan of a spatially sharded run (xequinet_b200/domain.py)
+
+# optional inputs / heads (xequinet/keys.py:44-57, 78-82)
+TOTAL_CHARGE = "charge"
+TOTAL_SPIN = "spin"
+ATOMIC_CHARGES = "atomic_charges"
+DIPOLE = "dipole"
+DIPOLE_MAGNITUDE = "dipole_magnitude"
+POLARIZABILITY = "polarizability"
+ISO_POLARIZABILITY = "iso_polarizability"
+SPATIAL_EXTENT = "spatial_extent"
+SCALAR_OUTPUT = "scalar_output"
+CARTESIAN_TENSOR = "cartesian_tensor"
+
+# unit systems of the MD engines the deployment wrappers talk to (xequinet/keys.py:101-120)
+LAMMPS_UNIT_STYLE = {
+    "metal": {TOTAL_ENERGY: "eV", POSITIONS: "Angstrom", FORCES: "eV/Angstrom", TOTAL_CHARGE: "e"},
+    "real": {TOTAL_ENERGY: "kcal/mol", POSITIONS: "Angstrom", FORCES: "kcal/mol/Angstrom", TOTAL_CHARGE: "e"},
+    "electron": {TOTAL_ENERGY: "Hartree", POSITIONS: "Bohr", FORCES: "Hartree/Bohr", TOTAL_CHARGE: "e"},
+}

@@ -52,13 +52,26 @@ def resolve_activation(activation: str) -> nn.Module:
 
 class Linear(nn.Linear):
     """nn.Linear (same parameters / state_dict names) evaluated by the tcgen05 GEMM kernel (K3,
-    csrc/node_gemm.cu) together with all of its derivatives.  Widths that are not multiples of 4
-    (only the 64 -> 1 energy read-out, nn/output.py:107-111) stay a torch op."""
+    csrc/node_gemm.cu) together with all of its derivatives.  The kernel addresses operands in 16-byte
+    units: widths that are not multiples of 4 (the 64 -> 1 energy read-out, nn/output.py:107-111; the
+    2 -> C / 1 -> C projections of the charge / spin embedding, nn/electronic.py:25-26) are zero-padded
+    to the next multiple of 4 and the result sliced, so no linear layer of the path leaves K3."""
 
     def forward(self, x: torch.Tensor) -> torch.Tensor:
-        if self.in_features % 4 or self.out_features % 4 or x.dim() != 2:
-            return F.linear(x, self.weight, self.bias)
-        return gemm.linear(x, self.weight, self.bias)
+        lead = None
+        if x.dim() != 2:
+            lead, x = x.shape[:-1], x.reshape(-1, x.shape[-1])
+        w, b = self.weight, self.bias
+        pk, pn = -self.in_features % 4, -self.out_features % 4
+        if pk:
+            x, w = F.pad(x, (0, pk)), F.pad(w, (0, pk))
+        if pn:
+            w = F.pad(w, (0, 0, 0, pn))
+            b = F.pad(b, (0, pn)) if b is not None else None
+        y = gemm.linear(x, w, b)
+        if pn:
+            y = y[:, : self.out_features]
+        return y if lead is None else y.reshape(*lead, self.out_features)
 
 
 class _E3nnBuffers(nn.Module):
@@ -187,3 +200,82 @@ class O3Linear(nn.Module):
     def forward(self, V: torch.Tensor) -> torch.Tensor:
         # one grouped tcgen05 launch: a problem per (l, m) block of the cm layout
         return gemm.irreps_linear(V, self.weight, self.bias if self.bias.numel() else None, self.muls)
+
+
+class O3LinearMap(nn.Module):
+    """e3nn o3.Linear between DIFFERENT multiplicities, as the read-out heads use it (nn/output.py:218-222,
+    282-286): every l present on both sides gets a path out[w,m] = sum_u W_l[u,w] in[u,m] / sqrt(mul_in_l); flat
+    weight with the blocks in ascending l, each row-major [u,w]; bias on the 0e outputs.  Both sides are held in
+    the cm layout, so a path is (2l+1) plain GEMMs on column slices (K3); 1-wide outputs are a weighted row sum."""
+
+    def __init__(self, muls_in, muls_out, biases: bool = False):
+        super().__init__()
+        self.muls_in, self.muls_out = tuple(muls_in), tuple(muls_out)
+        self.paths = [l for l in range(3) if self.muls_in[l] and self.muls_out[l]]
+        self.weight = nn.Parameter(torch.randn(sum(self.muls_in[l] * self.muls_out[l] for l in self.paths)))
+        nb = self.muls_out[0] if biases else 0
+        if nb:
+            self.bias = nn.Parameter(torch.zeros(nb))
+        else:  # e3nn registers an empty buffer when there is no bias: the state_dict key exists either way
+            self.register_buffer("bias", torch.Tensor())
+        self.register_buffer("output_mask", torch.ones(irreps_dim(self.muls_out)))
+
+    def forward(self, V: torch.Tensor) -> torch.Tensor:
+        N = V.shape[0]
+        outs, woff, ioff = [], 0, 0
+        for l in range(3):
+            mi, mo, d = self.muls_in[l], self.muls_out[l], 2 * l + 1
+            if mo and l not in self.paths:
+                outs.append(V.new_zeros(N, d * mo))
+            elif mo:
+                W = self.weight[woff : woff + mi * mo].view(mi, mo)
+                woff += mi * mo
+                alpha = 1.0 / math.sqrt(mi)
+                if mo % 4 == 0 and mi % 4 == 0:
+                    bias = self.bias if (l == 0 and self.bias.numel()) else None
+                    blk = [gemm.mm(V[:, ioff + m * mi : ioff + (m + 1) * mi], W, alpha=alpha, bias=bias)
+                           for m in range(d)]
+                    outs.append(torch.cat(blk, dim=1) if d > 1 else blk[0])
+                else:
+                    y = (V[:, ioff : ioff + d * mi].reshape(N, d, mi, 1) * W.view(1, 1, mi, mo)).sum(2) * alpha
+                    if l == 0 and self.bias.numel():
+                        y = y + self.bias
+                    outs.append(y.reshape(N, d * mo))
+            ioff += d * mi
+        return torch.cat(outs, dim=1) if len(outs) > 1 else outs[0]
+
+
+class Gate(nn.Module):
+    """nn/o3layer.py:47-75 (refine=False): x * act'(Invariant(x)) per irrep with act' = activation / x
+    (silu -> sigmoid, nn/basic.py:244-246), on the cm layout."""
+
+    def __init__(self, muls, activation: str = "silu"):
+        super().__init__()
+        self.muls = tuple(muls)
+        self.invariant = _TPHolder(num_irreps(muls))
+        div_x = {"silu": "sigmoid", "relu": "identity", "leakyrelu": "identity"}
+        name = activation.lower()
+        self.activation = resolve_activation(div_x.get(name, name))
+        self.scalar_mul = _E3nnBuffers(irreps_dim(muls))
+        self.eps = 1e-5
+
+    def forward(self, x: torch.Tensor) -> torch.Tensor:
+        inv = torch.sqrt(cm.irrep_dot(x, x, self.muls) + self.eps * self.eps) - self.eps  # nn/o3layer.py:40-44
+        return x * cm.expand_gate(self.activation(inv), self.muls)
+
+
+class ResidualLayer(nn.Module):
+    """nn/basic.py:11-31: (x + mlp(x)) / sqrt(2), mlp = n_layers x (bias-free Linear, activation) with ONE shared
+    activation module (state_dict keys mlp.0.weight, mlp.2.weight, ...)."""
+
+    def __init__(self, node_dim: int = 128, n_layers: int = 2, activation: str = "silu"):
+        super().__init__()
+        act_fn = resolve_activation(activation)
+        self.mlp = nn.Sequential()
+        for _ in range(n_layers):
+            self.mlp.append(Linear(node_dim, node_dim, bias=False))
+            self.mlp.append(act_fn)
+        self.inv_sqrt_2 = 1 / math.sqrt(2)
+
+    def forward(self, x: torch.Tensor) -> torch.Tensor:
+        return self.inv_sqrt_2 * (x + self.mlp(x))

@@ -8,6 +8,7 @@ import torch.nn as nn
 
 from ..graph import NeighborTransform
 from .basic import compute_edge_data, compute_properties
+from .electronic import ChargeEmbedding, SpinEmbedding
 from .output import resolve_output
 from .xpainn import XEmbedding, XPainnMessage, XPainnUpdate
 
@@ -47,13 +48,14 @@ class XPaiNN(BaseModel):
         charge_embed: bool = kwargs.get("charge_embed", False)
         spin_embed: bool = kwargs.get("spin_embed", False)
         output_modes: Union[str, List[str]] = kwargs.get("output_modes", ["energy"])
-        if charge_embed or spin_embed:
-            raise NotImplementedError("charge/spin embedding is outside the B200 hot path (defaults False, "
-                                      "nn/model.py:68-69)")
         self.cutoff_radius = cutoff
         self.mods["embedding"] = XEmbedding(node_dim=node_dim, node_irreps=node_irreps, embed_basis=embed_basis,
                                             aux_basis=aux_basis, num_basis=num_basis, rbf_kernel=rbf_kernel,
                                             cutoff=cutoff, cutoff_fn=cutoff_fn)
+        if charge_embed:
+            self.mods["charge_embedding"] = ChargeEmbedding(node_dim=node_dim, activation=activation)
+        if spin_embed:
+            self.mods["spin_embedding"] = SpinEmbedding(node_dim=node_dim, activation=activation)
         for i in range(action_blocks):
             self.mods[f"message_{i}"] = XPainnMessage(node_dim=node_dim, node_irreps=node_irreps, num_basis=num_basis,
                                                       activation=activation, layer_norm=layer_norm)
