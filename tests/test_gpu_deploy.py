@@ -54,10 +54,12 @@ def test_lammps_wrapper_units(name):
             d["cell"] = d["cell"] / len_fac
         out = m(d, compute_forces=True, compute_virial=virial)
         assert set(out) == set(ref)
-        torch.testing.assert_close(out["energy"], ref["energy"] * e_fac, rtol=2e-6, atol=1e-7)
-        torch.testing.assert_close(out["forces"], ref["forces"] * (e_fac * len_fac), rtol=1e-5, atol=2e-6 * e_fac * len_fac)
+        torch.testing.assert_close(out["energy"], ref["energy"] * e_fac, rtol=2e-6 if len_fac == 1.0 else 1e-5, atol=1e-7)
+        # Bohr coordinates are rounded to fp32 before the wrapper scales them back: positions differ by an ulp
+        f_tol = (2e-6 if len_fac == 1.0 else 5e-5) * e_fac * len_fac
+        torch.testing.assert_close(out["forces"], ref["forces"] * (e_fac * len_fac), rtol=1e-5, atol=f_tol)
         if virial:
-            torch.testing.assert_close(out["virial"], ref["virial"] * e_fac, rtol=1e-5, atol=5e-6 * e_fac)
+            torch.testing.assert_close(out["virial"], ref["virial"] * e_fac, rtol=1e-5, atol=(5e-6 if len_fac == 1.0 else 1e-4) * e_fac)
         assert m.cutoff_radius == pytest.approx(5.0 / len_fac)
     if name == "mol_small":  # and the golden of the reference itself (first molecule: independent of the others)
         np.testing.assert_allclose(ref["energy"].detach().cpu().numpy(), z["f64:energy"][:1], rtol=1e-5, atol=1e-6)

@@ -78,6 +78,9 @@ def test_head_param_grads_match_reference_golden():
     np.testing.assert_allclose(loss.item(), float(z["loss_heads"]), rtol=2e-5)
     loss.backward()
     n = 0
+    # absolute floor for gradients that vanish analytically (the last bias of the charge-conserving head is removed
+    # by the conservation step, nn/output.py:165-177: fp64 leaves 1e-15, fp32 1e-7): 1e-6 of the largest gradient norm
+    floor = 1e-6 * max(float(z[f][1]) for f in z.files if f.startswith("gH:sum:"))
     for k, p in model.named_parameters():
         key = f"gH:sum:{k}"
         if key not in z.files:
@@ -86,8 +89,8 @@ def test_head_param_grads_match_reference_golden():
         g = p.grad.detach().double().reshape(-1).cpu()
         ref_norm = float(z[key][1])
         smp = g[:: max(1, g.numel() // 64)][:64].numpy()
-        assert abs(float(g.norm()) - ref_norm) <= 2e-3 * ref_norm + 1e-7, (k, float(g.norm()), ref_norm)
-        assert np.abs(smp - z[f"gH:smp:{k}"]).max() <= 2e-3 * max(np.abs(z[f"gH:smp:{k}"]).max(), ref_norm / np.sqrt(g.numel())) + 1e-7, k
+        assert abs(float(g.norm()) - ref_norm) <= 2e-3 * ref_norm + floor, (k, float(g.norm()), ref_norm)
+        assert np.abs(smp - z[f"gH:smp:{k}"]).max() <= 2e-3 * max(np.abs(z[f"gH:smp:{k}"]).max(), ref_norm / np.sqrt(g.numel())) + floor, k
         n += 1
     assert n > 100
 
