@@ -232,6 +232,19 @@ int xeq_segment_sum(const float* src, const int32_t* seg_ptr /* [G+1] */, int32_
 int xeq_colsum(const float* src, int32_t n_rows, int32_t n_cols, int32_t ld, float* out /* [n_cols] */,
                xeq_stream_t stream);
 
+/* An nn.Linear with ONE output feature -- the 64 -> 1 energy read-out (nn/output.py:107-111, F.linear in the
+ * reference) -- and its derivatives, closed under differentiation (each op's gradients are the other two):
+ *   rowdot           y[r]     = sum_c x[r, c] w[c] (+ bias[0])      forward
+ *   outer            out[r,c] = g[r] w[c]                           gradient w.r.t. x
+ *   colsum_weighted  out[c]   = sum_r row_weight[r] src[r, c]       gradient w.r.t. w (deterministic, as xeq_colsum)
+ * x / src may be row-strided views (ld floats between rows). */
+int xeq_rowdot(const float* x, int32_t ld, const float* w /* [n_cols] */, const float* bias /* NULL or [1] */,
+               int32_t n_rows, int32_t n_cols, float* y /* [n_rows] */, xeq_stream_t stream);
+int xeq_outer(const float* g /* [n_rows] */, const float* w /* [n_cols] */, int32_t n_rows, int32_t n_cols,
+              float* out /* [n_rows, n_cols] */, xeq_stream_t stream);
+int xeq_colsum_weighted(const float* src, const float* row_weight /* [n_rows] */, int32_t n_rows, int32_t n_cols,
+                        int32_t ld, float* out /* [n_cols] */, xeq_stream_t stream);
+
 /* e3nn (mul-major, m-fastest) <-> cm (component-major) layout of [N, D] tensors.
  * direction 0: e3nn -> cm, 1: cm -> e3nn. */
 int xeq_layout_convert(const float* src, float* dst, int32_t n_nodes, const xeq_dims_t* dims,

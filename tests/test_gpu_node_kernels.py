@@ -187,3 +187,34 @@ def test_colsum_matches_torch(shape):
         w = torch.randn(shape[1], device=DEV)
         (gemm.colsum(x) * w).sum().backward()
         assert torch.allclose(x.grad, w.expand_as(x))
+
+
+def test_linear_to_scalar_kernels_match_torch():
+    """xeq_rowdot / xeq_outer / xeq_colsum_weighted (the one-output Linear = energy read-out, nn/output.py:107-111)
+    against fp64 torch: values, first and second derivatives through the registered formulas; row-strided input."""
+    from xequinet_b200 import gemm
+
+    gen = torch.Generator().manual_seed(11)
+    for n, k in ((5376, 64), (1, 64), (333, 20), (7, 128)):
+        big = torch.randn(n, k + 8, generator=gen, dtype=torch.float64)
+        x0, w0, b0 = big[:, 4:4 + k], torch.randn(1, k, generator=gen, dtype=torch.float64), torch.randn(1, generator=gen, dtype=torch.float64)
+        r1, r2 = torch.randn(n, 1, generator=gen, dtype=torch.float64), torch.randn(n, k, generator=gen, dtype=torch.float64)
+
+        def run(fn, dt, dev):
+            xs = big.to(dev, dt).requires_grad_(True)
+            w, b = (t.to(dev, dt).clone().requires_grad_(True) for t in (w0, b0))
+            x = xs[:, 4:4 + k]  # a row-strided view: the kernels take the row stride
+            y = fn(x, w, b)
+            (gx,) = torch.autograd.grad((y * r1.to(dev, dt)).sum(), xs, create_graph=True)
+            loss = (y ** 2).sum() + (gx[:, 4:4 + k] * r2.to(dev, dt)).sum() + (gx ** 2).sum()
+            return [y.detach(), gx.detach(), *torch.autograd.grad(loss, (xs, w, b))]
+
+        ref = run(torch.nn.functional.linear, torch.float64, "cpu")
+        got = run(gemm.linear_to_scalar, torch.float32, DEV)
+        for name, a, r in zip(("y", "gx", "dx", "dw", "db"), got, ref):
+            scale = float(r.abs().max()) + 1e-30
+            assert float((a.double().cpu() - r).abs().max()) <= 2e-5 * scale, (n, k, name)
+    # bitwise reproducible
+    x = torch.randn(4096, 64, generator=gen).to(DEV)
+    g = torch.randn(4096, generator=gen).to(DEV)
+    assert torch.equal(gemm.wsum_raw(g, x), gemm.wsum_raw(g, x))

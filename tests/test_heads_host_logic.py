@@ -24,6 +24,10 @@ def torch_kernels(monkeypatch):
     monkeypatch.setattr(gemm, "mm", mm)
     monkeypatch.setattr(gemm, "linear", lambda x, w, b=None: F.linear(x, w, b))
     monkeypatch.setattr(nodeops, "silu", F.silu)
+    monkeypatch.setattr(gemm, "rowdot_raw", lambda x, w, b=None: x @ w.reshape(-1) + (b.reshape(-1)[0] if b is not None else 0.0))
+    monkeypatch.setattr(gemm, "outer_raw", lambda g, w: g.reshape(-1, 1) * w.reshape(1, -1))
+    monkeypatch.setattr(gemm, "wsum_raw", lambda g, x: g.reshape(-1) @ x)
+    monkeypatch.setattr(gemm, "colsum_raw", lambda g: g.sum(0))
     monkeypatch.setattr(ops, "segment_sum", lambda src, ptr, batch: torch.zeros(ptr.numel() - 1, dtype=src.dtype).index_add(0, batch, src))
 
 
@@ -78,6 +82,37 @@ def test_narrow_linear_is_padded_to_the_kernel_granularity(torch_kernels, monkey
         x = torch.randn(7, fin, dtype=torch.float64, requires_grad=True)
         y = lin(x)
         np.testing.assert_allclose(y.detach().numpy(), F.linear(x, lin.weight, lin.bias).detach().numpy(), rtol=1e-13, atol=1e-14)
-        assert seen[-1][0][1] % 4 == 0 and seen[-1][1][0] % 4 == 0 and seen[-1][1][1] % 4 == 0
+        if fout == 1:  # one output feature: the row-dot kernels, not a GEMM tile
+            assert not seen
+        else:
+            assert seen[-1][0][1] % 4 == 0 and seen[-1][1][0] % 4 == 0 and seen[-1][1][1] % 4 == 0
         y.sum().backward()
         assert lin.weight.grad.shape == (fout, fin) and x.grad.shape == (7, fin)
+
+
+def test_linear_to_scalar_formulas_are_closed_under_differentiation(monkeypatch):
+    """rowdot / outer / wsum (xeq_rowdot, xeq_outer, xeq_colsum_weighted): the derivative FORMULAS of the one-output
+    Linear, with the three kernels replaced by torch stand-ins, against torch autograd of F.linear to second order
+    (force training differentiates the read-out twice)."""
+    from xequinet_b200 import gemm
+
+    monkeypatch.setattr(gemm, "rowdot_raw", lambda x, w, b=None: x @ w.reshape(-1) + (b.reshape(-1)[0] if b is not None else 0.0))
+    monkeypatch.setattr(gemm, "outer_raw", lambda g, w: g.reshape(-1, 1) * w.reshape(1, -1))
+    monkeypatch.setattr(gemm, "wsum_raw", lambda g, x: g.reshape(-1) @ x)
+    monkeypatch.setattr(gemm, "colsum_raw", lambda g: g.sum(0))
+    gen = torch.Generator().manual_seed(3)
+    x0 = torch.randn(9, 64, generator=gen, dtype=torch.float64)
+    w0 = torch.randn(1, 64, generator=gen, dtype=torch.float64)
+    b0 = torch.randn(1, generator=gen, dtype=torch.float64)
+    r1 = torch.randn(9, 1, generator=gen, dtype=torch.float64)
+    r2 = torch.randn(9, 64, generator=gen, dtype=torch.float64)
+
+    def run(fn):
+        x, w, b = (t.clone().requires_grad_(True) for t in (x0, w0, b0))
+        y = fn(torch.tanh(x), w, b)
+        (gx,) = torch.autograd.grad((y * r1).sum(), x, create_graph=True)   # "forces"
+        loss = (y ** 2).sum() + (gx * r2).sum() + (gx ** 2).sum()            # loss on values and on the first derivative
+        return [y.detach(), gx.detach(), *torch.autograd.grad(loss, (x, w, b))]
+
+    for a, b in zip(run(gemm.linear_to_scalar), run(F.linear)):
+        np.testing.assert_allclose(a.numpy(), b.numpy(), rtol=1e-12, atol=1e-12)

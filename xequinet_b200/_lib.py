@@ -62,6 +62,9 @@ _SIGNATURES = {
     "xeq_edge_message_bwdbwd": (c_int, [POINTER(XeqGraph), POINTER(XeqDims)] + [c_void_p] * 20 + [c_void_p, c_size_t, c_void_p]),
     "xeq_segment_sum": (c_int, [c_void_p, c_void_p, c_int32, c_void_p, c_void_p]),
     "xeq_colsum": (c_int, [c_void_p, c_int32, c_int32, c_int32, c_void_p, c_void_p]),
+    "xeq_colsum_weighted": (c_int, [c_void_p, c_void_p, c_int32, c_int32, c_int32, c_void_p, c_void_p]),
+    "xeq_rowdot": (c_int, [c_void_p, c_int32, c_void_p, c_void_p, c_int32, c_int32, c_void_p, c_void_p]),
+    "xeq_outer": (c_int, [c_void_p, c_void_p, c_int32, c_int32, c_void_p, c_void_p]),
     "xeq_edge_cell_grad_rows": (c_int, [POINTER(XeqGraph), POINTER(XeqDims), c_void_p, c_void_p, c_void_p]),
     "xeq_gemm_workspace_bytes": (c_size_t, [POINTER(XeqGemm), c_int32, c_int32]),
     "xeq_gemm_tf32x3": (c_int, [POINTER(XeqGemm), c_int32, c_int32, c_void_p, c_size_t, c_void_p]),

@@ -61,7 +61,7 @@ __global__ void segment_sum_kernel(const float* __restrict__ src, const int* __r
 // no workspace.  Bias gradients of the Linear layers (sum of the output gradient over the nodes).
 constexpr int COLSUM_CLUSTER = 8, COLSUM_WARPS = 16;
 __global__ void __cluster_dims__(1, COLSUM_CLUSTER, 1) __launch_bounds__(COLSUM_WARPS * 32)
-    colsum_kernel(const float* __restrict__ src, int n_rows, int n_cols, int ld, float* __restrict__ out) {
+    colsum_kernel(const float* __restrict__ src, const float* __restrict__ wgt, int n_rows, int n_cols, int ld, float* __restrict__ out) {
   namespace cg = cooperative_groups;
   __shared__ float part[COLSUM_WARPS][33];
   __shared__ float tot[32];
@@ -74,13 +74,23 @@ __global__ void __cluster_dims__(1, COLSUM_CLUSTER, 1) __launch_bounds__(COLSUM_
   float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
   if (col < n_cols) {
     int r = rank * chunk + warp;
-    for (; r + 3 * COLSUM_WARPS < r_end; r += 4 * COLSUM_WARPS) {
-      a0 += src[(size_t)r * ld + col];
-      a1 += src[(size_t)(r + COLSUM_WARPS) * ld + col];
-      a2 += src[(size_t)(r + 2 * COLSUM_WARPS) * ld + col];
-      a3 += src[(size_t)(r + 3 * COLSUM_WARPS) * ld + col];
+    if (wgt == nullptr) {
+      for (; r + 3 * COLSUM_WARPS < r_end; r += 4 * COLSUM_WARPS) {
+        a0 += src[(size_t)r * ld + col];
+        a1 += src[(size_t)(r + COLSUM_WARPS) * ld + col];
+        a2 += src[(size_t)(r + 2 * COLSUM_WARPS) * ld + col];
+        a3 += src[(size_t)(r + 3 * COLSUM_WARPS) * ld + col];
+      }
+      for (; r < r_end; r += COLSUM_WARPS) a0 += src[(size_t)r * ld + col];
+    } else {  // rows weighted by wgt[r] (same order of additions)
+      for (; r + 3 * COLSUM_WARPS < r_end; r += 4 * COLSUM_WARPS) {
+        a0 = fmaf(wgt[r], src[(size_t)r * ld + col], a0);
+        a1 = fmaf(wgt[r + COLSUM_WARPS], src[(size_t)(r + COLSUM_WARPS) * ld + col], a1);
+        a2 = fmaf(wgt[r + 2 * COLSUM_WARPS], src[(size_t)(r + 2 * COLSUM_WARPS) * ld + col], a2);
+        a3 = fmaf(wgt[r + 3 * COLSUM_WARPS], src[(size_t)(r + 3 * COLSUM_WARPS) * ld + col], a3);
+      }
+      for (; r < r_end; r += COLSUM_WARPS) a0 = fmaf(wgt[r], src[(size_t)r * ld + col], a0);
     }
-    for (; r < r_end; r += COLSUM_WARPS) a0 += src[(size_t)r * ld + col];
   }
   part[warp][lane] = (a0 + a1) + (a2 + a3);
   __syncthreads();
@@ -98,6 +108,32 @@ __global__ void __cluster_dims__(1, COLSUM_CLUSTER, 1) __launch_bounds__(COLSUM_
     out[col] = acc;
   }
   cluster.sync();  // the partials of the other CTAs stay alive until CTA 0 has read them
+}
+
+// y[r] = sum_c x[r, c] w[c] (+ bias[0]): one warp per row, lanes stride over the columns, fixed-order butterfly
+__global__ void rowdot_kernel(const float* __restrict__ x, int ld, const float* __restrict__ w, const float* __restrict__ bias,
+                              int n_rows, int n_cols, float* __restrict__ y) {
+  pdl_trigger();
+  pdl_wait();
+  const int row = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (row >= n_rows) return;
+  const float* xr = x + (size_t)row * ld;
+  float acc = 0.f;
+  for (int c = lane; c < n_cols; c += 32) acc = fmaf(xr[c], w[c], acc);
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+  if (lane == 0) y[row] = acc + (bias ? bias[0] : 0.f);
+}
+
+// out[r, c] = g[r] w[c]
+__global__ void outer_kernel(const float* __restrict__ g, const float* __restrict__ w, int n_rows, int n_cols, float* __restrict__ out) {
+  pdl_trigger();
+  pdl_wait();
+  const size_t idx = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= (size_t)n_rows * n_cols) return;
+  const int r = (int)(idx / n_cols), c = (int)(idx % n_cols);
+  out[idx] = g[r] * w[c];
 }
 
 __global__ void layout_convert_kernel(const float* __restrict__ src, float* __restrict__ dst, int n, int m0, int m1,
@@ -141,7 +177,38 @@ int xeq_colsum(const float* src, int32_t n_rows, int32_t n_cols, int32_t ld, flo
   XEQ_CHECK_ARG(out && n_rows >= 0 && n_cols >= 0 && ld >= n_cols, "colsum: bad arguments");
   if (n_cols == 0) return XEQ_OK;
   XEQ_CHECK_ARG(src || n_rows == 0, "colsum: src is NULL");
-  colsum_kernel<<<dim3((n_cols + 31) / 32, COLSUM_CLUSTER), COLSUM_WARPS * 32, 0, (cudaStream_t)stream>>>(src, n_rows, n_cols, ld, out);
+  colsum_kernel<<<dim3((n_cols + 31) / 32, COLSUM_CLUSTER), COLSUM_WARPS * 32, 0, (cudaStream_t)stream>>>(src, nullptr, n_rows, n_cols, ld, out);
+  XEQ_LAUNCHED(1);
+  return XEQ_OK;
+}
+
+int xeq_colsum_weighted(const float* src, const float* row_weight, int32_t n_rows, int32_t n_cols, int32_t ld, float* out,
+                        xeq_stream_t stream) {
+  XEQ_CHECK_ARG(out && n_rows >= 0 && n_cols >= 0 && ld >= n_cols, "colsum_weighted: bad arguments");
+  if (n_cols == 0) return XEQ_OK;
+  XEQ_CHECK_ARG((src && row_weight) || n_rows == 0, "colsum_weighted: src / row_weight is NULL");
+  colsum_kernel<<<dim3((n_cols + 31) / 32, COLSUM_CLUSTER), COLSUM_WARPS * 32, 0, (cudaStream_t)stream>>>(src, row_weight, n_rows, n_cols, ld, out);
+  XEQ_LAUNCHED(1);
+  return XEQ_OK;
+}
+
+int xeq_rowdot(const float* x, int32_t ld, const float* w, const float* bias, int32_t n_rows, int32_t n_cols, float* y,
+               xeq_stream_t stream) {
+  XEQ_CHECK_ARG(n_rows >= 0 && n_cols >= 0 && ld >= n_cols, "rowdot: bad arguments");
+  if (n_rows == 0) return XEQ_OK;
+  XEQ_CHECK_ARG(y && (n_cols == 0 || (x && w)), "rowdot: NULL operand");
+  const int blocks = (int)(((size_t)n_rows * 32 + 255) / 256);
+  XEQ_CUDA(launch_pdl(rowdot_kernel, dim3(blocks), dim3(256), (size_t)(0), (cudaStream_t)stream, x, ld, w, bias, n_rows, n_cols, y));
+  XEQ_LAUNCHED(1);
+  return XEQ_OK;
+}
+
+int xeq_outer(const float* g, const float* w, int32_t n_rows, int32_t n_cols, float* out, xeq_stream_t stream) {
+  XEQ_CHECK_ARG(n_rows >= 0 && n_cols >= 0, "outer: bad arguments");
+  const size_t total = (size_t)n_rows * n_cols;
+  if (total == 0) return XEQ_OK;
+  XEQ_CHECK_ARG(g && w && out, "outer: NULL operand");
+  XEQ_CUDA(launch_pdl(outer_kernel, dim3((unsigned)((total + 255) / 256)), dim3(256), (size_t)(0), (cudaStream_t)stream, g, w, n_rows, n_cols, out));
   XEQ_LAUNCHED(1);
   return XEQ_OK;
 }

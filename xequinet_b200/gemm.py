@@ -153,6 +153,97 @@ def linear(x: torch.Tensor, weight: torch.Tensor, bias: Optional[torch.Tensor] =
 
 
 # ------------------------------------------------------------------------------------------
+# nn.Linear with ONE output feature (the 64 -> 1 energy read-out, nn/output.py:107-111): a GEMM tile would be
+# 127/128 padding.  Three small kernels, closed under differentiation:
+#   rowdot(x, w, b)  y[r] = <x[r], w> + b        d/dx = outer(gy, w)      d/dw = wsum(gy, x)   d/db = colsum(gy)
+#   outer(g, w)      o[r, c] = g[r] w[c]         d/dg = rowdot(go, w)     d/dw = wsum(g, go)
+#   wsum(g, x)       o[c] = sum_r g[r] x[r, c]   d/dg = rowdot(x, go)     d/dx = outer(g, go)
+# ------------------------------------------------------------------------------------------
+def _rows2d(t: torch.Tensor) -> torch.Tensor:
+    if t.dtype != torch.float32 or not t.is_cuda or t.dim() != 2:
+        raise RuntimeError("xequinet_b200 ops need 2-D fp32 CUDA tensors here: there is no CPU fallback")
+    return t if (t.stride(1) == 1 and t.stride(0) >= t.shape[1]) else t.contiguous()
+
+
+def _vec(t: torch.Tensor) -> torch.Tensor:
+    if t.dtype != torch.float32 or not t.is_cuda:
+        raise RuntimeError("xequinet_b200 ops need fp32 CUDA tensors: there is no CPU fallback")
+    return t.reshape(-1).contiguous()
+
+
+def rowdot_raw(x, w, bias=None):
+    x, w = _rows2d(x), _vec(w)
+    y = torch.empty(x.shape[0], dtype=torch.float32, device=x.device)
+    b = _vec(bias) if bias is not None else None
+    _lib.check(_lib.get().xeq_rowdot(x.data_ptr() if x.numel() else None, max(x.stride(0), x.shape[1]), _lib.ptr(w), _lib.ptr(b),
+                                     x.shape[0], x.shape[1], _lib.ptr(y), _lib.stream()), "xeq_rowdot")
+    return y
+
+
+def outer_raw(g, w):
+    g, w = _vec(g), _vec(w)
+    out = torch.empty((g.numel(), w.numel()), dtype=torch.float32, device=g.device)
+    _lib.check(_lib.get().xeq_outer(_lib.ptr(g), _lib.ptr(w), g.numel(), w.numel(), _lib.ptr(out), _lib.stream()), "xeq_outer")
+    return out
+
+
+def wsum_raw(g, x):
+    g, x = _vec(g), _rows2d(x)
+    out = torch.empty(x.shape[1], dtype=torch.float32, device=x.device)
+    _lib.check(_lib.get().xeq_colsum_weighted(x.data_ptr() if x.numel() else None, _lib.ptr(g), x.shape[0], x.shape[1],
+                                              max(x.stride(0), x.shape[1]), _lib.ptr(out), _lib.stream()), "xeq_colsum_weighted")
+    return out
+
+
+class _RowDot(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, w, bias):
+        ctx.save_for_backward(x, w)
+        return rowdot_raw(x, w, bias)
+
+    @staticmethod
+    def backward(ctx, gy):
+        x, w = ctx.saved_tensors
+        gx = _Outer.apply(gy, w) if input_wanted(ctx, 0) else None
+        gw = _WSum.apply(gy, x).view_as(w) if input_wanted(ctx, 1) else None
+        gb = colsum(gy.reshape(-1, 1)) if input_wanted(ctx, 2) else None
+        return gx, gw, gb
+
+
+class _Outer(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, g, w):
+        ctx.save_for_backward(g, w)
+        return outer_raw(g, w)
+
+    @staticmethod
+    def backward(ctx, go):
+        g, w = ctx.saved_tensors
+        gg = _RowDot.apply(go, w, None).view_as(g) if input_wanted(ctx, 0) else None
+        gw = _WSum.apply(g, go).view_as(w) if input_wanted(ctx, 1) else None
+        return gg, gw
+
+
+class _WSum(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, g, x):
+        ctx.save_for_backward(g, x)
+        return wsum_raw(g, x)
+
+    @staticmethod
+    def backward(ctx, go):
+        g, x = ctx.saved_tensors
+        gg = _RowDot.apply(x, go, None).view_as(g) if input_wanted(ctx, 0) else None
+        gx = _Outer.apply(g, go) if input_wanted(ctx, 1) else None
+        return gg, gx
+
+
+def linear_to_scalar(x: torch.Tensor, weight: torch.Tensor, bias: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """F.linear(x, weight, bias) for weight [1, in] -> [N, 1], differentiable to any order."""
+    return _RowDot.apply(x, weight, bias).unsqueeze(1)
+
+
+# ------------------------------------------------------------------------------------------
 # o3.Linear on the cm layout [mul0 | 3 x mul1 | 5 x mul2]
 # ------------------------------------------------------------------------------------------
 def _blocks(muls):

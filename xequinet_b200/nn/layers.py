@@ -53,15 +53,20 @@ def resolve_activation(activation: str) -> nn.Module:
 class Linear(nn.Linear):
     """nn.Linear (same parameters / state_dict names) evaluated by the tcgen05 GEMM kernel (K3,
     csrc/node_gemm.cu) together with all of its derivatives.  The kernel addresses operands in 16-byte
-    units: widths that are not multiples of 4 (the 64 -> 1 energy read-out, nn/output.py:107-111; the
-    2 -> C / 1 -> C projections of the charge / spin embedding, nn/electronic.py:25-26) are zero-padded
-    to the next multiple of 4 and the result sliced, so no linear layer of the path leaves K3."""
+    units.  A single output feature (the 64 -> 1 energy read-out, nn/output.py:107-111) is a row-dot
+    kernel with kernel-backed derivatives (gemm.linear_to_scalar); other widths that are not multiples of 4
+    (the 2 -> C / 1 -> C projections of the charge / spin embedding, nn/electronic.py:25-26, the 64 -> 2
+    polarizability read-out) are zero-padded to the next multiple of 4 and the result sliced: no linear
+    layer of the path is a library call."""
 
     def forward(self, x: torch.Tensor) -> torch.Tensor:
         lead = None
         if x.dim() != 2:
             lead, x = x.shape[:-1], x.reshape(-1, x.shape[-1])
         w, b = self.weight, self.bias
+        if self.out_features == 1:
+            y = gemm.linear_to_scalar(x, w, b)
+            return y if lead is None else y.reshape(*lead, 1)
         pk, pn = -self.in_features % 4, -self.out_features % 4
         if pk:
             x, w = F.pad(x, (0, pk)), F.pad(w, (0, pk))
