@@ -346,6 +346,47 @@ int xeq_silu_fwd(const float* u, size_t n, float* y, xeq_stream_t stream);
 int xeq_silu_bwd(const float* u, const float* g, size_t n, float* gu, xeq_stream_t stream);
 int xeq_silu_bwdbwd(const float* u, const float* g, const float* c, size_t n, float* dg, float* du, xeq_stream_t stream);
 
+/* ------------------------------------------------------------------------------------
+ * Whole-model inference runtime (csrc/model_runtime.cu): XPaiNN energy + forces as ONE call, no Python / torch /
+ * autograd in the host process.  Deployment form of the path: the reference exports a TorchScript archive that a
+ * LAMMPS pair style / the GROMACS NNP interface drives through libtorch (run/jit_script.py:28-86,
+ * interface/jit_model.py:12-216: compute_edge_data -> mods -> compute_properties, forces by torch.autograd.grad);
+ * here the engine links this library and passes its own neighbour list as an xeq_graph_t
+ * (xeq_csr_from_sorted_coo + xeq_csr_transpose + xeq_csr_tile_bounds, or K1).
+ *
+ * Default model only (nn/model.py:57-70: layer_norm, silu, output_modes = ["energy"], no charge / spin conditioning).
+ * `weights`: ONE flat fp32 DEVICE blob, caller-owned and kept alive while the handle is used, 16-byte aligned, every
+ * tensor padded to a multiple of 4 floats, in this order (state_dict names of the reference):
+ *   embedding.embedding.0.embed_ten [n_species, embed_dim], embedding.embedding.1.{weight [C, embed_dim], bias [C]},
+ *   embedding.rbf.freq [B];
+ *   per action block i:  message_i.{norm.weight, norm.bias, o3norm.affine_weight, o3norm.affine_bias,
+ *                          scalar_mlp.0.weight, .0.bias, scalar_mlp.2.weight, .2.bias, rbf_lin.weight, rbf_lin.bias},
+ *                        update_i.{norm.weight, norm.bias, o3norm.affine_weight, o3norm.affine_bias, update_U.weight,
+ *                          update_U.bias, update_V.weight, update_V.bias, dot_lin.weight, update_mlp.0.weight, .0.bias,
+ *                          update_mlp.2.weight, .2.bias};
+ *   output_energy.out_mlp.{0.weight, 0.bias, 2.weight, 2.bias}.
+ * xeq_model_weight_count() gives the blob length; xeq_model_create() only records the description (no device
+ * allocation, no copy); the handle is immutable and may be shared by threads / streams.
+ *
+ * xeq_model_energy_forces(): energy [G], atomic_energies [N], forces [N,3] = -dE/dpos (NULL: energies only).
+ * The forward pass issues the entry points above in the order of the nn modules; the force pass is the reverse sweep
+ * torch.autograd.grad(E, pos) performs over them (nn/basic.py:143-159) with the same kernels, arguments and summation
+ * order: results are bit-identical to the Python module path.  Asynchronous on `stream`, no allocation, no host
+ * synchronisation; the workspace must be 256-byte aligned.
+ * ---------------------------------------------------------------------------------- */
+typedef struct xeq_model xeq_model_t;
+size_t xeq_model_weight_count(const xeq_dims_t* dims, int32_t n_layers, int32_t hidden_dim, int32_t embed_dim,
+                              int32_t n_species);
+int xeq_model_create(const xeq_dims_t* dims, int32_t n_layers /* action_blocks */, int32_t hidden_dim /* EnergyOut: 64 */,
+                     int32_t embed_dim /* aux56: 56 */, int32_t n_species /* rows of embed_ten */,
+                     const float* weights /* device */, size_t n_weights, xeq_model_t** model);
+void xeq_model_destroy(xeq_model_t* model);
+size_t xeq_model_workspace_bytes(const xeq_model_t* model, const xeq_graph_t* g, int want_forces);
+int xeq_model_energy_forces(const xeq_model_t* model, const xeq_graph_t* g, const float* pos /* [N,3] */,
+                            const int32_t* atomic_numbers /* [N] */, const int32_t* seg_ptr /* [G+1] */,
+                            float* energy /* [G] */, float* atomic_energies /* [N] */, float* forces /* [N,3] or NULL */,
+                            void* workspace, size_t workspace_bytes, xeq_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -1,0 +1,106 @@
+"""GPU tests of the whole-model inference runtime (csrc/model_runtime.cu, xeq_model_energy_forces): energy + forces as
+ONE C call without autograd -- the deployment form of the path.  It issues the same kernels
+with the same arguments and summation order as the nn modules + torch.autograd.grad, so it must agree with them
+BIT FOR BIT; the module path itself is pinned to the reference's golden vectors (tests/test_gpu_parity.py)."""
+import numpy as np
+import pytest
+import torch
+
+from helpers import cast_data, force_gate, load_golden
+from oracle import xpainn_oracle as orc
+
+pytestmark = pytest.mark.gpu
+
+import xequinet_b200 as xb  # noqa: E402
+from xequinet_b200 import runtime  # noqa: E402
+
+DEV = "cuda"
+
+
+def _dev(data):
+    return {k: (v.to(DEV) if torch.is_tensor(v) else v) for k, v in data.items() if k != "pbc"}
+
+
+def _model(cfg, seed):
+    model = xb.resolve_model("xpainn", **cfg.model_kwargs())
+    model.load_state_dict(orc.synthetic_state_dict(cfg, seed), strict=False)
+    return model.to(DEV).eval()
+
+
+@pytest.mark.parametrize("name", ["mol_small", "mol_c4_small", "pbc_small", "pbc_tiny", "pbc_slab", "pbc_two_graphs"])
+def test_runtime_is_bit_identical_to_the_module_path_and_matches_the_golden(name):
+    z, cfg, data = load_golden(name)
+    model = _model(cfg, int(z["sd_seed"]))
+    native = runtime.NativeModel(model)
+    ref = model(_dev(cast_data(data, torch.float32)), compute_forces=True)
+    out = native(_dev(cast_data(data, torch.float32)), compute_forces=True)
+    assert set(out) == {"energy", "atomic_energies", "forces"}
+    for k in out:
+        assert torch.equal(out[k], ref[k].detach()), (k, float((out[k] - ref[k]).abs().max()))
+    np.testing.assert_allclose(out["energy"].cpu().numpy(), z["f64:energy"], rtol=1e-5, atol=1e-6)
+    force_gate(out["forces"].cpu().numpy(), z["f64:forces"], z["f32:forces"])
+    e_only = native(_dev(cast_data(data, torch.float32)), compute_forces=False)
+    assert set(e_only) == {"energy", "atomic_energies"} and torch.equal(e_only["energy"], out["energy"])
+
+
+def test_runtime_c1_shape_with_k1_graph_and_cuda_graph_replay():
+    """64 x 18 atoms (config c1), neighbour list from K1; then the whole E+F evaluation captured as ONE CUDA graph
+    (the runtime allocates nothing and never synchronises) and replayed on moved atoms."""
+    cfg = orc.CONFIG_DEFAULT
+    model = _model(cfg, 1234)
+    native = runtime.NativeModel(model)
+    d0 = orc.make_molecule_batch(64, 18, seed=0, with_edges=False)
+    data = xb.NeighborTransform(5.0)(_dev(d0))
+    ref = model(dict(data), compute_forces=True)
+    out = native(dict(data), compute_forces=True)
+    for k in out:
+        assert torch.equal(out[k], ref[k].detach()), k
+    # capture: static positions buffer, same neighbour structure (small displacements keep every pair inside the list)
+    static = dict(data)
+    static["pos"] = data["pos"].clone()
+    s = torch.cuda.Stream()
+    s.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(s):
+        native(dict(static))  # warm-up outside the capture
+    torch.cuda.current_stream().wait_stream(s)
+    graph = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(graph):
+        cap = native(dict(static))
+    moved = data["pos"] + 1e-3 * torch.randn_like(data["pos"])
+    static["pos"].copy_(moved)
+    graph.replay()
+    eager = native(dict(data, pos=moved))
+    for k in cap:
+        assert torch.equal(cap[k], eager[k]), k
+    assert float((cap["forces"] - out["forces"]).abs().max()) > 0
+
+
+def test_runtime_edge_cases_and_weight_file(tmp_path):
+    cfg = orc.CONFIG_DEFAULT
+    model = _model(cfg, 7)
+    native = runtime.NativeModel(model)
+    # isolated atoms (rows without edges) next to a dimer and a small molecule, three graphs
+    pos = torch.tensor([[0.0, 0, 0], [50.0, 0, 0], [51.1, 0, 0], [100.0, 0, 0], [100.9, 0.3, 0], [100.2, 1.0, 0.4]], device=DEV)
+    data = {"pos": pos, "atomic_numbers": torch.tensor([8, 1, 1, 6, 1, 8], device=DEV),
+            "batch": torch.tensor([0, 1, 1, 2, 2, 2], device=DEV), "ptr": torch.tensor([0, 1, 3, 6], device=DEV)}
+    data = xb.NeighborTransform(5.0)(data)
+    ref = model(dict(data), compute_forces=True)
+    out = native(dict(data), compute_forces=True)
+    for k in out:
+        assert torch.equal(out[k], ref[k].detach()), k
+    assert float(out["forces"][0].abs().max()) == 0.0
+    # the weight file a C / C++ host reads
+    path = tmp_path / "model.xeqw"
+    native.save(str(path))
+    hdr, blob = runtime.read_weight_file(str(path))
+    assert hdr["node_dim"] == 128 and hdr["n_layers"] == 3 and hdr["n_species"] == 87 and hdr["cutoff"] == 5.0
+    assert torch.equal(blob, native.blob.cpu())
+    # too small a workspace is refused, not overrun
+    from xequinet_b200 import _lib
+    lib = _lib.get()
+    g = data["_xeq_graph"]
+    e = torch.empty(3, device=DEV); ea = torch.empty(6, device=DEV); ws = torch.empty(1024, dtype=torch.uint8, device=DEV)
+    rc = lib.xeq_model_energy_forces(native._handle, g.struct, pos.data_ptr(), data["atomic_numbers"].to(torch.int32).data_ptr(),
+                                     data["ptr"].to(torch.int32).data_ptr(), e.data_ptr(), ea.data_ptr(), None, ws.data_ptr(), 1024,
+                                     _lib.stream())
+    assert rc == -3 and b"workspace too small" in lib.xeq_last_error()
