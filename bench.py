@@ -446,6 +446,7 @@ def run_gpu(args):
     sampler = ClockSampler(local_rank) if rank == 0 else None
     if sampler:
         sampler.start()
+    native_runtime = False
     if use_graph:
         total_ms, _ = timed(False, args.steps, args.warmup, False, graph_step)
         e2e_ms, _ = timed(True, args.steps, max(3, args.warmup // 2), False, graph_step)
@@ -459,8 +460,29 @@ def run_gpu(args):
         kern = ops.KernelTimer.summary()
         launches = launches * args.steps // kern_steps
     else:
-        total_ms, launches = timed(False, args.steps, args.warmup, False)
-        e2e_ms, _ = timed(True, args.steps, max(3, args.warmup // 2), False)
+        # eagerly launched INFERENCE steps go through the C inference runtime (xequinet_b200.runtime.NativeModel ->
+        # xeq_model_energy_forces: forward + force pass scheduled inside the library, bit-identical to the module path):
+        # no autograd graph and no per-op Python between the ~110 launches of a step
+        headline = step
+        if not train and not sharded and not args.eager:
+            from xequinet_b200 import runtime
+            native = runtime.NativeModel(model)
+            chk_mod = model(transform({k: resident[0][k] for k in h2d_keys}), compute_forces=forces)
+            chk_nat = native(transform({k: resident[0][k] for k in h2d_keys}), compute_forces=forces)
+            assert all(torch.equal(chk_nat[k], chk_mod[k].detach()) for k in chk_nat), "inference runtime differs from the module path"
+
+            def headline(batch, e2e: bool):
+                d = {k: (batch[k].to(dev, non_blocking=True) if e2e else batch[k]) for k in h2d_keys}
+                out = native(transform(d), compute_forces=forces)
+                if e2e:
+                    energy_host.copy_(out["energy"], non_blocking=True)
+                    if forces:
+                        forces_host[: out["forces"].shape[0]].copy_(out["forces"], non_blocking=True)
+                return out["energy"]
+
+            native_runtime = True
+        total_ms, launches = timed(False, args.steps, args.warmup, False, headline)
+        e2e_ms, _ = timed(True, args.steps, max(3, args.warmup // 2), False, headline)
         # kernel-level timings from a separate pass: the per-call events and the call profile cost host time, which
         # an eagerly launched step is bound by
         kern_steps = min(args.steps, 5)
@@ -566,7 +588,10 @@ def run_gpu(args):
                                    (f"spatial slabs x{world} + per-layer halo exchange (NCCL all-to-all), one CUDA graph per rank" if sharded else "single GPU")),
                    "execution": ("whole step replayed as one CUDA graph per rank (xequinet_b200.domain.ShardedStep)" if sharded else
                                  "whole step replayed as one CUDA graph (xequinet_b200.replay.CapturedStep, K1 in capacity mode)") if use_graph else
-                                ("eager launches" if args.eager else "eager launches (batch shapes vary: no static graph)")},
+                                ("eager launches" if args.eager else
+                                 ("eager launches (batch shapes vary: no static graph)" +
+                                  (", E+F through the C inference runtime xeq_model_energy_forces (bit-identical to the module path)"
+                                   if native_runtime else "")))},
         "e2e": {"value": round(e2e_value, 2), "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h)},
         "gpu_launches": int(launches),
         "roofline": roofline,
