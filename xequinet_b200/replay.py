@@ -43,7 +43,7 @@ class CapturedStep:
             input_keys = [k for k, v in example.items() if torch.is_tensor(v) and not k.startswith("_xeq")
                           and k not in (keys.EDGE_INDEX, keys.CELL_OFFSETS)]
         self.input_keys = list(input_keys)
-        self.static = {k: example[k].clone() for k in self.input_keys}
+        self.static = {k: example[k].detach().clone() for k in self.input_keys}  # detached: an earlier eager call may have marked pos for differentiation
         if keys.BATCH_PTR not in self.static:
             n = pos.shape[0]
             self.static[keys.BATCH] = torch.zeros(n, dtype=torch.long, device=pos.device)
