@@ -104,3 +104,41 @@ def test_runtime_edge_cases_and_weight_file(tmp_path):
                                      data["ptr"].to(torch.int32).data_ptr(), e.data_ptr(), ea.data_ptr(), None, ws.data_ptr(), 1024,
                                      _lib.stream())
     assert rc == -3 and b"workspace too small" in lib.xeq_last_error()
+
+
+def test_python_free_host_process_matches_the_module_path(tmp_path):
+    """examples/md_host.cpp: a C++ process that links libxeq_b200.so only (no Python, no torch), reads the weight file
+    written by NativeModel.save(), builds its neighbour list with K1 through the C ABI and calls
+    xeq_model_energy_forces -- the engine side of the deployment path.  Bit-identical to model(data) in this process."""
+    import struct
+    import subprocess
+    import sys
+    from pathlib import Path
+
+    root = Path(__file__).resolve().parent.parent
+    exe = root / "examples" / "md_host"
+    if not exe.exists():
+        sys.path.insert(0, str(root))
+        import __graft_entry__ as entry
+        entry.build_md_host()
+    ldd = subprocess.run(["ldd", str(exe)], capture_output=True, text=True).stdout
+    assert "libxeq_b200.so" in ldd and "torch" not in ldd and "python" not in ldd
+    cfg = orc.CONFIG_DEFAULT
+    model = _model(cfg, 1234)
+    runtime.NativeModel(model).save(str(tmp_path / "model.xeqw"))
+    d = orc.make_molecule_batch(1, 100, seed=4, with_edges=False)  # > 64 atoms: edge-block tiles on both sides
+    n = d["pos"].shape[0]
+    with open(tmp_path / "structure.bin", "wb") as f:
+        f.write(struct.pack("<i", n))
+        f.write(d["pos"].float().numpy().tobytes())
+        f.write(d["atomic_numbers"].to(torch.int32).numpy().tobytes())
+    r = subprocess.run([str(exe), str(tmp_path / "model.xeqw"), str(tmp_path / "structure.bin"), str(tmp_path / "out.bin"), "20"],
+                       capture_output=True, text=True, timeout=120)
+    assert r.returncode == 0, r.stderr
+    print(r.stdout.strip())
+    raw = np.fromfile(tmp_path / "out.bin", dtype=np.float32)
+    assert raw.size == 1 + n + 3 * n
+    ref = model(xb.NeighborTransform(5.0)(_dev(d)), compute_forces=True)
+    assert raw[0] == float(ref["energy"][0])
+    assert np.array_equal(raw[1 : 1 + n], ref["atomic_energies"].detach().cpu().numpy())
+    assert np.array_equal(raw[1 + n :].reshape(n, 3), ref["forces"].cpu().numpy())
