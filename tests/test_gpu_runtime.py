@@ -139,6 +139,6 @@ def test_python_free_host_process_matches_the_module_path(tmp_path):
     raw = np.fromfile(tmp_path / "out.bin", dtype=np.float32)
     assert raw.size == 1 + n + 3 * n
     ref = model(xb.NeighborTransform(5.0)(_dev(d)), compute_forces=True)
-    assert raw[0] == float(ref["energy"][0])
+    assert raw[0] == float(ref["energy"].detach()[0])
     assert np.array_equal(raw[1 : 1 + n], ref["atomic_energies"].detach().cpu().numpy())
     assert np.array_equal(raw[1 + n :].reshape(n, 3), ref["forces"].cpu().numpy())
