@@ -86,7 +86,10 @@ class NativeModel:
     def __del__(self):
         h, self._handle = getattr(self, "_handle", None), None
         if h:
-            _lib.get().xeq_model_destroy(h)
+            try:
+                _lib.get().xeq_model_destroy(h)
+            except Exception:  # interpreter shutdown: the library may already be gone
+                pass
 
     def __call__(self, data: Dict[str, torch.Tensor], compute_forces: bool = True) -> Dict[str, torch.Tensor]:
         data = compute_edge_data(data, compute_forces=False)  # resolves the neighbour structure and the batch bookkeeping
