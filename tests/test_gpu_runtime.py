@@ -142,3 +142,24 @@ def test_python_free_host_process_matches_the_module_path(tmp_path):
     assert raw[0] == float(ref["energy"].detach()[0])
     assert np.array_equal(raw[1 : 1 + n], ref["atomic_energies"].detach().cpu().numpy())
     assert np.array_equal(raw[1 + n :].reshape(n, 3), ref["forces"].cpu().numpy())
+
+
+@pytest.mark.parametrize("which", ["c4", "box"])
+def test_runtime_at_benchmark_shapes(which):
+    """c4: 128 molecules of 30..70 atoms at 256 channels (two channel slices, mixed staged / unstaged tiles);
+    box: a 1536-atom periodic water box (cell-list K1, edge-block tiles, L2 gathers) -- bit-identical to the module path."""
+    if which == "c4":
+        cfg = orc.CONFIG_C4
+        d = orc.make_molecule_batch(128, (30, 70), seed=1, with_edges=False, z_table=orc._Z_SPICE)
+    else:
+        cfg = orc.CONFIG_DEFAULT
+        d = orc.make_water_box(8, seed=2)
+    model = _model(cfg, 1234)
+    native = runtime.NativeModel(model)
+    data = xb.NeighborTransform(5.0)({k: v.to(DEV) for k, v in d.items() if torch.is_tensor(v)})
+    data.pop("pbc", None)
+    ref = model(dict(data), compute_forces=True)
+    out = native(dict(data), compute_forces=True)
+    for k in out:
+        assert torch.equal(out[k], ref[k].detach()), k
+    assert float(out["forces"].abs().max()) > 1e-3
