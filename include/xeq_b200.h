@@ -386,6 +386,16 @@ int xeq_model_energy_forces(const xeq_model_t* model, const xeq_graph_t* g, cons
                             const int32_t* atomic_numbers /* [N] */, const int32_t* seg_ptr /* [G+1] */,
                             float* energy /* [G] */, float* atomic_energies /* [N] */, float* forces /* [N,3] or NULL */,
                             void* workspace, size_t workspace_bytes, xeq_stream_t stream);
+/* Same call with a second stream for the independent branches of the module graph (norm(x) -> scalar MLP beside
+ * o3norm(V), update_U beside update_V, dot_lin beside the update MLP, and their mirror images in the force pass):
+ * at MD sizes every kernel is a fraction of a wave and the step is a latency chain, so the branches overlap.  Forks
+ * and joins are event record / wait pairs between `stream` and `aux_stream` (capturable; everything is joined back
+ * into `stream` before the call returns).  Same kernels and arguments: the results are identical.  aux_stream NULL
+ * (or == stream) = the single-stream schedule. */
+int xeq_model_energy_forces_mt(const xeq_model_t* model, const xeq_graph_t* g, const float* pos,
+                               const int32_t* atomic_numbers, const int32_t* seg_ptr,
+                               float* energy, float* atomic_energies, float* forces,
+                               void* workspace, size_t workspace_bytes, xeq_stream_t stream, xeq_stream_t aux_stream);
 
 #ifdef __cplusplus
 }

@@ -40,7 +40,8 @@ def main(which):
     model = xb.resolve_model("xpainn", **cfg.model_kwargs())
     model.load_state_dict(orc.synthetic_state_dict(cfg, 1234), strict=False)
     model = model.to(DEV).eval()
-    native = runtime.NativeModel(model)
+    native = runtime.NativeModel(model)                         # independent branches on a second stream
+    native1 = runtime.NativeModel(model, branch_stream=False)   # single-stream schedule
     nt = xb.NeighborTransform(5.0)
     full = nt(dict(data))
     res = {"workload": which, "atoms": int(data["pos"].shape[0]), "edges": int(full["edge_index"].shape[1])}
@@ -52,8 +53,11 @@ def main(which):
     res["own_kernels_module_path"], res["own_kernels_runtime"] = int(n1 - n0), int(n2 - n1)
     res["ms_module_eager"] = timed(lambda: model(dict(full), compute_forces=True))
     res["ms_runtime_eager"] = timed(lambda: native(dict(full), compute_forces=True))
+    res["ms_runtime_eager_1stream"] = timed(lambda: native1(dict(full), compute_forces=True))
+    o1 = native1(dict(full), compute_forces=True)
+    res["streams_bit_identical"] = bool(torch.equal(o1["forces"], out["forces"]) and torch.equal(o1["energy"], out["energy"]))
     inp = {k: v for k, v in data.items()}
-    for name, m in (("module", model), ("runtime", native)):
+    for name, m in (("module", model), ("runtime", native), ("runtime_1stream", native1)):
         try:
             step = CapturedStep(m, inp, compute_forces=True)
             res[f"ms_{name}_graph_with_k1"] = timed(lambda: step(inp))

@@ -39,6 +39,9 @@ def test_runtime_is_bit_identical_to_the_module_path_and_matches_the_golden(name
         assert torch.equal(out[k], ref[k].detach()), (k, float((out[k] - ref[k]).abs().max()))
     np.testing.assert_allclose(out["energy"].cpu().numpy(), z["f64:energy"], rtol=1e-5, atol=1e-6)
     force_gate(out["forces"].cpu().numpy(), z["f64:forces"], z["f32:forces"])
+    one = runtime.NativeModel(model, branch_stream=False)(_dev(cast_data(data, torch.float32)), compute_forces=True)
+    for k in out:  # the second stream only reorders independent launches
+        assert torch.equal(out[k], one[k]), k
     e_only = native(_dev(cast_data(data, torch.float32)), compute_forces=False)
     assert set(e_only) == {"energy", "atomic_energies"} and torch.equal(e_only["energy"], out["energy"])
 

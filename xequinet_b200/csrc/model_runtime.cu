@@ -164,6 +164,14 @@ __global__ void forces_kernel(PosGrads pg, float* __restrict__ out, size_t n) {
 }
 inline unsigned blocks_for(size_t n) { return (unsigned)((n + 255) / 256); }
 
+struct EventPair {  // released on every return path; destroying an event with pending work is allowed
+  cudaEvent_t f = nullptr, j = nullptr;
+  ~EventPair() {
+    if (f) cudaEventDestroy(f);
+    if (j) cudaEventDestroy(j);
+  }
+};
+
 #define XEQ_TRY(call)        \
   do {                       \
     const int _rc = (call);  \
@@ -260,6 +268,13 @@ size_t xeq_model_workspace_bytes(const xeq_model_t* model, const xeq_graph_t* g,
 int xeq_model_energy_forces(const xeq_model_t* model, const xeq_graph_t* g, const float* pos, const int32_t* atomic_numbers,
                             const int32_t* seg_ptr, float* energy, float* atomic_energies, float* forces,
                             void* workspace, size_t workspace_bytes, xeq_stream_t stream) {
+  return xeq_model_energy_forces_mt(model, g, pos, atomic_numbers, seg_ptr, energy, atomic_energies, forces, workspace,
+                                    workspace_bytes, stream, nullptr);
+}
+
+int xeq_model_energy_forces_mt(const xeq_model_t* model, const xeq_graph_t* g, const float* pos, const int32_t* atomic_numbers,
+                               const int32_t* seg_ptr, float* energy, float* atomic_energies, float* forces,
+                               void* workspace, size_t workspace_bytes, xeq_stream_t stream, xeq_stream_t aux_stream) {
   XEQ_CHECK_ARG(model && g && seg_ptr && energy && atomic_energies, "model_energy_forces: NULL argument");
   const int N = g->n_nodes, G = g->n_graphs, L = model->n_layers;
   XEQ_CHECK_ARG(N >= 0 && G >= 0, "model_energy_forces: bad graph");
@@ -283,6 +298,32 @@ int xeq_model_energy_forces(const xeq_model_t* model, const xeq_graph_t* g, cons
   const float* w = model->w;
   const int C = s.C, D = s.D, M = s.M, H = s.H, Hu = s.Hu, CM = s.C + s.M;
 
+  // Independent branches of the module graph (norm(x) -> scalar MLP beside o3norm(V); update_U beside update_V; dot_lin
+  // beside the update MLP; and their mirror images in the force pass) run on `aux_stream` when the caller gives one:
+  // at MD sizes every kernel is a fraction of a wave, so the step is a latency chain and the branches overlap.  Same
+  // kernels and arguments either way: the results do not depend on it.  fork: aux waits for everything issued on the
+  // main stream so far; join: the main stream waits for the branch.  Plain event record / wait pairs -- capturable.
+  cudaStream_t sb = aux_stream ? (cudaStream_t)aux_stream : st;
+  EventPair ev;
+  if (aux_stream && sb != st) {
+    XEQ_CUDA(cudaEventCreateWithFlags(&ev.f, cudaEventDisableTiming));
+    XEQ_CUDA(cudaEventCreateWithFlags(&ev.j, cudaEventDisableTiming));
+  } else {
+    sb = st;
+  }
+  auto fork = [&]() -> int {
+    if (sb == st) return XEQ_OK;
+    XEQ_CUDA(cudaEventRecord(ev.f, st));
+    XEQ_CUDA(cudaStreamWaitEvent(sb, ev.f, 0));
+    return XEQ_OK;
+  };
+  auto join = [&]() -> int {
+    if (sb == st) return XEQ_OK;
+    XEQ_CUDA(cudaEventRecord(ev.j, sb));
+    XEQ_CUDA(cudaStreamWaitEvent(st, ev.j, 0));
+    return XEQ_OK;
+  };
+
   // ---- XEmbedding (nn/xpainn.py:55-83): x0 = Linear(embed_ten[Z]); V0 = 0 ----
   gather_rows_kernel<<<blocks_for((size_t)N * s.E), 256, 0, st>>>(w + lo.table, atomic_numbers, N, s.E, model->n_species, b.emb_in);
   XEQ_LAUNCHED(1);
@@ -293,26 +334,33 @@ int xeq_model_energy_forces(const xeq_model_t* model, const xeq_graph_t* g, cons
     // ---- XPainnMessage.forward (nn/xpainn.py:128-161) ----
     const MsgW& mw = lo.msg[l];
     const float *x_in = b.x[2 * l], *V_in = b.V[2 * l];
+    XEQ_TRY(fork());
+    XEQ_TRY(xeq_irreps_norm_fwd(V_in, w + mw.on_w, w + mw.on_b, N, s.m0, s.m1, s.m2, NORM_EPS, b.vn[l], sb));
     XEQ_TRY(xeq_irreps_norm_fwd(x_in, w + mw.ln_w, w + mw.ln_b, N, C, 0, 0, NORM_EPS, b.xn, st));
-    XEQ_TRY(xeq_irreps_norm_fwd(V_in, w + mw.on_w, w + mw.on_b, N, s.m0, s.m1, s.m2, NORM_EPS, b.vn[l], st));
     XEQ_TRY(linear(b.xn, C, w + mw.W1, w + mw.b1, b.u1[l], N, C, C, st));
     XEQ_TRY(xeq_silu_fwd(b.u1[l], (size_t)N * C, b.h, st));
     XEQ_TRY(linear(b.h, C, w + mw.W2, w + mw.b2, b.s[l], N, H, C, st));
+    XEQ_TRY(join());
     XEQ_TRY(xeq_edge_message_fwd(g, dims, pos, b.s[l], b.vn[l], x_in, V_in, w + mw.Wrbf, w + mw.brbf, w + lo.freq,
                                  b.x[2 * l + 1], b.V[2 * l + 1], b.edge_ws, b.edge_ws_bytes, st));
     // ---- XPainnUpdate.forward (nn/xpainn.py:206-231) ----
     const UpdW& uw = lo.upd[l];
     const float *x1 = b.x[2 * l + 1], *V1 = b.V[2 * l + 1];
+    XEQ_TRY(fork());
+    XEQ_TRY(xeq_irreps_norm_fwd(V1, w + uw.on_w, w + uw.on_b, N, s.m0, s.m1, s.m2, NORM_EPS, b.vn2, sb));
+    XEQ_TRY(join());  // the main stream sees o3norm(V); the branch goes on with update_U
+    XEQ_TRY(irreps_linear(b.vn2, w + uw.Uw, w + uw.Ub, b.U[l], N, s, false, sb));
     XEQ_TRY(xeq_irreps_norm_fwd(x1, w + uw.ln_w, w + uw.ln_b, N, C, 0, 0, NORM_EPS, b.xn, st));
     XEQ_CUDA(cudaMemcpy2DAsync(b.cat, sizeof(float) * CM, b.xn, sizeof(float) * C, sizeof(float) * C, N, cudaMemcpyDeviceToDevice, st));
-    XEQ_TRY(xeq_irreps_norm_fwd(V1, w + uw.on_w, w + uw.on_b, N, s.m0, s.m1, s.m2, NORM_EPS, b.vn2, st));
-    XEQ_TRY(irreps_linear(b.vn2, w + uw.Uw, w + uw.Ub, b.U[l], N, s, false, st));
     XEQ_TRY(irreps_linear(b.vn2, w + uw.Vw, w + uw.Vb, b.Wt[l], N, s, false, st));
+    XEQ_TRY(join());
     XEQ_TRY(xeq_invariant_dot_fwd(b.U[l], b.Wt[l], N, s.m0, s.m1, s.m2, b.cat + C, CM, b.t0, st));  // [xn | Invariant(W)]
+    XEQ_TRY(fork());
+    XEQ_TRY(linear(b.t0, M, w + uw.dotW, nullptr, b.t[l], N, C, M, sb));
     XEQ_TRY(linear(b.cat, CM, w + uw.M1, w + uw.m1b, b.u2[l], N, C, CM, st));
     XEQ_TRY(xeq_silu_fwd(b.u2[l], (size_t)N * C, b.h, st));
     XEQ_TRY(linear(b.h, C, w + uw.M2, w + uw.m2b, b.a[l], N, Hu, C, st));
-    XEQ_TRY(linear(b.t0, M, w + uw.dotW, nullptr, b.t[l], N, C, M, st));
+    XEQ_TRY(join());
     XEQ_TRY(xeq_gate_residual_fwd(b.a[l], b.U[l], b.t[l], x1, V1, N, s.m0, s.m1, s.m2, b.x[2 * l + 2], b.V[2 * l + 2], st));
   }
 
@@ -337,17 +385,21 @@ int xeq_model_energy_forces(const xeq_model_t* model, const xeq_graph_t* g, cons
     const MsgW& mw = lo.msg[l];
     // update block
     XEQ_TRY(xeq_gate_residual_bwd(b.a[l], b.U[l], b.t[l], b.gx[cur], b.gV[cur], N, s.m0, s.m1, s.m2, b.ga, b.gU, b.gt, st));
-    XEQ_TRY(linear_bwd(b.gt, C, w + uw.dotW, b.g_t0, N, C, M, st));
+    XEQ_TRY(fork());
+    XEQ_TRY(linear_bwd(b.gt, C, w + uw.dotW, b.g_t0, N, C, M, sb));
     XEQ_TRY(linear_bwd(b.ga, Hu, w + uw.M2, b.g_h, N, Hu, C, st));
     XEQ_TRY(xeq_silu_bwd(b.u2[l], b.g_h, (size_t)N * C, b.g_u, st));
     XEQ_TRY(linear_bwd(b.g_u, C, w + uw.M1, b.g_cat, N, C, CM, st));
+    XEQ_TRY(join());
     XEQ_TRY(xeq_invariant_dot_bwd(b.U[l], b.Wt[l], b.g_cat + C, CM, b.g_t0, b.gU, N, s.m0, s.m1, s.m2, b.gU2, b.gWt, st));
+    XEQ_TRY(fork());
+    XEQ_TRY(irreps_linear(b.gWt, w + uw.Vw, nullptr, b.gvnB, N, s, true, sb));
+    XEQ_TRY(norm_bwd_x(b.x[2 * l + 1], w + uw.ln_w, b.g_cat, CM, b.gx[cur], N, C, 0, 0, b.gx[cur ^ 1], sb));
     XEQ_TRY(irreps_linear(b.gU2, w + uw.Uw, nullptr, b.gvnA, N, s, true, st));
-    XEQ_TRY(irreps_linear(b.gWt, w + uw.Vw, nullptr, b.gvnB, N, s, true, st));
+    XEQ_TRY(join());
     add2_kernel<<<blocks_for((size_t)N * D), 256, 0, st>>>(b.gvnA, b.gvnB, b.gvn, (size_t)N * D);
     XEQ_LAUNCHED(1);
     XEQ_TRY(norm_bwd_x(b.V[2 * l + 1], w + uw.on_w, b.gvn, 0, b.gV[cur], N, s.m0, s.m1, s.m2, b.gV[cur ^ 1], st));
-    XEQ_TRY(norm_bwd_x(b.x[2 * l + 1], w + uw.ln_w, b.g_cat, CM, b.gx[cur], N, C, 0, 0, b.gx[cur ^ 1], st));
     cur ^= 1;
     // message block; the first layer's inputs do not depend on the positions
     const bool first = (l == 0);
@@ -355,11 +407,13 @@ int xeq_model_energy_forces(const xeq_model_t* model, const xeq_graph_t* g, cons
                                  first ? nullptr : b.gs, first ? nullptr : b.gv, b.gpos[l], nullptr, nullptr, nullptr,
                                  b.edge_ws, b.edge_ws_bytes, st));
     if (!first) {
+      XEQ_TRY(fork());
+      XEQ_TRY(norm_bwd_x(b.V[2 * l], w + mw.on_w, b.gv, 0, b.gV[cur], N, s.m0, s.m1, s.m2, b.gV[cur ^ 1], sb));
       XEQ_TRY(linear_bwd(b.gs, H, w + mw.W2, b.g_h, N, H, C, st));
       XEQ_TRY(xeq_silu_bwd(b.u1[l], b.g_h, (size_t)N * C, b.g_u, st));
       XEQ_TRY(linear_bwd(b.g_u, C, w + mw.W1, b.g_cat, N, C, C, st));  // g_cat reused as the [N, C] gradient of norm(x)
       XEQ_TRY(norm_bwd_x(b.x[2 * l], w + mw.ln_w, b.g_cat, 0, b.gx[cur], N, C, 0, 0, b.gx[cur ^ 1], st));
-      XEQ_TRY(norm_bwd_x(b.V[2 * l], w + mw.on_w, b.gv, 0, b.gV[cur], N, s.m0, s.m1, s.m2, b.gV[cur ^ 1], st));
+      XEQ_TRY(join());
       cur ^= 1;
     }
   }

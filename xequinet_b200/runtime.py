@@ -53,7 +53,9 @@ def export_weights(state_dict: Dict[str, torch.Tensor], n_layers: int) -> torch.
 class NativeModel:
     """The default XPaiNN model (layer norms, SiLU, energy head, no charge / spin conditioning) on the C runtime."""
 
-    def __init__(self, model: torch.nn.Module) -> None:
+    def __init__(self, model: torch.nn.Module, branch_stream: bool = True) -> None:
+        """branch_stream: run the independent branches of the module graph on a second CUDA stream
+        (xeq_model_energy_forces_mt); the results do not depend on it."""
         mods = list(model.mods)
         n_layers = sum(1 for m in mods if m.startswith("message_"))
         expect = ["embedding"] + [f"{k}_{i}" for i in range(n_layers) for k in ("message", "update")] + ["output_energy"]
@@ -82,6 +84,7 @@ class NativeModel:
         _lib.check(lib.xeq_model_create(ctypes.byref(self.dims), n_layers, self.hidden_dim, self.embed_dim, self.n_species,
                                         self.blob.data_ptr(), self.blob.numel(), ctypes.byref(handle)), "xeq_model_create")
         self._handle = handle
+        self._aux = torch.cuda.Stream(device=dev) if branch_stream else None
 
     def __del__(self):
         h, self._handle = getattr(self, "_handle", None), None
@@ -103,9 +106,10 @@ class NativeModel:
         lib = _lib.get()
         nbytes = lib.xeq_model_workspace_bytes(self._handle, graph.struct, int(compute_forces))
         ws = torch.empty(nbytes, dtype=torch.uint8, device=dev)
-        _lib.check(lib.xeq_model_energy_forces(self._handle, graph.struct, _lib.ptr(pos), _lib.ptr(z), _lib.ptr(ptr32),
-                                               _lib.ptr(energy), _lib.ptr(e_atom), _lib.ptr(forces), _lib.ptr(ws), nbytes,
-                                               _lib.stream()), "xeq_model_energy_forces")
+        aux = self._aux.cuda_stream if self._aux is not None else None
+        _lib.check(lib.xeq_model_energy_forces_mt(self._handle, graph.struct, _lib.ptr(pos), _lib.ptr(z), _lib.ptr(ptr32),
+                                                  _lib.ptr(energy), _lib.ptr(e_atom), _lib.ptr(forces), _lib.ptr(ws), nbytes,
+                                                  _lib.stream(), aux), "xeq_model_energy_forces_mt")
         out = {keys.TOTAL_ENERGY: energy, keys.ATOMIC_ENERGIES: e_atom}
         if compute_forces:
             out[keys.FORCES] = forces
