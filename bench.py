@@ -355,6 +355,7 @@ def run_gpu(args):
     # + backward + gradient all-reduce + AdamW captured once; static input buffers, no host work inside the step;
     # tests/test_gpu_bench_shapes.py checks replay == eager bit for bit).  A captured graph needs one static batch
     # structure: workloads whose batches differ in size (c4: 30..70 atoms per molecule) are replayed eagerly.
+    native_runtime = False
     same_shape = all(d["pos"].shape == resident[0]["pos"].shape and torch.equal(d["ptr"], resident[0]["ptr"]) for d in resident)
     use_graph = (not args.eager) and same_shape
     graph_step = None
@@ -382,7 +383,19 @@ def run_gpu(args):
             e_max = max(e_max, g_dyn.n_edges)
         if train:
             opt = torch.optim.AdamW(params, lr=5e-4, fused=True, capturable=True)
-        captured = CapturedStep(model, {k: resident[0][k] for k in h2d_keys}, compute_forces=forces,
+        step_model = model
+        if not train:
+            # inference: the captured step runs the C inference runtime (xequinet_b200.runtime.NativeModel ->
+            # xeq_model_energy_forces_mt: forward + force pass scheduled inside the library, independent branches on a
+            # second stream); checked bit for bit against the autograd module path before it is timed
+            from xequinet_b200 import runtime
+            step_model = runtime.NativeModel(model)
+            chk_in = transform({k: resident[0][k] for k in h2d_keys})
+            chk_mod = model(dict(chk_in), compute_forces=forces)
+            chk_nat = step_model(dict(chk_in), compute_forces=forces)
+            assert all(torch.equal(chk_nat[k], chk_mod[k].detach()) for k in chk_nat), "inference runtime differs from the module path"
+            native_runtime = True
+        captured = CapturedStep(step_model, {k: resident[0][k] for k in h2d_keys}, compute_forces=forces,
                                 loss_fn=(lambda out, d: loss_fn(out, d, forces)) if train else None, optimizer=opt,
                                 flat_grads=flat, edge_capacity=int(e_max * 1.15) + 1024, input_keys=h2d_keys)
         copied_keys = [k for k in h2d_keys if k not in ("ptr", "batch", "pbc")]  # the batch structure is static
@@ -446,7 +459,6 @@ def run_gpu(args):
     sampler = ClockSampler(local_rank) if rank == 0 else None
     if sampler:
         sampler.start()
-    native_runtime = False
     if use_graph:
         total_ms, _ = timed(False, args.steps, args.warmup, False, graph_step)
         e2e_ms, _ = timed(True, args.steps, max(3, args.warmup // 2), False, graph_step)
@@ -587,7 +599,9 @@ def run_gpu(args):
                    "parallelism": (f"dp{world}" if args.workload != "c5" else
                                    (f"spatial slabs x{world} + per-layer halo exchange (NCCL all-to-all), one CUDA graph per rank" if sharded else "single GPU")),
                    "execution": ("whole step replayed as one CUDA graph per rank (xequinet_b200.domain.ShardedStep)" if sharded else
-                                 "whole step replayed as one CUDA graph (xequinet_b200.replay.CapturedStep, K1 in capacity mode)") if use_graph else
+                                 ("whole step replayed as one CUDA graph (xequinet_b200.replay.CapturedStep, K1 in capacity mode)" +
+                                  (", E+F through the C inference runtime xeq_model_energy_forces_mt (bit-identical to the module path)"
+                                   if native_runtime else ""))) if use_graph else
                                 ("eager launches" if args.eager else
                                  ("eager launches (batch shapes vary: no static graph)" +
                                   (", E+F through the C inference runtime xeq_model_energy_forces (bit-identical to the module path)"
