@@ -368,7 +368,9 @@ int xeq_silu_bwdbwd(const float* u, const float* g, const float* c, size_t n, fl
  * xeq_model_weight_count() gives the blob length; xeq_model_create() only records the description (no device
  * allocation, no copy); the handle is immutable and may be shared by threads / streams.
  *
- * xeq_model_energy_forces(): energy [G], atomic_energies [N], forces [N,3] = -dE/dpos (NULL: energies only).
+ * xeq_model_energy_forces(): energy [G], atomic_energies [N], forces [N,3] = -d(sum_g energy[g])/dpos (NULL: energies
+ * only).  Nodes outside [seg_ptr[0], seg_ptr[G]) -- an MD engine's ghost atoms, appended after its local atoms -- act
+ * as neighbours and receive forces (to be reverse-communicated) but contribute no energy.
  * The forward pass issues the entry points above in the order of the nn modules; the force pass is the reverse sweep
  * torch.autograd.grad(E, pos) performs over them (nn/basic.py:143-159) with the same kernels, arguments and summation
  * order: results are bit-identical to the Python module path.  Asynchronous on `stream`, no allocation, no host

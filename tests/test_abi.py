@@ -55,3 +55,20 @@ def test_ops_fail_loudly_without_cuda():
         pytest.skip("has a GPU")
     with pytest.raises(RuntimeError, match="no CPU fallback"):
         build_graph(torch.zeros(4, 3), 5.0)
+
+
+def test_md_host_example_links_only_the_c_abi(lib_path):
+    """examples/md_host.cpp (the engine-side host of the inference runtime) builds against include/xeq_b200.h and
+    links libxeq_b200.so + cudart only: no torch, no Python in the process (it is RUN by tests/test_gpu_runtime.py)."""
+    import subprocess
+    import sys
+
+    sys.path.insert(0, str(ROOT))
+    import __graft_entry__ as entry
+
+    exe = entry.build_md_host()
+    assert exe.exists()
+    ldd = subprocess.run(["ldd", str(exe)], capture_output=True, text=True).stdout
+    assert "libxeq_b200.so" in ldd and "torch" not in ldd and "python" not in ldd.lower()
+    r = subprocess.run([str(exe)], capture_output=True, text=True)
+    assert r.returncode == 1 and "usage" in r.stderr

@@ -166,3 +166,32 @@ def test_runtime_at_benchmark_shapes(which):
     for k in out:
         assert torch.equal(out[k], ref[k].detach()), k
     assert float(out["forces"].abs().max()) > 1e-3
+
+
+def test_runtime_ghost_nodes_get_forces_but_contribute_no_energy():
+    """An MD engine appends ghost atoms after its local atoms and sums the energy over the local ones (seg_ptr covers
+    the local atoms only): forces = -d(sum of LOCAL atomic energies)/d(all positions), ghosts included."""
+    cfg = orc.CONFIG_DEFAULT
+    model = _model(cfg, 1234)
+    native = runtime.NativeModel(model)
+    d = orc.make_molecule_batch(1, 40, seed=6, with_edges=False)
+    data = xb.NeighborTransform(5.0)(_dev(d))
+    n, n_loc = 40, 29
+    pos = data["pos"].clone().requires_grad_(True)
+    ref = model(dict(data, pos=pos), compute_forces=False)
+    e_loc = ref["atomic_energies"][:n_loc].sum()
+    f_ref = -torch.autograd.grad(e_loc, pos)[0]
+    from xequinet_b200 import _lib
+    lib = _lib.get()
+    g = data["_xeq_graph"]
+    seg = torch.tensor([0, n_loc], dtype=torch.int32, device=DEV)
+    e, ea, f = torch.empty(1, device=DEV), torch.empty(n, device=DEV), torch.empty(n, 3, device=DEV)
+    nbytes = lib.xeq_model_workspace_bytes(native._handle, g.struct, 1)
+    ws = torch.empty(nbytes, dtype=torch.uint8, device=DEV)
+    _lib.check(lib.xeq_model_energy_forces(native._handle, g.struct, data["pos"].data_ptr(), data["atomic_numbers"].to(torch.int32).data_ptr(),
+                                           seg.data_ptr(), e.data_ptr(), ea.data_ptr(), f.data_ptr(), ws.data_ptr(), nbytes, _lib.stream()),
+               "xeq_model_energy_forces")
+    assert torch.equal(ea, ref["atomic_energies"].detach())
+    torch.testing.assert_close(e[0], e_loc.detach(), rtol=1e-6, atol=1e-6)
+    torch.testing.assert_close(f, f_ref, rtol=1e-5, atol=2e-6)
+    assert float(f[n_loc:].abs().max()) > 1e-3  # ghosts do receive forces

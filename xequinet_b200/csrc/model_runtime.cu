@@ -145,9 +145,11 @@ __global__ void gather_rows_kernel(const float* __restrict__ table, const int* _
   z = z < 0 ? 0 : (z >= n_table ? n_table - 1 : z);
   out[i] = table[(size_t)z * width + c];
 }
-__global__ void fill_kernel(float* __restrict__ p, float v, size_t n) {
+// d sum_g E_g / d atomic_energies[i]: 1 for the nodes inside the segments, 0 for nodes outside [seg_ptr[0], seg_ptr[G])
+// (an MD engine's ghost atoms: neighbours that receive forces but contribute no energy)
+__global__ void energy_seed_kernel(float* __restrict__ p, const int* __restrict__ seg_ptr, int n_seg, size_t n) {
   const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i < n) p[i] = v;
+  if (i < n) p[i] = (n_seg > 0 && (long long)i >= seg_ptr[0] && (long long)i < seg_ptr[n_seg]) ? 1.0f : 0.0f;
 }
 __global__ void add2_kernel(const float* __restrict__ a, const float* __restrict__ b, float* __restrict__ out, size_t n) {
   const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -373,7 +375,7 @@ int xeq_model_energy_forces_mt(const xeq_model_t* model, const xeq_graph_t* g, c
 
   // ---- forces = -dE/dpos (nn/basic.py:143-159): reverse sweep over the modules above, d/dpos only ----
   int cur = 0;
-  fill_kernel<<<blocks_for((size_t)N), 256, 0, st>>>(b.ones, 1.0f, (size_t)N);  // d sum(E) / d atomic_energies
+  energy_seed_kernel<<<blocks_for((size_t)N), 256, 0, st>>>(b.ones, seg_ptr, G, (size_t)N);  // d sum(E) / d atomic_energies
   XEQ_LAUNCHED(1);
   XEQ_TRY(xeq_outer(b.ones, w + lo.O2, N, s.hid, b.g_h, st));
   XEQ_TRY(xeq_silu_bwd(b.uo, b.g_h, (size_t)N * s.hid, b.g_u, st));
