@@ -114,6 +114,54 @@ def cpu_step_fn(workload: str, n_mol: int):
     return step, float(mols), f"{mols} molecule(s), {batch['pos'].shape[0]} atoms per step"
 
 
+def time_torch_gpu(workload: str, n_mol: int, dev, steps: int = 5, warmup: int = 2):
+    """SURVEY.md 8d "reference-on-GPU" line: the SAME oracle (the reference's algorithm as stock PyTorch ops: index_select /
+    index_add, E-sized intermediates, autograd for forces and the double backward) on the B200, full workload size, edge
+    list precomputed and not timed.  A reported baseline next to cpu_baseline -- what running the reference's code path
+    on this GPU through PyTorch costs; rank 0, single GPU only."""
+    import xequinet_b200 as xb
+
+    w = WORKLOADS[workload]
+    cfg = w["cfg"]
+    table = torch.from_numpy(np.load(ROOT / "xequinet_b200" / "data" / "gfn2-xtb_aux56.npy")).float().to(dev)
+    sd = {k: v.to(dev).requires_grad_(w["train"]) for k, v in orc.synthetic_state_dict(cfg, 1234).items()}
+    batch = make_batch(workload, n_mol, 0)
+    d0 = {k: (v.to(dev) if torch.is_tensor(v) else v) for k, v in batch.items()}
+    # the edge list comes from K1 (bit-exact against the oracle's search, tests/test_gpu_parity.py) and is not timed
+    if workload == "c5":
+        n = torch.tensor([batch["pos"].shape[0]], device=dev)
+        d0["edge_index"], d0["cell_offsets"] = xb.radius_graph_pbc(d0["pos"], n, d0["pbc"], d0["cell"], cfg.cutoff)
+    else:
+        d0["edge_index"] = xb.radius_graph(d0["pos"], cfg.cutoff, batch=d0["batch"])
+    batch["edge_index"] = d0["edge_index"]
+    opt = torch.optim.AdamW(list(sd.values()), lr=5e-4, fused=True) if w["train"] else None
+
+    def step():
+        d = dict(d0)
+        if w["forces"]:
+            out = orc.xpainn_energy_forces(sd, table, d, cfg, create_graph=w["train"])
+        else:
+            out = {"energy": orc.xpainn_energy(sd, table, d, cfg)[0]}
+        if w["train"]:
+            opt.zero_grad(set_to_none=True)
+            loss_fn(out, d, w["forces"]).backward()
+            opt.step()
+
+    for _ in range(warmup):
+        step()
+    torch.cuda.synchronize()
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record()
+    for _ in range(steps):
+        step()
+    b.record()
+    torch.cuda.synchronize()
+    ms = a.elapsed_time(b) / steps
+    mols = batch["ptr"].numel() - 1 if workload != "c5" else batch["pos"].shape[0] // 3
+    peak_gb = torch.cuda.max_memory_allocated() / 2**30
+    return mols / (ms * 1e-3), ms, f"{mols} molecule(s), {batch['pos'].shape[0]} atoms, {batch['edge_index'].shape[1]} edges per step"
+
+
 def time_cpu(workload: str, n_mol: int, steps: int, warmup: int):
     step, mols, sample = cpu_step_fn(workload, n_mol)
     for _ in range(warmup):
@@ -590,6 +638,16 @@ def run_gpu(args):
     else:
         cpu_val, cpu_ms, cpu_sample = time_cpu(args.workload, cpu_mols, steps=2, warmup=1)
 
+    torch_gpu = None
+    if world == 1 and not args.no_cpu_baseline:
+        try:
+            tg_val, tg_ms, tg_sample = time_torch_gpu(args.workload, n_mol, dev)
+            torch_gpu = {"value": round(tg_val, 2), "unit": UNIT, "ms_per_step": round(tg_ms, 3), "kind": "port on stock PyTorch CUDA ops",
+                         "sample": f"oracle/xpainn_oracle.py on this GPU (eager, edge list not timed), {tg_sample}"}
+        except Exception as e:  # a baseline must never take the bench line down (e.g. out of memory at c5)
+            torch_gpu = {"unavailable": f"{type(e).__name__}: {e}"[:200]}
+            torch.cuda.empty_cache()
+
     line = {
         "metric": METRIC, "value": round(value, 2), "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": round(ms_per_step, 4), "higher_is_better": True, "scaling": "strong" if sharded else "weak", "vs_baseline": None,
@@ -615,6 +673,7 @@ def run_gpu(args):
         "step_shares": step_shares,
         "cpu_baseline": {"value": round(cpu_val, 3), "unit": UNIT, "cores": os.cpu_count(), "kind": "port",
                          "sample": f"CPU oracle (oracle/xpainn_oracle.py), {cpu_sample}, {round(cpu_ms, 1)} ms/step, 2 timed steps"},
+        "torch_gpu_baseline": torch_gpu,
         "clocks": sampler.summary() if sampler else None,
     }
     print(json.dumps(line), flush=True)

@@ -294,7 +294,7 @@ def xpainn_features(
     ei = data["edge_index"]
     batch = data.get("batch")
     if batch is None:
-        batch = torch.zeros(pos.shape[0], dtype=torch.long)
+        batch = torch.zeros(pos.shape[0], dtype=torch.long, device=pos.device)
     G = int(data["ptr"].numel() - 1) if "ptr" in data else int(batch.max().item()) + 1
     center, neighbor = ei[0], ei[1]
     m0, m1, m2 = cfg.muls
@@ -360,7 +360,7 @@ def xpainn_energy(
     p = "mods.output_energy."
     e_atom = F.linear(F.silu(F.linear(x, sd[p + "out_mlp.0.weight"], sd[p + "out_mlp.0.bias"])),
                       sd[p + "out_mlp.2.weight"], sd[p + "out_mlp.2.bias"]).reshape(-1)
-    energy = torch.zeros(G, dtype=e_atom.dtype).index_add(0, batch, e_atom)
+    energy = torch.zeros(G, dtype=e_atom.dtype, device=e_atom.device).index_add(0, batch, e_atom)
     return energy, e_atom
 
 
