@@ -2,10 +2,12 @@
 // MD engine's pair style does per step (the reference's counterpart is a TorchScript archive run through libtorch,
 // xequinet/run/jit_script.py:28-86, xequinet/interface/jit_model.py:12-89).
 //
-//   md_host model.xeqw structure.bin out.bin [n_steps]
+//   md_host model.xeqw structure.bin out.bin [n_steps] [graph]
 //     model.xeqw     written by xequinet_b200.runtime.NativeModel(model).save()
 //     structure.bin  int32 N | float32 pos[N,3] | int32 Z[N]          (one non-periodic structure)
 //     out.bin        float32 E | float32 e_atom[N] | float32 F[N,3]   (+ ms per evaluation on stdout)
+//     graph          capture the evaluation (two-stream schedule) once as a CUDA graph and replay it n_steps times --
+//                    what an MD loop does between neighbour-list rebuilds: the call allocates nothing and never syncs
 //
 // build: nvcc -o md_host examples/md_host.cpp -Iinclude -Lxequinet_b200 -lxeq_b200  (or g++ with -lcudart)
 #include <cuda_runtime.h>
@@ -42,6 +44,7 @@ static void read_exact(FILE* f, void* dst, size_t bytes, const char* what) {
 int main(int argc, char** argv) {
   if (argc < 4) { fprintf(stderr, "usage: %s model.xeqw structure.bin out.bin [n_steps]\n", argv[0]); return 1; }
   const int n_steps = argc > 4 ? atoi(argv[4]) : 1;
+  const bool use_graph = argc > 5 && strcmp(argv[5], "graph") == 0;
 
   // ---- model: header + weight blob -> device, handle ----
   FILE* f = fopen(argv[1], "rb");
@@ -117,8 +120,23 @@ int main(int argc, char** argv) {
   float *e_d = dev_alloc<float>(1), *ea_d = dev_alloc<float>(N), *f_d = dev_alloc<float>(3 * (size_t)N);
   XQ(xeq_model_energy_forces(model, &g, pos_d, z_d, ptr_d, e_d, ea_d, f_d, ws, ws_bytes, st));  // warm-up
   CU(cudaStreamSynchronize(st));
+  cudaGraphExec_t exec = nullptr;
+  if (use_graph) {
+    cudaStream_t aux;
+    CU(cudaStreamCreateWithFlags(&aux, cudaStreamNonBlocking));
+    cudaGraph_t graph;
+    CU(cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));
+    XQ(xeq_model_energy_forces_mt(model, &g, pos_d, z_d, ptr_d, e_d, ea_d, f_d, ws, ws_bytes, st, aux));
+    CU(cudaStreamEndCapture(st, &graph));
+    CU(cudaGraphInstantiate(&exec, graph, 0));
+    CU(cudaGraphLaunch(exec, st));  // warm-up replay
+    CU(cudaStreamSynchronize(st));
+  }
   const auto t0 = std::chrono::steady_clock::now();
-  for (int i = 0; i < n_steps; ++i) XQ(xeq_model_energy_forces(model, &g, pos_d, z_d, ptr_d, e_d, ea_d, f_d, ws, ws_bytes, st));
+  for (int i = 0; i < n_steps; ++i) {
+    if (exec) CU(cudaGraphLaunch(exec, st));
+    else XQ(xeq_model_energy_forces(model, &g, pos_d, z_d, ptr_d, e_d, ea_d, f_d, ws, ws_bytes, st));
+  }
   CU(cudaStreamSynchronize(st));
   const double ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count() / n_steps;
 
@@ -133,7 +151,8 @@ int main(int argc, char** argv) {
   fwrite(ea_h.data(), 4, ea_h.size(), f);
   fwrite(f_h.data(), 4, f_h.size(), f);
   fclose(f);
-  printf("atoms %d edges %d energy %.6f ms_per_evaluation %.4f kernels %lld\n", N, E, e_h, ms, xeq_launch_count());
+  printf("atoms %d edges %d energy %.6f ms_per_evaluation %.4f (%s) kernels %lld\n", N, E, e_h, ms,
+         exec ? "CUDA graph replay, two streams" : "eager launches", xeq_launch_count());
   xeq_model_destroy(model);
   return 0;
 }

@@ -376,6 +376,17 @@ int xeq_silu_bwdbwd(const float* u, const float* g, const float* c, size_t n, fl
  * order: results are bit-identical to the Python module path.  Asynchronous on `stream`, no allocation, no host
  * synchronisation; the workspace must be 256-byte aligned.
  * ---------------------------------------------------------------------------------- */
+/* An engine's edge list -> xeq_graph_t in one call: CSR + transposed CSR + work tiles (xeq_csr_from_sorted_coo,
+ * xeq_csr_transpose, xeq_csr_tile_bounds x 2) carved out of ONE caller-owned device buffer `storage` (256-byte aligned,
+ * xeq_graph_from_coo_bytes() long), and the HOST struct *graph_host filled with pointers into it (plus the caller's
+ * `cell` / `node_graph`).  edge_index [2,E] int64 sorted by center (row 0); periodic structures pass cell [G,3,3] and
+ * cell_offsets [E,3] together.  Launches only; `storage` must outlive every use of the struct. */
+size_t xeq_graph_from_coo_bytes(int32_t n_nodes, int32_t n_edges, int periodic);
+int xeq_graph_from_coo(const int64_t* edge_index, const float* cell_offsets /* or NULL */, const float* cell /* or NULL */,
+                       const int32_t* node_graph /* [N], needed for several periodic graphs, else NULL */,
+                       int32_t n_nodes, int32_t n_edges, int32_t n_graphs, void* storage, size_t storage_bytes,
+                       xeq_graph_t* graph_host, xeq_stream_t stream);
+
 typedef struct xeq_model xeq_model_t;
 size_t xeq_model_weight_count(const xeq_dims_t* dims, int32_t n_layers, int32_t hidden_dim, int32_t embed_dim,
                               int32_t n_species);

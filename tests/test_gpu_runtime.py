@@ -135,16 +135,17 @@ def test_python_free_host_process_matches_the_module_path(tmp_path):
         f.write(struct.pack("<i", n))
         f.write(d["pos"].float().numpy().tobytes())
         f.write(d["atomic_numbers"].to(torch.int32).numpy().tobytes())
-    r = subprocess.run([str(exe), str(tmp_path / "model.xeqw"), str(tmp_path / "structure.bin"), str(tmp_path / "out.bin"), "20"],
-                       capture_output=True, text=True, timeout=120)
-    assert r.returncode == 0, r.stderr
-    print(r.stdout.strip())
-    raw = np.fromfile(tmp_path / "out.bin", dtype=np.float32)
-    assert raw.size == 1 + n + 3 * n
     ref = model(xb.NeighborTransform(5.0)(_dev(d)), compute_forces=True)
-    assert raw[0] == float(ref["energy"].detach()[0])
-    assert np.array_equal(raw[1 : 1 + n], ref["atomic_energies"].detach().cpu().numpy())
-    assert np.array_equal(raw[1 + n :].reshape(n, 3), ref["forces"].cpu().numpy())
+    for extra in ([], ["graph"]):  # eager launches; the evaluation captured as a CUDA graph by the C++ host itself
+        r = subprocess.run([str(exe), str(tmp_path / "model.xeqw"), str(tmp_path / "structure.bin"), str(tmp_path / "out.bin"), "20"] + extra,
+                           capture_output=True, text=True, timeout=120)
+        assert r.returncode == 0, r.stderr
+        print(r.stdout.strip())
+        raw = np.fromfile(tmp_path / "out.bin", dtype=np.float32)
+        assert raw.size == 1 + n + 3 * n
+        assert raw[0] == float(ref["energy"].detach()[0])
+        assert np.array_equal(raw[1 : 1 + n], ref["atomic_energies"].detach().cpu().numpy())
+        assert np.array_equal(raw[1 + n :].reshape(n, 3), ref["forces"].cpu().numpy())
 
 
 @pytest.mark.parametrize("which", ["c4", "box"])
@@ -195,3 +196,44 @@ def test_runtime_ghost_nodes_get_forces_but_contribute_no_energy():
     torch.testing.assert_close(e[0], e_loc.detach(), rtol=1e-6, atol=1e-6)
     torch.testing.assert_close(f, f_ref, rtol=1e-5, atol=2e-6)
     assert float(f[n_loc:].abs().max()) > 1e-3  # ghosts do receive forces
+
+
+@pytest.mark.parametrize("name", ["mol_small", "pbc_small", "pbc_two_graphs"])
+def test_graph_from_coo_feeds_the_runtime(name):
+    """xeq_graph_from_coo: an engine's sorted COO edge list (+ cell offsets) -> xeq_graph_t in one call; the runtime on
+    that structure (edge-block tiles) agrees bit for bit with the module path (molecule tiles for the small molecules)."""
+    import ctypes
+
+    from xequinet_b200 import _lib
+
+    z, cfg, data = load_golden(name)
+    model = _model(cfg, int(z["sd_seed"]))
+    native = runtime.NativeModel(model)
+    d = _dev(cast_data(data, torch.float32))
+    ref = model(dict(d), compute_forces=True)
+    ei, co = orc.canonical_sort(data["edge_index"], data.get("cell_offsets"))
+    ei = ei.to(DEV).contiguous()
+    periodic = "cell" in d
+    co = co.float().to(DEV).contiguous() if periodic else None
+    cell = d["cell"].reshape(-1, 3, 3).contiguous() if periodic else None
+    N, E, G = d["pos"].shape[0], ei.shape[1], d["ptr"].numel() - 1
+    node_graph = d["batch"].to(torch.int32).contiguous()
+    lib = _lib.get()
+    nbytes = lib.xeq_graph_from_coo_bytes(N, E, int(periodic))
+    storage = torch.empty(nbytes, dtype=torch.uint8, device=DEV)
+    g = _lib.XeqGraph()
+    _lib.check(lib.xeq_graph_from_coo(ei.data_ptr(), _lib.ptr(co), _lib.ptr(cell), node_graph.data_ptr(), N, E, G,
+                                      storage.data_ptr(), nbytes, ctypes.byref(g), _lib.stream()), "xeq_graph_from_coo")
+    assert g.n_nodes == N and g.n_edges == E and g.tile_mode == 0 and bool(g.offsets) == periodic
+    seg = d["ptr"].to(torch.int32).contiguous()
+    e, ea, f = torch.empty(G, device=DEV), torch.empty(N, device=DEV), torch.empty(N, 3, device=DEV)
+    wbytes = lib.xeq_model_workspace_bytes(native._handle, ctypes.byref(g), 1)
+    ws = torch.empty(wbytes, dtype=torch.uint8, device=DEV)
+    _lib.check(lib.xeq_model_energy_forces(native._handle, ctypes.byref(g), d["pos"].data_ptr(), d["atomic_numbers"].to(torch.int32).data_ptr(),
+                                           seg.data_ptr(), e.data_ptr(), ea.data_ptr(), f.data_ptr(), ws.data_ptr(), wbytes, _lib.stream()),
+               "xeq_model_energy_forces")
+    assert torch.equal(e, ref["energy"].detach()) and torch.equal(ea, ref["atomic_energies"].detach())
+    assert torch.equal(f, ref["forces"])
+    # too small a buffer is refused
+    assert lib.xeq_graph_from_coo(ei.data_ptr(), _lib.ptr(co), _lib.ptr(cell), node_graph.data_ptr(), N, E, G, storage.data_ptr(), 256,
+                                  ctypes.byref(g), _lib.stream()) == -3

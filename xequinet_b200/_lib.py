@@ -82,6 +82,8 @@ _SIGNATURES = {
     "xeq_silu_bwd": (c_int, [c_void_p, c_void_p, c_size_t, c_void_p, c_void_p]),
     "xeq_silu_bwdbwd": (c_int, [c_void_p, c_void_p, c_void_p, c_size_t, c_void_p, c_void_p, c_void_p]),
     "xeq_layout_convert": (c_int, [c_void_p, c_void_p, c_int32, POINTER(XeqDims), c_int, c_void_p]),
+    "xeq_graph_from_coo_bytes": (c_size_t, [c_int32, c_int32, c_int]),
+    "xeq_graph_from_coo": (c_int, [c_void_p] * 4 + [c_int32] * 3 + [c_void_p, c_size_t, POINTER(XeqGraph), c_void_p]),
     "xeq_model_weight_count": (c_size_t, [POINTER(XeqDims), c_int32, c_int32, c_int32, c_int32]),
     "xeq_model_create": (c_int, [POINTER(XeqDims), c_int32, c_int32, c_int32, c_int32, c_void_p, c_size_t, POINTER(c_void_p)]),
     "xeq_model_destroy": (None, [c_void_p]),
@@ -116,7 +118,7 @@ def get():
 # ---------------------------------------------------------------------------------------------------------
 # per-entry-point device timing (bench.py: step shares by kernel group, tensor-pipe roofline of K3)
 # ---------------------------------------------------------------------------------------------------------
-_UNTIMED = {"xeq_model_weight_count", "xeq_model_create", "xeq_model_destroy", "xeq_csr_tile_count", "xeq_version", "xeq_last_error", "xeq_num_sms", "xeq_launch_count", "xeq_center_tile_edges", "xeq_neighbor_tile_edges"}
+_UNTIMED = {"xeq_graph_from_coo_bytes", "xeq_model_weight_count", "xeq_model_create", "xeq_model_destroy", "xeq_csr_tile_count", "xeq_version", "xeq_last_error", "xeq_num_sms", "xeq_launch_count", "xeq_center_tile_edges", "xeq_neighbor_tile_edges"}
 
 
 class _Profiled:

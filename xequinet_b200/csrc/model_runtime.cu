@@ -13,6 +13,7 @@
 // conditioning).  Weights arrive as one flat fp32 device blob in the order of `layout()` below
 // (xequinet_b200/runtime.py::export_weights writes it from a state_dict); the caller owns it and the workspace.
 #include <math.h>
+#include <string.h>
 
 #include <new>
 
@@ -234,6 +235,70 @@ int norm_bwd_x(const float* x, const float* gamma, const float* g, int ld_g, con
 using namespace xeq;
 
 extern "C" {
+
+// ---- one-call construction of an xeq_graph_t from an engine's edge list ----
+namespace {
+struct GraphParts {
+  int32_t *rowptr, *col, *t_rowptr, *t_row, *t_eid, *tile_ptr, *t_tile_ptr;
+  int8_t* offsets;
+  void* t_ws;
+  size_t t_ws_bytes;
+  int n_tiles, t_n_tiles;
+};
+size_t carve_graph(int32_t N, int32_t E, bool periodic, void* base, GraphParts& p) {
+  const size_t e = (size_t)(E > 0 ? E : 1);
+  p.n_tiles = xeq_csr_tile_count(N, E, xeq_center_tile_edges());
+  p.t_n_tiles = xeq_csr_tile_count(N, E, xeq_neighbor_tile_edges());
+  Carver cv(base);
+  p.rowptr = cv.take<int32_t>((size_t)N + 1);
+  p.col = cv.take<int32_t>(e);
+  p.offsets = periodic ? cv.take<int8_t>(4 * e) : nullptr;
+  p.t_rowptr = cv.take<int32_t>((size_t)N + 1);
+  p.t_row = cv.take<int32_t>(e);
+  p.t_eid = cv.take<int32_t>(e);
+  p.tile_ptr = cv.take<int32_t>((size_t)p.n_tiles + 1);
+  p.t_tile_ptr = cv.take<int32_t>((size_t)p.t_n_tiles + 1);
+  p.t_ws_bytes = xeq_csr_transpose_workspace_bytes(N, E);
+  p.t_ws = cv.take<char>(p.t_ws_bytes);
+  return align_up(cv.off, 256);
+}
+}  // namespace
+
+size_t xeq_graph_from_coo_bytes(int32_t n_nodes, int32_t n_edges, int periodic) {
+  if (n_nodes < 0 || n_edges < 0) return 0;
+  GraphParts p;
+  return carve_graph(n_nodes, n_edges, periodic != 0, nullptr, p);
+}
+
+int xeq_graph_from_coo(const int64_t* edge_index, const float* cell_offsets, const float* cell, const int32_t* node_graph,
+                       int32_t n_nodes, int32_t n_edges, int32_t n_graphs, void* storage, size_t storage_bytes,
+                       xeq_graph_t* graph_host, xeq_stream_t stream) {
+  XEQ_CHECK_ARG(graph_host && storage && n_nodes >= 0 && n_edges >= 0 && n_graphs >= 1, "graph_from_coo: bad arguments");
+  XEQ_CHECK_ARG(edge_index || n_edges == 0, "graph_from_coo: edge_index is NULL");
+  XEQ_CHECK_ARG((cell == nullptr) == (cell_offsets == nullptr), "graph_from_coo: cell and cell_offsets go together");
+  XEQ_CHECK_ARG(!(cell && n_graphs > 1) || node_graph, "graph_from_coo: node_graph is needed for several periodic graphs");
+  XEQ_CHECK_ARG(((uintptr_t)storage & 255) == 0, "graph_from_coo: storage must be 256-byte aligned");
+  const bool periodic = cell != nullptr;
+  GraphParts p;
+  const size_t need = carve_graph(n_nodes, n_edges, periodic, storage, p);
+  if (storage_bytes < need) {
+    set_error("graph_from_coo: storage too small (%zu < %zu bytes)", storage_bytes, need);
+    return XEQ_ERR_WORKSPACE;
+  }
+  XEQ_TRY(xeq_csr_from_sorted_coo(edge_index, cell_offsets, n_nodes, n_edges, p.rowptr, p.col, p.offsets, stream));
+  XEQ_TRY(xeq_csr_transpose(p.rowptr, p.col, n_nodes, n_edges, p.t_rowptr, p.t_row, p.t_eid, p.t_ws, p.t_ws_bytes, stream));
+  XEQ_TRY(xeq_csr_tile_bounds(p.rowptr, n_nodes, n_edges, xeq_center_tile_edges(), p.tile_ptr, stream));
+  XEQ_TRY(xeq_csr_tile_bounds(p.t_rowptr, n_nodes, n_edges, xeq_neighbor_tile_edges(), p.t_tile_ptr, stream));
+  xeq_graph_t g;
+  memset(&g, 0, sizeof(g));
+  g.n_nodes = n_nodes; g.n_edges = n_edges; g.n_graphs = n_graphs;
+  g.rowptr = p.rowptr; g.col = p.col; g.t_rowptr = p.t_rowptr; g.t_row = p.t_row; g.t_eid = p.t_eid;
+  g.offsets = p.offsets; g.cell = cell; g.node_graph = (periodic && n_graphs > 1) ? node_graph : nullptr;
+  g.tile_ptr = p.tile_ptr; g.t_tile_ptr = p.t_tile_ptr; g.n_tiles = p.n_tiles; g.t_n_tiles = p.t_n_tiles;
+  g.tile_mode = 0; g.max_tile_nodes = 0;
+  *graph_host = g;
+  return XEQ_OK;
+}
 
 size_t xeq_model_weight_count(const xeq_dims_t* dims, int32_t n_layers, int32_t hidden_dim, int32_t embed_dim, int32_t n_species) {
   if (!dims || n_layers < 1 || n_layers > MAX_LAYERS || hidden_dim < 4 || embed_dim < 4 || n_species < 1) return 0;
