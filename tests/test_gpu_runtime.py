@@ -92,6 +92,12 @@ def test_runtime_edge_cases_and_weight_file(tmp_path):
     for k in out:
         assert torch.equal(out[k], ref[k].detach()), k
     assert float(out["forces"][0].abs().max()) == 0.0
+    # the runtime reads a copy of the weights: refresh() follows a changed model
+    with torch.no_grad():
+        model.mods["output_energy"].out_mlp[2].weight.mul_(2.0)
+    assert not torch.equal(native(dict(data))["energy"], model(dict(data), compute_forces=False)["energy"].detach())
+    native.refresh(model)
+    assert torch.equal(native(dict(data))["energy"], model(dict(data), compute_forces=False)["energy"].detach())
     # the weight file a C / C++ host reads
     path = tmp_path / "model.xeqw"
     native.save(str(path))

@@ -86,6 +86,11 @@ class NativeModel:
         self._handle = handle
         self._aux = torch.cuda.Stream(device=dev) if branch_stream else None
 
+    def refresh(self, model: torch.nn.Module) -> None:
+        """Re-export the weights into the existing device blob (the runtime reads a COPY of the parameters taken at
+        construction: call this after the model's parameters have changed, e.g. after more training)."""
+        self.blob.copy_(export_weights(model.state_dict(), self.n_layers))
+
     def __del__(self):
         h, self._handle = getattr(self, "_handle", None), None
         if h:
