@@ -409,6 +409,14 @@ int xeq_model_energy_forces_mt(const xeq_model_t* model, const xeq_graph_t* g, c
                                const int32_t* atomic_numbers, const int32_t* seg_ptr,
                                float* energy, float* atomic_energies, float* forces,
                                void* workspace, size_t workspace_bytes, xeq_stream_t stream, xeq_stream_t aux_stream);
+/* ... and with the virial [G,3,3] = -dE/dstrain of the reference's strain trick (nn/basic.py:93-107, 162-199: positions
+ * and cell displaced by a symmetrised per-graph strain): sum_i pos_i (x) dE/dpos_i plus, for periodic graphs, the cell
+ * term from the per-edge d/dr records of the force pass (xeq_edge_cell_grad_rows), symmetrised.  stress = virial /
+ * volume (interface/ase_calculator.py:104-110).  virial NULL = the call above; forces must not be NULL. */
+int xeq_model_energy_forces_virial(const xeq_model_t* model, const xeq_graph_t* g, const float* pos,
+                                   const int32_t* atomic_numbers, const int32_t* seg_ptr,
+                                   float* energy, float* atomic_energies, float* forces, float* virial,
+                                   void* workspace, size_t workspace_bytes, xeq_stream_t stream, xeq_stream_t aux_stream);
 
 #ifdef __cplusplus
 }

@@ -243,3 +243,26 @@ def test_graph_from_coo_feeds_the_runtime(name):
     # too small a buffer is refused
     assert lib.xeq_graph_from_coo(ei.data_ptr(), _lib.ptr(co), _lib.ptr(cell), node_graph.data_ptr(), N, E, G, storage.data_ptr(), 256,
                                   ctypes.byref(g), _lib.stream()) == -3
+
+
+@pytest.mark.parametrize("name", ["mol_small", "pbc_small", "pbc_slab", "pbc_two_graphs"])
+def test_runtime_virial_matches_module_path_and_reference_golden(name):
+    """xeq_model_energy_forces_virial: the strain-trick virial (nn/basic.py:93-107, 162-199) assembled from the force
+    pass's own records, against the autograd module path and the reference's fp64 virial (tests/golden/virial.npz)."""
+    from helpers import GOLDEN
+
+    z, cfg, data = load_golden(name)
+    gold = np.load(GOLDEN / "virial.npz")[f"{name}:virial"]
+    model = _model(cfg, int(z["sd_seed"]))
+    native = runtime.NativeModel(model)
+    ref = model(_dev(cast_data(data, torch.float32)), compute_forces=True, compute_virial=True)
+    out = native(_dev(cast_data(data, torch.float32)), compute_forces=True, compute_virial=True)
+    assert set(out) == {"energy", "atomic_energies", "forces", "virial"}
+    assert torch.equal(out["forces"], ref["forces"].detach()) and torch.equal(out["energy"], ref["energy"].detach())
+    vir, vref = out["virial"].cpu().numpy(), ref["virial"].detach().cpu().numpy()
+    scale = max(1.0, float(np.abs(gold).max()))
+    assert np.abs(vir - vref).max() <= 2e-5 * scale, (np.abs(vir - vref).max(), scale)
+    assert np.abs(vir - gold).max() <= 3e-4 * scale, (np.abs(vir - gold).max(), scale)
+    np.testing.assert_allclose(vir, np.swapaxes(vir, 1, 2), atol=1e-6 * scale)
+    v_only = native(_dev(cast_data(data, torch.float32)), compute_forces=False, compute_virial=True)
+    assert "forces" not in v_only and np.array_equal(v_only["virial"].cpu().numpy(), vir)

@@ -89,6 +89,7 @@ _SIGNATURES = {
     "xeq_model_destroy": (None, [c_void_p]),
     "xeq_model_workspace_bytes": (c_size_t, [c_void_p, POINTER(XeqGraph), c_int]),
     "xeq_model_energy_forces": (c_int, [c_void_p, POINTER(XeqGraph)] + [c_void_p] * 6 + [c_void_p, c_size_t, c_void_p]),
+    "xeq_model_energy_forces_virial": (c_int, [c_void_p, POINTER(XeqGraph)] + [c_void_p] * 7 + [c_void_p, c_size_t, c_void_p, c_void_p]),
     "xeq_model_energy_forces_mt": (c_int, [c_void_p, POINTER(XeqGraph)] + [c_void_p] * 6 + [c_void_p, c_size_t, c_void_p, c_void_p]),
 }
 

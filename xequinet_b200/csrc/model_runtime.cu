@@ -92,6 +92,7 @@ struct Buffers {
   // force pass
   float *gx[2], *gV[2], *ga, *gU, *gt, *g_t0, *g_h, *g_u, *g_cat, *gU2, *gWt, *gvnA, *gvnB, *gvn, *gs, *gv, *ones;
   float* gpos[MAX_LAYERS];
+  float* crow[MAX_LAYERS];  // [9, N] per layer: per-node pieces of the cell gradient (periodic graphs)
   void* edge_ws;
   size_t edge_ws_bytes;
 };
@@ -125,6 +126,7 @@ size_t carve(const xeq_model& mdl, const xeq_graph_t& g, void* base, bool with_f
     b.gvnA = cv.take<float>(N * s.D); b.gvnB = cv.take<float>(N * s.D); b.gvn = cv.take<float>(N * s.D);
     b.gs = cv.take<float>(N * s.H); b.gv = cv.take<float>(N * s.D); b.ones = cv.take<float>(N);
     for (int l = 0; l < L; ++l) b.gpos[l] = cv.take<float>(N * 3);
+    for (int l = 0; l < L; ++l) b.crow[l] = g.offsets ? cv.take<float>(N * 9) : nullptr;
   }
   size_t ews = xeq_edge_message_fwd_workspace_bytes(&g, &mdl.dims);
   if (with_forces) {
@@ -164,6 +166,61 @@ __global__ void forces_kernel(PosGrads pg, float* __restrict__ out, size_t n) {
   float acc = pg.g[pg.n - 1][i];
   for (int l = pg.n - 2; l >= 0; --l) acc += pg.g[l][i];
   out[i] = -1.0f * acc;
+}
+// virial[g] = -dE/dstrain of the reference's strain trick (nn/basic.py:93-107, 162-199): positions and cell displaced by a
+// symmetrised strain, S[a][b] = sum_i pos_i[a] dE/dpos_i[b] + sum_c cell[c][a] dE/dcell[c][b], virial = -(S + S^T) / 2,
+// with dE/dpos = -forces and dE/dcell[c][b] = -sum_n sum_layers rows[3c+b][n] (xeq_edge_cell_grad_rows).
+// One CTA per graph; fixed-order reductions (deterministic).
+struct CellRows { const float* r[MAX_LAYERS]; int n; };
+__global__ void __launch_bounds__(256) virial_kernel(const float* __restrict__ pos, const float* __restrict__ forces, CellRows cr,
+                                                     const float* __restrict__ cell, const int* __restrict__ seg_ptr, int n_nodes,
+                                                     float* __restrict__ virial) {
+  __shared__ float red[8][18];
+  const int gidx = blockIdx.x, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int n0 = seg_ptr[gidx], n1 = seg_ptr[gidx + 1];
+  float acc[18];
+#pragma unroll
+  for (int k = 0; k < 18; ++k) acc[k] = 0.f;
+  for (int i = n0 + (int)threadIdx.x; i < n1; i += 256) {
+    const float p[3] = {pos[3 * i], pos[3 * i + 1], pos[3 * i + 2]};
+    const float gp[3] = {-forces[3 * i], -forces[3 * i + 1], -forces[3 * i + 2]};
+#pragma unroll
+    for (int a = 0; a < 3; ++a)
+#pragma unroll
+      for (int bb = 0; bb < 3; ++bb) acc[3 * a + bb] = fmaf(p[a], gp[bb], acc[3 * a + bb]);
+    if (cell) {
+#pragma unroll
+      for (int k = 0; k < 9; ++k) {
+        float v = 0.f;
+        for (int l = cr.n - 1; l >= 0; --l) v += cr.r[l][(size_t)k * n_nodes + i];
+        acc[9 + k] += v;
+      }
+    }
+  }
+#pragma unroll
+  for (int k = 0; k < 18; ++k) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) acc[k] += __shfl_xor_sync(0xffffffffu, acc[k], o);
+    if (lane == 0) red[warp][k] = acc[k];
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float S[9], R[9];
+    for (int k = 0; k < 9; ++k) {
+      float a = 0.f, r = 0.f;
+      for (int w = 0; w < 8; ++w) { a += red[w][k]; r += red[w][9 + k]; }
+      S[k] = a;
+      R[k] = -r;  // dE/dcell[c][b]
+    }
+    if (cell) {
+      const float* cg = cell + 9 * (size_t)gidx;
+      for (int a = 0; a < 3; ++a)
+        for (int bb = 0; bb < 3; ++bb)
+          for (int c = 0; c < 3; ++c) S[3 * a + bb] = fmaf(cg[3 * c + a], R[3 * c + bb], S[3 * a + bb]);
+    }
+    for (int a = 0; a < 3; ++a)
+      for (int bb = 0; bb < 3; ++bb) virial[9 * (size_t)gidx + 3 * a + bb] = -0.5f * (S[3 * a + bb] + S[3 * bb + a]);
+  }
 }
 inline unsigned blocks_for(size_t n) { return (unsigned)((n + 255) / 256); }
 
@@ -342,12 +399,21 @@ int xeq_model_energy_forces(const xeq_model_t* model, const xeq_graph_t* g, cons
 int xeq_model_energy_forces_mt(const xeq_model_t* model, const xeq_graph_t* g, const float* pos, const int32_t* atomic_numbers,
                                const int32_t* seg_ptr, float* energy, float* atomic_energies, float* forces,
                                void* workspace, size_t workspace_bytes, xeq_stream_t stream, xeq_stream_t aux_stream) {
+  return xeq_model_energy_forces_virial(model, g, pos, atomic_numbers, seg_ptr, energy, atomic_energies, forces, nullptr,
+                                        workspace, workspace_bytes, stream, aux_stream);
+}
+
+int xeq_model_energy_forces_virial(const xeq_model_t* model, const xeq_graph_t* g, const float* pos, const int32_t* atomic_numbers,
+                                   const int32_t* seg_ptr, float* energy, float* atomic_energies, float* forces, float* virial,
+                                   void* workspace, size_t workspace_bytes, xeq_stream_t stream, xeq_stream_t aux_stream) {
   XEQ_CHECK_ARG(model && g && seg_ptr && energy && atomic_energies, "model_energy_forces: NULL argument");
+  XEQ_CHECK_ARG(!virial || forces, "model_energy_forces: the virial needs the force pass (forces != NULL)");
   const int N = g->n_nodes, G = g->n_graphs, L = model->n_layers;
   XEQ_CHECK_ARG(N >= 0 && G >= 0, "model_energy_forces: bad graph");
   cudaStream_t st = (cudaStream_t)stream;
   if (N == 0) {
     if (G) XEQ_CUDA(cudaMemsetAsync(energy, 0, sizeof(float) * G, st));
+    if (G && virial) XEQ_CUDA(cudaMemsetAsync(virial, 0, sizeof(float) * 9 * G, st));
     return XEQ_OK;
   }
   XEQ_CHECK_ARG(pos && atomic_numbers && workspace, "model_energy_forces: NULL argument");
@@ -473,6 +539,7 @@ int xeq_model_energy_forces_mt(const xeq_model_t* model, const xeq_graph_t* g, c
     XEQ_TRY(xeq_edge_message_bwd(g, dims, pos, b.s[l], b.vn[l], w + mw.Wrbf, w + mw.brbf, w + lo.freq, b.gx[cur], b.gV[cur],
                                  first ? nullptr : b.gs, first ? nullptr : b.gv, b.gpos[l], nullptr, nullptr, nullptr,
                                  b.edge_ws, b.edge_ws_bytes, st));
+    if (virial && g->offsets) XEQ_TRY(xeq_edge_cell_grad_rows(g, dims, b.edge_ws, b.crow[l], st));  // before the workspace is reused
     if (!first) {
       XEQ_TRY(fork());
       XEQ_TRY(norm_bwd_x(b.V[2 * l], w + mw.on_w, b.gv, 0, b.gV[cur], N, s.m0, s.m1, s.m2, b.gV[cur ^ 1], sb));
@@ -489,6 +556,13 @@ int xeq_model_energy_forces_mt(const xeq_model_t* model, const xeq_graph_t* g, c
   for (int l = 0; l < L; ++l) pg.g[l] = b.gpos[l];
   forces_kernel<<<blocks_for((size_t)N * 3), 256, 0, st>>>(pg, forces, (size_t)N * 3);
   XEQ_LAUNCHED(1);
+  if (virial && G > 0) {
+    CellRows cr;
+    cr.n = L;
+    for (int l = 0; l < L; ++l) cr.r[l] = b.crow[l];
+    virial_kernel<<<G, 256, 0, st>>>(pos, forces, cr, g->offsets ? g->cell : nullptr, seg_ptr, N, virial);
+    XEQ_LAUNCHED(1);
+  }
   return XEQ_OK;
 }
 

@@ -14,8 +14,9 @@ call (interface/ase_calculator.py:86-96 rebuilds the neighbour list on the host 
     positions and one device -> host copy of the results;
   * energies / forces of the default model go through the C inference runtime (`runtime.NativeModel` ->
     `xeq_model_energy_forces`: forward and force pass scheduled inside the library, no autograd graph; bit-identical to
-    the module path and ~4x faster per call on small molecules when launched eagerly).  Stress, and models with
-    conditioning modules or extra heads, use the module path.
+    the module path and ~4x faster per call on small molecules when launched eagerly), stress included (the virial
+    of the strain trick from the force pass's own records).  Models with conditioning modules or extra heads use the
+    module path.
 
 `atoms.wrap()` of the reference (:86) is not needed: K1 wraps internally and returns offsets that refer to the
 unwrapped positions (data/radius_graph.py:186-190), so the caller's Atoms object is left untouched."""
@@ -103,8 +104,8 @@ class XequiCalculator(_AseCalculator):
         else:
             data = self.transform({k: v.to(self.device) for k, v in host.items()})
             data.pop(keys.PBC, None)
-            if self.native is not None and not want_s:
-                out = self.native(data, compute_forces=want_f)
+            if self.native is not None:
+                out = self.native(data, compute_forces=want_f, compute_virial=want_s)
             else:
                 out = self.model(data, compute_forces=want_f, compute_virial=want_s)
         # one device -> host transfer of everything that was asked for

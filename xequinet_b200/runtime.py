@@ -99,7 +99,7 @@ class NativeModel:
             except Exception:  # interpreter shutdown: the library may already be gone
                 pass
 
-    def __call__(self, data: Dict[str, torch.Tensor], compute_forces: bool = True) -> Dict[str, torch.Tensor]:
+    def __call__(self, data: Dict[str, torch.Tensor], compute_forces: bool = True, compute_virial: bool = False) -> Dict[str, torch.Tensor]:
         data = compute_edge_data(data, compute_forces=False)  # resolves the neighbour structure and the batch bookkeeping
         graph, ptr32 = data[keys.GRAPH], data["_xeq_ptr32"]
         pos = data[keys.POSITIONS].detach().contiguous()
@@ -107,17 +107,21 @@ class NativeModel:
         N, G, dev = pos.shape[0], ptr32.numel() - 1, pos.device
         energy = torch.empty(G, dtype=torch.float32, device=dev)
         e_atom = torch.empty(N, dtype=torch.float32, device=dev)
-        forces = torch.empty((N, 3), dtype=torch.float32, device=dev) if compute_forces else None
+        want_f = compute_forces or compute_virial  # the virial comes out of the force pass
+        forces = torch.empty((N, 3), dtype=torch.float32, device=dev) if want_f else None
+        virial = torch.empty((G, 3, 3), dtype=torch.float32, device=dev) if compute_virial else None
         lib = _lib.get()
-        nbytes = lib.xeq_model_workspace_bytes(self._handle, graph.struct, int(compute_forces))
+        nbytes = lib.xeq_model_workspace_bytes(self._handle, graph.struct, int(want_f))
         ws = torch.empty(nbytes, dtype=torch.uint8, device=dev)
         aux = self._aux.cuda_stream if self._aux is not None else None
-        _lib.check(lib.xeq_model_energy_forces_mt(self._handle, graph.struct, _lib.ptr(pos), _lib.ptr(z), _lib.ptr(ptr32),
-                                                  _lib.ptr(energy), _lib.ptr(e_atom), _lib.ptr(forces), _lib.ptr(ws), nbytes,
-                                                  _lib.stream(), aux), "xeq_model_energy_forces_mt")
+        _lib.check(lib.xeq_model_energy_forces_virial(self._handle, graph.struct, _lib.ptr(pos), _lib.ptr(z), _lib.ptr(ptr32),
+                                                      _lib.ptr(energy), _lib.ptr(e_atom), _lib.ptr(forces), _lib.ptr(virial),
+                                                      _lib.ptr(ws), nbytes, _lib.stream(), aux), "xeq_model_energy_forces_virial")
         out = {keys.TOTAL_ENERGY: energy, keys.ATOMIC_ENERGIES: e_atom}
         if compute_forces:
             out[keys.FORCES] = forces
+        if compute_virial:
+            out[keys.VIRIAL] = virial
         return out
 
     def save(self, path: str) -> None:
